@@ -1,0 +1,144 @@
+/* rtb200.h — C ABI of librtb200.so, the B200 (sm_100a) render backend for the per-pixel ray-cast path of
+ * TobiasDeBruijn/UU-INFOGR-Raytracer, Raytracer/RayTracer.cs.
+ *
+ * The reference exposes no plugin / FFI interface: its trace methods are private members of `RayTracer`.
+ * The seam this library fills is the pixel loop in `RayTracer.Tick()` (RayTracer.cs:898-901): the C# host keeps
+ * its scene arrays (:441-465), camera state (:494-523), `Surface` (surface.cs:7-20) and display path, and replaces
+ * that loop by one P/Invoke call to rt_render() per frame.  INTEGRATION.md shows the C# binding.
+ *
+ * Conventions: every function returns 0 on success or a negative rt_status; nothing throws or aborts across the
+ * ABI; rt_last_error() returns the message of the last failing call on that context.  A context is
+ * single-caller (the reference renders from one thread, template.cs:175-179); distinct contexts are independent.
+ * There is NO CPU fallback: without a CUDA device every entry point fails with RT_ERR_CUDA.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB200_ABI_VERSION 1
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,    /* bad argument */
+    RT_ERR_CUDA = -2,       /* CUDA runtime error / no device */
+    RT_ERR_NO_SCENE = -3,   /* rt_render before rt_set_scene */
+    RT_ERR_UNSUPPORTED = -4,/* e.g. max_depth above RT_MAX_DEPTH */
+    RT_ERR_PEER = -5        /* peer access / IPC mapping failed */
+} rt_status;
+
+#define RT_MAX_DEPTH 32     /* the reference's ReflectionRecursionLimit, RayTracer.cs:490 */
+
+/* accel for rt_set_scene */
+#define RT_ACCEL_AUTO 0
+#define RT_ACCEL_BRUTE 1    /* the reference's loop over every sphere (RayTracer.cs:577,792,975) */
+#define RT_ACCEL_LBVH 2     /* LBVH over spheres; returns the same hits as RT_ACCEL_BRUTE (tests/test_lbvh*.py) */
+
+typedef struct rt_context rt_context;   /* opaque, library-owned; one per C# `RayTracer` instance (RayTracer.cs:437) */
+
+/* Camera of one frame, by value.  Replaces the per-pixel evaluation of _cameraPosition, CameraRightDirection,
+ * CameraUpDirection, CameraForwardDirection (RayTracer.cs:494-523, used at :967-971) and `viewParams`
+ * (planeWidth, planeHeight, NearClip; RayTracer.cs:892-896).  All f64 trig stays on the C# side. */
+typedef struct rt_camera {
+    float pos[3];
+    float right[3];
+    float up[3];
+    float forward[3];
+    float view_params[3];
+} rt_camera;
+
+/* Ray counters use the nearest-first deterministic accounting: primary = w*h*spp; secondary = number of
+ * TraceSecondaryRay calls on the selected hit chain (RayTracer.cs:746,857); shadow = IntersectShadowLight calls on
+ * the selected chain (:752,864).  Counters are filled only by rt_render_debug (instrumented kernel); rt_render
+ * fills the timings and leaves the counters 0. */
+typedef struct rt_stats {
+    uint64_t primary, shadow, secondary;
+    float kernel_ms;   /* device time of the render kernel(s), max over devices */
+    float gather_ms;   /* extra device time for the row-tile gather to device 0 (0 when fused into the kernel) */
+    float d2h_ms;      /* device->host copy into host_pixels (0 when headless) */
+} rt_stats;
+
+/* Creates a context on `n_devices` CUDA devices (1, 2, 4 or 8; device_ids NULL => 0..n-1).  With n > 1 every frame is
+ * partitioned by interleaved row tiles and gathered on device_ids[0] over NVLink by peer stores fused into the
+ * render kernel.  Replaces `new RayTracer(screen)` (RayTracer.cs:535, template.cs:80). */
+int rt_create(rt_context** out, const int* device_ids, int n_devices);
+
+/* Uploads (copies) the scene: the arrays RayTracer.cs:441-465 and `_ambientLightColor` :469, in C# field order.
+ *   spheres: n x 18 floats  center[3], radius, Kd[3], Ka[3], Ks[3], n, Km[3], radiusSquared   (:308-338, :60-80)
+ *   planes : n x 20 floats  center[3], normal[3], Kd[3], Ka[3], Ks[3], n, Km[3], isTiled(0/1)  (:260-303)
+ *            isTiled is accepted but ignored: the reference's constructor forces it to true (:289).
+ *   lights : n x 4 floats   position[3], intensity                                             (:236-255)
+ * radiusSquared is passed through, not recomputed (:336). */
+int rt_set_scene(rt_context* ctx, const float* spheres, int n_spheres, const float* planes, int n_planes,
+                 const float* lights, int n_lights, const float ambient[3], int accel);
+
+/* Renders one frame — the replacement for the loop RayTracer.cs:898-901 (TracePixel for every x,y).
+ *   max_depth : the reference's ReflectionRecursionLimit (32)   spp : 1 in the reference; >1 = jittered extension
+ *   host_pixels: w*h int32, 0x00RRGGBB, row-major (`Surface.pixels`, surface.cs:9-20; written as :1038); NULL => headless
+ * Synchronous: returns after the frame is in host_pixels (or, headless, after the kernel finished). */
+int rt_render(rt_context* ctx, const rt_camera* cam, int width, int height, int max_depth, int spp, uint32_t seed,
+              int32_t* host_pixels, rt_stats* stats);
+
+/* Headless batch: renders n_frames frames (one camera each) in one persistent launch per device into a ring of
+ * device framebuffers (benchmarks / offline fly-throughs).  host_pixels: n_frames*w*h int32 or NULL. */
+int rt_render_batch(rt_context* ctx, const rt_camera* cams, int n_frames, int width, int height, int max_depth,
+                    int spp, uint32_t seed, int32_t* host_pixels, rt_stats* stats);
+
+/* Instrumented render (separate kernel instantiation; not for timing).  All outputs nullable:
+ *   host_hash  w*h uint32 : order-independent hash of every (ray kind, hit id, t bits, shadow result) on the chain
+ *   host_aov_id/t w*h     : primary hit id (sphere index, n_spheres+plane index, -1 none) and its distance
+ *   counters[12]          : primary, shadow, secondary, sphere_tests, sphere_disc_pos, plane_tests, shade_diffuse,
+ *                           shade_specular, shade_mirror, shaded_hits, 0, 0 (same order as the oracle's) */
+int rt_render_debug(rt_context* ctx, const rt_camera* cam, int width, int height, int max_depth, int spp, uint32_t seed,
+                    int32_t* host_pixels, uint32_t* host_hash, int32_t* host_aov_id, float* host_aov_t,
+                    uint64_t* counters, rt_stats* stats);
+
+/* Single-ray sphere queries against the uploaded scene (LBVH == brute-force equality harness).
+ *   rays6: n x 6 floats origin[3], direction[3] (direction need not be normalised)
+ *   kind : 0 primary fold (:975-981), 1 secondary fold (:792-808), 2 shadow any-hit eps=0.001 (:573-582; id = 1 occluded / 0 clear)
+ *   accel: RT_ACCEL_BRUTE or RT_ACCEL_LBVH */
+int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, int accel, int32_t* out_id, float* out_t);
+
+/* ---- device-pointer / multi-process interface (torchrun: one process per GPU) --------------------------------- */
+
+/* Row-tile partition of this context inside a `world` of cooperating contexts (default rank 0 of 1). Tile t of
+ * `tile_rows` rows belongs to rank t % world. */
+int rt_set_partition(rt_context* ctx, int rank, int world, int tile_rows);
+
+/* Renders this context's row tiles of one frame (or of n_frames frames, frame f at dev_pixels + f*w*h) into a
+ * caller-provided DEVICE buffer, asynchronously on `cuda_stream` (a cudaStream_t, NULL = the legacy default stream).
+ * dev_pixels may be a peer mapping of another GPU's framebuffer (CUDA IPC): the gather is then the kernel's own stores. */
+int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int width, int height, int max_depth, int spp,
+                     uint32_t seed, void* dev_pixels, void* cuda_stream);
+
+/* CUDA IPC plumbing so that ranks 1..N-1 can store straight into rank 0's framebuffer. handle64 = 64 bytes. */
+int rt_ipc_export(rt_context* ctx, void* dev_ptr, void* handle64);
+int rt_ipc_open(rt_context* ctx, const void* handle64, void** out_dev_ptr);
+int rt_ipc_close(rt_context* ctx, void* dev_ptr);
+
+/* Device memory owned by the context (so that non-torch hosts need no CUDA runtime of their own). */
+int rt_dev_alloc(rt_context* ctx, uint64_t bytes, void** out_dev_ptr);
+int rt_dev_free(rt_context* ctx, void* dev_ptr);
+int rt_dev_to_host(rt_context* ctx, void* host_dst, const void* dev_src, uint64_t bytes);
+int rt_sync(rt_context* ctx);
+
+/* Page-locks (cudaHostRegister) a host buffer the caller keeps alive — e.g. the pinned `Surface.pixels` array — so that
+ * the device->host copy of rt_render runs at full PCIe rate instead of through a staging buffer. Optional. */
+int rt_host_register(rt_context* ctx, void* host_ptr, uint64_t bytes);
+int rt_host_unregister(rt_context* ctx, void* host_ptr);
+
+/* Number of render-kernel launches issued by this context so far (bench.py reports it as gpu_launches). */
+uint64_t rt_launch_count(const rt_context* ctx);
+
+int rt_destroy(rt_context* ctx);
+const char* rt_last_error(const rt_context* ctx);   /* valid until the next call on ctx; ctx NULL => last create error */
+int rt_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */

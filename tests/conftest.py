@@ -1,0 +1,46 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "uu-infogr-raytracer_b200"))
+sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def _has_gpu():
+    try:
+        import ctypes
+        lib = ctypes.CDLL("libcuda.so.1")
+        n = ctypes.c_int(0)
+        if lib.cuInit(0) != 0:
+            return False
+        lib.cuDeviceGetCount(ctypes.byref(n))
+        return n.value > 0
+    except OSError:
+        return False
+
+
+HAS_GPU = _has_gpu()
+
+
+def pytest_collection_modifyitems(config, items):
+    if HAS_GPU:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Builds the oracle, the host-emulation test library and (if missing) librtb200.so."""
+    import __graft_entry__ as g
+    g.build()
+    return True

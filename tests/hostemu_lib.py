@@ -1,0 +1,42 @@
+"""ctypes binding of tests/hostemu/libhostemu.so: the DEVICE trace code compiled as plain C++ (test-only)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        subprocess.run(["make", "-C", HERE, "-s"], check=True)
+        _lib = C.CDLL(os.path.join(HERE, "libhostemu.so"))
+        fp = C.POINTER(C.c_float)
+        _lib.emu_render.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
+                                    C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), fp, C.POINTER(C.c_uint64)]
+        _lib.emu_render.restype = C.c_int
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None and a.size else None
+
+
+def render(scene, cam, w, h, max_depth=32, spp=1, seed=0, tiny=False, debug=False):
+    lib = load()
+    n = w * h
+    px = np.zeros(n, np.int32)
+    hsh = np.zeros(n, np.uint32); aid = np.zeros(n, np.int32); at = np.zeros(n, np.float32); cnt = np.zeros(10, np.uint64)
+    cam = np.ascontiguousarray(cam, np.float32)
+    rc = lib.emu_render(_fp(scene.spheres), len(scene.spheres), _fp(scene.planes), len(scene.planes), _fp(scene.lights),
+                        len(scene.lights), _fp(scene.ambient), _fp(cam), w, h, max_depth, spp, seed, 1 if tiny else 0,
+                        px.ctypes.data_as(C.POINTER(C.c_int32)),
+                        hsh.ctypes.data_as(C.POINTER(C.c_uint32)) if debug else None,
+                        aid.ctypes.data_as(C.POINTER(C.c_int32)) if debug else None, _fp(at) if debug else None,
+                        cnt.ctypes.data_as(C.POINTER(C.c_uint64)) if debug else None)
+    assert rc == 0
+    return dict(pixels=px.reshape(h, w), hash=hsh.reshape(h, w), aov_id=aid.reshape(h, w), aov_t=at.reshape(h, w),
+                counters=[int(v) for v in cnt])

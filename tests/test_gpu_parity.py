@@ -1,0 +1,222 @@
+"""GPU parity tests: librtb200.so (through the C ABI) vs the CPU oracle and the committed golden fixtures.
+Bar (BASELINE.json): per-channel error <= 1/255 on >= 99.9 % of pixels, none above 4/255.  Geometry must be exact:
+the per-pixel chain hash (hit ids, t bits, shadow results) and the ray counters must equal the oracle's."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import scenes
+from common import GOLDEN_SCENES, assert_image_parity, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt(built):
+    import rtb200
+    return rtb200
+
+
+@pytest.fixture()
+def ctx(rt):
+    c = rt.Context([0])
+    yield c
+    c.close()
+
+
+def _check_debug(ctx, sc, cam, w, h, depth, spp=1, seed=0):
+    ref = O.render(sc, cam, w, h, depth, spp, seed, want_hash=True, want_aov=True)
+    got = ctx.render_debug(cam, w, h, depth, spp, seed)
+    assert np.array_equal(got["hash"], ref["hash"]), "chain hash differs on %d pixels" % (got["hash"] != ref["hash"]).sum()
+    assert np.array_equal(got["aov_id"], ref["aov_id"])
+    assert np.array_equal(got["aov_t"].view(np.uint32), ref["aov_t"].view(np.uint32))
+    assert got["counters"] == {k: ref["counters"][k] for k in got["counters"]}
+    assert_image_parity(got["pixels"], ref["pixels"], "debug kernel")
+    return ref
+
+
+@pytest.mark.parametrize("w,h,depth,camkw", [
+    (1280, 720, 32, dict()),                                             # BASELINE configs[0]
+    (1280, 720, 32, dict(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15)),
+    (640, 360, 8, dict(pos=(-2.0, 2.5, 3.0), yaw=-0.4, pitch=0.5)),
+    (640, 360, 0, dict(pos=(0, 4.0, 6.0), pitch=1.2)),
+])
+def test_default_scene_vs_oracle(ctx, w, h, depth, camkw):
+    sc = scenes.default_scene()
+    cam = scenes.make_camera(width=w, height=h, **camkw)
+    ctx.set_scene(sc)
+    ref = _check_debug(ctx, sc, cam, w, h, depth)
+    px, st = ctx.render(cam, w, h, depth)
+    ndiff = assert_image_parity(px, ref["pixels"], "render kernel")
+    assert ndiff == 0, "render kernel differs from the oracle on %d pixels (strict fp32: expected 0)" % ndiff
+    assert st.kernel_ms > 0
+
+
+def test_default_scene_4k_depth8(ctx):
+    """BASELINE configs[1] at full size."""
+    w, h = 3840, 2160
+    sc = scenes.default_scene()
+    cam = scenes.make_camera(width=w, height=h)
+    ctx.set_scene(sc)
+    ref = O.render(sc, cam, w, h, 8)
+    px, _ = ctx.render(cam, w, h, 8)
+    assert assert_image_parity(px, ref["pixels"], "4K") == 0
+    # size-independent properties (Appendix B)
+    got = ctx.render_debug(cam, w, h, 8)
+    ids = got["aov_id"]
+    assert np.all(px[ids == -1] == 0) and abs((ids == -1).mean() - 0.4367) < 0.002
+    assert got["counters"]["primary"] == w * h
+    assert got["counters"]["sphere_tests"] == 3 * (got["counters"]["primary"] + got["counters"]["secondary"] + got["counters"]["shadow"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fixtures(ctx, name):
+    g = load_golden(name)
+    sc = GOLDEN_SCENES[name]()
+    ctx.set_scene(sc)
+    w, h, depth, spp, seed = int(g["w"]), int(g["h"]), int(g["depth"]), int(g["spp"]), int(g["seed"])
+    got = ctx.render_debug(g["cam"], w, h, depth, spp, seed)
+    assert np.array_equal(got["hash"], g["hash"])
+    assert [got["counters"][k] for k in O.COUNTER_NAMES[:10]] == [int(v) for v in g["counters"]]
+    px, _ = ctx.render(g["cam"], w, h, depth, spp, seed)
+    assert_image_parity(px, g["pixels"], name)
+    assert np.array_equal(px, g["pixels"])
+
+
+@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (12, 1), (16, 2), (17, 9), (40, 3), (200, 4)])
+def test_random_scenes(ctx, n, seed):
+    """tiny (kernel-parameter) and global-memory scene paths, every material class, 2 planes, 3 lights."""
+    sc = scenes.small_random_scene(n, seed)
+    cam = scenes.make_camera(pos=(0, 1.5, -4.0), pitch=0.1, width=320, height=200)
+    ctx.set_scene(sc)
+    ref = _check_debug(ctx, sc, cam, 320, 200, 8)
+    px, _ = ctx.render(cam, 320, 200, 8)
+    assert assert_image_parity(px, ref["pixels"]) == 0
+
+
+def test_supersampling_extension(ctx):
+    sc = scenes.default_scene()
+    cam = scenes.make_camera(pos=(-2, 2.5, 3), yaw=-0.4, pitch=0.5, width=256, height=144)
+    ctx.set_scene(sc)
+    ref = _check_debug(ctx, sc, cam, 256, 144, 8, spp=16, seed=123)
+    px, _ = ctx.render(cam, 256, 144, 8, spp=16, seed=123)
+    assert assert_image_parity(px, ref["pixels"]) == 0
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (3, 2), (37, 23), (255, 9), (1023, 5), (4, 4096)])
+def test_odd_sizes_and_unaligned_rows(ctx, w, h):
+    sc = scenes.default_scene()
+    cam = scenes.make_camera(width=w, height=h)
+    ctx.set_scene(sc)
+    ref = O.render(sc, cam, w, h, 8)["pixels"]
+    px, _ = ctx.render(cam, w, h, 8)
+    assert np.array_equal(px, ref)
+
+
+def test_empty_scene_and_no_lights(ctx):
+    empty = scenes.Scene(np.zeros((0, 18), np.float32), np.zeros((0, 20), np.float32), np.zeros((0, 4), np.float32), scenes.REF_AMBIENT)
+    cam = scenes.make_camera(width=64, height=48)
+    ctx.set_scene(empty)
+    px, _ = ctx.render(cam, 64, 48, 32)
+    assert np.all(px == 0)
+    d = scenes.default_scene()
+    nolights = scenes.Scene(d.spheres, d.planes, np.zeros((0, 4), np.float32), d.ambient)
+    ctx.set_scene(nolights)
+    px, _ = ctx.render(cam, 64, 48, 32)
+    assert np.array_equal(px, O.render(nolights, cam, 64, 48, 32)["pixels"])
+
+
+def test_batch_equals_single_frames(ctx):
+    sc = scenes.default_scene()
+    ctx.set_scene(sc)
+    w, h = 320, 180
+    cams = [scenes.make_camera(pos=(0.1 * i, 0.05 * i, -0.2 * i), yaw=0.03 * i, pitch=0.02 * i, width=w, height=h) for i in range(5)]
+    batch, st = ctx.render_batch(np.stack(cams), w, h, 8, headless=False)
+    for i, cam in enumerate(cams):
+        single, _ = ctx.render(cam, w, h, 8)
+        assert np.array_equal(batch[i], single)
+        assert np.array_equal(single, O.render(sc, cam, w, h, 8)["pixels"])
+
+
+@pytest.mark.parametrize("world,tile_rows", [(2, 8), (4, 3), (8, 16), (8, 1)])
+def test_row_tile_partition_covers_frame(rt, world, tile_rows):
+    """Multi-GPU partition logic on one GPU: `world` partitioned contexts render their interleaved row tiles into ONE
+    shared device framebuffer; the union must be byte-identical to the unpartitioned frame, and each rank must touch
+    only its own rows."""
+    sc = scenes.default_scene()
+    w, h = 250, 131
+    cam = scenes.make_camera(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15, width=w, height=h)
+    base = rt.Context([0]); base.set_scene(sc)
+    full, _ = base.render(cam, w, h, 8)
+    fb = base.dev_alloc(w * h * 4)
+    for rank in range(world):
+        c = rt.Context([0]); c.set_scene(sc); c.set_partition(rank, world, tile_rows)
+        c.render_device(cam[None], w, h, 8, 1, 0, fb)
+        c.sync()
+        c.close()
+    got = base.dev_to_host(fb, w * h * 4).reshape(h, w)
+    assert np.array_equal(got, full)
+    # ownership: render rank 1 alone into a zeroed buffer
+    fb2 = base.dev_alloc(w * h * 4)
+    c = rt.Context([0]); c.set_scene(sc); c.set_partition(1 % world, world, tile_rows)
+    # cudaMalloc memory is not zeroed: render rank-owned rows, then compare only those rows
+    c.render_device(cam[None], w, h, 8, 1, 0, fb2); c.sync()
+    part = base.dev_to_host(fb2, w * h * 4).reshape(h, w)
+    rows = np.arange(h)
+    mine = (rows // tile_rows) % world == (1 % world)
+    assert np.array_equal(part[mine], full[mine])
+    c.close()
+    base.dev_free(fb); base.dev_free(fb2); base.close()
+
+
+def test_host_mirror_tick_and_input(rt):
+    """The RayTracer/Surface mirror: Tick() fills screen.pixels like RayTracer.cs:886-901; WASD / mouse handlers move
+    the camera like :543-554 / :1058-1061."""
+    screen = rt.Surface(320, 180)
+    app = rt.RayTracer(screen)
+    app.Tick()
+    sc = scenes.default_scene()
+    assert np.array_equal(screen.pixels.reshape(180, 320), O.render(sc, scenes.make_camera(width=320, height=180), 320, 180, 32)["pixels"])
+    for k in "WWWDDA":
+        app.OnKeyPress(k)
+    app.OnKeyPress("Space")
+    app.OnMouseMove(36.0, 18.0)
+    app.Tick()
+    cam = app.camera()
+    assert abs(float(app._yaw) - 0.1) < 1e-6 and abs(float(app._pitch) - 0.05) < 1e-6
+    assert np.array_equal(screen.pixels.reshape(180, 320), O.render(sc, cam, 320, 180, 32)["pixels"])
+    app.close()
+
+
+def test_error_behaviour(rt):
+    c = rt.Context([0])
+    cam = scenes.make_camera(width=16, height=16)
+    with pytest.raises(rt.RtError) as e:
+        c.render(cam, 16, 16)
+    assert e.value.code == -3                      # RT_ERR_NO_SCENE
+    c.set_scene(scenes.default_scene())
+    with pytest.raises(rt.RtError) as e:
+        c.render(cam, 0, 16)
+    assert e.value.code == -1
+    with pytest.raises(rt.RtError) as e:
+        c.render(cam, 16, 16, max_depth=33)
+    assert e.value.code == -4
+    with pytest.raises(rt.RtError):
+        rt.Context([0, 1, 2])                      # 3 devices is not a supported partition
+    px, _ = c.render(cam, 16, 16)                   # context still usable after errors
+    assert px.shape == (16, 16)
+    c.close()
+
+
+def test_query_spheres_matches_oracle(ctx):
+    sc = scenes.small_random_scene(200, 4)
+    ctx.set_scene(sc)
+    rng = np.random.default_rng(3)
+    o = rng.uniform(-6, 6, (5000, 3)).astype(np.float32); o[:, 1] = np.abs(o[:, 1])
+    d = rng.normal(size=(5000, 3)).astype(np.float32) * rng.uniform(0.1, 30, (5000, 1)).astype(np.float32)
+    rays = np.concatenate([o, d], 1)
+    for kind in (0, 1, 2):
+        gi, gt = ctx.query_spheres(rays, kind)
+        oi, ot = O.query_spheres(sc.spheres, rays, kind)
+        assert np.array_equal(gi, oi), kind
+        assert np.array_equal(gt.view(np.uint32), ot.view(np.uint32)), kind

@@ -1,0 +1,65 @@
+"""The DEVICE trace code (csrc/rt_trace.cuh, rt_scene.cuh) compiled as plain C++ must equal the oracle bit for bit:
+pixels, per-pixel chain hash (every hit id / t bits / shadow result), primary-hit AOVs and ray counters.
+This checks the kernel's logic on a box without a GPU; the -m gpu tests check the compiled kernels themselves."""
+import numpy as np
+import pytest
+
+import hostemu_lib as E
+import oracle_lib as O
+import scenes
+from common import GOLDEN_SCENES, golden_names, load_golden
+
+
+def _compare(sc, cam, w, h, depth, spp=1, seed=0, tiny=False):
+    a = O.render(sc, cam, w, h, depth, spp, seed, want_hash=True, want_aov=True)
+    b = E.render(sc, cam, w, h, depth, spp, seed, tiny=tiny, debug=True)
+    c = E.render(sc, cam, w, h, depth, spp, seed, tiny=tiny, debug=False)
+    assert np.array_equal(a["pixels"], b["pixels"])
+    assert np.array_equal(a["pixels"], c["pixels"])          # fast path (early-outs enabled) == instrumented path
+    assert np.array_equal(a["hash"], b["hash"])
+    assert np.array_equal(a["aov_id"], b["aov_id"])
+    assert np.array_equal(a["aov_t"].view(np.uint32), b["aov_t"].view(np.uint32))
+    assert [a["counters"][k] for k in O.COUNTER_NAMES[:10]] == b["counters"]
+
+
+@pytest.mark.parametrize("tiny", [True, False])
+@pytest.mark.parametrize("camkw,depth", [(dict(), 32), (dict(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15), 8),
+                                         (dict(pos=(-2.0, 2.5, 3.0), yaw=-0.4, pitch=0.5), 0), (dict(pos=(0, 4.0, 6.0), pitch=1.2), 32)])
+def test_default_scene(built, tiny, camkw, depth):
+    _compare(scenes.default_scene(), scenes.make_camera(width=320, height=180, **camkw), 320, 180, depth, tiny=tiny)
+
+
+def test_supersampling(built):
+    _compare(scenes.default_scene(), scenes.make_camera(pos=(-2, 2.5, 3), yaw=-0.4, pitch=0.5, width=128, height=96), 128, 96, 3, spp=4, seed=7, tiny=True)
+
+
+@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (12, 1), (16, 2), (40, 3), (200, 4)])
+def test_random_scenes(built, n, seed):
+    sc = scenes.small_random_scene(n, seed)
+    cam = scenes.make_camera(pos=(0, 1.5, -4.0), pitch=0.1, width=160, height=100)
+    _compare(sc, cam, 160, 100, 8, tiny=(n <= 16))
+
+
+def test_empty_scene(built):
+    sc = scenes.Scene(np.zeros((0, 18), np.float32), np.zeros((0, 20), np.float32), np.zeros((0, 4), np.float32), scenes.REF_AMBIENT)
+    cam = scenes.make_camera(width=33, height=17)
+    r = E.render(sc, cam, 33, 17, 32, tiny=True)
+    assert np.all(r["pixels"] == 0)
+    _compare(sc, cam, 33, 17, 32, tiny=True)
+
+
+def test_no_lights_and_odd_sizes(built):
+    sc = scenes.default_scene()
+    sc = scenes.Scene(sc.spheres, sc.planes, np.zeros((0, 4), np.float32), sc.ambient)
+    _compare(sc, scenes.make_camera(width=37, height=23), 37, 23, 4, tiny=True)
+    _compare(scenes.default_scene(), scenes.make_camera(width=1, height=1), 1, 1, 4, tiny=False)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(built, name):
+    g = load_golden(name)
+    sc = GOLDEN_SCENES[name]()
+    r = E.render(sc, g["cam"], int(g["w"]), int(g["h"]), int(g["depth"]), int(g["spp"]), int(g["seed"]),
+                 tiny=len(sc.spheres) <= 16, debug=True)
+    assert np.array_equal(r["pixels"], g["pixels"])
+    assert np.array_equal(r["hash"], g["hash"])

@@ -1,0 +1,311 @@
+// rt_trace.cuh — the per-sample trace of RayTracer.cs restructured for a GPU thread:
+//   descent : geometry only — resolve the nearest hit, reflect, repeat (one ray chain)
+//   unwind  : shade the recorded hits back-to-front, accumulating colour in the reference's exact order
+// The reference shades every intersected primitive and then keeps the nearest (RayTracer.cs:975-993, :792-825);
+// all its trace functions are pure, so select-then-shade returns the same bits (oracle test
+// test_faithful_equals_nearest).  Every arithmetic expression below keeps the reference's operation order; the
+// only liberties taken are hoists of loop-invariant subexpressions and early-outs proven equivalent in DESIGN.md.
+//
+// Templated on a scene policy SC that supplies the records and the three sphere queries, so the brute-force loops
+// and the LBVH traversal share all shading code:
+//   int  n_spheres()/n_planes()/n_lights();  f3 ambient();
+//   f4   sphere_geom(i)  -> (cx, cy, cz, r^2);      const MatRec& sphere_mat(i)
+//   const PlaneRec& plane(i);  const LightRec& light(i)
+//   void nearest_primary  (o, dir, a, a2, a4, &sel, &d, dbg)     RayTracer.cs:975-981
+//   void nearest_secondary(o, dir, a, a2, a4, &sel, &d, dbg)     RayTracer.cs:792-808
+//   bool shadow_any       (hit, light, dbg)                       RayTracer.cs:573-582
+#pragma once
+#include "rt_math.cuh"
+
+namespace rtb {
+
+enum { MAT_MIRROR = 1u, MAT_DIFFUSE = 2u, MAT_SPEC = 4u };
+
+struct MatRec {            // 16 words; Material RayTracer.cs:60-93
+    f3 kd; float n;        // diffuseColor, specularity
+    f3 ka; uint32_t flags; // ambientColor, IsMirror/IsDiffuse/HasSpecularity (:85-93) evaluated at upload
+    f3 ks; float pad0;     // specularColor
+    f3 km; float pad1;     // mirrorColor
+};
+struct PlaneRec {          // Plane RayTracer.cs:260-303 + upload-time invariants
+    f3 n; float cn;        // normal (as given, not normalised), Dot(center, normal) (:594)
+    f3 e1; float pad0;     // checkerboard basis (:760-765), depends on the plane only
+    f3 e2; float pad1;
+    MatRec m;
+};
+struct LightRec {          // Light RayTracer.cs:236-255 + invariants of the shadow ray whose DIRECTION is `position` (:574)
+    f3 p; float intensity;
+    float a, a2, a4, pad;  // Dot(p,p), 2*a, 4*a  (:617, :624, :621)
+};
+struct CamRec { f3 pos, right, up, fwd, view; };
+
+struct HitRec { f3 o; f3 dir; float d; int prim; };   // prim >= 0: sphere index; prim < 0: ~plane index
+
+#ifndef RT_INF
+#define RT_INF (bits2f(0x7f800000u))
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// Debug policies
+// ---------------------------------------------------------------------------------------------------------
+struct NoDbg {
+    static constexpr bool enabled = false;
+    RT_HD void sphere_test(bool) {}
+    RT_HD void plane_test() {}
+    RT_HD void ray(uint32_t, uint32_t, uint32_t, float) {}
+    RT_HD void shadow(uint32_t, uint32_t, bool) {}
+    RT_HD void shaded(bool, bool) {}
+    RT_HD void spec() {}
+    RT_HD void primary_aov(int, float) {}
+};
+struct FullDbg {
+    static constexpr bool enabled = true;
+    uint32_t hash = 0;
+    uint32_t primary = 0, n_shadow = 0, secondary = 0, sphere_tests = 0, sphere_disc_pos = 0, plane_tests = 0;
+    uint32_t shade_diffuse = 0, shade_specular = 0, shade_mirror = 0, shaded_hits = 0;
+    int aov_id = -1; float aov_t = 0.0f; bool aov_set = false;
+    RT_HD void sphere_test(bool disc_pos) { sphere_tests++; if (disc_pos) sphere_disc_pos++; }
+    RT_HD void plane_test() { plane_tests++; }
+    RT_HD void ray(uint32_t level, uint32_t kind, uint32_t code, float d) {
+        hash += event_hash(level, kind, code, f2bits(d));
+        if (kind == 1) primary++; else secondary++;
+    }
+    RT_HD void shadow(uint32_t level, uint32_t li, bool occluded) {
+        hash += event_hash(level, 3, li, occluded ? 1u : 0u); n_shadow++; shade_diffuse++;
+    }
+    RT_HD void shaded(bool mirror, bool) { shaded_hits++; if (mirror) shade_mirror++; }
+    RT_HD void spec() { shade_specular++; }
+    RT_HD void primary_aov(int id, float t) { if (!aov_set) { aov_id = id; aov_t = t; aov_set = true; } }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Sphere test — IntersectsSphere RayTracer.cs:613-642.
+// Given per-ray a = Dot(d,d), a2 = 2*a, a4 = 4*a (hoisted; `4 * a * c` associates as (4*a)*c).
+// Returns true and *t = distance iff the reference reports a collision with this epsilon.
+// Equivalences used (DESIGN.md §sphere test):  with s = sqrt(D) >= 0 and a2 >= 0,  t1 = (-b-s)/a2 <= t2 = (-b+s)/a2
+// (monotone rounding) or t1 is NaN, hence  distanceEps > 0  <=>  t1 - eps > 0,  and then distance = min(t1,t2) = t1;
+// and t1 > 0 requires b < 0, so b >= 0 (or NaN) is a miss without evaluating the discriminant.
+// ---------------------------------------------------------------------------------------------------------
+template <class DBG>
+RT_HD bool sphere_hit(f3 oc, f3 dir, float r2, float a2, float a4, float eps, float* t, DBG& dbg) {
+    float b = 2 * dot3(oc, dir);                                  // :618
+    if (!DBG::enabled && !(b < 0)) return false;
+    float c = dot3(oc, oc) - r2;                                  // :619
+    float D = b * b - a4 * c;                                     // :621
+    dbg.sphere_test(D >= 0);
+    if (!(D >= 0)) return false;                                  // :622
+    float s = sqrtf(D);                                           // :623  (float)Math.Sqrt((double)D) == sqrtf(D)
+    float t1 = (-b - s) / a2;                                     // :627
+    if (!(t1 - eps > 0)) return false;                            // :629-635
+    *t = t1;                                                      // :632
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Brute-force sphere queries: the reference's loops over every sphere, in array order.
+// Mixed into scene policies that expose n_spheres() and sphere_geom(i).
+// ---------------------------------------------------------------------------------------------------------
+template <class SC, class DBG>
+RT_HD void brute_nearest_primary(const SC& sc, f3 o, f3 dir, float a2, float a4, int* sel, float* dsel, DBG& dbg) {
+    int best = -1; float nearest = RT_INF;
+    const int ns = sc.n_spheres();
+    for (int i = 0; i < ns; i++) {                                // :975
+        f4 g = sc.sphere_geom(i);
+        float t;
+        if (sphere_hit(sub3(o, mk3(g.x, g.y, g.z)), dir, g.w, a2, a4, 0.0f, &t, dbg))
+            if (nearest > t) { nearest = t; best = i; }           // :977 (t > 0 is implied by the hit)
+    }
+    *sel = best; *dsel = nearest;
+}
+template <class SC, class DBG>
+RT_HD void brute_nearest_secondary(const SC& sc, f3 o, f3 dir, float a2, float a4, int* sel, float* dsel, DBG& dbg) {
+    int best = -1; float closest = RT_INF;
+    const int ns = sc.n_spheres();
+    for (int i = 0; i < ns; i++) {                                // :792
+        f4 g = sc.sphere_geom(i);
+        float t;
+        if (sphere_hit(sub3(o, mk3(g.x, g.y, g.z)), dir, g.w, a2, a4, 0.0f, &t, dbg)) {
+            float te = t - 0.01f;
+            if (te > 0 && te < closest) { closest = t; best = i; } // :804-805 — offset compared with un-offset: order dependent
+        }
+    }
+    *sel = best; *dsel = closest;
+}
+template <class SC, class DBG>
+RT_HD bool brute_shadow_any(const SC& sc, f3 hit, const LightRec& l, DBG& dbg) {
+    bool occluded = false;
+    const int ns = sc.n_spheres();
+    for (int i = 0; i < ns; i++) {                                // :577
+        f4 g = sc.sphere_geom(i);
+        float t;
+        if (sphere_hit(sub3(hit, mk3(g.x, g.y, g.z)), l.p, g.w, l.a2, l.a4, 0.001f, &t, dbg)) {   // :578
+            occluded = true;
+            if (!DBG::enabled) break;     // the result is a boolean OR: leaving early cannot change it
+        }
+    }
+    return occluded;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Shading — ShapePhongShading RayTracer.cs:665-695
+// ---------------------------------------------------------------------------------------------------------
+template <class DBG>
+RT_HD f3 shape_phong(f3 hit, f3 V, f3 N, const MatRec& m, const LightRec& l, DBG& dbg) {
+    f3 L = normalize3(sub3(l.p, hit));                            // :667
+    f3 diff = mk3(0, 0, 0);
+    if (m.flags & MAT_DIFFUSE) {                                  // :671
+        float angle = dot3(N, L);                                 // :672
+        diff = mulf3(m.kd, cs_maxf(0.0f, angle));                 // :677-678
+    }
+    f3 spec = mk3(0, 0, 0);
+    if (m.flags & MAT_SPEC) {                                     // :682
+        f3 rv = sub3(L, mulf3(N, 2 * dot3(L, N)));                // :683-684
+        float s = dot3(V, normalize3(rv));                        // :685-688
+        float base = cs_maxf(0.0f, s);
+        float pw;
+        // (float)Math.Pow((double)base, (double)n) :691.  pow(x,1) == x exactly; pow(x,.5) rounds as sqrtf.
+        if (m.n == 1.0f) pw = base;
+        else if (m.n == 0.5f) pw = sqrtf(base);
+        else pw = (float)pow((double)base, (double)m.n);
+        spec = mulv3(m.ks, splat3(pw));
+        dbg.spec();
+    }
+    return add3(diff, spec);                                      // :694
+}
+
+// Colour of one recorded hit given the colour Cin seen by its reflection ray: TraceSphere :846-875 / TracePlane :736-779
+template <class SC, class DBG>
+RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& dbg) {
+    f3 hit = add3(h.o, mulf3(h.dir, h.d));                        // :846 / :736
+    f3 col = mk3(0, 0, 0);
+    if (h.prim >= 0) {
+        const MatRec& m = sc.sphere_mat(h.prim);
+        dbg.shaded((m.flags & MAT_MIRROR) != 0, true);
+        if (m.flags & MAT_MIRROR) col = add3(col, mulv3(Cin, m.km));                       // :857-858
+        if (m.flags & MAT_DIFFUSE) {                                                       // :862
+            f4 g = sc.sphere_geom(h.prim);
+            f3 N = normalize3(sub3(hit, mk3(g.x, g.y, g.z)));                              // :706
+            f3 V = normalize3(h.dir);                                                      // :668
+            float att = 1 / h.d * h.d;                                                     // :866  ((1/d)*d)
+            const int nl = sc.n_lights();
+            for (int li = 0; li < nl; li++) {                                              // :863
+                const LightRec& l = sc.light(li);
+                bool occ = sc.shadow_any(hit, l, dbg);                                     // :864
+                dbg.shadow(level, (uint32_t)li, occ);
+                float I = occ ? 0.0f : l.intensity;                                        // :581
+                f3 ph = shape_phong(hit, V, N, m, l, dbg);
+                col = add3(col, mulv3(mulf3(splat3(I), att), ph));                         // :868-869
+            }
+        }
+        col = add3(col, mulv3(sc.ambient(), m.ka));                                        // :873
+    } else {
+        const PlaneRec& p = sc.plane(~h.prim);
+        const MatRec& m = p.m;
+        dbg.shaded((m.flags & MAT_MIRROR) != 0, false);
+        if (m.flags & MAT_MIRROR) col = add3(col, mulv3(Cin, m.km));                       // :746-747
+        if (m.flags & MAT_DIFFUSE) {                                                       // :750
+            f3 V = normalize3(h.dir);
+            double dd = (double)h.d;
+            float att = (float)(1.0 / (dd * dd));                                          // :754  Math.Pow(d,2) == d*d exactly in f64
+            float u = dot3(p.e1, hit);                                                     // :766
+            float v = dot3(p.e2, hit);                                                     // :767
+            int32_t cb = (int32_t)(((uint32_t)cs_f2i(u) + (uint32_t)cs_f2i(v)) & 1u);      // :769  ((int)u + (int)v) & 1
+            f3 tile = splat3((float)cb);                                                   // :770
+            const int nl = sc.n_lights();
+            for (int li = 0; li < nl; li++) {                                              // :751
+                const LightRec& l = sc.light(li);
+                bool occ = sc.shadow_any(hit, l, dbg);                                     // :752
+                dbg.shadow(level, (uint32_t)li, occ);
+                float I = occ ? 0.0f : l.intensity;
+                f3 ph = shape_phong(hit, V, p.n, m, l, dbg);                               // :652-654
+                f3 t = mulv3(mulv3(mulf3(splat3(I), att), ph), tile);                      // :774
+                col = add3(col, mk3(cs_maxf(t.x, 0.0f), cs_maxf(t.y, 0.0f), cs_maxf(t.z, 0.0f)));   // :775 (.Max(0))
+            }
+        }
+        col = add3(col, mulv3(sc.ambient(), m.ka));                                        // :778
+    }
+    return col;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One sample: TracePixel RayTracer.cs:962-1002 with (fx, fy) in place of (x, y).
+// `stack` must hold cap+1 records.
+// ---------------------------------------------------------------------------------------------------------
+template <class SC, class DBG>
+RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float fw, float fh, int cap,
+                      HitRec* stack, DBG& dbg) {
+    float u = fx / fw - 0.5f;                                                              // :964
+    float v = fy / fh - 0.5f;
+    f3 local = mulv3(mk3(u, v, 1.0f), cam.view);                                           // :965
+    f3 vp = add3(add3(add3(cam.pos, mulf3(cam.right, local.x)), mulf3(cam.up, local.y)), mulf3(cam.fwd, local.z));   // :967-969
+    f3 o = cam.pos;
+    f3 dir = normalize3(sub3(vp, cam.pos));                                                // :971
+
+    int bounce = 0, top = 0;
+    f3 C = mk3(0, 0, 0);
+    const int np = sc.n_planes();
+    for (;;) {
+        float a = dot3(dir, dir);                                                          // :617
+        float a2 = 2 * a;                                                                  // :624
+        float a4 = 4 * a;                                                                  // :621
+        int sel_s; float d_s;
+        if (bounce == 0) sc.nearest_primary(o, dir, a2, a4, &sel_s, &d_s, dbg);
+        else sc.nearest_secondary(o, dir, a2, a4, &sel_s, &d_s, dbg);
+        int sel_p = -1; float d_p = RT_INF;
+        for (int i = 0; i < np; i++) {                                                     // :985 / :812
+            const PlaneRec& p = sc.plane(i);
+            float t = (-o.x * p.n.x - o.y * p.n.y - o.z * p.n.z + p.cn) / dot3(dir, p.n);  // :591-596
+            dbg.plane_test();
+            if (t > 0 && t < d_p) { d_p = t; sel_p = i; }                                  // :598 + :987 / :819
+        }
+        bool pick_s = d_s < d_p;                                                           // :993 / :825
+        bool none = !pick_s && sel_p < 0;
+        float d = pick_s ? d_s : (none ? 0.0f : d_p);
+        uint32_t code = pick_s ? (uint32_t)sel_s : (none ? 0xFFFFFFFFu : (uint32_t)(sc.n_spheres() + sel_p));
+        dbg.ray((uint32_t)top, bounce == 0 ? 1u : 2u, code, d);
+        if (bounce == 0) dbg.primary_aov((int)code, d);
+        if (none) break;                                                                   // nothing hit: black
+        if (d - 0.01f <= 0) break;                                                         // :839 / :731 (distance kept, colour black)
+        if (bounce > cap) { if (!pick_s) C = mk3(1, 1, 1); break; }                        // :843 black / :734 white
+        HitRec& h = stack[top++];
+        h.o = o; h.dir = dir; h.d = d; h.prim = pick_s ? sel_s : ~sel_p;
+        uint32_t flags = pick_s ? sc.sphere_mat(sel_s).flags : sc.plane(sel_p).m.flags;
+        if (!(flags & MAT_MIRROR)) break;                                                  // :850 / :739
+        bounce++;                                                                          // :851 / :740
+        f3 hit = add3(o, mulf3(dir, d));                                                   // :846 / :736
+        f3 N;
+        if (pick_s) { f4 g = sc.sphere_geom(sel_s); N = normalize3(sub3(hit, mk3(g.x, g.y, g.z))); }   // :854
+        else N = sc.plane(sel_p).n;                                                        // :743
+        dir = sub3(dir, mulf3(N, 2 * dot3(dir, N)));                                       // :719
+        o = hit;
+    }
+    while (top > 0) {
+        --top;
+        C = shade_hit(sc, stack[top], C, (uint32_t)top, dbg);
+    }
+    return C;
+}
+
+// One pixel: spp == 1 is the reference; spp > 1 is the jittered extension (BASELINE.json configs[4]).
+template <class SC, class DBG>
+RT_HD uint32_t trace_pixel(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int cap, int spp, uint32_t seed,
+                           HitRec* stack, DBG& dbg) {
+    float fw = (float)w, fh = (float)h;
+    f3 col;
+    if (spp <= 1) {
+        col = trace_sample(sc, cam, (float)x, (float)y, fw, fh, cap, stack, dbg);
+    } else {
+        f3 acc = mk3(0, 0, 0);
+        for (int s = 0; s < spp; s++) {
+            uint32_t k = ((uint32_t)y * (uint32_t)w + (uint32_t)x) * (uint32_t)spp + (uint32_t)s;
+            uint32_t h1 = pcg_hash(k ^ seed), h2 = pcg_hash(h1);
+            float jx = (float)(h1 >> 8) * 5.9604644775390625e-08f;
+            float jy = (float)(h2 >> 8) * 5.9604644775390625e-08f;
+            acc = add3(acc, trace_sample(sc, cam, (float)x + jx, (float)y + jy, fw, fh, cap, stack, dbg));
+        }
+        col = mulf3(acc, 1.0f / (float)spp);
+    }
+    return pack_color(col);                                                                // :1000 -> :1038, :1046-1052
+}
+
+}  // namespace rtb

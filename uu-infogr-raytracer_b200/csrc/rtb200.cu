@@ -1,0 +1,619 @@
+// rtb200.cu — render kernels and the C ABI (include/rtb200.h) of the B200 ray-cast backend.
+//
+// Replaces the pixel loop of RayTracer.Tick() (Raytracer/RayTracer.cs:898-901) and everything it calls
+// (TracePixel :962-1002, TraceSphere :835-876, TracePlane :729-780, TraceSecondaryRay :789-826,
+// IntersectsSphere :613-642, IntersectPlane :590-604, IntersectShadowLight :573-582, ShapePhongShading :665-695,
+// ShiftColor/SetPixel :1037-1052).  Strict fp32 (see rt_math.cuh); no tensor cores (no dense contraction on this path).
+//
+// Work decomposition: a frame is cut into ROW TILES of `tile_rows` rows (contiguous pixel ranges in the row-major
+// framebuffer); tile t belongs to rank t % world (multi-GPU row interleave).  A rank's tiles are cut into chunks of
+// CHUNK = 256 threads x PPT pixels; a grid of (SMs x resident CTAs) walks its chunks with a grid stride, which
+// interleaves sky / floor / sphere chunks over all CTAs.  Each thread owns PPT=4 adjacent pixels and writes them with
+// one 128-bit store; the store address may be a peer (NVLink) mapping of rank 0's framebuffer — the gather is fused.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rtb200.h"
+#include "rt_scene.cuh"
+
+using namespace rtb;
+
+namespace {
+
+constexpr int BLOCK = 256;
+constexpr int PPT = 4;                      // pixels per thread (one 128-bit store)
+constexpr int CHUNK = BLOCK * PPT;          // pixels per CTA work item
+constexpr int STACK_RECS = RT_MAX_DEPTH + 1;
+constexpr int INLINE_CAMS = 16;
+
+struct FrameParams {
+    int w, h, cap, spp;
+    uint32_t seed;
+    int n_frames;
+    int rank, world, tile_rows;
+    int tiles_total;            // ceil(h / tile_rows)
+    int tiles_mine;             // tiles owned by this rank
+    int chunks_per_tile;        // ceil(tile_rows * w / CHUNK)
+    long long frame_stride;     // pixels between consecutive frames in `out`
+    uint32_t* out;              // framebuffer(s): 0x00RRGGBB, row-major (Surface.pixels, surface.cs:9-20)
+    const CamRec* cams;         // n_frames cameras (device), or nullptr => cam_inline
+    CamRec cam_inline[INLINE_CAMS];   // small batches travel in the parameter block: no upload, no host sync
+};
+
+struct DebugOut {
+    uint32_t* hash; int32_t* aov_id; float* aov_t; unsigned long long* counters;
+};
+
+template <class SC, class DBG>
+__device__ __forceinline__ uint32_t render_one(const SC& sc, const CamRec& cam, const FrameParams& fp, long long p,
+                                               HitRec* stack, DBG& dbg) {
+    int y = (int)(p / fp.w);
+    int x = (int)(p - (long long)y * fp.w);
+    return trace_pixel(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg);
+}
+
+// Walks this rank's (frame, tile, chunk) work items with a grid stride.
+template <class SC, class SCD>
+__device__ __forceinline__ void render_loop(const SCD& scd, const FrameParams& fp) {
+    SC sc(scd);
+    HitRec stack[STACK_RECS];
+    NoDbg dbg;
+    const long long npix = (long long)fp.w * fp.h;
+    const long long tile_pix = (long long)fp.tile_rows * fp.w;
+    const long long items_per_frame = (long long)fp.tiles_mine * fp.chunks_per_tile;
+    const long long n_items = items_per_frame * fp.n_frames;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int frame = (int)(item / items_per_frame);
+        long long r = item - (long long)frame * items_per_frame;
+        int k = (int)(r / fp.chunks_per_tile);                 // my k-th tile
+        int j = (int)(r - (long long)k * fp.chunks_per_tile);  // chunk inside the tile
+        long long tile = (long long)k * fp.world + fp.rank;
+        long long base = tile * tile_pix;
+        long long end = base + tile_pix; if (end > npix) end = npix;
+        long long p0 = base + (long long)j * CHUNK + (long long)threadIdx.x * PPT;
+        if (p0 >= end) continue;
+        const CamRec& cam = fp.cams ? fp.cams[frame] : fp.cam_inline[frame];
+        uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
+        uint32_t px[PPT];
+#pragma unroll 1
+        for (int q = 0; q < PPT; q++) {
+            long long p = p0 + q;
+            px[q] = (p < end) ? render_one(sc, cam, fp, p, stack, dbg) : 0u;
+        }
+        if (p0 + PPT <= end && ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0)) {
+            *reinterpret_cast<uint4*>(out + p0) = make_uint4(px[0], px[1], px[2], px[3]);
+        } else {
+            for (int q = 0; q < PPT; q++) if (p0 + q < end) out[p0 + q] = px[q];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_render_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp) {
+    render_loop<TinyScene>(scd, fp);
+}
+__global__ void __launch_bounds__(BLOCK) k_render_global(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp) {
+    render_loop<GlobalScene>(scd, fp);
+}
+
+// Instrumented kernel: one thread per pixel, no early-outs in sphere tests, writes hash / AOVs / counters.
+template <class SC, class SCD>
+__device__ __forceinline__ void debug_loop(const SCD& scd, const FrameParams& fp, const DebugOut& dout) {
+    SC sc(scd);
+    HitRec stack[STACK_RECS];
+    const long long npix = (long long)fp.w * fp.h;
+    unsigned long long cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+        FullDbg dbg;
+        uint32_t c = render_one(sc, fp.cam_inline[0], fp, p, stack, dbg);
+        fp.out[p] = c;
+        if (dout.hash) dout.hash[p] = dbg.hash;
+        if (dout.aov_id) dout.aov_id[p] = dbg.aov_id;
+        if (dout.aov_t) dout.aov_t[p] = dbg.aov_t;
+        cnt[0] += dbg.primary; cnt[1] += dbg.n_shadow; cnt[2] += dbg.secondary; cnt[3] += dbg.sphere_tests;
+        cnt[4] += dbg.sphere_disc_pos; cnt[5] += dbg.plane_tests; cnt[6] += dbg.shade_diffuse; cnt[7] += dbg.shade_specular;
+        cnt[8] += dbg.shade_mirror; cnt[9] += dbg.shaded_hits;
+    }
+    if (dout.counters)
+        for (int i = 0; i < 10; i++) if (cnt[i]) atomicAdd(dout.counters + i, cnt[i]);
+}
+__global__ void __launch_bounds__(BLOCK) k_debug_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
+    debug_loop<TinyScene>(scd, fp, dout);
+}
+__global__ void __launch_bounds__(BLOCK) k_debug_global(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
+    debug_loop<GlobalScene>(scd, fp, dout);
+}
+
+// Sphere-query kernel (LBVH == brute equality harness, rt_query_spheres).
+__global__ void __launch_bounds__(BLOCK) k_query_brute(const __grid_constant__ GlobalSceneData scd, const float* rays6, int n, int kind,
+                                                        int32_t* out_id, float* out_t) {
+    GlobalScene sc(scd);
+    NoDbg dbg;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        f3 o = mk3(rays6[6 * r], rays6[6 * r + 1], rays6[6 * r + 2]);
+        f3 d = mk3(rays6[6 * r + 3], rays6[6 * r + 4], rays6[6 * r + 5]);
+        float a = dot3(d, d), a2 = 2 * a, a4 = 4 * a;
+        int sel = -1; float t = 0.0f;
+        if (kind == 0) { sc.nearest_primary(o, d, a2, a4, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
+        else if (kind == 1) { sc.nearest_secondary(o, d, a2, a4, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
+        else {
+            LightRec l; l.p = d; l.intensity = 1.0f; l.a = a; l.a2 = a2; l.a4 = a4; l.pad = 0;
+            sel = sc.shadow_any(o, l, dbg) ? 1 : 0; t = 0.0f;
+        }
+        out_id[r] = sel; out_t[r] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------
+struct DeviceState {
+    int dev = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // scene
+    f4* sgeom = nullptr; MatRec* smat = nullptr; PlaneRec* planes = nullptr; LightRec* lights = nullptr;
+    CamRec* cams = nullptr; int cams_cap = 0;
+    // framebuffer ring (device 0 of the context only, unless partitioned multi-process)
+    uint32_t* fb = nullptr; size_t fb_pixels = 0;
+};
+
+}  // namespace
+
+struct rt_context {
+    std::vector<DeviceState> devs;
+    std::string err;
+    bool has_scene = false;
+    bool tiny = false;
+    TinySceneData tiny_data;
+    GlobalSceneData gdata_host;     // counts + ambient (pointers per device filled at launch)
+    int accel = RT_ACCEL_BRUTE;
+    int rank = 0, world = 1, tile_rows = 8;
+    bool peer_ok = false;
+    std::atomic<uint64_t> launches{0};
+};
+
+namespace {
+
+std::string g_create_err;
+std::mutex g_err_mu;
+
+int fail(rt_context* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else { std::lock_guard<std::mutex> lk(g_err_mu); g_create_err = msg; }
+    if (getenv("RT_LOG")) fprintf(stderr, "[rtb200] error %d: %s\n", code, msg.c_str());
+    return code;
+}
+#define CU_TRY(ctx, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, RT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+void free_scene(DeviceState& d) {
+    cudaSetDevice(d.dev);
+    cudaFree(d.sgeom); cudaFree(d.smat); cudaFree(d.planes); cudaFree(d.lights);
+    d.sgeom = nullptr; d.smat = nullptr; d.planes = nullptr; d.lights = nullptr;
+}
+
+int ensure_fb(rt_context* ctx, size_t pixels) {
+    DeviceState& d0 = ctx->devs[0];
+    if (d0.fb_pixels >= pixels) return RT_OK;
+    CU_TRY(ctx, cudaSetDevice(d0.dev));
+    if (d0.fb) CU_TRY(ctx, cudaFree(d0.fb));
+    d0.fb = nullptr; d0.fb_pixels = 0;
+    CU_TRY(ctx, cudaMalloc(&d0.fb, pixels * sizeof(uint32_t)));
+    d0.fb_pixels = pixels;
+    return RT_OK;
+}
+
+CamRec to_cam(const rt_camera& c) {
+    CamRec r;
+    r.pos = mk3(c.pos[0], c.pos[1], c.pos[2]); r.right = mk3(c.right[0], c.right[1], c.right[2]);
+    r.up = mk3(c.up[0], c.up[1], c.up[2]); r.fwd = mk3(c.forward[0], c.forward[1], c.forward[2]);
+    r.view = mk3(c.view_params[0], c.view_params[1], c.view_params[2]);
+    return r;
+}
+
+int check_frame_args(rt_context* ctx, const void* cam, int w, int h, int depth, int spp) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!cam) return fail(ctx, RT_ERR_INVALID, "camera is NULL");
+    if (w <= 0 || h <= 0) return fail(ctx, RT_ERR_INVALID, "width/height must be positive");
+    if (depth < 0 || depth > RT_MAX_DEPTH) return fail(ctx, RT_ERR_UNSUPPORTED, "max_depth must be in [0, 32]");
+    if (spp < 1 || spp > 1024) return fail(ctx, RT_ERR_INVALID, "spp must be in [1, 1024]");
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_set_scene has not been called");
+    return RT_OK;
+}
+
+FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp, uint32_t seed, int n_frames,
+                        int rank, int world, uint32_t* out, long long frame_stride) {
+    FrameParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.w = w; fp.h = h; fp.cap = depth; fp.spp = spp; fp.seed = seed; fp.n_frames = n_frames;
+    fp.rank = rank; fp.world = world; fp.tile_rows = ctx->tile_rows;
+    fp.tiles_total = (h + fp.tile_rows - 1) / fp.tile_rows;
+    fp.tiles_mine = fp.tiles_total > rank ? (fp.tiles_total - rank + world - 1) / world : 0;
+    fp.chunks_per_tile = (int)(((long long)fp.tile_rows * w + CHUNK - 1) / CHUNK);
+    fp.frame_stride = frame_stride;
+    fp.out = out;
+    fp.cams = nullptr;
+    return fp;
+}
+
+// Launches the render kernel for one device's share. Asynchronous on `stream`.
+int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaStream_t stream) {
+    long long n_items = (long long)fp.tiles_mine * fp.chunks_per_tile * fp.n_frames;
+    if (n_items == 0) return RT_OK;
+    int resident = 2048 / BLOCK;
+    long long grid = (long long)d.sm_count * resident;
+    if (grid > n_items) grid = n_items;
+    if (ctx->tiny) {
+        k_render_tiny<<<(unsigned)grid, BLOCK, 0, stream>>>(ctx->tiny_data, fp);
+    } else {
+        GlobalSceneData g = ctx->gdata_host;
+        g.sgeom = d.sgeom; g.smat = d.smat; g.planes = d.planes; g.lights = d.lights;
+        k_render_global<<<(unsigned)grid, BLOCK, 0, stream>>>(g, fp);
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return RT_OK;
+}
+
+int upload_cams(rt_context* ctx, DeviceState& d, const rt_camera* cams, int n, cudaStream_t stream) {
+    if (d.cams_cap < n) {
+        if (d.cams) CU_TRY(ctx, cudaFree(d.cams));
+        d.cams = nullptr; d.cams_cap = 0;
+        CU_TRY(ctx, cudaMalloc(&d.cams, sizeof(CamRec) * (size_t)n));
+        d.cams_cap = n;
+    }
+    std::vector<CamRec> h((size_t)n);
+    for (int i = 0; i < n; i++) h[i] = to_cam(cams[i]);
+    CU_TRY(ctx, cudaMemcpyAsync(d.cams, h.data(), sizeof(CamRec) * (size_t)n, cudaMemcpyHostToDevice, stream));
+    CU_TRY(ctx, cudaStreamSynchronize(stream));   // h goes out of scope
+    return RT_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+int rt_abi_version(void) { return RTB200_ABI_VERSION; }
+
+const char* rt_last_error(const rt_context* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    return g_create_err.c_str();
+}
+
+int rt_create(rt_context** out, const int* device_ids, int n_devices) {
+    if (!out) return fail(nullptr, RT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!(n_devices == 1 || n_devices == 2 || n_devices == 4 || n_devices == 8))
+        return fail(nullptr, RT_ERR_INVALID, "n_devices must be 1, 2, 4 or 8");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, RT_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (librtb200 has no CPU fallback)");
+    rt_context* ctx = new rt_context();
+    ctx->devs.resize((size_t)n_devices);
+    for (int i = 0; i < n_devices; i++) {
+        int dev = device_ids ? device_ids[i] : i;
+        if (dev < 0 || dev >= count) { delete ctx; return fail(nullptr, RT_ERR_INVALID, "device id out of range"); }
+        DeviceState& d = ctx->devs[(size_t)i];
+        d.dev = dev;
+        cudaDeviceProp prop;
+        if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreate(&d.ev0)) != cudaSuccess || (e = cudaEventCreate(&d.ev1)) != cudaSuccess) {
+            std::string m = std::string("device init: ") + cudaGetErrorString(e);
+            delete ctx; return fail(nullptr, RT_ERR_CUDA, m);
+        }
+        d.sm_count = prop.multiProcessorCount;
+    }
+    // Peer access so that devices 1..n-1 can store straight into device 0's framebuffer (fused gather over NVLink).
+    ctx->peer_ok = true;
+    for (int i = 1; i < n_devices; i++) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctx->devs[(size_t)i].dev, ctx->devs[0].dev);
+        if (!can) { ctx->peer_ok = false; break; }
+        cudaSetDevice(ctx->devs[(size_t)i].dev);
+        e = cudaDeviceEnablePeerAccess(ctx->devs[0].dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ctx->peer_ok = false; break; }
+        cudaGetLastError();
+    }
+    if (n_devices > 1 && !ctx->peer_ok) { delete ctx; return fail(nullptr, RT_ERR_PEER, "peer access to device 0 unavailable"); }
+    *out = ctx;
+    return RT_OK;
+}
+
+int rt_destroy(rt_context* ctx) {
+    if (!ctx) return RT_ERR_INVALID;
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.dev);
+        cudaStreamSynchronize(d.stream);
+        free_scene(d);
+        cudaFree(d.cams); cudaFree(d.fb);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+    return RT_OK;
+}
+
+int rt_set_scene(rt_context* ctx, const float* spheres, int ns, const float* planes, int np, const float* lights, int nl,
+                 const float ambient[3], int accel) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (ns < 0 || np < 0 || nl < 0 || (ns > 0 && !spheres) || (np > 0 && !planes) || (nl > 0 && !lights) || !ambient)
+        return fail(ctx, RT_ERR_INVALID, "bad scene arrays");
+    if (accel < RT_ACCEL_AUTO || accel > RT_ACCEL_LBVH) return fail(ctx, RT_ERR_INVALID, "bad accel");
+    if (accel == RT_ACCEL_LBVH) return fail(ctx, RT_ERR_UNSUPPORTED, "LBVH not built in this revision");
+    ctx->has_scene = false;
+    std::vector<f4> sg((size_t)ns); std::vector<MatRec> sm((size_t)ns);
+    std::vector<PlaneRec> pl((size_t)np); std::vector<LightRec> li((size_t)nl);
+    for (int i = 0; i < ns; i++) {
+        const float* f = spheres + 18 * (size_t)i;
+        sg[(size_t)i].x = f[0]; sg[(size_t)i].y = f[1]; sg[(size_t)i].z = f[2]; sg[(size_t)i].w = f[17];   // radiusSquared passed through (:336)
+        sm[(size_t)i] = make_mat(f + 4);
+    }
+    for (int i = 0; i < np; i++) pl[(size_t)i] = make_plane(planes + 20 * (size_t)i);
+    for (int i = 0; i < nl; i++) li[(size_t)i] = make_light(lights + 4 * (size_t)i);
+
+    ctx->tiny = (ns <= TINY_MAX_SPHERES && np <= TINY_MAX_PLANES && nl <= TINY_MAX_LIGHTS);
+    memset(&ctx->tiny_data, 0, sizeof(ctx->tiny_data));
+    if (ctx->tiny) {
+        TinySceneData& t = ctx->tiny_data;
+        t.ns = ns; t.np = np; t.nl = nl; t.amb = mk3(ambient[0], ambient[1], ambient[2]);
+        for (int i = 0; i < ns; i++) { t.sgeom[i] = sg[(size_t)i]; t.smat[i] = sm[(size_t)i]; }
+        for (int i = 0; i < np; i++) t.planes[i] = pl[(size_t)i];
+        for (int i = 0; i < nl; i++) t.lights[i] = li[(size_t)i];
+    }
+    memset(&ctx->gdata_host, 0, sizeof(ctx->gdata_host));
+    ctx->gdata_host.ns = ns; ctx->gdata_host.np = np; ctx->gdata_host.nl = nl;
+    ctx->gdata_host.amb = mk3(ambient[0], ambient[1], ambient[2]);
+    // The global-memory copy is always uploaded (rt_query_spheres and the debug kernels of non-tiny scenes use it).
+    for (auto& d : ctx->devs) {
+        CU_TRY(ctx, cudaSetDevice(d.dev));
+        free_scene(d);
+        CU_TRY(ctx, cudaMalloc(&d.sgeom, sizeof(f4) * (size_t)(ns > 0 ? ns : 1)));
+        CU_TRY(ctx, cudaMalloc(&d.smat, sizeof(MatRec) * (size_t)(ns > 0 ? ns : 1)));
+        CU_TRY(ctx, cudaMalloc(&d.planes, sizeof(PlaneRec) * (size_t)(np > 0 ? np : 1)));
+        CU_TRY(ctx, cudaMalloc(&d.lights, sizeof(LightRec) * (size_t)(nl > 0 ? nl : 1)));
+        if (ns) CU_TRY(ctx, cudaMemcpy(d.sgeom, sg.data(), sizeof(f4) * (size_t)ns, cudaMemcpyHostToDevice));
+        if (ns) CU_TRY(ctx, cudaMemcpy(d.smat, sm.data(), sizeof(MatRec) * (size_t)ns, cudaMemcpyHostToDevice));
+        if (np) CU_TRY(ctx, cudaMemcpy(d.planes, pl.data(), sizeof(PlaneRec) * (size_t)np, cudaMemcpyHostToDevice));
+        if (nl) CU_TRY(ctx, cudaMemcpy(d.lights, li.data(), sizeof(LightRec) * (size_t)nl, cudaMemcpyHostToDevice));
+    }
+    ctx->accel = RT_ACCEL_BRUTE;
+    ctx->has_scene = true;
+    return RT_OK;
+}
+
+int rt_set_partition(rt_context* ctx, int rank, int world, int tile_rows) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (world < 1 || rank < 0 || rank >= world || tile_rows < 1) return fail(ctx, RT_ERR_INVALID, "bad partition");
+    if (ctx->devs.size() != 1 && world != 1) return fail(ctx, RT_ERR_INVALID, "rt_set_partition needs a single-device context");
+    ctx->rank = rank; ctx->world = world; ctx->tile_rows = tile_rows;
+    return RT_OK;
+}
+
+int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int w, int h, int depth, int spp, uint32_t seed,
+                     void* dev_pixels, void* cuda_stream) {
+    int rc = check_frame_args(ctx, cams, w, h, depth, spp);
+    if (rc) return rc;
+    if (n_frames < 1 || !dev_pixels) return fail(ctx, RT_ERR_INVALID, "n_frames/dev_pixels");
+    if (ctx->devs.size() != 1) return fail(ctx, RT_ERR_INVALID, "rt_render_device needs a single-device context");
+    DeviceState& d = ctx->devs[0];
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    FrameParams fp = make_params(ctx, w, h, depth, spp, seed, n_frames, ctx->rank, ctx->world, (uint32_t*)dev_pixels, (long long)w * h);
+    if (n_frames <= INLINE_CAMS) for (int i = 0; i < n_frames; i++) fp.cam_inline[i] = to_cam(cams[i]);
+    else { rc = upload_cams(ctx, d, cams, n_frames, st); if (rc) return rc; fp.cams = d.cams; }
+    return launch_render(ctx, d, fp, st);
+}
+
+static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, int w, int h, int depth, int spp, uint32_t seed,
+                         int32_t* host_pixels, rt_stats* stats) {
+    int rc = check_frame_args(ctx, cams, w, h, depth, spp);
+    if (rc) return rc;
+    if (n_frames < 1) return fail(ctx, RT_ERR_INVALID, "n_frames");
+    const size_t npix = (size_t)w * h;
+    rc = ensure_fb(ctx, npix * (size_t)n_frames); if (rc) return rc;
+    const int G = (int)ctx->devs.size();
+    DeviceState& d0 = ctx->devs[0];
+    // All devices render their interleaved row tiles straight into device 0's framebuffer (peer stores).
+    for (int g = 0; g < G; g++) {
+        DeviceState& d = ctx->devs[(size_t)g];
+        CU_TRY(ctx, cudaSetDevice(d.dev));
+        int rank = G > 1 ? g : ctx->rank, world = G > 1 ? G : ctx->world;
+        FrameParams fp = make_params(ctx, w, h, depth, spp, seed, n_frames, rank, world, d0.fb, (long long)npix);
+        if (n_frames <= INLINE_CAMS) for (int i = 0; i < n_frames; i++) fp.cam_inline[i] = to_cam(cams[i]);
+        else { rc = upload_cams(ctx, d, cams, n_frames, d.stream); if (rc) return rc; fp.cams = d.cams; }
+        CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
+        rc = launch_render(ctx, d, fp, d.stream); if (rc) return rc;
+        CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
+    }
+    float kernel_ms = 0.0f;
+    for (int g = 0; g < G; g++) {
+        DeviceState& d = ctx->devs[(size_t)g];
+        CU_TRY(ctx, cudaSetDevice(d.dev));
+        CU_TRY(ctx, cudaStreamSynchronize(d.stream));
+        float ms = 0.0f;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        if (ms > kernel_ms) kernel_ms = ms;
+    }
+    float d2h_ms = 0.0f;
+    if (host_pixels) {
+        CU_TRY(ctx, cudaSetDevice(d0.dev));
+        CU_TRY(ctx, cudaEventRecord(d0.ev0, d0.stream));
+        // host_pixels is the caller's (pageable, possibly pinned-by-GC) Surface.pixels array.
+        CU_TRY(ctx, cudaMemcpyAsync(host_pixels, d0.fb, npix * (size_t)n_frames * sizeof(uint32_t), cudaMemcpyDeviceToHost, d0.stream));
+        CU_TRY(ctx, cudaEventRecord(d0.ev1, d0.stream));
+        CU_TRY(ctx, cudaStreamSynchronize(d0.stream));
+        CU_TRY(ctx, cudaEventElapsedTime(&d2h_ms, d0.ev0, d0.ev1));
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->kernel_ms = kernel_ms; stats->gather_ms = 0.0f; stats->d2h_ms = d2h_ms;
+    }
+    return RT_OK;
+}
+
+int rt_render(rt_context* ctx, const rt_camera* cam, int w, int h, int depth, int spp, uint32_t seed, int32_t* host_pixels, rt_stats* stats) {
+    return render_frames(ctx, cam, 1, w, h, depth, spp, seed, host_pixels, stats);
+}
+
+int rt_render_batch(rt_context* ctx, const rt_camera* cams, int n_frames, int w, int h, int depth, int spp, uint32_t seed,
+                    int32_t* host_pixels, rt_stats* stats) {
+    return render_frames(ctx, cams, n_frames, w, h, depth, spp, seed, host_pixels, stats);
+}
+
+int rt_render_debug(rt_context* ctx, const rt_camera* cam, int w, int h, int depth, int spp, uint32_t seed, int32_t* host_pixels,
+                    uint32_t* host_hash, int32_t* host_aov_id, float* host_aov_t, uint64_t* counters, rt_stats* stats) {
+    int rc = check_frame_args(ctx, cam, w, h, depth, spp);
+    if (rc) return rc;
+    const size_t npix = (size_t)w * h;
+    rc = ensure_fb(ctx, npix); if (rc) return rc;
+    DeviceState& d = ctx->devs[0];
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    DebugOut dout; memset(&dout, 0, sizeof(dout));
+    unsigned long long* dcnt = nullptr;
+    CU_TRY(ctx, cudaMalloc(&dcnt, 12 * sizeof(unsigned long long)));
+    CU_TRY(ctx, cudaMemset(dcnt, 0, 12 * sizeof(unsigned long long)));
+    dout.counters = dcnt;
+    if (host_hash) CU_TRY(ctx, cudaMalloc(&dout.hash, npix * 4));
+    if (host_aov_id) CU_TRY(ctx, cudaMalloc(&dout.aov_id, npix * 4));
+    if (host_aov_t) CU_TRY(ctx, cudaMalloc(&dout.aov_t, npix * 4));
+    FrameParams fp = make_params(ctx, w, h, depth, spp, seed, 1, 0, 1, d.fb, (long long)npix);
+    fp.cam_inline[0] = to_cam(*cam);
+    long long grid = ((long long)npix + BLOCK - 1) / BLOCK;
+    long long maxgrid = (long long)d.sm_count * 8 * 4;
+    if (grid > maxgrid) grid = maxgrid;
+    CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
+    if (ctx->tiny) k_debug_tiny<<<(unsigned)grid, BLOCK, 0, d.stream>>>(ctx->tiny_data, fp, dout);
+    else {
+        GlobalSceneData g = ctx->gdata_host;
+        g.sgeom = d.sgeom; g.smat = d.smat; g.planes = d.planes; g.lights = d.lights;
+        k_debug_global<<<(unsigned)grid, BLOCK, 0, d.stream>>>(g, fp, dout);
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
+    CU_TRY(ctx, cudaStreamSynchronize(d.stream));
+    float ms = 0; CU_TRY(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+    if (host_pixels) CU_TRY(ctx, cudaMemcpy(host_pixels, d.fb, npix * 4, cudaMemcpyDeviceToHost));
+    if (host_hash) CU_TRY(ctx, cudaMemcpy(host_hash, dout.hash, npix * 4, cudaMemcpyDeviceToHost));
+    if (host_aov_id) CU_TRY(ctx, cudaMemcpy(host_aov_id, dout.aov_id, npix * 4, cudaMemcpyDeviceToHost));
+    if (host_aov_t) CU_TRY(ctx, cudaMemcpy(host_aov_t, dout.aov_t, npix * 4, cudaMemcpyDeviceToHost));
+    unsigned long long hc[12];
+    CU_TRY(ctx, cudaMemcpy(hc, dcnt, sizeof(hc), cudaMemcpyDeviceToHost));
+    if (counters) for (int i = 0; i < 12; i++) counters[i] = hc[i];
+    cudaFree(dcnt); cudaFree(dout.hash); cudaFree(dout.aov_id); cudaFree(dout.aov_t);
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->primary = hc[0]; stats->shadow = hc[1]; stats->secondary = hc[2]; stats->kernel_ms = ms;
+    }
+    return RT_OK;
+}
+
+int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, int accel, int32_t* out_id, float* out_t) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_set_scene has not been called");
+    if (!rays6 || n_rays < 0 || kind < 0 || kind > 2 || !out_id || !out_t) return fail(ctx, RT_ERR_INVALID, "bad query args");
+    if (accel != RT_ACCEL_BRUTE) return fail(ctx, RT_ERR_UNSUPPORTED, "only RT_ACCEL_BRUTE queries in this revision");
+    if (n_rays == 0) return RT_OK;
+    DeviceState& d = ctx->devs[0];
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    float* dr = nullptr; int32_t* di = nullptr; float* dt = nullptr;
+    CU_TRY(ctx, cudaMalloc(&dr, (size_t)n_rays * 24));
+    CU_TRY(ctx, cudaMalloc(&di, (size_t)n_rays * 4));
+    CU_TRY(ctx, cudaMalloc(&dt, (size_t)n_rays * 4));
+    CU_TRY(ctx, cudaMemcpy(dr, rays6, (size_t)n_rays * 24, cudaMemcpyHostToDevice));
+    GlobalSceneData g = ctx->gdata_host;
+    g.sgeom = d.sgeom; g.smat = d.smat; g.planes = d.planes; g.lights = d.lights;
+    int grid = (n_rays + BLOCK - 1) / BLOCK; if (grid > d.sm_count * 32) grid = d.sm_count * 32;
+    k_query_brute<<<grid, BLOCK, 0, d.stream>>>(g, dr, n_rays, kind, di, dt);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    CU_TRY(ctx, cudaStreamSynchronize(d.stream));
+    CU_TRY(ctx, cudaMemcpy(out_id, di, (size_t)n_rays * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(ctx, cudaMemcpy(out_t, dt, (size_t)n_rays * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dr); cudaFree(di); cudaFree(dt);
+    return RT_OK;
+}
+
+int rt_ipc_export(rt_context* ctx, void* dev_ptr, void* handle64) {
+    if (!ctx || !dev_ptr || !handle64) return RT_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    cudaIpcMemHandle_t h;
+    CU_TRY(ctx, cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle64, &h, 64);
+    return RT_OK;
+}
+int rt_ipc_open(rt_context* ctx, const void* handle64, void** out_dev_ptr) {
+    if (!ctx || !handle64 || !out_dev_ptr) return RT_ERR_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    cudaIpcMemHandle_t h; memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(out_dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_PEER, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+int rt_ipc_close(rt_context* ctx, void* dev_ptr) {
+    if (!ctx || !dev_ptr) return RT_ERR_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    CU_TRY(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    return RT_OK;
+}
+
+int rt_dev_alloc(rt_context* ctx, uint64_t bytes, void** out_dev_ptr) {
+    if (!ctx || !out_dev_ptr || bytes == 0) return RT_ERR_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    CU_TRY(ctx, cudaMalloc(out_dev_ptr, (size_t)bytes));
+    return RT_OK;
+}
+int rt_dev_free(rt_context* ctx, void* dev_ptr) {
+    if (!ctx) return RT_ERR_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    CU_TRY(ctx, cudaFree(dev_ptr));
+    return RT_OK;
+}
+int rt_dev_to_host(rt_context* ctx, void* host_dst, const void* dev_src, uint64_t bytes) {
+    if (!ctx || !host_dst || !dev_src) return RT_ERR_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    CU_TRY(ctx, cudaMemcpy(host_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+int rt_sync(rt_context* ctx) {
+    if (!ctx) return RT_ERR_INVALID;
+    for (auto& d : ctx->devs) {
+        CU_TRY(ctx, cudaSetDevice(d.dev));
+        CU_TRY(ctx, cudaDeviceSynchronize());
+    }
+    return RT_OK;
+}
+int rt_host_register(rt_context* ctx, void* host_ptr, uint64_t bytes) {
+    if (!ctx || !host_ptr || bytes == 0) return RT_ERR_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    CU_TRY(ctx, cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return RT_OK;
+}
+int rt_host_unregister(rt_context* ctx, void* host_ptr) {
+    if (!ctx || !host_ptr) return RT_ERR_INVALID;
+    CU_TRY(ctx, cudaHostUnregister(host_ptr));
+    return RT_OK;
+}
+uint64_t rt_launch_count(const rt_context* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+}  // extern "C"

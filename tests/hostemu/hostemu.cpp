@@ -8,6 +8,67 @@
 
 using namespace rtb;
 
+// Host-side LBVH build with the same pieces the CUDA build kernels use (morton_key, karras_node, sphere_box, box_union).
+#include <algorithm>
+struct HostBvh {
+    std::vector<BvhNode> nodes; std::vector<f4> sorted; std::vector<int> orig; float r2max = 0; int n = 0;
+    BvhView view() const { BvhView v; v.nodes = nodes.data(); v.sgeom_sorted = sorted.data(); v.orig = orig.data(); v.n = n; v.r2max = r2max; return v; }
+};
+static BvhBox host_refit(HostBvh& b, const std::vector<float>& reff, int child) {
+    if (child < 0) return sphere_box(b.sorted[~child], reff[b.orig[~child]]);
+    BvhNode& nd = b.nodes[child];
+    BvhBox b0 = host_refit(b, reff, nd.c0), b1 = host_refit(b, reff, nd.c1);
+    node_set_child_box(nd, 0, b0); node_set_child_box(nd, 1, b1);
+    return box_union(b0, b1);
+}
+static void host_build(const std::vector<f4>& sg, HostBvh& b) {
+    const int n = (int)sg.size();
+    b.n = n; b.nodes.clear(); b.sorted.clear(); b.orig.clear(); b.r2max = 0;
+    if (n < 2) return;
+    float bmin[3] = {sg[0].x, sg[0].y, sg[0].z}, bmax[3] = {sg[0].x, sg[0].y, sg[0].z};
+    std::vector<float> reff(n);
+    for (int i = 0; i < n; i++) {
+        bmin[0] = fminf(bmin[0], sg[i].x); bmin[1] = fminf(bmin[1], sg[i].y); bmin[2] = fminf(bmin[2], sg[i].z);
+        bmax[0] = fmaxf(bmax[0], sg[i].x); bmax[1] = fmaxf(bmax[1], sg[i].y); bmax[2] = fmaxf(bmax[2], sg[i].z);
+        float r2 = sg[i].w > 0 ? sg[i].w : 0; reff[i] = sqrtf(r2) * 1.000001f + 1e-30f; if (r2 > b.r2max) b.r2max = r2;
+    }
+    float binv[3];
+    for (int k = 0; k < 3; k++) { float e = bmax[k] - bmin[k]; binv[k] = e > 0 ? 1023.0f / e : 0.0f; }
+    std::vector<uint64_t> keys(n);
+    for (int i = 0; i < n; i++) keys[i] = morton_key(sg[i].x, sg[i].y, sg[i].z, bmin, binv, (uint32_t)i);
+    std::sort(keys.begin(), keys.end());
+    b.sorted.resize(n); b.orig.resize(n); b.nodes.resize(n - 1);
+    for (int j = 0; j < n; j++) { int idx = (int)(keys[j] & 0xFFFFFFFFull); b.sorted[j] = sg[idx]; b.orig[j] = idx; }
+    for (int i = 0; i < n - 1; i++) { int l, r; karras_node(keys.data(), n, i, &l, &r); memset(&b.nodes[i], 0, sizeof(BvhNode)); b.nodes[i].c0 = l; b.nodes[i].c1 = r; }
+    host_refit(b, reff, 0);
+}
+
+template <class SC, class DBG>
+static uint32_t px_of(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int d, int spp, uint32_t seed, HitRec* st, DBG& dbg) {
+    return trace_pixel(sc, cam, x, y, w, h, d, spp, seed, st, dbg);
+}
+// use_tiny: 0 global-memory policy, 1 TinyScene<-1> (run-time count), 2 TinyScene<NS> with the exact compile-time count,
+//           3 LBVH policy, 4 shared-memory-staged policy (here: an ordinary host array)
+static const HostBvh* g_bvh = nullptr;
+template <class DBG>
+static uint32_t dispatch(int use_tiny, const TinySceneData& t, const GlobalSceneData& g, const CamRec& cam, int x, int y, int w, int h,
+                         int d, int spp, uint32_t seed, HitRec* st, DBG& dbg) {
+    if (use_tiny == 0) return px_of(GlobalScene(g), cam, x, y, w, h, d, spp, seed, st, dbg);
+    if (use_tiny == 3) return px_of(LbvhScene(g, g_bvh->view()), cam, x, y, w, h, d, spp, seed, st, dbg);
+    if (use_tiny == 4) return px_of(StagedScene(g, g.sgeom), cam, x, y, w, h, d, spp, seed, st, dbg);
+    if (use_tiny == 2) {
+        switch (t.ns) {
+            case 0: return px_of(TinyScene<0>(t), cam, x, y, w, h, d, spp, seed, st, dbg);
+            case 1: return px_of(TinyScene<1>(t), cam, x, y, w, h, d, spp, seed, st, dbg);
+            case 2: return px_of(TinyScene<2>(t), cam, x, y, w, h, d, spp, seed, st, dbg);
+            case 3: return px_of(TinyScene<3>(t), cam, x, y, w, h, d, spp, seed, st, dbg);
+            case 4: return px_of(TinyScene<4>(t), cam, x, y, w, h, d, spp, seed, st, dbg);
+            default: break;
+        }
+    }
+    return px_of(TinyScene<-1>(t), cam, x, y, w, h, d, spp, seed, st, dbg);
+}
+
 extern "C" int emu_render(const float* spheres, int ns, const float* planes, int np, const float* lights, int nl,
                           const float* ambient, const float* cam15, int w, int h, int max_depth, int spp, uint32_t seed,
                           int use_tiny, int32_t* pixels, uint32_t* hash, int32_t* aov_id, float* aov_t, uint64_t* counters) {
@@ -28,8 +89,10 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
     GlobalSceneData g; memset(&g, 0, sizeof(g));
     g.ns = ns; g.np = np; g.nl = nl; g.amb = mk3(ambient[0], ambient[1], ambient[2]);
     g.sgeom = sg.data(); g.smat = sm.data(); g.planes = pl.data(); g.lights = li.data();
+    HostBvh bvh;
+    if (use_tiny == 3) { if (ns < 2) return -2; host_build(sg, bvh); g_bvh = &bvh; }
     TinySceneData t; memset(&t, 0, sizeof(t));
-    if (use_tiny) {
+    if (use_tiny == 1 || use_tiny == 2) {
         if (ns > TINY_MAX_SPHERES || np > TINY_MAX_PLANES || nl > TINY_MAX_LIGHTS) return -1;
         t.ns = ns; t.np = np; t.nl = nl; t.amb = g.amb;
         for (int i = 0; i < ns; i++) { t.sgeom[i] = sg[i]; t.smat[i] = sm[i]; }
@@ -48,8 +111,7 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
                 size_t p = (size_t)y * w + x;
                 if (dbg_mode) {
                     FullDbg dbg;
-                    uint32_t c = use_tiny ? trace_pixel(TinyScene(t), cam, x, y, w, h, max_depth, spp, seed, stack, dbg)
-                                          : trace_pixel(GlobalScene(g), cam, x, y, w, h, max_depth, spp, seed, stack, dbg);
+                    uint32_t c = dispatch(use_tiny, t, g, cam, x, y, w, h, max_depth, spp, seed, stack, dbg);
                     pixels[p] = (int32_t)c;
                     if (hash) hash[p] = dbg.hash;
                     if (aov_id) aov_id[p] = dbg.aov_id;
@@ -59,8 +121,7 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
                     lc[8] += dbg.shade_mirror; lc[9] += dbg.shaded_hits;
                 } else {
                     NoDbg dbg;
-                    uint32_t c = use_tiny ? trace_pixel(TinyScene(t), cam, x, y, w, h, max_depth, spp, seed, stack, dbg)
-                                          : trace_pixel(GlobalScene(g), cam, x, y, w, h, max_depth, spp, seed, stack, dbg);
+                    uint32_t c = dispatch(use_tiny, t, g, cam, x, y, w, h, max_depth, spp, seed, stack, dbg);
                     pixels[p] = (int32_t)c;
                 }
             }
@@ -68,5 +129,35 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         for (int i = 0; i < 10; i++) cnt[i] += lc[i];
     }
     if (counters) for (int i = 0; i < 10; i++) counters[i] = cnt[i];
+    return 0;
+}
+
+// Single-ray sphere queries through the device query code: accel 1 brute, 2 LBVH (same semantics as rt_query_spheres).
+extern "C" int emu_query(const float* spheres, int ns, const float* rays6, int n_rays, int kind, int accel, int32_t* out_id, float* out_t) {
+    std::vector<f4> sg((size_t)ns); std::vector<MatRec> sm((size_t)ns);
+    for (int i = 0; i < ns; i++) {
+        const float* f = spheres + 18 * (size_t)i;
+        sg[i].x = f[0]; sg[i].y = f[1]; sg[i].z = f[2]; sg[i].w = f[17]; sm[i] = make_mat(f + 4);
+    }
+    GlobalSceneData g; memset(&g, 0, sizeof(g));
+    g.ns = ns; g.sgeom = sg.data(); g.smat = sm.data();
+    HostBvh bvh;
+    if (accel == 2) { if (ns < 2) return -2; host_build(sg, bvh); }
+    BvhView bv = bvh.view();
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int r = 0; r < n_rays; r++) {
+        NoDbg dbg;
+        f3 o = mk3(rays6[6 * r], rays6[6 * r + 1], rays6[6 * r + 2]);
+        f3 d = mk3(rays6[6 * r + 3], rays6[6 * r + 4], rays6[6 * r + 5]);
+        float a = dot3(d, d), a2 = 2 * a, a4 = 4 * a;
+        int sel = -1; float t = 0.0f;
+        auto run = [&](auto sc) {
+            if (kind == 0) { sc.nearest(o, d, a2, a4, 0.0f, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
+            else if (kind == 1) { sc.nearest(o, d, a2, a4, 0.01f, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
+            else { sel = sc.shadow_any(o, d, a2, a4, dbg) ? 1 : 0; t = 0.0f; }
+        };
+        if (accel == 2) run(LbvhScene(g, bv)); else run(GlobalScene(g));
+        out_id[r] = sel; out_t[r] = t;
+    }
     return 0;
 }

@@ -18,6 +18,8 @@ def load():
         _lib.emu_render.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                     C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), fp, C.POINTER(C.c_uint64)]
         _lib.emu_render.restype = C.c_int
+        _lib.emu_query.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), fp]
+        _lib.emu_query.restype = C.c_int
     return _lib
 
 
@@ -25,14 +27,15 @@ def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None and a.size else None
 
 
-def render(scene, cam, w, h, max_depth=32, spp=1, seed=0, tiny=False, debug=False):
+def render(scene, cam, w, h, max_depth=32, spp=1, seed=0, tiny=0, debug=False):
+    """tiny: 0 global-memory policy, 1 TinyScene<-1>, 2 TinyScene<exact NS>, 3 LBVH, 4 staged (see hostemu.cpp)"""
     lib = load()
     n = w * h
     px = np.zeros(n, np.int32)
     hsh = np.zeros(n, np.uint32); aid = np.zeros(n, np.int32); at = np.zeros(n, np.float32); cnt = np.zeros(10, np.uint64)
     cam = np.ascontiguousarray(cam, np.float32)
     rc = lib.emu_render(_fp(scene.spheres), len(scene.spheres), _fp(scene.planes), len(scene.planes), _fp(scene.lights),
-                        len(scene.lights), _fp(scene.ambient), _fp(cam), w, h, max_depth, spp, seed, 1 if tiny else 0,
+                        len(scene.lights), _fp(scene.ambient), _fp(cam), w, h, max_depth, spp, seed, int(tiny),
                         px.ctypes.data_as(C.POINTER(C.c_int32)),
                         hsh.ctypes.data_as(C.POINTER(C.c_uint32)) if debug else None,
                         aid.ctypes.data_as(C.POINTER(C.c_int32)) if debug else None, _fp(at) if debug else None,
@@ -40,3 +43,14 @@ def render(scene, cam, w, h, max_depth=32, spp=1, seed=0, tiny=False, debug=Fals
     assert rc == 0
     return dict(pixels=px.reshape(h, w), hash=hsh.reshape(h, w), aov_id=aid.reshape(h, w), aov_t=at.reshape(h, w),
                 counters=[int(v) for v in cnt])
+
+
+def query(spheres, rays6, kind, accel):
+    """accel: 1 brute, 2 LBVH"""
+    lib = load()
+    spheres = np.ascontiguousarray(spheres, np.float32); rays6 = np.ascontiguousarray(rays6, np.float32).reshape(-1, 6)
+    n = len(rays6)
+    ids = np.zeros(n, np.int32); ts = np.zeros(n, np.float32)
+    rc = lib.emu_query(_fp(spheres), len(spheres), _fp(rays6), n, kind, accel, ids.ctypes.data_as(C.POINTER(C.c_int32)), _fp(ts))
+    assert rc == 0, rc
+    return ids, ts

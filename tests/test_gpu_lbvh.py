@@ -1,0 +1,134 @@
+"""GPU tests of the scaled-scene paths: shared-memory-staged brute force and the LBVH must both equal the oracle, and each
+other, bit for bit (hit index, t bits, image) — BASELINE.json configs[2] and configs[3]."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt(built):
+    import rtb200
+    return rtb200
+
+
+def mk(c, r):
+    return scenes.sphere(c, r, scenes.mat_diffuse((1, 1, 1)))
+
+
+def _scene_of(spheres):
+    d = scenes.default_scene()
+    return scenes.Scene(spheres, d.planes, d.lights, d.ambient)
+
+
+def _check_queries(rt, spheres, rays):
+    ctx = rt.Context([0])
+    ctx.set_scene(_scene_of(spheres), rt.RT_ACCEL_LBVH)
+    for kind in (0, 1, 2):
+        oi, ot = O.query_spheres(spheres, rays, kind)
+        for accel in (rt.RT_ACCEL_BRUTE, rt.RT_ACCEL_LBVH):
+            gi, gt = ctx.query_spheres(rays, kind, accel)
+            assert np.array_equal(gi, oi), "kind %d accel %d: %d id mismatches" % (kind, accel, (gi != oi).sum())
+            assert np.array_equal(gt.view(np.uint32), ot.view(np.uint32)), "kind %d accel %d: t bits" % (kind, accel)
+    ctx.close()
+
+
+def test_queries_random_and_chains(rt):
+    rng = np.random.default_rng(11)
+    sph = []
+    for _ in range(60):
+        c = rng.uniform(-5, 5, 3); c[2] += 12
+        for _ in range(rng.integers(2, 9)):
+            sph.append(mk(c + rng.normal(size=3) * 0.004, 1.0 + rng.normal() * 0.003))
+    sph = np.stack(sph)[rng.permutation(len(sph))]
+    n = 50000
+    o = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    tgt = sph[rng.integers(0, len(sph), n), :3] + rng.normal(size=(n, 3)).astype(np.float32) * 0.7
+    d = (tgt - o).astype(np.float32) * rng.uniform(0.05, 20, (n, 1)).astype(np.float32)
+    _check_queries(rt, sph, np.concatenate([o, d], 1))
+
+
+def test_queries_far_spheres_fp_noise(rt):
+    rng = np.random.default_rng(11)
+    n = 100000
+    sph = np.stack([mk((rng.uniform(-400, 400), rng.uniform(0, 30), rng.uniform(300, 900)), rng.uniform(0.05, 0.3)) for _ in range(3000)])
+    o = np.tile(np.array([[0, 3, -6]], np.float32), (n, 1))
+    k = rng.integers(0, len(sph), n)
+    v = sph[k, :3] - o; v /= np.linalg.norm(v, axis=1, keepdims=True)
+    perp = np.cross(v, rng.normal(size=(n, 3))); perp /= np.linalg.norm(perp, axis=1, keepdims=True)
+    tgt = sph[k, :3] + perp * sph[k, 3:4] * rng.uniform(0.9, 1.15, (n, 1))
+    d = (tgt - o); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[: n // 2] *= rng.uniform(1e-3, 1e3, (n // 2, 1))
+    _check_queries(rt, sph, np.concatenate([o, d.astype(np.float32)], 1))
+
+
+def test_queries_degenerate(rt):
+    rng = np.random.default_rng(5)
+    n = 20000
+    sph = np.stack([mk((1.0, 0.5, 5 + 0.5 * (i % 7)), 0.4) for i in range(50)])
+    o = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32); d[:, 2] = np.abs(d[:, 2])
+    d[:n // 3, 0] = 0; d[n // 3:2 * n // 3, 1] = 0; d[:100] = 0
+    o[:500] = sph[rng.integers(0, 50, 500), :3]
+    _check_queries(rt, sph, np.concatenate([o, d], 1))
+    _check_queries(rt, sph[:2], np.concatenate([o, d], 1))
+
+
+def test_config3_reduced_vs_oracle(rt):
+    """1,024 spheres + plane + 4 lights: staged brute force and LBVH vs the oracle at 480x270 (oracle = brute force)."""
+    sc = scenes.config3_scene()
+    w, h = 480, 270
+    cam = scenes.make_camera(width=w, height=h, **scenes.SCALED_CAMERA)
+    ref = O.render(sc, cam, w, h, 8, want_hash=True, want_aov=True)
+    for accel in (rt.RT_ACCEL_BRUTE, rt.RT_ACCEL_LBVH, rt.RT_ACCEL_AUTO):
+        ctx = rt.Context([0]); ctx.set_scene(sc, accel)
+        got = ctx.render_debug(cam, w, h, 8)
+        assert np.array_equal(got["hash"], ref["hash"]), accel
+        assert np.array_equal(got["aov_id"], ref["aov_id"]) and np.array_equal(got["aov_t"].view(np.uint32), ref["aov_t"].view(np.uint32))
+        for k in ("primary", "shadow", "secondary", "plane_tests", "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"):
+            assert got["counters"][k] == ref["counters"][k], (accel, k)
+        px, _ = ctx.render(cam, w, h, 8)
+        assert np.array_equal(px, ref["pixels"]), accel
+        ctx.close()
+
+
+def test_config3_4k_brute_equals_lbvh(rt):
+    """BASELINE configs[2] at full size: identical (hit id, t bits) per ray — via the chain hash — and identical image."""
+    sc = scenes.config3_scene()
+    w, h = 3840, 2160
+    cam = scenes.make_camera(width=w, height=h, **scenes.SCALED_CAMERA)
+    out = {}
+    for name, accel in (("brute", rt.RT_ACCEL_BRUTE), ("lbvh", rt.RT_ACCEL_LBVH)):
+        ctx = rt.Context([0]); ctx.set_scene(sc, accel)
+        dbg = ctx.render_debug(cam, w, h, 8)
+        px, st = ctx.render(cam, w, h, 8)
+        assert np.array_equal(px, dbg["pixels"])
+        out[name] = (px, dbg["hash"], dbg["aov_id"], dbg["aov_t"])
+        ctx.close()
+    assert np.array_equal(out["brute"][0], out["lbvh"][0])
+    assert np.array_equal(out["brute"][1], out["lbvh"][1])
+    assert np.array_equal(out["brute"][2], out["lbvh"][2])
+    assert np.array_equal(out["brute"][3].view(np.uint32), out["lbvh"][3].view(np.uint32))
+    # and a pixel subset against the oracle at full resolution
+    idx = np.random.default_rng(7).choice(w * h, 4096, replace=False).astype(np.int32)
+    ref = O.render(sc, cam, w, h, 8, subset=idx)["pixels"]
+    assert np.array_equal(out["lbvh"][0].reshape(-1)[idx], ref)
+
+
+def test_config4_100k_lbvh_vs_oracle_subset(rt):
+    """BASELINE configs[3]: 100k spheres, LBVH, 4K; CPU equality on a fixed 65,536-pixel subset (seed 7) with brute force."""
+    sc = scenes.config4_scene()
+    w, h = 3840, 2160
+    cam = scenes.make_camera(width=w, height=h, **scenes.SCALED_CAMERA)
+    ctx = rt.Context([0]); ctx.set_scene(sc, rt.RT_ACCEL_AUTO)
+    px, st = ctx.render(cam, w, h, 8)
+    idx = np.random.default_rng(7).choice(w * h, 65536, replace=False).astype(np.int32)
+    ref = O.render(sc, cam, w, h, 8, subset=idx, want_hash=True)
+    assert np.array_equal(px.reshape(-1)[idx], ref["pixels"])
+    dbg = ctx.render_debug(cam, w, h, 8)
+    assert np.array_equal(dbg["hash"].reshape(-1)[idx], ref["hash"])
+    assert np.array_equal(dbg["pixels"], px)
+    ctx.close()

@@ -22,7 +22,7 @@ def _compare(sc, cam, w, h, depth, spp=1, seed=0, tiny=False):
     assert [a["counters"][k] for k in O.COUNTER_NAMES[:10]] == b["counters"]
 
 
-@pytest.mark.parametrize("tiny", [True, False])
+@pytest.mark.parametrize("tiny", [0, 1, 2])
 @pytest.mark.parametrize("camkw,depth", [(dict(), 32), (dict(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15), 8),
                                          (dict(pos=(-2.0, 2.5, 3.0), yaw=-0.4, pitch=0.5), 0), (dict(pos=(0, 4.0, 6.0), pitch=1.2), 32)])
 def test_default_scene(built, tiny, camkw, depth):
@@ -30,14 +30,14 @@ def test_default_scene(built, tiny, camkw, depth):
 
 
 def test_supersampling(built):
-    _compare(scenes.default_scene(), scenes.make_camera(pos=(-2, 2.5, 3), yaw=-0.4, pitch=0.5, width=128, height=96), 128, 96, 3, spp=4, seed=7, tiny=True)
+    _compare(scenes.default_scene(), scenes.make_camera(pos=(-2, 2.5, 3), yaw=-0.4, pitch=0.5, width=128, height=96), 128, 96, 3, spp=4, seed=7, tiny=2)
 
 
-@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (12, 1), (16, 2), (40, 3), (200, 4)])
+@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (2, 7), (3, 8), (4, 9), (12, 1), (16, 2), (40, 3), (200, 4)])
 def test_random_scenes(built, n, seed):
     sc = scenes.small_random_scene(n, seed)
     cam = scenes.make_camera(pos=(0, 1.5, -4.0), pitch=0.1, width=160, height=100)
-    _compare(sc, cam, 160, 100, 8, tiny=(n <= 16))
+    _compare(sc, cam, 160, 100, 8, tiny=(2 if n <= 4 else 1 if n <= 16 else 0))
 
 
 def test_empty_scene(built):

@@ -1,0 +1,234 @@
+// rt_lbvh.cuh — LBVH over the spheres (Morton codes -> radix sort -> Karras 2012 hierarchy -> bottom-up refit) and a
+// traversal that returns EXACTLY what the reference's brute-force loops return (RayTracer.cs:577, :792, :975).
+//
+// Exactness contract:
+//  * Leaves run the reference's own sphere test (sphere_hit, bit-exact), so traversal can never invent a hit; it can
+//    only lose one by culling a node.  Culling is therefore made conservative against the fp32 NOISE of the reference
+//    test, not against the exact sphere: the reference's discriminant b*b - 4*a*c carries an absolute error of up to
+//    68u * a * (|oc|^2 + r^2) (u = 2^-24; derivation in DESIGN.md), so it reports hits for rays that pass as far as
+//    sqrt(r^2 + ~1.0e-6 (|oc|^2 + r^2)) from the centre, and the reported point o + t*d can lie that far outside too.
+//    Every node box is inflated, per ray, by  pad = 2.02e-3 * sqrt(max|oc|^2 + max r^2)  (>= 2x the bound, plus 1 % for
+//    the rounding of the slab test itself), with max|oc| taken to the farthest corner of the box.
+//  * primary fold (:977, strict '>'): lexicographic min over (t, original index) — ties keep the lower index.
+//  * secondary fold (:804-805) is ORDER DEPENDENT (offset distance compared with stored un-offset distance): the
+//    traversal collects every candidate within a window above the running minimum and replays the reference's fold
+//    over them in original index order; if the replay could have reached beyond the window (chains of hits < 0.01
+//    apart) or the candidate buffer overflows, the ray falls back to the brute-force loop.  Both fallbacks are exact.
+//  * shadow any-hit (:573-582): boolean OR over all spheres, unbounded t, so the first confirmed hit ends the search.
+#pragma once
+#include "rt_trace.cuh"
+
+namespace rtb {
+
+struct alignas(16) BvhNode {            // 64 B: both children's boxes live in the parent (one fetch = two box tests)
+    float lo0x, lo0y, lo0z; int c0;     // child >= 0: internal node index; child < 0: ~leaf (sorted sphere position)
+    float hi0x, hi0y, hi0z; int c1;
+    float lo1x, lo1y, lo1z; int pad0;
+    float hi1x, hi1y, hi1z; int pad1;
+};
+struct BvhBox { float lox, loy, loz, hix, hiy, hiz; };
+
+// ---- build pieces (shared by the CUDA build kernels and the host-emulation tests) ------------------------------------
+RT_HD uint32_t expand_bits10(uint32_t v) {          // 10 bits -> every third bit
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+// 30-bit Morton code of the sphere centre inside the centre bounds; key = code << 32 | original index (unique keys).
+RT_HD uint64_t morton_key(float cx, float cy, float cz, const float* bmin, const float* binv, uint32_t index) {
+    float fx = (cx - bmin[0]) * binv[0], fy = (cy - bmin[1]) * binv[1], fz = (cz - bmin[2]) * binv[2];
+    fx = fx < 0.0f ? 0.0f : (fx > 1023.0f ? 1023.0f : fx);
+    fy = fy < 0.0f ? 0.0f : (fy > 1023.0f ? 1023.0f : fy);
+    fz = fz < 0.0f ? 0.0f : (fz > 1023.0f ? 1023.0f : fz);
+    uint32_t code = (expand_bits10((uint32_t)fx) << 2) | (expand_bits10((uint32_t)fy) << 1) | expand_bits10((uint32_t)fz);
+    return ((uint64_t)code << 32) | (uint64_t)index;
+}
+RT_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+// Karras 2012: children of internal node i over n sorted unique keys. Leaves are encoded as ~position.
+RT_HD void karras_node(const uint64_t* keys, int n, int i, int* left, int* right) {
+    auto delta = [&](int a, int b) -> int { return (b < 0 || b >= n) ? -1 : clz64(keys[a] ^ keys[b]); };
+    int d = (delta(i, i + 1) - delta(i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(i, i - d);
+    int lmax = 2;
+    while (delta(i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta(i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(i, j);
+    int s = 0;
+    for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+        if (delta(i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    int gamma = i + s * d + (d < 0 ? -1 : 0);
+    int lo = i < j ? i : j, hi = i < j ? j : i;
+    *left = (lo == gamma) ? ~gamma : gamma;
+    *right = (hi == gamma + 1) ? ~(gamma + 1) : (gamma + 1);
+}
+RT_HD BvhBox sphere_box(f4 g, float radius) {
+    BvhBox b;
+    b.lox = g.x - radius; b.loy = g.y - radius; b.loz = g.z - radius;
+    b.hix = g.x + radius; b.hiy = g.y + radius; b.hiz = g.z + radius;
+    return b;
+}
+RT_HD BvhBox box_union(const BvhBox& a, const BvhBox& b) {
+    BvhBox r;
+    r.lox = fminf(a.lox, b.lox); r.loy = fminf(a.loy, b.loy); r.loz = fminf(a.loz, b.loz);
+    r.hix = fmaxf(a.hix, b.hix); r.hiy = fmaxf(a.hiy, b.hiy); r.hiz = fmaxf(a.hiz, b.hiz);
+    return r;
+}
+RT_HD void node_set_child_box(BvhNode& nd, int which, const BvhBox& b) {
+    if (which == 0) { nd.lo0x = b.lox; nd.lo0y = b.loy; nd.lo0z = b.loz; nd.hi0x = b.hix; nd.hi0y = b.hiy; nd.hi0z = b.hiz; }
+    else { nd.lo1x = b.lox; nd.lo1y = b.loy; nd.lo1z = b.loz; nd.hi1x = b.hix; nd.hi1y = b.hiy; nd.hi1z = b.hiz; }
+}
+
+// ---- traversal ---------------------------------------------------------------------------------------------------------
+struct BvhView {
+    const BvhNode* nodes;       // n-1 internal nodes, root = 0
+    const f4* sgeom_sorted;     // leaf position -> (cx, cy, cz, r^2)
+    const int* orig;            // leaf position -> original sphere index
+    int n;
+    float r2max;                // max radiusSquared (and radius^2) over the scene, for the pad
+};
+
+RT_HD float approx_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return x * __frsqrt_rn(x + 1e-30f);     // MUFU.RSQ, 2 ulp — the 1 % pad head-room covers it
+#else
+    return sqrtf(x);
+#endif
+}
+
+#ifndef RT_BVH_PAD_K
+#define RT_BVH_PAD_K 2.02e-3f                // see header comment; overridable only to demonstrate that it is needed
+#endif
+constexpr float BVH_PAD_K = RT_BVH_PAD_K;
+constexpr float BVH_T_SLACK = 1.0f + 4e-6f; // relative head-room on the pruning bound (t values carry ~3u error)
+constexpr int BVH_STACK = 72;               // Karras tree depth <= key bits (64) + 1
+constexpr int BVH_CAND = 6;                 // secondary-fold candidate buffer
+constexpr float BVH_WINDOW = 0.045f;        // candidates within this distance above the minimum are replayed
+
+// Entry parameter of the ray into the box inflated by pad (conservative), or +inf when it misses t in [0, tmax].
+RT_HD float box_entry(f3 o, f3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float r2max, float tmax) {
+    float dx = fmaxf(fabsf(lox - o.x), fabsf(hix - o.x));
+    float dy = fmaxf(fabsf(loy - o.y), fabsf(hiy - o.y));
+    float dz = fmaxf(fabsf(loz - o.z), fabsf(hiz - o.z));
+    float pad = BVH_PAD_K * approx_sqrt(dx * dx + dy * dy + dz * dz + r2max);
+    float t0x = (lox - pad - o.x) * inv.x, t1x = (hix + pad - o.x) * inv.x;
+    float t0y = (loy - pad - o.y) * inv.y, t1y = (hiy + pad - o.y) * inv.y;
+    float t0z = (loz - pad - o.z) * inv.z, t1z = (hiz + pad - o.z) * inv.z;
+    // fminf/fmaxf drop NaNs (0 * inf when the origin sits exactly on an inflated face of a parallel slab)
+    float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+    return (tn <= tf * BVH_T_SLACK) ? tn : RT_INF;
+}
+
+RT_HD f3 safe_inv(f3 d) { return mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
+
+// Nearest fold.  off == 0: primary (:977).  off == 0.01f: secondary (:804-805), exact incl. its order dependence.
+// BRUTE is a callable fallback  void(int* sel, float* t)  running the reference loop.
+template <class DBG, class BRUTE>
+RT_HD void bvh_nearest(const BvhView& bv, f3 o, f3 dir, float a2, float a4, float off, int* sel, float* dsel, DBG& dbg, BRUTE brute) {
+    const bool secondary = off != 0.0f;
+    const float window = secondary ? BVH_WINDOW : 0.0f;
+    const f3 inv = safe_inv(dir);
+    int best = -1; float best_t = RT_INF;                // lexicographic min over (t, original index)
+    int cand_i[BVH_CAND]; float cand_t[BVH_CAND]; int ncand = 0; bool overflow = false;
+    int stack[BVH_STACK]; int sp = 0;
+    int node = 0;
+    for (;;) {
+        const BvhNode nd = bv.nodes[node];
+        const float bound = (best_t + window) * BVH_T_SLACK;
+        float e0 = box_entry(o, inv, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, bound);
+        float e1 = box_entry(o, inv, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, bound);
+        int c0 = nd.c0, c1 = nd.c1;
+        if (e1 < e0) { float te = e0; e0 = e1; e1 = te; int tc = c0; c0 = c1; c1 = tc; }   // near child first
+        int next = -1;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int c = k == 0 ? c0 : c1;
+            const float e = k == 0 ? e0 : e1;
+            if (!(e < RT_INF)) continue;
+            if (c >= 0) {
+                if (next < 0) next = c; else stack[sp++] = c;
+                continue;
+            }
+            const int leaf = ~c;
+            const f4 g = bv.sgeom_sorted[leaf];
+            float t;
+            if (sphere_hit(sub3(o, mk3(g.x, g.y, g.z)), dir, g.w, a2, a4, 0.0f, &t, dbg)) {
+                const float key = t - off;
+                if (key > 0) {
+                    const int oi = bv.orig[leaf];
+                    if (secondary) {
+                        if (t <= best_t + window) {
+                            if (ncand < BVH_CAND) { cand_i[ncand] = oi; cand_t[ncand] = t; ncand++; }
+                            else overflow = true;
+                        }
+                    }
+                    if (t < best_t || (t == best_t && oi < best)) { best_t = t; best = oi; }
+                }
+            }
+        }
+        if (next >= 0) { node = next; continue; }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    if (!secondary || best < 0) { *sel = best; *dsel = best_t; return; }
+    if (overflow) { brute(sel, dsel); return; }
+    // Replay the reference's fold (:792-808) over the candidates near the minimum, in original index order.
+    int s_sel = -1; float closest = RT_INF, cmax = 0.0f;
+    for (int done = 0; done < ncand; done++) {
+        int k = -1;
+        for (int q = 0; q < ncand; q++) if (cand_i[q] >= 0 && (k < 0 || cand_i[q] < cand_i[k])) k = q;   // next lowest index
+        const float t = cand_t[k]; const int oi = cand_i[k]; cand_i[k] = -1;
+        if (t > best_t + window) continue;              // collected against an older, larger minimum
+        const float key = t - off;
+        if (key > 0 && key < closest) { closest = t; s_sel = oi; if (oi >= best && t > cmax) cmax = t; }
+    }
+    // A sphere outside the window (t > best_t + window) could only have been accepted after the minimum if its offset
+    // distance were below some running `closest` >= best_t; cmax bounds those.  Otherwise: exact fallback.
+    if (cmax + 0.0101f + cmax * 2.4e-7f >= best_t + window) { brute(sel, dsel); return; }
+    *sel = s_sel; *dsel = closest;
+}
+
+// Shadow any-hit (:573-582): eps = 0.001, unbounded t, boolean result.
+template <class DBG>
+RT_HD bool bvh_shadow_any(const BvhView& bv, f3 hit, f3 lp, float a2, float a4, DBG& dbg) {
+    const f3 inv = safe_inv(lp);
+    int stack[BVH_STACK]; int sp = 0;
+    int node = 0;
+    bool occluded = false;
+    for (;;) {
+        const BvhNode nd = bv.nodes[node];
+        float e0 = box_entry(hit, inv, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, RT_INF);
+        float e1 = box_entry(hit, inv, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, RT_INF);
+        int next = -1;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int c = k == 0 ? nd.c0 : nd.c1;
+            const float e = k == 0 ? e0 : e1;
+            if (!(e < RT_INF)) continue;
+            if (c >= 0) { if (next < 0) next = c; else stack[sp++] = c; continue; }
+            const f4 g = bv.sgeom_sorted[~c];
+            float t;
+            if (sphere_hit(sub3(hit, mk3(g.x, g.y, g.z)), lp, g.w, a2, a4, 0.001f, &t, dbg)) occluded = true;
+        }
+        if (occluded && !DBG::enabled) return true;      // boolean OR: the first hit decides
+        if (next >= 0) { node = next; continue; }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return occluded;
+}
+
+}  // namespace rtb

@@ -4,6 +4,7 @@
 //   GlobalScene : records in global memory (L1/L2-resident), any size; base of the shared-memory staged and LBVH paths.
 #pragma once
 #include "rt_trace.cuh"
+#include "rt_lbvh.cuh"
 
 namespace rtb {
 
@@ -18,25 +19,31 @@ struct TinySceneData {
     LightRec lights[TINY_MAX_LIGHTS];
 };
 
+// NS >= 0: the sphere count is a compile-time constant — the sphere loops unroll and every record is addressed
+// statically in the constant bank (operands fold into the FMUL/FADD, no load instructions). NS < 0: run-time count.
+// NL likewise for the light loop of the shading code.
+template <int NS, int NL = -1>
 struct TinyScene {
     const TinySceneData& s;
     RT_HD explicit TinyScene(const TinySceneData& d) : s(d) {}
-    RT_HD int n_spheres() const { return s.ns; }
+    RT_HD int n_spheres() const { return NS >= 0 ? NS : s.ns; }
     RT_HD int n_planes() const { return s.np; }
-    RT_HD int n_lights() const { return s.nl; }
+    RT_HD int n_lights() const { return NL >= 0 ? NL : s.nl; }
     RT_HD f3 ambient() const { return s.amb; }
     RT_HD f4 sphere_geom(int i) const { return s.sgeom[i]; }
-    RT_HD const MatRec& sphere_mat(int i) const { return s.smat[i]; }
-    RT_HD const PlaneRec& plane(int i) const { return s.planes[i]; }
-    RT_HD const LightRec& light(int i) const { return s.lights[i]; }
-    template <class DBG> RT_HD void nearest_primary(f3 o, f3 d, float a2, float a4, int* sel, float* t, DBG& dbg) const {
-        brute_nearest_primary(*this, o, d, a2, a4, sel, t, dbg);
+    RT_HD MatRec sphere_mat(int i) const { return s.smat[i]; }
+    RT_HD uint32_t sphere_flags(int i) const { return s.smat[i].flags; }
+    RT_HD f4 plane_n(int i) const { f4 r; r.x = s.planes[i].n.x; r.y = s.planes[i].n.y; r.z = s.planes[i].n.z; r.w = s.planes[i].cn; return r; }
+    RT_HD f3 plane_e1(int i) const { return s.planes[i].e1; }
+    RT_HD f3 plane_e2(int i) const { return s.planes[i].e2; }
+    RT_HD MatRec plane_mat(int i) const { return s.planes[i].m; }
+    RT_HD uint32_t plane_flags(int i) const { return s.planes[i].m.flags; }
+    RT_HD LightRec light(int i) const { return s.lights[i]; }
+    template <class DBG> RT_HD void nearest(f3 o, f3 d, float a2, float a4, float off, int* sel, float* t, DBG& dbg) const {
+        brute_nearest<NS>(*this, o, d, a2, a4, off, sel, t, dbg);
     }
-    template <class DBG> RT_HD void nearest_secondary(f3 o, f3 d, float a2, float a4, int* sel, float* t, DBG& dbg) const {
-        brute_nearest_secondary(*this, o, d, a2, a4, sel, t, dbg);
-    }
-    template <class DBG> RT_HD bool shadow_any(f3 hit, const LightRec& l, DBG& dbg) const {
-        return brute_shadow_any(*this, hit, l, dbg);
+    template <class DBG> RT_HD bool shadow_any(f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
+        return brute_shadow_any<NS>(*this, hit, lp, a2, a4, dbg);
     }
 };
 
@@ -58,6 +65,19 @@ RT_HD f4 load_f4(const f4* p) {
 #endif
 }
 
+RT_HD MatRec load_mat(const MatRec* p) {
+#if defined(__CUDA_ARCH__)
+    const float4* q = reinterpret_cast<const float4*>(p);
+    float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    MatRec m;
+    m.kd = mk3(a.x, a.y, a.z); m.n = a.w; m.ka = mk3(b.x, b.y, b.z); m.flags = __float_as_uint(b.w);
+    m.ks = mk3(c.x, c.y, c.z); m.pad0 = 0; m.km = mk3(d.x, d.y, d.z); m.pad1 = 0;
+    return m;
+#else
+    return *p;
+#endif
+}
+
 struct GlobalScene {
     const GlobalSceneData& s;
     RT_HD explicit GlobalScene(const GlobalSceneData& d) : s(d) {}
@@ -66,17 +86,47 @@ struct GlobalScene {
     RT_HD int n_lights() const { return s.nl; }
     RT_HD f3 ambient() const { return s.amb; }
     RT_HD f4 sphere_geom(int i) const { return load_f4(s.sgeom + i); }
-    RT_HD const MatRec& sphere_mat(int i) const { return s.smat[i]; }
-    RT_HD const PlaneRec& plane(int i) const { return s.planes[i]; }
-    RT_HD const LightRec& light(int i) const { return s.lights[i]; }
-    template <class DBG> RT_HD void nearest_primary(f3 o, f3 d, float a2, float a4, int* sel, float* t, DBG& dbg) const {
-        brute_nearest_primary(*this, o, d, a2, a4, sel, t, dbg);
+    RT_HD MatRec sphere_mat(int i) const { return load_mat(s.smat + i); }
+    RT_HD uint32_t sphere_flags(int i) const { return s.smat[i].flags; }
+    RT_HD f4 plane_n(int i) const { return load_f4(reinterpret_cast<const f4*>(&s.planes[i].n)); }
+    RT_HD f3 plane_e1(int i) const { return s.planes[i].e1; }
+    RT_HD f3 plane_e2(int i) const { return s.planes[i].e2; }
+    RT_HD MatRec plane_mat(int i) const { return load_mat(&s.planes[i].m); }
+    RT_HD uint32_t plane_flags(int i) const { return s.planes[i].m.flags; }
+    RT_HD LightRec light(int i) const { return s.lights[i]; }
+    template <class DBG> RT_HD void nearest(f3 o, f3 d, float a2, float a4, float off, int* sel, float* t, DBG& dbg) const {
+        brute_nearest<-1>(*this, o, d, a2, a4, off, sel, t, dbg);
     }
-    template <class DBG> RT_HD void nearest_secondary(f3 o, f3 d, float a2, float a4, int* sel, float* t, DBG& dbg) const {
-        brute_nearest_secondary(*this, o, d, a2, a4, sel, t, dbg);
+    template <class DBG> RT_HD bool shadow_any(f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
+        return brute_shadow_any<-1>(*this, hit, lp, a2, a4, dbg);
     }
-    template <class DBG> RT_HD bool shadow_any(f3 hit, const LightRec& l, DBG& dbg) const {
-        return brute_shadow_any(*this, hit, l, dbg);
+};
+
+// Brute force with the sphere geometry staged in shared memory (LDS.128 broadcast per test): BASELINE.json configs[2]
+// ("1,024 random spheres ... shared-memory staged").  Materials / planes / lights stay in global memory.
+struct StagedScene : GlobalScene {
+    const f4* sm_geom;          // ns records in shared memory
+    RT_HD StagedScene(const GlobalSceneData& d, const f4* smem) : GlobalScene(d), sm_geom(smem) {}
+    RT_HD f4 sphere_geom(int i) const { return sm_geom[i]; }
+    template <class DBG> RT_HD void nearest(f3 o, f3 d, float a2, float a4, float off, int* sel, float* t, DBG& dbg) const {
+        brute_nearest<-1>(*this, o, d, a2, a4, off, sel, t, dbg);
+    }
+    template <class DBG> RT_HD bool shadow_any(f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
+        return brute_shadow_any<-1>(*this, hit, lp, a2, a4, dbg);
+    }
+};
+
+// LBVH over the spheres (rt_lbvh.cuh); planes stay in the brute-force side list (they are infinite).
+struct LbvhScene : GlobalScene {
+    BvhView bv;
+    RT_HD LbvhScene(const GlobalSceneData& d, const BvhView& v) : GlobalScene(d), bv(v) {}
+    template <class DBG> RT_HD void nearest(f3 o, f3 d, float a2, float a4, float off, int* sel, float* t, DBG& dbg) const {
+        const GlobalScene& base = *this;
+        bvh_nearest(bv, o, d, a2, a4, off, sel, t, dbg,
+                    [&](int* s2, float* t2) { NoDbg nd; brute_nearest<-1>(base, o, d, a2, a4, off, s2, t2, nd); });
+    }
+    template <class DBG> RT_HD bool shadow_any(f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
+        return bvh_shadow_any(bv, hit, lp, a2, a4, dbg);
     }
 };
 

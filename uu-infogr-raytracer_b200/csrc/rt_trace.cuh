@@ -4,16 +4,18 @@
 // The reference shades every intersected primitive and then keeps the nearest (RayTracer.cs:975-993, :792-825);
 // all its trace functions are pure, so select-then-shade returns the same bits (oracle test
 // test_faithful_equals_nearest).  Every arithmetic expression below keeps the reference's operation order; the
-// only liberties taken are hoists of loop-invariant subexpressions and early-outs proven equivalent in DESIGN.md.
+// only liberties taken are hoists of loop-invariant subexpressions, merged call sites (one sphere loop for the
+// primary and secondary folds, one light loop for spheres and planes — this keeps the kernel inside the
+// instruction cache) and early-outs proven equivalent in DESIGN.md.
 //
-// Templated on a scene policy SC that supplies the records and the three sphere queries, so the brute-force loops
+// Templated on a scene policy SC that supplies the records and the two sphere queries, so the brute-force loops
 // and the LBVH traversal share all shading code:
 //   int  n_spheres()/n_planes()/n_lights();  f3 ambient();
-//   f4   sphere_geom(i)  -> (cx, cy, cz, r^2);      const MatRec& sphere_mat(i)
-//   const PlaneRec& plane(i);  const LightRec& light(i)
-//   void nearest_primary  (o, dir, a, a2, a4, &sel, &d, dbg)     RayTracer.cs:975-981
-//   void nearest_secondary(o, dir, a, a2, a4, &sel, &d, dbg)     RayTracer.cs:792-808
-//   bool shadow_any       (hit, light, dbg)                       RayTracer.cs:573-582
+//   f4   sphere_geom(i)  -> (cx, cy, cz, r^2);      MatRec sphere_mat(i) / uint32_t sphere_flags(i)
+//   PlaneRec access: plane_n(i) (normal + Dot(center,normal)), plane_e1/e2(i), plane_mat(i), plane_flags(i)
+//   LightRec light(i)
+//   void nearest   (o, dir, a2, a4, off, &sel, &d, dbg)   RayTracer.cs:975-981 (off = 0) / :792-808 (off = 0.01f)
+//   bool shadow_any(hit, light, dbg)                       RayTracer.cs:573-582
 #pragma once
 #include "rt_math.cuh"
 
@@ -54,7 +56,7 @@ struct NoDbg {
     RT_HD void plane_test() {}
     RT_HD void ray(uint32_t, uint32_t, uint32_t, float) {}
     RT_HD void shadow(uint32_t, uint32_t, bool) {}
-    RT_HD void shaded(bool, bool) {}
+    RT_HD void shaded(bool) {}
     RT_HD void spec() {}
     RT_HD void primary_aov(int, float) {}
 };
@@ -73,27 +75,26 @@ struct FullDbg {
     RT_HD void shadow(uint32_t level, uint32_t li, bool occluded) {
         hash += event_hash(level, 3, li, occluded ? 1u : 0u); n_shadow++; shade_diffuse++;
     }
-    RT_HD void shaded(bool mirror, bool) { shaded_hits++; if (mirror) shade_mirror++; }
+    RT_HD void shaded(bool mirror) { shaded_hits++; if (mirror) shade_mirror++; }
     RT_HD void spec() { shade_specular++; }
     RT_HD void primary_aov(int id, float t) { if (!aov_set) { aov_id = id; aov_t = t; aov_set = true; } }
 };
 
 // ---------------------------------------------------------------------------------------------------------
 // Sphere test — IntersectsSphere RayTracer.cs:613-642.
-// Given per-ray a = Dot(d,d), a2 = 2*a, a4 = 4*a (hoisted; `4 * a * c` associates as (4*a)*c).
+// Given per-ray a2 = 2*Dot(d,d), a4 = 4*Dot(d,d) (hoisted; `4 * a * c` associates as (4*a)*c).
 // Returns true and *t = distance iff the reference reports a collision with this epsilon.
 // Equivalences used (DESIGN.md §sphere test):  with s = sqrt(D) >= 0 and a2 >= 0,  t1 = (-b-s)/a2 <= t2 = (-b+s)/a2
 // (monotone rounding) or t1 is NaN, hence  distanceEps > 0  <=>  t1 - eps > 0,  and then distance = min(t1,t2) = t1;
-// and t1 > 0 requires b < 0, so b >= 0 (or NaN) is a miss without evaluating the discriminant.
+// and t1 > 0 requires b < 0, so b >= 0 (or NaN) is a miss without a square root or a division.
 // ---------------------------------------------------------------------------------------------------------
 template <class DBG>
 RT_HD bool sphere_hit(f3 oc, f3 dir, float r2, float a2, float a4, float eps, float* t, DBG& dbg) {
     float b = 2 * dot3(oc, dir);                                  // :618
-    if (!DBG::enabled && !(b < 0)) return false;
     float c = dot3(oc, oc) - r2;                                  // :619
     float D = b * b - a4 * c;                                     // :621
     dbg.sphere_test(D >= 0);
-    if (!(D >= 0)) return false;                                  // :622
+    if (!(b < 0 && D >= 0)) return false;                         // :622 (+ the b >= 0 early-out)
     float s = sqrtf(D);                                           // :623  (float)Math.Sqrt((double)D) == sqrtf(D)
     float t1 = (-b - s) / a2;                                     // :627
     if (!(t1 - eps > 0)) return false;                            // :629-635
@@ -101,130 +102,114 @@ RT_HD bool sphere_hit(f3 oc, f3 dir, float r2, float a2, float a4, float eps, fl
     return true;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Brute-force sphere queries: the reference's loops over every sphere, in array order.
-// Mixed into scene policies that expose n_spheres() and sphere_geom(i).
-// ---------------------------------------------------------------------------------------------------------
-template <class SC, class DBG>
-RT_HD void brute_nearest_primary(const SC& sc, f3 o, f3 dir, float a2, float a4, int* sel, float* dsel, DBG& dbg) {
-    int best = -1; float nearest = RT_INF;
-    const int ns = sc.n_spheres();
-    for (int i = 0; i < ns; i++) {                                // :975
-        f4 g = sc.sphere_geom(i);
-        float t;
-        if (sphere_hit(sub3(o, mk3(g.x, g.y, g.z)), dir, g.w, a2, a4, 0.0f, &t, dbg))
-            if (nearest > t) { nearest = t; best = i; }           // :977 (t > 0 is implied by the hit)
-    }
-    *sel = best; *dsel = nearest;
-}
-template <class SC, class DBG>
-RT_HD void brute_nearest_secondary(const SC& sc, f3 o, f3 dir, float a2, float a4, int* sel, float* dsel, DBG& dbg) {
+// The reference's loops over every sphere, in array order.  One loop serves both folds:
+//   primary   (:977)  `d > 0 && nearest > d`                    == key > 0 && key < closest with key = d - 0
+//   secondary (:804)  `d - 0.01f > 0 && d - 0.01f < closest`    == the same with key = d - 0.01f
+// (d - 0.0f == d bit for bit; the stored distance is the un-offset d in both: the secondary fold is order dependent).
+// NS >= 0: compile-time sphere count (fully unrolled, records addressed statically); NS < 0: run-time count.
+template <int NS, class SC, class DBG>
+RT_HD void brute_nearest(const SC& sc, f3 o, f3 dir, float a2, float a4, float off, int* sel, float* dsel, DBG& dbg) {
     int best = -1; float closest = RT_INF;
-    const int ns = sc.n_spheres();
-    for (int i = 0; i < ns; i++) {                                // :792
+    const int ns = NS >= 0 ? NS : sc.n_spheres();
+#pragma unroll
+    for (int i = 0; i < ns; i++) {                                // :975 / :792
         f4 g = sc.sphere_geom(i);
         float t;
         if (sphere_hit(sub3(o, mk3(g.x, g.y, g.z)), dir, g.w, a2, a4, 0.0f, &t, dbg)) {
-            float te = t - 0.01f;
-            if (te > 0 && te < closest) { closest = t; best = i; } // :804-805 — offset compared with un-offset: order dependent
+            float key = t - off;
+            if (key > 0 && key < closest) { closest = t; best = i; }
         }
     }
     *sel = best; *dsel = closest;
 }
-template <class SC, class DBG>
-RT_HD bool brute_shadow_any(const SC& sc, f3 hit, const LightRec& l, DBG& dbg) {
+template <int NS, class SC, class DBG>
+RT_HD bool brute_shadow_any(const SC& sc, f3 hit, f3 lp, float a2, float a4, DBG& dbg) {
     bool occluded = false;
-    const int ns = sc.n_spheres();
+    const int ns = NS >= 0 ? NS : sc.n_spheres();
+#pragma unroll
     for (int i = 0; i < ns; i++) {                                // :577
         f4 g = sc.sphere_geom(i);
         float t;
-        if (sphere_hit(sub3(hit, mk3(g.x, g.y, g.z)), l.p, g.w, l.a2, l.a4, 0.001f, &t, dbg)) {   // :578
-            occluded = true;
-            if (!DBG::enabled) break;     // the result is a boolean OR: leaving early cannot change it
-        }
+        if (sphere_hit(sub3(hit, mk3(g.x, g.y, g.z)), lp, g.w, a2, a4, 0.001f, &t, dbg))   // :578
+            occluded = true;                                      // boolean OR over all spheres (no early-out in the reference)
     }
     return occluded;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Shading — ShapePhongShading RayTracer.cs:665-695
-// ---------------------------------------------------------------------------------------------------------
-template <class DBG>
-RT_HD f3 shape_phong(f3 hit, f3 V, f3 N, const MatRec& m, const LightRec& l, DBG& dbg) {
-    f3 L = normalize3(sub3(l.p, hit));                            // :667
-    f3 diff = mk3(0, 0, 0);
-    if (m.flags & MAT_DIFFUSE) {                                  // :671
-        float angle = dot3(N, L);                                 // :672
-        diff = mulf3(m.kd, cs_maxf(0.0f, angle));                 // :677-678
-    }
-    f3 spec = mk3(0, 0, 0);
-    if (m.flags & MAT_SPEC) {                                     // :682
-        f3 rv = sub3(L, mulf3(N, 2 * dot3(L, N)));                // :683-684
-        float s = dot3(V, normalize3(rv));                        // :685-688
-        float base = cs_maxf(0.0f, s);
-        float pw;
-        // (float)Math.Pow((double)base, (double)n) :691.  pow(x,1) == x exactly; pow(x,.5) rounds as sqrtf.
-        if (m.n == 1.0f) pw = base;
-        else if (m.n == 0.5f) pw = sqrtf(base);
-        else pw = (float)pow((double)base, (double)m.n);
-        spec = mulv3(m.ks, splat3(pw));
-        dbg.spec();
-    }
-    return add3(diff, spec);                                      // :694
+// (float)Math.Pow((double)base, (double)n) — RayTracer.cs:691.  pow(x,1) == x exactly; pow(x,.5) rounds as sqrtf(x)
+// (SURVEY A.12); everything else takes the f64 pow.
+RT_HD float spec_pow(float base, float n) {
+    if (n == 1.0f) return base;
+    if (n == 0.5f) return sqrtf(base);
+#if defined(__CUDA_ARCH__)
+    // The f64 pow is ~1 K instructions with a long side-effect-free prologue that ptxas otherwise hoists above the two
+    // tests and executes for every light sample.  Routing the operand through a volatile asm pins it inside this branch.
+    float pinned;
+    asm volatile("mov.f32 %0, %1;" : "=f"(pinned) : "f"(base));
+    return (float)pow((double)pinned, (double)n);
+#else
+    return (float)pow((double)base, (double)n);
+#endif
 }
 
-// Colour of one recorded hit given the colour Cin seen by its reflection ray: TraceSphere :846-875 / TracePlane :736-779
+// ---------------------------------------------------------------------------------------------------------
+// Colour of one recorded hit given the colour Cin seen by its reflection ray:
+// TraceSphere :846-875 / TracePlane :736-779 with ShapePhongShading :665-695 inlined into ONE light loop.
+//   sphere: col += ((I,I,I) * att) * phong                      att = (1/d)*d                       (:866-869)
+//   plane : col += Max((((I,I,I) * att) * phong) * tile, 0)     att = (float)(1/Math.Pow(d,2))      (:754-775)
+// `x * tile` with tile = (1,1,1) is exact, so spheres run the plane expression with tile = 1 and skip only the Max.
+// ---------------------------------------------------------------------------------------------------------
 template <class SC, class DBG>
 RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& dbg) {
-    f3 hit = add3(h.o, mulf3(h.dir, h.d));                        // :846 / :736
-    f3 col = mk3(0, 0, 0);
-    if (h.prim >= 0) {
-        const MatRec& m = sc.sphere_mat(h.prim);
-        dbg.shaded((m.flags & MAT_MIRROR) != 0, true);
-        if (m.flags & MAT_MIRROR) col = add3(col, mulv3(Cin, m.km));                       // :857-858
-        if (m.flags & MAT_DIFFUSE) {                                                       // :862
-            f4 g = sc.sphere_geom(h.prim);
-            f3 N = normalize3(sub3(hit, mk3(g.x, g.y, g.z)));                              // :706
-            f3 V = normalize3(h.dir);                                                      // :668
-            float att = 1 / h.d * h.d;                                                     // :866  ((1/d)*d)
-            const int nl = sc.n_lights();
-            for (int li = 0; li < nl; li++) {                                              // :863
-                const LightRec& l = sc.light(li);
-                bool occ = sc.shadow_any(hit, l, dbg);                                     // :864
-                dbg.shadow(level, (uint32_t)li, occ);
-                float I = occ ? 0.0f : l.intensity;                                        // :581
-                f3 ph = shape_phong(hit, V, N, m, l, dbg);
-                col = add3(col, mulv3(mulf3(splat3(I), att), ph));                         // :868-869
-            }
-        }
-        col = add3(col, mulv3(sc.ambient(), m.ka));                                        // :873
+    const f3 hit = add3(h.o, mulf3(h.dir, h.d));                  // :846 / :736
+    const bool is_plane = h.prim < 0;
+    MatRec m; f3 N; float att, tile;
+    if (!is_plane) {
+        m = sc.sphere_mat(h.prim);
+        f4 g = sc.sphere_geom(h.prim);
+        N = normalize3(sub3(hit, mk3(g.x, g.y, g.z)));            // :706
+        att = 1 / h.d * h.d;                                      // :866  ((1/d)*d)
+        tile = 1.0f;
     } else {
-        const PlaneRec& p = sc.plane(~h.prim);
-        const MatRec& m = p.m;
-        dbg.shaded((m.flags & MAT_MIRROR) != 0, false);
-        if (m.flags & MAT_MIRROR) col = add3(col, mulv3(Cin, m.km));                       // :746-747
-        if (m.flags & MAT_DIFFUSE) {                                                       // :750
-            f3 V = normalize3(h.dir);
-            double dd = (double)h.d;
-            float att = (float)(1.0 / (dd * dd));                                          // :754  Math.Pow(d,2) == d*d exactly in f64
-            float u = dot3(p.e1, hit);                                                     // :766
-            float v = dot3(p.e2, hit);                                                     // :767
-            int32_t cb = (int32_t)(((uint32_t)cs_f2i(u) + (uint32_t)cs_f2i(v)) & 1u);      // :769  ((int)u + (int)v) & 1
-            f3 tile = splat3((float)cb);                                                   // :770
-            const int nl = sc.n_lights();
-            for (int li = 0; li < nl; li++) {                                              // :751
-                const LightRec& l = sc.light(li);
-                bool occ = sc.shadow_any(hit, l, dbg);                                     // :752
-                dbg.shadow(level, (uint32_t)li, occ);
-                float I = occ ? 0.0f : l.intensity;
-                f3 ph = shape_phong(hit, V, p.n, m, l, dbg);                               // :652-654
-                f3 t = mulv3(mulv3(mulf3(splat3(I), att), ph), tile);                      // :774
-                col = add3(col, mk3(cs_maxf(t.x, 0.0f), cs_maxf(t.y, 0.0f), cs_maxf(t.z, 0.0f)));   // :775 (.Max(0))
-            }
-        }
-        col = add3(col, mulv3(sc.ambient(), m.ka));                                        // :778
+        const int pi = ~h.prim;
+        m = sc.plane_mat(pi);
+        f4 pn = sc.plane_n(pi);
+        N = mk3(pn.x, pn.y, pn.z);                                // :653 plane.normal as given
+        double dd = (double)h.d;
+        att = (float)(1.0 / (dd * dd));                           // :754  Math.Pow(d,2) == d*d exactly in f64
+        float u = dot3(sc.plane_e1(pi), hit);                     // :766
+        float v = dot3(sc.plane_e2(pi), hit);                     // :767
+        tile = (float)(int32_t)(((uint32_t)cs_f2i(u) + (uint32_t)cs_f2i(v)) & 1u);   // :769-770  ((int)u + (int)v) & 1
     }
-    return col;
+    dbg.shaded((m.flags & MAT_MIRROR) != 0);
+    f3 col = mk3(0, 0, 0);
+    if (m.flags & MAT_MIRROR) col = mulv3(Cin, m.km);             // :857-858 / :746-747   (0 + x == x)
+    if (m.flags & MAT_DIFFUSE) {                                  // :862 / :750
+        const f3 V = normalize3(h.dir);                           // :668
+        const int nl = sc.n_lights();
+#pragma unroll
+        for (int li = 0; li < nl; li++) {                         // :863 / :751
+            const LightRec l = sc.light(li);
+            bool occ = sc.shadow_any(hit, l.p, l.a2, l.a4, dbg);  // :864 / :752
+            dbg.shadow(level, (uint32_t)li, occ);
+            float I = occ ? 0.0f : l.intensity;                   // :581
+            // ShapePhongShading :665-695
+            f3 L = normalize3(sub3(l.p, hit));                    // :667
+            f3 ph = mulf3(m.kd, cs_maxf(0.0f, dot3(N, L)));       // :672-678 (IsDiffuse holds inside this loop)
+            if (m.flags & MAT_SPEC) {                             // :682
+                f3 rv = sub3(L, mulf3(N, 2 * dot3(L, N)));        // :683-684
+                float s = dot3(V, normalize3(rv));                // :685-688
+                float pw = spec_pow(cs_maxf(0.0f, s), m.n);       // :691
+                ph = add3(ph, mulv3(m.ks, splat3(pw)));           // :690-694
+                dbg.spec();
+            }
+            float ia = I * att;                                   // (I,I,I) * att
+            f3 t = mulf3(mulv3(splat3(ia), ph), tile);            // :868-869 / :774
+            if (is_plane) t = mk3(cs_maxf(t.x, 0.0f), cs_maxf(t.y, 0.0f), cs_maxf(t.z, 0.0f));   // :775 (.Max(0))
+            col = add3(col, t);
+        }
+    }
+    return add3(col, mulv3(sc.ambient(), m.ka));                  // :873 / :778
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -249,33 +234,34 @@ RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float
         float a2 = 2 * a;                                                                  // :624
         float a4 = 4 * a;                                                                  // :621
         int sel_s; float d_s;
-        if (bounce == 0) sc.nearest_primary(o, dir, a2, a4, &sel_s, &d_s, dbg);
-        else sc.nearest_secondary(o, dir, a2, a4, &sel_s, &d_s, dbg);
+        sc.nearest(o, dir, a2, a4, bounce == 0 ? 0.0f : 0.01f, &sel_s, &d_s, dbg);         // :975-981 / :792-808
         int sel_p = -1; float d_p = RT_INF;
         for (int i = 0; i < np; i++) {                                                     // :985 / :812
-            const PlaneRec& p = sc.plane(i);
-            float t = (-o.x * p.n.x - o.y * p.n.y - o.z * p.n.z + p.cn) / dot3(dir, p.n);  // :591-596
+            f4 pn = sc.plane_n(i);
+            float t = (-o.x * pn.x - o.y * pn.y - o.z * pn.z + pn.w) / dot3(dir, mk3(pn.x, pn.y, pn.z));   // :591-596
             dbg.plane_test();
             if (t > 0 && t < d_p) { d_p = t; sel_p = i; }                                  // :598 + :987 / :819
         }
         bool pick_s = d_s < d_p;                                                           // :993 / :825
         bool none = !pick_s && sel_p < 0;
         float d = pick_s ? d_s : (none ? 0.0f : d_p);
-        uint32_t code = pick_s ? (uint32_t)sel_s : (none ? 0xFFFFFFFFu : (uint32_t)(sc.n_spheres() + sel_p));
-        dbg.ray((uint32_t)top, bounce == 0 ? 1u : 2u, code, d);
-        if (bounce == 0) dbg.primary_aov((int)code, d);
+        if (DBG::enabled) {
+            uint32_t code = pick_s ? (uint32_t)sel_s : (none ? 0xFFFFFFFFu : (uint32_t)(sc.n_spheres() + sel_p));
+            dbg.ray((uint32_t)top, bounce == 0 ? 1u : 2u, code, d);
+            if (bounce == 0) dbg.primary_aov((int)code, d);
+        }
         if (none) break;                                                                   // nothing hit: black
         if (d - 0.01f <= 0) break;                                                         // :839 / :731 (distance kept, colour black)
         if (bounce > cap) { if (!pick_s) C = mk3(1, 1, 1); break; }                        // :843 black / :734 white
         HitRec& h = stack[top++];
         h.o = o; h.dir = dir; h.d = d; h.prim = pick_s ? sel_s : ~sel_p;
-        uint32_t flags = pick_s ? sc.sphere_mat(sel_s).flags : sc.plane(sel_p).m.flags;
+        uint32_t flags = pick_s ? sc.sphere_flags(sel_s) : sc.plane_flags(sel_p);
         if (!(flags & MAT_MIRROR)) break;                                                  // :850 / :739
         bounce++;                                                                          // :851 / :740
         f3 hit = add3(o, mulf3(dir, d));                                                   // :846 / :736
         f3 N;
         if (pick_s) { f4 g = sc.sphere_geom(sel_s); N = normalize3(sub3(hit, mk3(g.x, g.y, g.z))); }   // :854
-        else N = sc.plane(sel_p).n;                                                        // :743
+        else { f4 pn = sc.plane_n(sel_p); N = mk3(pn.x, pn.y, pn.z); }                     // :743
         dir = sub3(dir, mulf3(N, 2 * dot3(dir, N)));                                       // :719
         o = hit;
     }
@@ -287,25 +273,23 @@ RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float
 }
 
 // One pixel: spp == 1 is the reference; spp > 1 is the jittered extension (BASELINE.json configs[4]).
+// A single call site of trace_sample: with spp == 1 the jitter is +0.0f and the average is *1.0f, both exact.
 template <class SC, class DBG>
 RT_HD uint32_t trace_pixel(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int cap, int spp, uint32_t seed,
                            HitRec* stack, DBG& dbg) {
-    float fw = (float)w, fh = (float)h;
-    f3 col;
-    if (spp <= 1) {
-        col = trace_sample(sc, cam, (float)x, (float)y, fw, fh, cap, stack, dbg);
-    } else {
-        f3 acc = mk3(0, 0, 0);
-        for (int s = 0; s < spp; s++) {
+    const float fw = (float)w, fh = (float)h;
+    f3 acc = mk3(0, 0, 0);
+    for (int s = 0; s < spp; s++) {
+        float jx = 0.0f, jy = 0.0f;
+        if (spp > 1) {
             uint32_t k = ((uint32_t)y * (uint32_t)w + (uint32_t)x) * (uint32_t)spp + (uint32_t)s;
             uint32_t h1 = pcg_hash(k ^ seed), h2 = pcg_hash(h1);
-            float jx = (float)(h1 >> 8) * 5.9604644775390625e-08f;
-            float jy = (float)(h2 >> 8) * 5.9604644775390625e-08f;
-            acc = add3(acc, trace_sample(sc, cam, (float)x + jx, (float)y + jy, fw, fh, cap, stack, dbg));
+            jx = (float)(h1 >> 8) * 5.9604644775390625e-08f;
+            jy = (float)(h2 >> 8) * 5.9604644775390625e-08f;
         }
-        col = mulf3(acc, 1.0f / (float)spp);
+        acc = add3(acc, trace_sample(sc, cam, (float)x + jx, (float)y + jy, fw, fh, cap, stack, dbg));
     }
-    return pack_color(col);                                                                // :1000 -> :1038, :1046-1052
+    return pack_color(mulf3(acc, 1.0f / (float)spp));                                      // :1000 -> :1038, :1046-1052
 }
 
 }  // namespace rtb

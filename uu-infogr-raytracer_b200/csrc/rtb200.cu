@@ -22,6 +22,7 @@
 
 #include "../../include/rtb200.h"
 #include "rt_scene.cuh"
+#include "rt_lbvh_build.cuh"
 
 using namespace rtb;
 
@@ -32,6 +33,12 @@ constexpr int PPT = 4;                      // pixels per thread (one 128-bit st
 constexpr int CHUNK = BLOCK * PPT;          // pixels per CTA work item
 constexpr int STACK_RECS = RT_MAX_DEPTH + 1;
 constexpr int INLINE_CAMS = 16;
+#ifndef RT_DEFAULT_WAVES
+#define RT_DEFAULT_WAVES 4     // grid-stride grid = SMs x resident CTAs x waves (profiles/r01/tune_*.log)
+#endif
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 4      // resident CTAs per SM the register allocator must allow (tuned on B200, profiles/)
+#endif
 
 struct FrameParams {
     int w, h, cap, spp;
@@ -51,67 +58,92 @@ struct DebugOut {
     uint32_t* hash; int32_t* aov_id; float* aov_t; unsigned long long* counters;
 };
 
-template <class SC, class DBG>
-__device__ __forceinline__ uint32_t render_one(const SC& sc, const CamRec& cam, const FrameParams& fp, long long p,
-                                               HitRec* stack, DBG& dbg) {
-    int y = (int)(p / fp.w);
-    int x = (int)(p - (long long)y * fp.w);
-    return trace_pixel(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg);
-}
 
-// Walks this rank's (frame, tile, chunk) work items with a grid stride.
-template <class SC, class SCD>
-__device__ __forceinline__ void render_loop(const SCD& scd, const FrameParams& fp) {
-    SC sc(scd);
+// Walks this rank's (frame, tile, chunk) work items with a grid stride.  All per-frame indices are 32-bit (w*h < 2^31).
+template <class SC>
+__device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp) {
     HitRec stack[STACK_RECS];
     NoDbg dbg;
-    const long long npix = (long long)fp.w * fp.h;
-    const long long tile_pix = (long long)fp.tile_rows * fp.w;
-    const long long items_per_frame = (long long)fp.tiles_mine * fp.chunks_per_tile;
-    const long long n_items = items_per_frame * fp.n_frames;
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        int frame = (int)(item / items_per_frame);
-        long long r = item - (long long)frame * items_per_frame;
-        int k = (int)(r / fp.chunks_per_tile);                 // my k-th tile
-        int j = (int)(r - (long long)k * fp.chunks_per_tile);  // chunk inside the tile
-        long long tile = (long long)k * fp.world + fp.rank;
-        long long base = tile * tile_pix;
-        long long end = base + tile_pix; if (end > npix) end = npix;
-        long long p0 = base + (long long)j * CHUNK + (long long)threadIdx.x * PPT;
+    const int npix = fp.w * fp.h;
+    const int tile_pix = fp.tile_rows * fp.w;
+    const int items_per_frame = fp.tiles_mine * fp.chunks_per_tile;
+    const int n_items = items_per_frame * fp.n_frames;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int frame = item / items_per_frame;
+        const int r = item - frame * items_per_frame;
+        const int k = r / fp.chunks_per_tile;                  // my k-th tile
+        const int j = r - k * fp.chunks_per_tile;              // chunk inside the tile
+        const int tile = k * fp.world + fp.rank;
+        const int base = tile * tile_pix;
+        int end = base + tile_pix; if (end > npix || end < base) end = npix;
+        const int p0 = base + j * CHUNK + (int)threadIdx.x * PPT;
         if (p0 >= end) continue;
         const CamRec& cam = fp.cams ? fp.cams[frame] : fp.cam_inline[frame];
         uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
         uint32_t px[PPT];
+        int y = p0 / fp.w, x = p0 - y * fp.w;                  // one division per work item; then step along the row
 #pragma unroll 1
         for (int q = 0; q < PPT; q++) {
-            long long p = p0 + q;
-            px[q] = (p < end) ? render_one(sc, cam, fp, p, stack, dbg) : 0u;
+            uint32_t c = (p0 + q < end) ? trace_pixel(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg) : 0u;
+            if (++x == fp.w) { x = 0; ++y; }
+#pragma unroll
+            for (int z = 0; z < PPT; z++) if (z == q) px[z] = c;   // keeps px[] in registers under `unroll 1`
         }
         if (p0 + PPT <= end && ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0)) {
-            *reinterpret_cast<uint4*>(out + p0) = make_uint4(px[0], px[1], px[2], px[3]);
+            *reinterpret_cast<uint4*>(out + p0) = make_uint4(px[0], px[1], px[2], px[3]);     // 128-bit coalesced store
         } else {
             for (int q = 0; q < PPT; q++) if (p0 + q < end) out[p0 + q] = px[q];
         }
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_render_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp) {
-    render_loop<TinyScene>(scd, fp);
+template <int NS, int NL>
+__global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp) {
+    render_loop(TinyScene<NS, NL>(scd), fp);
 }
-__global__ void __launch_bounds__(BLOCK) k_render_global(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp) {
-    render_loop<GlobalScene>(scd, fp);
+using TinyKernel = void (*)(const TinySceneData, const FrameParams);
+// Exact-count instantiations (sphere and light loops unrolled, records addressed statically) for scenes of the
+// reference's size; everything else up to the TINY_MAX_* limits takes the run-time-count instantiation.
+constexpr int EXACT_MAX = 4;
+template <int NS, int NL> struct TinyTable {
+    static TinyKernel get(int ns, int nl) {
+        if (ns == NS && nl == NL) return k_render_tiny<NS, NL>;
+        if constexpr (NL < EXACT_MAX) return TinyTable<NS, NL + 1>::get(ns, nl);
+        else if constexpr (NS < EXACT_MAX) return TinyTable<NS + 1, 0>::get(ns, nl);
+        else return k_render_tiny<-1, -1>;
+    }
+};
+TinyKernel tiny_kernel(int ns, int nl) { return TinyTable<0, 0>::get(ns, nl); }
+__global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_global(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp) {
+    render_loop(GlobalScene(scd), fp);
+}
+// Brute force with the sphere geometry staged in shared memory (dynamic: 16 B per sphere).
+__device__ __forceinline__ const f4* stage_spheres(const GlobalSceneData& scd) {
+    extern __shared__ float4 sm_raw[];
+    f4* sm = reinterpret_cast<f4*>(sm_raw);
+    for (int i = threadIdx.x; i < scd.ns; i += blockDim.x) sm[i] = load_f4(scd.sgeom + i);
+    __syncthreads();
+    return sm;
+}
+__global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_staged(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp) {
+    render_loop(StagedScene(scd, stage_spheres(scd)), fp);
+}
+struct LbvhSceneData { GlobalSceneData g; BvhView bv; };
+__global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_lbvh(const __grid_constant__ LbvhSceneData scd, const __grid_constant__ FrameParams fp) {
+    render_loop(LbvhScene(scd.g, scd.bv), fp);
 }
 
-// Instrumented kernel: one thread per pixel, no early-outs in sphere tests, writes hash / AOVs / counters.
-template <class SC, class SCD>
-__device__ __forceinline__ void debug_loop(const SCD& scd, const FrameParams& fp, const DebugOut& dout) {
-    SC sc(scd);
+// Instrumented kernel: one thread per pixel, writes hash / AOVs / counters.
+template <class SC>
+__device__ __forceinline__ void debug_loop(const SC& sc, const FrameParams& fp, const DebugOut& dout) {
     HitRec stack[STACK_RECS];
-    const long long npix = (long long)fp.w * fp.h;
+    const int npix = fp.w * fp.h;
     unsigned long long cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    for (long long pl = (long long)blockIdx.x * blockDim.x + threadIdx.x; pl < npix; pl += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)pl;
         FullDbg dbg;
-        uint32_t c = render_one(sc, fp.cam_inline[0], fp, p, stack, dbg);
+        const int y = p / fp.w, x = p - y * fp.w;
+        uint32_t c = trace_pixel(sc, fp.cam_inline[0], x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg);
         fp.out[p] = c;
         if (dout.hash) dout.hash[p] = dbg.hash;
         if (dout.aov_id) dout.aov_id[p] = dbg.aov_id;
@@ -124,30 +156,40 @@ __device__ __forceinline__ void debug_loop(const SCD& scd, const FrameParams& fp
         for (int i = 0; i < 10; i++) if (cnt[i]) atomicAdd(dout.counters + i, cnt[i]);
 }
 __global__ void __launch_bounds__(BLOCK) k_debug_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
-    debug_loop<TinyScene>(scd, fp, dout);
+    debug_loop(TinyScene<-1, -1>(scd), fp, dout);
 }
 __global__ void __launch_bounds__(BLOCK) k_debug_global(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
-    debug_loop<GlobalScene>(scd, fp, dout);
+    debug_loop(GlobalScene(scd), fp, dout);
+}
+__global__ void __launch_bounds__(BLOCK) k_debug_staged(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
+    debug_loop(StagedScene(scd, stage_spheres(scd)), fp, dout);
+}
+__global__ void __launch_bounds__(BLOCK) k_debug_lbvh(const __grid_constant__ LbvhSceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
+    debug_loop(LbvhScene(scd.g, scd.bv), fp, dout);
 }
 
-// Sphere-query kernel (LBVH == brute equality harness, rt_query_spheres).
-__global__ void __launch_bounds__(BLOCK) k_query_brute(const __grid_constant__ GlobalSceneData scd, const float* rays6, int n, int kind,
-                                                        int32_t* out_id, float* out_t) {
-    GlobalScene sc(scd);
+// Sphere-query kernels (LBVH == brute equality harness, rt_query_spheres).
+template <class SC>
+__device__ __forceinline__ void query_loop(const SC& sc, const float* rays6, int n, int kind, int32_t* out_id, float* out_t) {
     NoDbg dbg;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
         f3 o = mk3(rays6[6 * r], rays6[6 * r + 1], rays6[6 * r + 2]);
         f3 d = mk3(rays6[6 * r + 3], rays6[6 * r + 4], rays6[6 * r + 5]);
         float a = dot3(d, d), a2 = 2 * a, a4 = 4 * a;
         int sel = -1; float t = 0.0f;
-        if (kind == 0) { sc.nearest_primary(o, d, a2, a4, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
-        else if (kind == 1) { sc.nearest_secondary(o, d, a2, a4, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
-        else {
-            LightRec l; l.p = d; l.intensity = 1.0f; l.a = a; l.a2 = a2; l.a4 = a4; l.pad = 0;
-            sel = sc.shadow_any(o, l, dbg) ? 1 : 0; t = 0.0f;
-        }
+        if (kind == 0) { sc.nearest(o, d, a2, a4, 0.0f, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
+        else if (kind == 1) { sc.nearest(o, d, a2, a4, 0.01f, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
+        else { sel = sc.shadow_any(o, d, a2, a4, dbg) ? 1 : 0; t = 0.0f; }
         out_id[r] = sel; out_t[r] = t;
     }
+}
+__global__ void __launch_bounds__(BLOCK) k_query_brute(const __grid_constant__ GlobalSceneData scd, const float* rays6, int n, int kind,
+                                                        int32_t* out_id, float* out_t) {
+    query_loop(GlobalScene(scd), rays6, n, kind, out_id, out_t);
+}
+__global__ void __launch_bounds__(BLOCK) k_query_lbvh(const __grid_constant__ LbvhSceneData scd, const float* rays6, int n, int kind,
+                                                       int32_t* out_id, float* out_t) {
+    query_loop(LbvhScene(scd.g, scd.bv), rays6, n, kind, out_id, out_t);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -161,9 +203,14 @@ struct DeviceState {
     // scene
     f4* sgeom = nullptr; MatRec* smat = nullptr; PlaneRec* planes = nullptr; LightRec* lights = nullptr;
     CamRec* cams = nullptr; int cams_cap = 0;
+    LbvhDevice bvh;
     // framebuffer ring (device 0 of the context only, unless partitioned multi-process)
     uint32_t* fb = nullptr; size_t fb_pixels = 0;
 };
+
+enum ScenePath { PATH_TINY = 0, PATH_STAGED = 1, PATH_GLOBAL = 2, PATH_LBVH = 3 };
+constexpr int STAGED_MAX_SPHERES = 12288;      // 192 KB of dynamic shared memory
+constexpr int AUTO_LBVH_MIN_SPHERES = 48;      // below this the brute-force loop is cheaper than a traversal
 
 }  // namespace
 
@@ -171,7 +218,9 @@ struct rt_context {
     std::vector<DeviceState> devs;
     std::string err;
     bool has_scene = false;
-    bool tiny = false;
+    bool tiny = false;              // scene fits the kernel-parameter block (TinySceneData)
+    int path = PATH_TINY;           // how rt_render traces spheres
+    bool has_bvh = false;
     TinySceneData tiny_data;
     GlobalSceneData gdata_host;     // counts + ambient (pointers per device filled at launch)
     int accel = RT_ACCEL_BRUTE;
@@ -200,6 +249,7 @@ int fail(rt_context* ctx, int code, const std::string& msg) {
 
 void free_scene(DeviceState& d) {
     cudaSetDevice(d.dev);
+    d.bvh.release();
     cudaFree(d.sgeom); cudaFree(d.smat); cudaFree(d.planes); cudaFree(d.lights);
     d.sgeom = nullptr; d.smat = nullptr; d.planes = nullptr; d.lights = nullptr;
 }
@@ -227,6 +277,7 @@ int check_frame_args(rt_context* ctx, const void* cam, int w, int h, int depth, 
     if (!ctx) return RT_ERR_INVALID;
     if (!cam) return fail(ctx, RT_ERR_INVALID, "camera is NULL");
     if (w <= 0 || h <= 0) return fail(ctx, RT_ERR_INVALID, "width/height must be positive");
+    if ((long long)w * h > 0x40000000LL) return fail(ctx, RT_ERR_UNSUPPORTED, "frames above 2^30 pixels are not supported");
     if (depth < 0 || depth > RT_MAX_DEPTH) return fail(ctx, RT_ERR_UNSUPPORTED, "max_depth must be in [0, 32]");
     if (spp < 1 || spp > 1024) return fail(ctx, RT_ERR_INVALID, "spp must be in [1, 1024]");
     if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_set_scene has not been called");
@@ -248,19 +299,42 @@ FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp,
     return fp;
 }
 
+GlobalSceneData global_data(const rt_context* ctx, const DeviceState& d) {
+    GlobalSceneData g = ctx->gdata_host;
+    g.sgeom = d.sgeom; g.smat = d.smat; g.planes = d.planes; g.lights = d.lights;
+    return g;
+}
+LbvhSceneData lbvh_data(const rt_context* ctx, const DeviceState& d) {
+    LbvhSceneData l;
+    l.g = global_data(ctx, d);
+    l.bv.nodes = d.bvh.nodes; l.bv.sgeom_sorted = d.bvh.sorted; l.bv.orig = d.bvh.orig; l.bv.n = d.bvh.n; l.bv.r2max = d.bvh.r2max;
+    return l;
+}
+
 // Launches the render kernel for one device's share. Asynchronous on `stream`.
 int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaStream_t stream) {
     long long n_items = (long long)fp.tiles_mine * fp.chunks_per_tile * fp.n_frames;
     if (n_items == 0) return RT_OK;
-    int resident = 2048 / BLOCK;
-    long long grid = (long long)d.sm_count * resident;
+    if (n_items > 0x7FFFFFFFLL) return fail(ctx, RT_ERR_UNSUPPORTED, "too many work items in one launch");
+    const size_t smem = ctx->path == PATH_STAGED ? sizeof(f4) * (size_t)ctx->gdata_host.ns : 0;
+    TinyKernel tk = ctx->path == PATH_TINY ? tiny_kernel(ctx->tiny_data.ns, ctx->tiny_data.nl) : nullptr;
+    int resident = 0;    // CTAs of this kernel that fit on one SM (registers / shared memory / launch bounds decide)
+    switch (ctx->path) {
+        case PATH_TINY: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, tk, BLOCK, 0); break;
+        case PATH_STAGED: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_render_staged, BLOCK, smem); break;
+        case PATH_GLOBAL: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_render_global, BLOCK, 0); break;
+        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_render_lbvh, BLOCK, 0); break;
+    }
+    if (resident < 1) resident = 1;
+    const char* wv = getenv("RTB200_WAVES");        // grid = SMs x resident CTAs x waves
+    int waves = wv ? atoi(wv) : RT_DEFAULT_WAVES; if (waves < 1) waves = 1;
+    long long grid = (long long)d.sm_count * resident * waves;
     if (grid > n_items) grid = n_items;
-    if (ctx->tiny) {
-        k_render_tiny<<<(unsigned)grid, BLOCK, 0, stream>>>(ctx->tiny_data, fp);
-    } else {
-        GlobalSceneData g = ctx->gdata_host;
-        g.sgeom = d.sgeom; g.smat = d.smat; g.planes = d.planes; g.lights = d.lights;
-        k_render_global<<<(unsigned)grid, BLOCK, 0, stream>>>(g, fp);
+    switch (ctx->path) {
+        case PATH_TINY: tk<<<(unsigned)grid, BLOCK, 0, stream>>>(ctx->tiny_data, fp); break;
+        case PATH_STAGED: k_render_staged<<<(unsigned)grid, BLOCK, smem, stream>>>(global_data(ctx, d), fp); break;
+        case PATH_GLOBAL: k_render_global<<<(unsigned)grid, BLOCK, 0, stream>>>(global_data(ctx, d), fp); break;
+        default: k_render_lbvh<<<(unsigned)grid, BLOCK, 0, stream>>>(lbvh_data(ctx, d), fp); break;
     }
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
@@ -358,7 +432,6 @@ int rt_set_scene(rt_context* ctx, const float* spheres, int ns, const float* pla
     if (ns < 0 || np < 0 || nl < 0 || (ns > 0 && !spheres) || (np > 0 && !planes) || (nl > 0 && !lights) || !ambient)
         return fail(ctx, RT_ERR_INVALID, "bad scene arrays");
     if (accel < RT_ACCEL_AUTO || accel > RT_ACCEL_LBVH) return fail(ctx, RT_ERR_INVALID, "bad accel");
-    if (accel == RT_ACCEL_LBVH) return fail(ctx, RT_ERR_UNSUPPORTED, "LBVH not built in this revision");
     ctx->has_scene = false;
     std::vector<f4> sg((size_t)ns); std::vector<MatRec> sm((size_t)ns);
     std::vector<PlaneRec> pl((size_t)np); std::vector<LightRec> li((size_t)nl);
@@ -395,7 +468,42 @@ int rt_set_scene(rt_context* ctx, const float* spheres, int ns, const float* pla
         if (np) CU_TRY(ctx, cudaMemcpy(d.planes, pl.data(), sizeof(PlaneRec) * (size_t)np, cudaMemcpyHostToDevice));
         if (nl) CU_TRY(ctx, cudaMemcpy(d.lights, li.data(), sizeof(LightRec) * (size_t)nl, cudaMemcpyHostToDevice));
     }
-    ctx->accel = RT_ACCEL_BRUTE;
+    // ---- how spheres are traced ----
+    const bool want_bvh = ns >= 2 && (accel == RT_ACCEL_LBVH || (accel == RT_ACCEL_AUTO && ns >= AUTO_LBVH_MIN_SPHERES));
+    ctx->has_bvh = false;
+    if (want_bvh) {
+        // bounds of the centres, effective radii (the reference's test only ever sees radiusSquared, :619) — O(n) on the host
+        float bmin[3] = {sg[0].x, sg[0].y, sg[0].z}, bmax[3] = {sg[0].x, sg[0].y, sg[0].z}, r2max = 0.0f;
+        std::vector<float> reff((size_t)ns);
+        for (int i = 0; i < ns; i++) {
+            const f4& g = sg[(size_t)i];
+            bmin[0] = fminf(bmin[0], g.x); bmin[1] = fminf(bmin[1], g.y); bmin[2] = fminf(bmin[2], g.z);
+            bmax[0] = fmaxf(bmax[0], g.x); bmax[1] = fmaxf(bmax[1], g.y); bmax[2] = fmaxf(bmax[2], g.z);
+            float r2 = g.w > 0.0f ? g.w : 0.0f;
+            reff[(size_t)i] = sqrtf(r2) * 1.000001f + 1e-30f;
+            if (r2 > r2max) r2max = r2;
+        }
+        for (auto& d : ctx->devs) {
+            CU_TRY(ctx, cudaSetDevice(d.dev));
+            uint64_t nl = 0;
+            cudaError_t e = lbvh_build(d.sgeom, reff.data(), ns, bmin, bmax, r2max, d.stream, &d.bvh, &nl);
+            if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh_build: ") + cudaGetErrorString(e));
+            ctx->launches += nl;
+        }
+        ctx->has_bvh = true;
+    }
+    if (ctx->has_bvh) ctx->path = PATH_LBVH;
+    else if (ctx->tiny) ctx->path = PATH_TINY;
+    else if (ns <= STAGED_MAX_SPHERES) ctx->path = PATH_STAGED;
+    else ctx->path = PATH_GLOBAL;
+    if (ctx->path == PATH_STAGED) {
+        for (auto& d : ctx->devs) {
+            CU_TRY(ctx, cudaSetDevice(d.dev));
+            CU_TRY(ctx, cudaFuncSetAttribute(k_render_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(f4) * STAGED_MAX_SPHERES)));
+            CU_TRY(ctx, cudaFuncSetAttribute(k_debug_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(f4) * STAGED_MAX_SPHERES)));
+        }
+    }
+    ctx->accel = accel;
     ctx->has_scene = true;
     return RT_OK;
 }
@@ -501,11 +609,11 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int w, int h, int dep
     long long maxgrid = (long long)d.sm_count * 8 * 4;
     if (grid > maxgrid) grid = maxgrid;
     CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
-    if (ctx->tiny) k_debug_tiny<<<(unsigned)grid, BLOCK, 0, d.stream>>>(ctx->tiny_data, fp, dout);
-    else {
-        GlobalSceneData g = ctx->gdata_host;
-        g.sgeom = d.sgeom; g.smat = d.smat; g.planes = d.planes; g.lights = d.lights;
-        k_debug_global<<<(unsigned)grid, BLOCK, 0, d.stream>>>(g, fp, dout);
+    switch (ctx->path) {
+        case PATH_TINY: k_debug_tiny<<<(unsigned)grid, BLOCK, 0, d.stream>>>(ctx->tiny_data, fp, dout); break;
+        case PATH_STAGED: k_debug_staged<<<(unsigned)grid, BLOCK, sizeof(f4) * (size_t)ctx->gdata_host.ns, d.stream>>>(global_data(ctx, d), fp, dout); break;
+        case PATH_GLOBAL: k_debug_global<<<(unsigned)grid, BLOCK, 0, d.stream>>>(global_data(ctx, d), fp, dout); break;
+        default: k_debug_lbvh<<<(unsigned)grid, BLOCK, 0, d.stream>>>(lbvh_data(ctx, d), fp, dout); break;
     }
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
@@ -531,7 +639,8 @@ int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, 
     if (!ctx) return RT_ERR_INVALID;
     if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_set_scene has not been called");
     if (!rays6 || n_rays < 0 || kind < 0 || kind > 2 || !out_id || !out_t) return fail(ctx, RT_ERR_INVALID, "bad query args");
-    if (accel != RT_ACCEL_BRUTE) return fail(ctx, RT_ERR_UNSUPPORTED, "only RT_ACCEL_BRUTE queries in this revision");
+    if (accel != RT_ACCEL_BRUTE && accel != RT_ACCEL_LBVH) return fail(ctx, RT_ERR_INVALID, "accel must be RT_ACCEL_BRUTE or RT_ACCEL_LBVH");
+    if (accel == RT_ACCEL_LBVH && !ctx->has_bvh) return fail(ctx, RT_ERR_UNSUPPORTED, "the scene was uploaded without an LBVH");
     if (n_rays == 0) return RT_OK;
     DeviceState& d = ctx->devs[0];
     CU_TRY(ctx, cudaSetDevice(d.dev));
@@ -540,10 +649,9 @@ int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, 
     CU_TRY(ctx, cudaMalloc(&di, (size_t)n_rays * 4));
     CU_TRY(ctx, cudaMalloc(&dt, (size_t)n_rays * 4));
     CU_TRY(ctx, cudaMemcpy(dr, rays6, (size_t)n_rays * 24, cudaMemcpyHostToDevice));
-    GlobalSceneData g = ctx->gdata_host;
-    g.sgeom = d.sgeom; g.smat = d.smat; g.planes = d.planes; g.lights = d.lights;
     int grid = (n_rays + BLOCK - 1) / BLOCK; if (grid > d.sm_count * 32) grid = d.sm_count * 32;
-    k_query_brute<<<grid, BLOCK, 0, d.stream>>>(g, dr, n_rays, kind, di, dt);
+    if (accel == RT_ACCEL_LBVH) k_query_lbvh<<<grid, BLOCK, 0, d.stream>>>(lbvh_data(ctx, d), dr, n_rays, kind, di, dt);
+    else k_query_brute<<<grid, BLOCK, 0, d.stream>>>(global_data(ctx, d), dr, n_rays, kind, di, dt);
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     CU_TRY(ctx, cudaStreamSynchronize(d.stream));

@@ -18,7 +18,7 @@ import numpy as np
 import scenes as _scenes
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtb200.so")
+LIB_PATH = os.environ.get("RTB200_LIB", os.path.join(_HERE, "librtb200.so"))   # RTB200_LIB: tuning variants only
 
 RT_ACCEL_AUTO, RT_ACCEL_BRUTE, RT_ACCEL_LBVH = 0, 1, 2
 COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_pos", "plane_tests",

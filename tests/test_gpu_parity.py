@@ -24,9 +24,16 @@ def ctx(rt):
     c.close()
 
 
-def _check_debug(ctx, sc, cam, w, h, depth, spp=1, seed=0):
+SPHERE_TEST_COUNTERS = ("sphere_tests", "sphere_disc_pos")     # equal to the oracle's only on the brute-force paths
+
+
+def _check_debug(ctx, sc, cam, w, h, depth, spp=1, seed=0, brute=True):
     ref = O.render(sc, cam, w, h, depth, spp, seed, want_hash=True, want_aov=True)
     got = ctx.render_debug(cam, w, h, depth, spp, seed)
+    if not brute:
+        for k in SPHERE_TEST_COUNTERS:
+            assert got["counters"][k] <= ref["counters"][k]        # an LBVH tests fewer spheres, never more
+            got["counters"][k] = ref["counters"][k]
     assert np.array_equal(got["hash"], ref["hash"]), "chain hash differs on %d pixels" % (got["hash"] != ref["hash"]).sum()
     assert np.array_equal(got["aov_id"], ref["aov_id"])
     assert np.array_equal(got["aov_t"].view(np.uint32), ref["aov_t"].view(np.uint32))
@@ -88,10 +95,12 @@ def test_random_scenes(ctx, n, seed):
     """tiny (kernel-parameter) and global-memory scene paths, every material class, 2 planes, 3 lights."""
     sc = scenes.small_random_scene(n, seed)
     cam = scenes.make_camera(pos=(0, 1.5, -4.0), pitch=0.1, width=320, height=200)
-    ctx.set_scene(sc)
-    ref = _check_debug(ctx, sc, cam, 320, 200, 8)
-    px, _ = ctx.render(cam, 320, 200, 8)
-    assert assert_image_parity(px, ref["pixels"]) == 0
+    import rtb200
+    for accel in (rtb200.RT_ACCEL_BRUTE, rtb200.RT_ACCEL_AUTO):
+        ctx.set_scene(sc, accel)
+        ref = _check_debug(ctx, sc, cam, 320, 200, 8, brute=(accel == rtb200.RT_ACCEL_BRUTE or n < 48))
+        px, _ = ctx.render(cam, 320, 200, 8)
+        assert assert_image_parity(px, ref["pixels"]) == 0
 
 
 def test_supersampling_extension(ctx):

@@ -99,6 +99,8 @@ def cpu_reference_run(frames: int, warm: int, threads: int = 0):
     reference actually does, RayTracer.cs:898-901) on all host cores. Returns (best_seconds_per_frame, all_times, rays)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
+    if threads <= 0:    # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may run on explicitly
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     sc = scenes.default_scene()
     cam = scenes.make_camera(width=W, height=H)
     cnt = O.render(sc, cam, W, H, DEPTH, mode="nearest", threads=threads)["counters"]
@@ -110,7 +112,7 @@ def cpu_reference_run(frames: int, warm: int, threads: int = 0):
         dt = time.perf_counter() - t0
         if i >= warm:
             times.append(dt)
-    return min(times), times, rays, (threads or O.max_threads())
+    return min(times), times, rays, threads
 
 
 def run_reference(args, rank, world):

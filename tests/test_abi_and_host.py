@@ -88,3 +88,15 @@ def test_synthetic_scene_is_deterministic():
     assert np.array_equal(a, b)
     assert np.all(a[:, 3] >= 0.15) and np.all(a[:, 3] <= 0.6) and np.all(a[:, 1] >= -1 + a[:, 3] - 1e-6)
     assert np.all(a[:, 17] == a[:, 3] * a[:, 3])
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-device error path")
+def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu(built, tmp_path):
+    """host/rt_demo (C++ mirror of RayTracer/Surface over the C ABI) links against librtb200.so; without a device it must
+    exit non-zero with the library's error message instead of rendering on the CPU."""
+    import subprocess
+    exe = os.path.join(ROOT, "uu-infogr-raytracer_b200", "host", "rt_demo")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe, str(tmp_path / "x.ppm"), "32", "18"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+    assert not (tmp_path / "x.ppm").exists()

@@ -229,3 +229,28 @@ def test_query_spheres_matches_oracle(ctx):
         oi, ot = O.query_spheres(sc.spheres, rays, kind)
         assert np.array_equal(gi, oi), kind
         assert np.array_equal(gt.view(np.uint32), ot.view(np.uint32)), kind
+
+
+def test_cpp_host_mirror_demo(built, tmp_path):
+    """host/rt_demo: the C++ mirror of the reference's RayTracer/Surface classes drives the C ABI for 3 ticks with key
+    presses and mouse moves (:543-554, :1058-1061); the last frame must equal the oracle at the same camera."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "uu-infogr-raytracer_b200", "host", "rt_demo")
+    out = tmp_path / "f.ppm"
+    r = subprocess.run([exe, str(out), "320", "180", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = out.read_bytes()
+    hdr = b"P6\n320 180\n255\n"
+    assert raw.startswith(hdr)
+    rgb = np.frombuffer(raw[len(hdr):], np.uint8).reshape(180, 320, 3).astype(np.int32)
+    got = (rgb[..., 0] << 16) | (rgb[..., 1] << 8) | rgb[..., 2]
+    # replay the same input with the Python mirror of the camera state
+    import rtb200
+    app = rtb200.RayTracer(rtb200.Surface(320, 180))
+    for _ in range(2):
+        app.OnKeyPress("W"); app.OnKeyPress("D"); app.OnMouseMove(3.6, 1.8)
+    cam = app.camera(); app.close()
+    ref = O.render(scenes.default_scene(), cam, 320, 180, 32)["pixels"]
+    assert np.array_equal(got, ref)

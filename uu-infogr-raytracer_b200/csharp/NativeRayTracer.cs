@@ -1,0 +1,95 @@
+// NativeRayTracer.cs — P/Invoke binding of librtb200.so for the reference host (Raytracer/, net6.0).
+//
+// Drop this file into Raytracer/ next to RayTracer.cs, ship librtb200.so beside the executable, and apply the
+// ~10-line patch shown in INTEGRATION.md to RayTracer.cs (constructor: create + upload scene; Tick(): replace the
+// pixel loop :898-901 by Render()).  Everything else — scene arrays (:441-465), camera state and input handlers
+// (:494-554, :1058-1061), Surface (surface.cs) and the OpenTK display path (template.cs) — stays as it is.
+//
+// This file cannot be compiled or run in the build image (no .NET toolchain there); it is kept deliberately thin so
+// that review == verification: every call maps 1:1 to a function of include/rtb200.h.
+using System;
+using System.Runtime.InteropServices;
+using OpenTK.Mathematics;
+
+namespace Template;
+
+internal sealed unsafe class NativeRayTracer : IDisposable {
+    private const string Lib = "rtb200";    // librtb200.so / rtb200.dll
+
+    [StructLayout(LayoutKind.Sequential)]
+    private struct RtCamera {                // include/rtb200.h: rt_camera (15 floats)
+        public Vector3 pos, right, up, forward, viewParams;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct RtStats {                  // include/rtb200.h: rt_stats
+        public ulong primary, shadow, secondary;
+        public float kernelMs, gatherMs, d2hMs;
+    }
+
+    [DllImport(Lib)] private static extern int rt_create(out IntPtr ctx, int[]? deviceIds, int nDevices);
+    [DllImport(Lib)] private static extern int rt_set_scene(IntPtr ctx, float* spheres, int nSpheres, float* planes, int nPlanes,
+                                                            float* lights, int nLights, float* ambient, int accel);
+    [DllImport(Lib)] private static extern int rt_render(IntPtr ctx, ref RtCamera cam, int width, int height, int maxDepth, int spp,
+                                                         uint seed, int* hostPixels, out RtStats stats);
+    [DllImport(Lib)] private static extern int rt_host_register(IntPtr ctx, void* hostPtr, ulong bytes);
+    [DllImport(Lib)] private static extern int rt_host_unregister(IntPtr ctx, void* hostPtr);
+    [DllImport(Lib)] private static extern int rt_destroy(IntPtr ctx);
+    [DllImport(Lib)] private static extern IntPtr rt_last_error(IntPtr ctx);
+
+    private IntPtr _ctx;
+    private GCHandle _pixelsHandle;          // Surface.pixels pinned for the lifetime of the renderer (zero-copy target)
+    private int* _pixels;
+
+    private void Check(int rc) {
+        if (rc != 0) throw new InvalidOperationException($"rtb200 error {rc}: {Marshal.PtrToStringAnsi(rt_last_error(_ctx))}");
+    }
+
+    /// <summary>Creates the backend on <paramref name="nDevices"/> GPUs (1, 2, 4 or 8) and page-locks the surface.</summary>
+    public NativeRayTracer(Surface screen, int nDevices = 1) {
+        int rc = rt_create(out _ctx, null, nDevices);
+        if (rc != 0) throw new InvalidOperationException($"rtb200 error {rc}: {Marshal.PtrToStringAnsi(rt_last_error(IntPtr.Zero))}");
+        _pixelsHandle = GCHandle.Alloc(screen.pixels, GCHandleType.Pinned);
+        _pixels = (int*)_pixelsHandle.AddrOfPinnedObject();
+        Check(rt_host_register(_ctx, _pixels, (ulong)screen.pixels.Length * sizeof(int)));
+    }
+
+    /// <summary>Uploads the scene arrays of RayTracer.cs:441-469. Sphere (18 floats) and Light (4 floats) are blittable and
+    /// passed as they lie in memory; Plane holds a bool, so it is packed into 20 floats here.</summary>
+    public void SetScene(Sphere[] spheres, Plane[] planes, Light[] lights, Vector3 ambient) {
+        float[] p = new float[planes.Length * 20];
+        for (int i = 0; i < planes.Length; i++) {
+            Plane pl = planes[i]; Material m = pl.material; int o = i * 20;
+            p[o + 0] = pl.center.X; p[o + 1] = pl.center.Y; p[o + 2] = pl.center.Z;
+            p[o + 3] = pl.normal.X; p[o + 4] = pl.normal.Y; p[o + 5] = pl.normal.Z;
+            p[o + 6] = m.diffuseColor.X; p[o + 7] = m.diffuseColor.Y; p[o + 8] = m.diffuseColor.Z;
+            p[o + 9] = m.ambientColor.X; p[o + 10] = m.ambientColor.Y; p[o + 11] = m.ambientColor.Z;
+            p[o + 12] = m.specularColor.X; p[o + 13] = m.specularColor.Y; p[o + 14] = m.specularColor.Z;
+            p[o + 15] = m.specularity;
+            p[o + 16] = m.mirrorColor.X; p[o + 17] = m.mirrorColor.Y; p[o + 18] = m.mirrorColor.Z;
+            p[o + 19] = pl.isTiled ? 1f : 0f;
+        }
+        // Sphere = {Vector3 center; float radius; Material (13 floats); float radiusSquared} = 18 sequential floats;
+        // Light = {Vector3 position; float intensity}. Add [StructLayout(LayoutKind.Sequential)] to both (and to Material).
+        fixed (Sphere* s = spheres) fixed (float* pp = p) fixed (Light* l = lights) {
+            float* amb = stackalloc float[3] { ambient.X, ambient.Y, ambient.Z };
+            Check(rt_set_scene(_ctx, (float*)s, spheres.Length, pp, planes.Length, (float*)l, lights.Length, amb, 0 /* RT_ACCEL_AUTO */));
+        }
+    }
+
+    /// <summary>One frame into Surface.pixels — the replacement of the loop RayTracer.cs:898-901.</summary>
+    public RtStats Render(Vector3 position, Vector3 right, Vector3 up, Vector3 forward, Vector3 viewParams,
+                          int width, int height, int maxDepth) {
+        RtCamera cam = new() { pos = position, right = right, up = up, forward = forward, viewParams = viewParams };
+        Check(rt_render(_ctx, ref cam, width, height, maxDepth, 1, 0u, _pixels, out RtStats stats));
+        return stats;
+    }
+
+    public void Dispose() {
+        if (_ctx == IntPtr.Zero) return;
+        rt_host_unregister(_ctx, _pixels);
+        rt_destroy(_ctx);
+        _ctx = IntPtr.Zero;
+        if (_pixelsHandle.IsAllocated) _pixelsHandle.Free();
+    }
+}

@@ -46,7 +46,8 @@ struct FrameParams {
     int n_frames;
     int rank, world, tile_rows;
     int tiles_total;            // ceil(h / tile_rows)
-    int tiles_mine;             // tiles owned by this rank
+    int tiles_mine;             // tiles of this rank rendered by this launch ...
+    int k_begin;                // ... starting at the rank's k_begin-th tile (band pipelining, see render_frames)
     int chunks_per_tile;        // ceil(tile_rows * w / CHUNK)
     long long frame_stride;     // pixels between consecutive frames in `out`
     uint32_t* out;              // framebuffer(s): 0x00RRGGBB, row-major (Surface.pixels, surface.cs:9-20)
@@ -71,8 +72,9 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int frame = item / items_per_frame;
         const int r = item - frame * items_per_frame;
-        const int k = r / fp.chunks_per_tile;                  // my k-th tile
-        const int j = r - k * fp.chunks_per_tile;              // chunk inside the tile
+        const int kk = r / fp.chunks_per_tile;
+        const int k = fp.k_begin + kk;                         // my k-th tile
+        const int j = r - kk * fp.chunks_per_tile;             // chunk inside the tile
         const int tile = k * fp.world + fp.rank;
         const int base = tile * tile_pix;
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
@@ -206,6 +208,10 @@ struct DeviceState {
     LbvhDevice bvh;
     // framebuffer ring (device 0 of the context only, unless partitioned multi-process)
     uint32_t* fb = nullptr; size_t fb_pixels = 0;
+    // band pipelining (render_frames): copy stream on device 0, per-segment "band rendered" events on every device
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t evc0 = nullptr, evc1 = nullptr;
+    std::vector<cudaEvent_t> band_events;
 };
 
 enum ScenePath { PATH_TINY = 0, PATH_STAGED = 1, PATH_GLOBAL = 2, PATH_LBVH = 3 };
@@ -389,6 +395,8 @@ int rt_create(rt_context** out, const int* device_ids, int n_devices) {
         cudaDeviceProp prop;
         if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreate(&d.evc0)) != cudaSuccess || (e = cudaEventCreate(&d.evc1)) != cudaSuccess ||
             (e = cudaEventCreate(&d.ev0)) != cudaSuccess || (e = cudaEventCreate(&d.ev1)) != cudaSuccess) {
             std::string m = std::string("device init: ") + cudaGetErrorString(e);
             delete ctx; return fail(nullptr, RT_ERR_CUDA, m);
@@ -420,6 +428,10 @@ int rt_destroy(rt_context* ctx) {
         cudaFree(d.cams); cudaFree(d.fb);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.evc0) cudaEventDestroy(d.evc0);
+        if (d.evc1) cudaEventDestroy(d.evc1);
+        for (cudaEvent_t ev : d.band_events) cudaEventDestroy(ev);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete ctx;
@@ -531,6 +543,11 @@ int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int w
     return launch_render(ctx, d, fp, st);
 }
 
+// Renders n_frames frames into device 0's framebuffer ring and, if host_pixels != NULL, returns them to the host.
+//  * headless: ONE launch per device covers all frames (work items = frame x tile x chunk).
+//  * with a host buffer: every frame is cut into BANDS of row tiles; band s+1 is rendered while band s crosses PCIe on a
+//    separate copy stream, so the device->host copy (33 MB per 4K frame, ~0.6 ms) hides the kernel instead of following it.
+//    Bands are multiples of `world` tiles so that every device owns the same share of each band.
 static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, int w, int h, int depth, int spp, uint32_t seed,
                          int32_t* host_pixels, rt_stats* stats) {
     int rc = check_frame_args(ctx, cams, w, h, depth, spp);
@@ -540,19 +557,77 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
     rc = ensure_fb(ctx, npix * (size_t)n_frames); if (rc) return rc;
     const int G = (int)ctx->devs.size();
     DeviceState& d0 = ctx->devs[0];
-    // All devices render their interleaved row tiles straight into device 0's framebuffer (peer stores).
+    const int world = G > 1 ? G : ctx->world;
+    const int tiles_total = (h + ctx->tile_rows - 1) / ctx->tile_rows;
+    // ---- band layout ----
+    int n_bands = 1;
+    if (host_pixels) {
+        const char* be = getenv("RTB200_BANDS");
+        n_bands = be ? atoi(be) : (int)((npix * 4 + (4u << 20) - 1) / (4u << 20));    // ~4 MB per band
+        if (n_bands > 16) n_bands = 16;
+        if (n_bands < 1) n_bands = 1;
+    }
+    int band_tiles = (tiles_total + n_bands - 1) / n_bands;
+    band_tiles = ((band_tiles + world - 1) / world) * world;
+    if (band_tiles < world) band_tiles = world;
+    n_bands = (tiles_total + band_tiles - 1) / band_tiles;
+    const bool pipelined = host_pixels != nullptr;
+    const int n_segments = pipelined ? n_frames * n_bands : 1;
+    if (pipelined) {
+        for (int g = 0; g < G; g++) {
+            DeviceState& d = ctx->devs[(size_t)g];
+            CU_TRY(ctx, cudaSetDevice(d.dev));
+            while ((int)d.band_events.size() < n_segments) {
+                cudaEvent_t ev; CU_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                d.band_events.push_back(ev);
+            }
+        }
+    }
     for (int g = 0; g < G; g++) {
         DeviceState& d = ctx->devs[(size_t)g];
         CU_TRY(ctx, cudaSetDevice(d.dev));
-        int rank = G > 1 ? g : ctx->rank, world = G > 1 ? G : ctx->world;
-        FrameParams fp = make_params(ctx, w, h, depth, spp, seed, n_frames, rank, world, d0.fb, (long long)npix);
-        if (n_frames <= INLINE_CAMS) for (int i = 0; i < n_frames; i++) fp.cam_inline[i] = to_cam(cams[i]);
-        else { rc = upload_cams(ctx, d, cams, n_frames, d.stream); if (rc) return rc; fp.cams = d.cams; }
+        if (!pipelined && n_frames > INLINE_CAMS) { rc = upload_cams(ctx, d, cams, n_frames, d.stream); if (rc) return rc; }
         CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
-        rc = launch_render(ctx, d, fp, d.stream); if (rc) return rc;
+    }
+    const long long tile_pix = (long long)ctx->tile_rows * w;
+    bool first_copy = true;
+    for (int s = 0; s < n_segments; s++) {
+        const int frame = pipelined ? s / n_bands : 0, band = pipelined ? s % n_bands : 0;
+        for (int g = 0; g < G; g++) {
+            DeviceState& d = ctx->devs[(size_t)g];
+            CU_TRY(ctx, cudaSetDevice(d.dev));
+            const int rank = G > 1 ? g : ctx->rank;
+            FrameParams fp = make_params(ctx, w, h, depth, spp, seed, pipelined ? 1 : n_frames, rank, world,
+                                         d0.fb + (pipelined ? (size_t)frame * npix : 0), (long long)npix);
+            if (pipelined) {
+                fp.cam_inline[0] = to_cam(cams[frame]);
+                const int k0 = band * (band_tiles / world), k1 = k0 + band_tiles / world;       // this rank's tiles of the band
+                const int mine = fp.tiles_mine;
+                fp.k_begin = k0 < mine ? k0 : mine;
+                fp.tiles_mine = (k1 < mine ? k1 : mine) - fp.k_begin;
+            } else if (n_frames <= INLINE_CAMS) {
+                for (int i = 0; i < n_frames; i++) fp.cam_inline[i] = to_cam(cams[i]);
+            } else fp.cams = d.cams;
+            rc = launch_render(ctx, d, fp, d.stream); if (rc) return rc;
+            if (pipelined) CU_TRY(ctx, cudaEventRecord(d.band_events[(size_t)s], d.stream));
+        }
+        if (pipelined) {
+            CU_TRY(ctx, cudaSetDevice(d0.dev));
+            for (int g = 0; g < G; g++) CU_TRY(ctx, cudaStreamWaitEvent(d0.copy_stream, ctx->devs[(size_t)g].band_events[(size_t)s], 0));
+            if (first_copy) { CU_TRY(ctx, cudaEventRecord(d0.evc0, d0.copy_stream)); first_copy = false; }
+            long long p0 = (long long)band * band_tiles * tile_pix, p1 = p0 + (long long)band_tiles * tile_pix;
+            if (p1 > (long long)npix) p1 = (long long)npix;
+            if (p1 > p0)
+                CU_TRY(ctx, cudaMemcpyAsync(host_pixels + (size_t)frame * npix + p0, d0.fb + (size_t)frame * npix + p0,
+                                            (size_t)(p1 - p0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, d0.copy_stream));
+        }
+    }
+    for (int g = 0; g < G; g++) {
+        DeviceState& d = ctx->devs[(size_t)g];
+        CU_TRY(ctx, cudaSetDevice(d.dev));
         CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
     }
-    float kernel_ms = 0.0f;
+    float kernel_ms = 0.0f, d2h_ms = 0.0f;
     for (int g = 0; g < G; g++) {
         DeviceState& d = ctx->devs[(size_t)g];
         CU_TRY(ctx, cudaSetDevice(d.dev));
@@ -561,19 +636,15 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         CU_TRY(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
         if (ms > kernel_ms) kernel_ms = ms;
     }
-    float d2h_ms = 0.0f;
-    if (host_pixels) {
+    if (pipelined) {
         CU_TRY(ctx, cudaSetDevice(d0.dev));
-        CU_TRY(ctx, cudaEventRecord(d0.ev0, d0.stream));
-        // host_pixels is the caller's (pageable, possibly pinned-by-GC) Surface.pixels array.
-        CU_TRY(ctx, cudaMemcpyAsync(host_pixels, d0.fb, npix * (size_t)n_frames * sizeof(uint32_t), cudaMemcpyDeviceToHost, d0.stream));
-        CU_TRY(ctx, cudaEventRecord(d0.ev1, d0.stream));
-        CU_TRY(ctx, cudaStreamSynchronize(d0.stream));
-        CU_TRY(ctx, cudaEventElapsedTime(&d2h_ms, d0.ev0, d0.ev1));
+        CU_TRY(ctx, cudaEventRecord(d0.evc1, d0.copy_stream));
+        CU_TRY(ctx, cudaStreamSynchronize(d0.copy_stream));
+        CU_TRY(ctx, cudaEventElapsedTime(&d2h_ms, d0.evc0, d0.evc1));
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));
-        stats->kernel_ms = kernel_ms; stats->gather_ms = 0.0f; stats->d2h_ms = d2h_ms;
+        stats->kernel_ms = kernel_ms; stats->gather_ms = 0.0f; stats->d2h_ms = d2h_ms;   // d2h overlaps the kernel when banded
     }
     return RT_OK;
 }

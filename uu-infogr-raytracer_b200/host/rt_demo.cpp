@@ -1,0 +1,34 @@
+// rt_demo — headless stand-in for the reference's window loop (template.cs:175-213): N ticks of the C++ host mirror,
+// a few simulated key presses / mouse moves, last frame written as a binary PPM.
+//   rt_demo out.ppm [width height [ticks [n_devices]]]
+#include <cstdio>
+#include <cstdlib>
+
+#include "raytracer_host.hpp"
+
+int main(int argc, char** argv) {
+    const char* out = argc > 1 ? argv[1] : "frame.ppm";
+    int w = argc > 3 ? atoi(argv[2]) : 1280, h = argc > 3 ? atoi(argv[3]) : 720;    // template.cs:65
+    int ticks = argc > 4 ? atoi(argv[4]) : 1, ndev = argc > 5 ? atoi(argv[5]) : 1;
+    try {
+        rthost::Surface screen(w, h);
+        rthost::RayTracer app(screen, ndev);
+        for (int t = 0; t < ticks; t++) {
+            if (t > 0) { app.OnKeyPress(rthost::Keys::W); app.OnKeyPress(rthost::Keys::D); app.OnMouseMove(3.6f, 1.8f); }
+            app.Tick();
+            fprintf(stderr, "tick %d: kernel %.3f ms, d2h %.3f ms\n", t, app.last_stats.kernel_ms, app.last_stats.d2h_ms);
+        }
+        FILE* f = fopen(out, "wb");
+        if (!f) { perror(out); return 2; }
+        fprintf(f, "P6\n%d %d\n255\n", w, h);
+        for (int32_t p : screen.pixels) {
+            unsigned char rgb[3] = {(unsigned char)((p >> 16) & 255), (unsigned char)((p >> 8) & 255), (unsigned char)(p & 255)};
+            fwrite(rgb, 1, 3, f);
+        }
+        fclose(f);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "rt_demo: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

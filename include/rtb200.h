@@ -91,8 +91,9 @@ int rt_render_batch(rt_context* ctx, const rt_camera* cams, int n_frames, int wi
 /* Instrumented render (separate kernel instantiation; not for timing).  All outputs nullable:
  *   host_hash  w*h uint32 : order-independent hash of every (ray kind, hit id, t bits, shadow result) on the chain
  *   host_aov_id/t w*h     : primary hit id (sphere index, n_spheres+plane index, -1 none) and its distance
- *   counters[12]          : primary, shadow, secondary, sphere_tests, sphere_disc_pos, plane_tests, shade_diffuse,
- *                           shade_specular, shade_mirror, shaded_hits, 0, 0 (same order as the oracle's) */
+ *   counters[16]          : primary, shadow, secondary, sphere_tests, sphere_disc_pos, plane_tests, shade_diffuse,
+ *                           shade_specular, shade_mirror, shaded_hits (same order as the oracle's), then LBVH statistics:
+ *                           node visits of primary / secondary / shadow rays, brute-force fallbacks, 0, 0 */
 int rt_render_debug(rt_context* ctx, const rt_camera* cam, int width, int height, int max_depth, int spp, uint32_t seed,
                     int32_t* host_pixels, uint32_t* host_hash, int32_t* host_aov_id, float* host_aov_t,
                     uint64_t* counters, rt_stats* stats);

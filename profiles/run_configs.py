@@ -18,7 +18,7 @@ def measure(name, sc, cam, w, h, depth, spp, accel, reps=5, count=True):
     t0 = time.perf_counter(); ctx.set_scene(sc, accel); t_scene = time.perf_counter() - t0
     if count:
         dbg = ctx.render_debug(cam, w, h, depth, spp, 1)
-        c = dbg["counters"]; rays = c["primary"] + c["shadow"] + c["secondary"]
+        c = dict(dbg["counters"]); rays = c["primary"] + c["shadow"] + c["secondary"]; c.update(dbg["lbvh"])
     else:
         c, rays = {}, 0
     ms = []

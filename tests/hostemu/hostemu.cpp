@@ -11,9 +11,24 @@ using namespace rtb;
 // Host-side LBVH build with the same pieces the CUDA build kernels use (morton_key, karras_node, sphere_box, box_union).
 #include <algorithm>
 struct HostBvh {
-    std::vector<BvhNode> nodes; std::vector<f4> sorted; std::vector<int> orig; float r2max = 0; int n = 0;
-    BvhView view() const { BvhView v; v.nodes = nodes.data(); v.sgeom_sorted = sorted.data(); v.orig = orig.data(); v.n = n; v.r2max = r2max; return v; }
+    std::vector<BvhNode> nodes, nodes_cam; std::vector<f4> sorted; std::vector<int> orig; float r2max = 0; int n = 0;
+    BvhView view() const {
+        BvhView v; v.nodes = nodes.data(); v.nodes_cam = nodes_cam.empty() ? nullptr : nodes_cam.data();
+        v.sgeom_sorted = sorted.data(); v.orig = orig.data(); v.n = n; v.r2max = r2max; return v;
+    }
 };
+// camera copy: same topology, leaf boxes inflated for rays starting at the camera (k_lbvh_refit_cam on the device)
+static BvhBox host_refit_cam(HostBvh& b, f3 cam, int child) {
+    if (child < 0) {
+        f4 g = b.sorted[~child];
+        float dx = cam.x - g.x, dy = cam.y - g.y, dz = cam.z - g.z;
+        return sphere_box(g, inflated_radius(g.w, dx * dx + dy * dy + dz * dz));
+    }
+    BvhNode& nd = b.nodes_cam[child];
+    BvhBox b0 = host_refit_cam(b, cam, nd.c0), b1 = host_refit_cam(b, cam, nd.c1);
+    node_set_child_box(nd, 0, b0); node_set_child_box(nd, 1, b1);
+    return box_union(b0, b1);
+}
 static BvhBox host_refit(HostBvh& b, const std::vector<float>& reff, int child) {
     if (child < 0) return sphere_box(b.sorted[~child], reff[b.orig[~child]]);
     BvhNode& nd = b.nodes[child];
@@ -90,7 +105,13 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
     g.ns = ns; g.np = np; g.nl = nl; g.amb = mk3(ambient[0], ambient[1], ambient[2]);
     g.sgeom = sg.data(); g.smat = sm.data(); g.planes = pl.data(); g.lights = li.data();
     HostBvh bvh;
-    if (use_tiny == 3) { if (ns < 2) return -2; host_build(sg, bvh); g_bvh = &bvh; }
+    if (use_tiny == 3) {
+        if (ns < 2) return -2;
+        host_build(sg, bvh);
+        bvh.nodes_cam = bvh.nodes;
+        host_refit_cam(bvh, mk3(cam15[0], cam15[1], cam15[2]), 0);
+        g_bvh = &bvh;
+    }
     TinySceneData t; memset(&t, 0, sizeof(t));
     if (use_tiny == 1 || use_tiny == 2) {
         if (ns > TINY_MAX_SPHERES || np > TINY_MAX_PLANES || nl > TINY_MAX_LIGHTS) return -1;

@@ -93,7 +93,8 @@ RT_HD void node_set_child_box(BvhNode& nd, int which, const BvhBox& b) {
 
 // ---- traversal ---------------------------------------------------------------------------------------------------------
 struct BvhView {
-    const BvhNode* nodes;       // n-1 internal nodes, root = 0
+    const BvhNode* nodes;       // n-1 internal nodes, root = 0; boxes = exact sphere boxes (inflated per ray while traversing)
+    const BvhNode* nodes_cam;   // same topology, boxes pre-inflated for rays that start at the frame's camera (nullable)
     const f4* sgeom_sorted;     // leaf position -> (cx, cy, cz, r^2)
     const int* orig;            // leaf position -> original sphere index
     int n;
@@ -102,7 +103,9 @@ struct BvhView {
 
 RT_HD float approx_sqrt(float x) {
 #if defined(__CUDA_ARCH__)
-    return x * __frsqrt_rn(x + 1e-30f);     // MUFU.RSQ, 2 ulp — the 1 % pad head-room covers it
+    float r;                                 // one MUFU.RSQ (2 ulp): the 1 % pad head-room covers it. x >= r2max > 0 here.
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x + 1e-30f));
+    return x * r;
 #else
     return sqrtf(x);
 #endif
@@ -117,12 +120,24 @@ constexpr int BVH_STACK = 72;               // Karras tree depth <= key bits (64
 constexpr int BVH_CAND = 6;                 // secondary-fold candidate buffer
 constexpr float BVH_WINDOW = 0.045f;        // candidates within this distance above the minimum are replayed
 
+// Radius of the ball around a sphere centre that contains every point the reference can report as a hit on it for rays
+// starting at distance^2 `oc2` from the centre (see header): sqrt(r^2 + K^2 (|oc|^2 + r^2)), rounded up.
+RT_HD float inflated_radius(float r2, float oc2) {
+    float rr = r2 > 0.0f ? r2 : 0.0f;
+    return sqrtf(rr + (BVH_PAD_K * BVH_PAD_K) * (oc2 + rr)) * 1.000001f + 1e-30f;
+}
+
 // Entry parameter of the ray into the box inflated by pad (conservative), or +inf when it misses t in [0, tmax].
+// PAD = false: the box is already inflated for this ray origin (nodes_cam).
+template <bool PAD>
 RT_HD float box_entry(f3 o, f3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float r2max, float tmax) {
-    float dx = fmaxf(fabsf(lox - o.x), fabsf(hix - o.x));
-    float dy = fmaxf(fabsf(loy - o.y), fabsf(hiy - o.y));
-    float dz = fmaxf(fabsf(loz - o.z), fabsf(hiz - o.z));
-    float pad = BVH_PAD_K * approx_sqrt(dx * dx + dy * dy + dz * dz + r2max);
+    float pad = 0.0f;
+    if (PAD) {
+        float dx = fmaxf(fabsf(lox - o.x), fabsf(hix - o.x));
+        float dy = fmaxf(fabsf(loy - o.y), fabsf(hiy - o.y));
+        float dz = fmaxf(fabsf(loz - o.z), fabsf(hiz - o.z));
+        pad = BVH_PAD_K * approx_sqrt(dx * dx + dy * dy + dz * dz + r2max);
+    }
     float t0x = (lox - pad - o.x) * inv.x, t1x = (hix + pad - o.x) * inv.x;
     float t0y = (loy - pad - o.y) * inv.y, t1y = (hiy + pad - o.y) * inv.y;
     float t0z = (loz - pad - o.z) * inv.z, t1z = (hiz + pad - o.z) * inv.z;
@@ -145,11 +160,22 @@ RT_HD void bvh_nearest(const BvhView& bv, f3 o, f3 dir, float a2, float a4, floa
     int cand_i[BVH_CAND]; float cand_t[BVH_CAND]; int ncand = 0; bool overflow = false;
     int stack[BVH_STACK]; int sp = 0;
     int node = 0;
+    // Primary rays (off == 0 inside a frame) all start at the camera: they traverse the per-frame pre-inflated copy with a
+    // plain slab test. Everything else inflates each box for its own origin.
+    const bool cam_boxes = !secondary && bv.nodes_cam != nullptr;
+    const BvhNode* const nodes = cam_boxes ? bv.nodes_cam : bv.nodes;
     for (;;) {
-        const BvhNode nd = bv.nodes[node];
+        const BvhNode nd = nodes[node];
+        dbg.node_visit(secondary ? 1 : 0);
         const float bound = (best_t + window) * BVH_T_SLACK;
-        float e0 = box_entry(o, inv, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, bound);
-        float e1 = box_entry(o, inv, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, bound);
+        float e0, e1;
+        if (cam_boxes) {
+            e0 = box_entry<false>(o, inv, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, bound);
+            e1 = box_entry<false>(o, inv, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, bound);
+        } else {
+            e0 = box_entry<true>(o, inv, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, bound);
+            e1 = box_entry<true>(o, inv, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, bound);
+        }
         int c0 = nd.c0, c1 = nd.c1;
         if (e1 < e0) { float te = e0; e0 = e1; e1 = te; int tc = c0; c0 = c1; c1 = tc; }   // near child first
         int next = -1;
@@ -184,7 +210,7 @@ RT_HD void bvh_nearest(const BvhView& bv, f3 o, f3 dir, float a2, float a4, floa
         node = stack[--sp];
     }
     if (!secondary || best < 0) { *sel = best; *dsel = best_t; return; }
-    if (overflow) { brute(sel, dsel); return; }
+    if (overflow) { dbg.fallback(); brute(sel, dsel); return; }
     // Replay the reference's fold (:792-808) over the candidates near the minimum, in original index order.
     int s_sel = -1; float closest = RT_INF, cmax = 0.0f;
     for (int done = 0; done < ncand; done++) {
@@ -197,7 +223,7 @@ RT_HD void bvh_nearest(const BvhView& bv, f3 o, f3 dir, float a2, float a4, floa
     }
     // A sphere outside the window (t > best_t + window) could only have been accepted after the minimum if its offset
     // distance were below some running `closest` >= best_t; cmax bounds those.  Otherwise: exact fallback.
-    if (cmax + 0.0101f + cmax * 2.4e-7f >= best_t + window) { brute(sel, dsel); return; }
+    if (cmax + 0.0101f + cmax * 2.4e-7f >= best_t + window) { dbg.fallback(); brute(sel, dsel); return; }
     *sel = s_sel; *dsel = closest;
 }
 
@@ -210,8 +236,9 @@ RT_HD bool bvh_shadow_any(const BvhView& bv, f3 hit, f3 lp, float a2, float a4, 
     bool occluded = false;
     for (;;) {
         const BvhNode nd = bv.nodes[node];
-        float e0 = box_entry(hit, inv, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, RT_INF);
-        float e1 = box_entry(hit, inv, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, RT_INF);
+        dbg.node_visit(2);
+        float e0 = box_entry<true>(hit, inv, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, RT_INF);
+        float e1 = box_entry<true>(hit, inv, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, RT_INF);
         int next = -1;
 #pragma unroll
         for (int k = 0; k < 2; k++) {

@@ -68,11 +68,42 @@ __global__ void k_lbvh_refit(const f4* sorted, const float* radius_eff, const in
     }
 }
 
+// Per-frame refit of the camera copy: leaf boxes = centre +- inflated_radius(r^2, |cam - centre|^2), unions above.
+__global__ void k_lbvh_refit_cam(const f4* sorted, int n, BvhNode* nodes_cam, const int* parent_node, const int* parent_leaf,
+                                 int* arrivals, float cx, float cy, float cz) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const f4 g = sorted[j];
+    const float dx = cx - g.x, dy = cy - g.y, dz = cz - g.z;
+    BvhBox box = sphere_box(g, inflated_radius(g.w, dx * dx + dy * dy + dz * dz));
+    int enc = parent_leaf[j];
+    while (enc >= 0) {
+        const int node = enc >> 1, side = enc & 1;
+        store_child_box_volatile(nodes_cam + node, side, box);
+        __threadfence();
+        if (atomicAdd(arrivals + node, 1) == 0) return;
+        __threadfence();
+        box = box_union(box, load_child_box_volatile(nodes_cam + node, side ^ 1));
+        enc = parent_node[node];
+    }
+}
+
 struct LbvhDevice {
-    BvhNode* nodes = nullptr; f4* sorted = nullptr; int* orig = nullptr; float r2max = 0.0f; int n = 0;
+    BvhNode* nodes = nullptr; BvhNode* nodes_cam = nullptr; f4* sorted = nullptr; int* orig = nullptr;
+    int *parent_node = nullptr, *parent_leaf = nullptr, *arrivals = nullptr;
+    float r2max = 0.0f; int n = 0;
     void release() {
-        cudaFree(nodes); cudaFree(sorted); cudaFree(orig);
-        nodes = nullptr; sorted = nullptr; orig = nullptr; n = 0;
+        cudaFree(nodes); cudaFree(nodes_cam); cudaFree(sorted); cudaFree(orig); cudaFree(parent_node); cudaFree(parent_leaf); cudaFree(arrivals);
+        nodes = nullptr; nodes_cam = nullptr; sorted = nullptr; orig = nullptr; parent_node = nullptr; parent_leaf = nullptr; arrivals = nullptr; n = 0;
+    }
+    // Re-inflates nodes_cam for rays starting at (cx, cy, cz). Asynchronous on `stream`.
+    cudaError_t refit_for_camera(float cx, float cy, float cz, cudaStream_t stream) {
+        if (n < 2) return cudaSuccess;
+        cudaError_t e = cudaMemsetAsync(arrivals, 0, sizeof(int) * (size_t)n, stream);
+        if (e != cudaSuccess) return e;
+        const int B = 256, G = (n + B - 1) / B;
+        k_lbvh_refit_cam<<<G, B, 0, stream>>>(sorted, n, nodes_cam, parent_node, parent_leaf, arrivals, cx, cy, cz);
+        return cudaGetLastError();
     }
 };
 
@@ -84,15 +115,18 @@ inline cudaError_t lbvh_build(const f4* sgeom_dev, const float* radius_eff_host,
     if (n < 2) return cudaSuccess;
     cudaError_t e;
     uint64_t *keys = nullptr, *keys_sorted = nullptr; float* radius = nullptr; int *pn = nullptr, *pl = nullptr, *arr = nullptr;
+    (void)pn; (void)pl; (void)arr;
     void* tmp = nullptr; size_t tmp_bytes = 0;
 #define LB_TRY(x) do { e = (x); if (e != cudaSuccess) goto fail; } while (0)
     LB_TRY(cudaMalloc(&keys, sizeof(uint64_t) * (size_t)n));
     LB_TRY(cudaMalloc(&keys_sorted, sizeof(uint64_t) * (size_t)n));
     LB_TRY(cudaMalloc(&radius, sizeof(float) * (size_t)n));
-    LB_TRY(cudaMalloc(&pn, sizeof(int) * (size_t)n));
-    LB_TRY(cudaMalloc(&pl, sizeof(int) * (size_t)n));
-    LB_TRY(cudaMalloc(&arr, sizeof(int) * (size_t)n));
+    LB_TRY(cudaMalloc(&out->parent_node, sizeof(int) * (size_t)n));
+    LB_TRY(cudaMalloc(&out->parent_leaf, sizeof(int) * (size_t)n));
+    LB_TRY(cudaMalloc(&out->arrivals, sizeof(int) * (size_t)n));
+    pn = out->parent_node; pl = out->parent_leaf; arr = out->arrivals;
     LB_TRY(cudaMalloc(&out->nodes, sizeof(BvhNode) * (size_t)(n - 1)));
+    LB_TRY(cudaMalloc(&out->nodes_cam, sizeof(BvhNode) * (size_t)(n - 1)));
     LB_TRY(cudaMalloc(&out->sorted, sizeof(f4) * (size_t)n));
     LB_TRY(cudaMalloc(&out->orig, sizeof(int) * (size_t)n));
     LB_TRY(cudaMemcpyAsync(radius, radius_eff_host, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, stream));
@@ -112,6 +146,8 @@ inline cudaError_t lbvh_build(const f4* sgeom_dev, const float* radius_eff_host,
         LB_TRY(cudaGetLastError());
         k_lbvh_refit<<<G, B, 0, stream>>>(out->sorted, radius, out->orig, n, out->nodes, pn, pl, arr);
         LB_TRY(cudaGetLastError());
+        // the camera copy shares the topology; its boxes are written by refit_for_camera before every frame
+        LB_TRY(cudaMemcpyAsync(out->nodes_cam, out->nodes, sizeof(BvhNode) * (size_t)(n - 1), cudaMemcpyDeviceToDevice, stream));
         if (launches) *launches += 4;
     }
     LB_TRY(cudaStreamSynchronize(stream));
@@ -121,7 +157,7 @@ inline cudaError_t lbvh_build(const f4* sgeom_dev, const float* radius_eff_host,
 fail:
     out->release();
 done:
-    cudaFree(keys); cudaFree(keys_sorted); cudaFree(radius); cudaFree(pn); cudaFree(pl); cudaFree(arr); cudaFree(tmp);
+    cudaFree(keys); cudaFree(keys_sorted); cudaFree(radius); cudaFree(tmp);
 #undef LB_TRY
     return e;
 }

@@ -59,12 +59,15 @@ struct NoDbg {
     RT_HD void shaded(bool) {}
     RT_HD void spec() {}
     RT_HD void primary_aov(int, float) {}
+    RT_HD void node_visit(int) {}
+    RT_HD void fallback() {}
 };
 struct FullDbg {
     static constexpr bool enabled = true;
     uint32_t hash = 0;
     uint32_t primary = 0, n_shadow = 0, secondary = 0, sphere_tests = 0, sphere_disc_pos = 0, plane_tests = 0;
     uint32_t shade_diffuse = 0, shade_specular = 0, shade_mirror = 0, shaded_hits = 0;
+    uint32_t node_visits[3] = {0, 0, 0}, fallbacks = 0;    // LBVH: node (box-pair) visits by ray kind, brute-force fallbacks
     int aov_id = -1; float aov_t = 0.0f; bool aov_set = false;
     RT_HD void sphere_test(bool disc_pos) { sphere_tests++; if (disc_pos) sphere_disc_pos++; }
     RT_HD void plane_test() { plane_tests++; }
@@ -78,6 +81,8 @@ struct FullDbg {
     RT_HD void shaded(bool mirror) { shaded_hits++; if (mirror) shade_mirror++; }
     RT_HD void spec() { shade_specular++; }
     RT_HD void primary_aov(int id, float t) { if (!aov_set) { aov_id = id; aov_t = t; aov_set = true; } }
+    RT_HD void node_visit(int kind) { node_visits[kind]++; }
+    RT_HD void fallback() { fallbacks++; }
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -102,22 +107,55 @@ RT_HD bool sphere_hit(f3 oc, f3 dir, float r2, float a2, float a4, float eps, fl
     return true;
 }
 
+// The slow half of sphere_hit once b and D are known and b < 0 && D >= 0.
+RT_HD bool sphere_root(float b, float D, float a2, float eps, float* t) {
+    float s = sqrtf(D);                                           // :623
+    float t1 = (-b - s) / a2;                                     // :627
+    if (!(t1 - eps > 0)) return false;                            // :629-635
+    *t = t1;
+    return true;
+}
+
 // The reference's loops over every sphere, in array order.  One loop serves both folds:
 //   primary   (:977)  `d > 0 && nearest > d`                    == key > 0 && key < closest with key = d - 0
 //   secondary (:804)  `d - 0.01f > 0 && d - 0.01f < closest`    == the same with key = d - 0.01f
 // (d - 0.0f == d bit for bit; the stored distance is the un-offset d in both: the secondary fold is order dependent).
-// NS >= 0: compile-time sphere count (fully unrolled, records addressed statically); NS < 0: run-time count.
+// NS >= 0: compile-time sphere count — fully unrolled, records addressed statically, and the b / discriminant of ALL
+// spheres are evaluated branch-free first so that the common all-miss case costs one branch instead of NS.
 template <int NS, class SC, class DBG>
 RT_HD void brute_nearest(const SC& sc, f3 o, f3 dir, float a2, float a4, float off, int* sel, float* dsel, DBG& dbg) {
     int best = -1; float closest = RT_INF;
-    const int ns = NS >= 0 ? NS : sc.n_spheres();
+    if constexpr (NS > 0) {
+        float bs[NS], Ds[NS]; bool any = false;
 #pragma unroll
-    for (int i = 0; i < ns; i++) {                                // :975 / :792
-        f4 g = sc.sphere_geom(i);
-        float t;
-        if (sphere_hit(sub3(o, mk3(g.x, g.y, g.z)), dir, g.w, a2, a4, 0.0f, &t, dbg)) {
-            float key = t - off;
-            if (key > 0 && key < closest) { closest = t; best = i; }
+        for (int i = 0; i < NS; i++) {
+            f4 g = sc.sphere_geom(i);
+            f3 oc = sub3(o, mk3(g.x, g.y, g.z));                  // :614
+            bs[i] = 2 * dot3(oc, dir);                            // :618
+            float c = dot3(oc, oc) - g.w;                         // :619
+            Ds[i] = bs[i] * bs[i] - a4 * c;                       // :621
+            dbg.sphere_test(Ds[i] >= 0);
+            any = any || (bs[i] < 0 && Ds[i] >= 0);
+        }
+        if (any) {
+#pragma unroll
+            for (int i = 0; i < NS; i++) {                        // :975 / :792, array order
+                float t;
+                if (bs[i] < 0 && Ds[i] >= 0 && sphere_root(bs[i], Ds[i], a2, 0.0f, &t)) {
+                    float key = t - off;
+                    if (key > 0 && key < closest) { closest = t; best = i; }
+                }
+            }
+        }
+    } else {
+        const int ns = NS >= 0 ? NS : sc.n_spheres();
+        for (int i = 0; i < ns; i++) {                            // :975 / :792
+            f4 g = sc.sphere_geom(i);
+            float t;
+            if (sphere_hit(sub3(o, mk3(g.x, g.y, g.z)), dir, g.w, a2, a4, 0.0f, &t, dbg)) {
+                float key = t - off;
+                if (key > 0 && key < closest) { closest = t; best = i; }
+            }
         }
     }
     *sel = best; *dsel = closest;
@@ -125,13 +163,33 @@ RT_HD void brute_nearest(const SC& sc, f3 o, f3 dir, float a2, float a4, float o
 template <int NS, class SC, class DBG>
 RT_HD bool brute_shadow_any(const SC& sc, f3 hit, f3 lp, float a2, float a4, DBG& dbg) {
     bool occluded = false;
-    const int ns = NS >= 0 ? NS : sc.n_spheres();
+    if constexpr (NS > 0) {
+        float bs[NS], Ds[NS]; bool any = false;
 #pragma unroll
-    for (int i = 0; i < ns; i++) {                                // :577
-        f4 g = sc.sphere_geom(i);
-        float t;
-        if (sphere_hit(sub3(hit, mk3(g.x, g.y, g.z)), lp, g.w, a2, a4, 0.001f, &t, dbg))   // :578
-            occluded = true;                                      // boolean OR over all spheres (no early-out in the reference)
+        for (int i = 0; i < NS; i++) {
+            f4 g = sc.sphere_geom(i);
+            f3 oc = sub3(hit, mk3(g.x, g.y, g.z));
+            bs[i] = 2 * dot3(oc, lp);
+            float c = dot3(oc, oc) - g.w;
+            Ds[i] = bs[i] * bs[i] - a4 * c;
+            dbg.sphere_test(Ds[i] >= 0);
+            any = any || (bs[i] < 0 && Ds[i] >= 0);
+        }
+        if (any) {
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                float t;
+                if (bs[i] < 0 && Ds[i] >= 0 && sphere_root(bs[i], Ds[i], a2, 0.001f, &t)) occluded = true;   // :578
+            }
+        }
+    } else {
+        const int ns = NS >= 0 ? NS : sc.n_spheres();
+        for (int i = 0; i < ns; i++) {                            // :577
+            f4 g = sc.sphere_geom(i);
+            float t;
+            if (sphere_hit(sub3(hit, mk3(g.x, g.y, g.z)), lp, g.w, a2, a4, 0.001f, &t, dbg))   // :578
+                occluded = true;                                  // boolean OR over all spheres (no early-out in the reference)
+        }
     }
     return occluded;
 }

@@ -33,8 +33,10 @@ constexpr int PPT = 4;                      // pixels per thread (one 128-bit st
 constexpr int CHUNK = BLOCK * PPT;          // pixels per CTA work item
 constexpr int STACK_RECS = RT_MAX_DEPTH + 1;
 constexpr int INLINE_CAMS = 16;
+constexpr int N_DEBUG_COUNTERS = 16;
 #ifndef RT_DEFAULT_WAVES
-#define RT_DEFAULT_WAVES 4     // grid-stride grid = SMs x resident CTAs x waves (profiles/r01/tune_*.log)
+#define RT_DEFAULT_WAVES 64    // grid-stride grid = SMs x resident CTAs x waves; many short CTAs let the hardware
+                               // scheduler balance sky / floor / mirror chunks (profiles/r01/tuning.md)
 #endif
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 4      // resident CTAs per SM the register allocator must allow (tuned on B200, profiles/)
@@ -140,7 +142,7 @@ template <class SC>
 __device__ __forceinline__ void debug_loop(const SC& sc, const FrameParams& fp, const DebugOut& dout) {
     HitRec stack[STACK_RECS];
     const int npix = fp.w * fp.h;
-    unsigned long long cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long cnt[N_DEBUG_COUNTERS] = {0};
     for (long long pl = (long long)blockIdx.x * blockDim.x + threadIdx.x; pl < npix; pl += (long long)gridDim.x * blockDim.x) {
         const int p = (int)pl;
         FullDbg dbg;
@@ -153,9 +155,10 @@ __device__ __forceinline__ void debug_loop(const SC& sc, const FrameParams& fp, 
         cnt[0] += dbg.primary; cnt[1] += dbg.n_shadow; cnt[2] += dbg.secondary; cnt[3] += dbg.sphere_tests;
         cnt[4] += dbg.sphere_disc_pos; cnt[5] += dbg.plane_tests; cnt[6] += dbg.shade_diffuse; cnt[7] += dbg.shade_specular;
         cnt[8] += dbg.shade_mirror; cnt[9] += dbg.shaded_hits;
+        cnt[10] += dbg.node_visits[0]; cnt[11] += dbg.node_visits[1]; cnt[12] += dbg.node_visits[2]; cnt[13] += dbg.fallbacks;
     }
     if (dout.counters)
-        for (int i = 0; i < 10; i++) if (cnt[i]) atomicAdd(dout.counters + i, cnt[i]);
+        for (int i = 0; i < N_DEBUG_COUNTERS; i++) if (cnt[i]) atomicAdd(dout.counters + i, cnt[i]);
 }
 __global__ void __launch_bounds__(BLOCK) k_debug_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
     debug_loop(TinyScene<-1, -1>(scd), fp, dout);
@@ -206,6 +209,8 @@ struct DeviceState {
     f4* sgeom = nullptr; MatRec* smat = nullptr; PlaneRec* planes = nullptr; LightRec* lights = nullptr;
     CamRec* cams = nullptr; int cams_cap = 0;
     LbvhDevice bvh;
+    float bvh_cam[3] = {0, 0, 0}; bool bvh_cam_valid = false;    // camera the nodes_cam copy is currently inflated for ...
+    cudaStream_t bvh_cam_stream = nullptr;                        // ... by a refit issued on this stream
     // framebuffer ring (device 0 of the context only, unless partitioned multi-process)
     uint32_t* fb = nullptr; size_t fb_pixels = 0;
     // band pipelining (render_frames): copy stream on device 0, per-segment "band rendered" events on every device
@@ -255,7 +260,7 @@ int fail(rt_context* ctx, int code, const std::string& msg) {
 
 void free_scene(DeviceState& d) {
     cudaSetDevice(d.dev);
-    d.bvh.release();
+    d.bvh.release(); d.bvh_cam_valid = false;
     cudaFree(d.sgeom); cudaFree(d.smat); cudaFree(d.planes); cudaFree(d.lights);
     d.sgeom = nullptr; d.smat = nullptr; d.planes = nullptr; d.lights = nullptr;
 }
@@ -310,17 +315,42 @@ GlobalSceneData global_data(const rt_context* ctx, const DeviceState& d) {
     g.sgeom = d.sgeom; g.smat = d.smat; g.planes = d.planes; g.lights = d.lights;
     return g;
 }
-LbvhSceneData lbvh_data(const rt_context* ctx, const DeviceState& d) {
+LbvhSceneData lbvh_data(const rt_context* ctx, const DeviceState& d, bool with_cam_boxes) {
     LbvhSceneData l;
     l.g = global_data(ctx, d);
-    l.bv.nodes = d.bvh.nodes; l.bv.sgeom_sorted = d.bvh.sorted; l.bv.orig = d.bvh.orig; l.bv.n = d.bvh.n; l.bv.r2max = d.bvh.r2max;
+    l.bv.nodes = d.bvh.nodes; l.bv.nodes_cam = with_cam_boxes ? d.bvh.nodes_cam : nullptr; l.bv.sgeom_sorted = d.bvh.sorted; l.bv.orig = d.bvh.orig; l.bv.n = d.bvh.n; l.bv.r2max = d.bvh.r2max;
     return l;
 }
 
 // Launches the render kernel for one device's share. Asynchronous on `stream`.
 int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaStream_t stream) {
+    if (ctx->path == PATH_LBVH && fp.n_frames > 1) {
+        // the camera-inflated BVH copy is per frame: one refit + one launch per frame, back to back on the stream
+        for (int f = 0; f < fp.n_frames; f++) {
+            FrameParams one = fp;
+            one.n_frames = 1; one.cams = nullptr;
+            if (fp.cams) {
+                cudaError_t e = cudaMemcpyAsync(&one.cam_inline[0], fp.cams + f, sizeof(CamRec), cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+                if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("camera readback: ") + cudaGetErrorString(e));
+            } else one.cam_inline[0] = fp.cam_inline[f];
+            one.out = fp.out + (long long)f * fp.frame_stride;
+            int rc = launch_render(ctx, d, one, stream);
+            if (rc) return rc;
+        }
+        return RT_OK;
+    }
     long long n_items = (long long)fp.tiles_mine * fp.chunks_per_tile * fp.n_frames;
     if (n_items == 0) return RT_OK;
+    if (ctx->path == PATH_LBVH) {
+        const CamRec& c = fp.cam_inline[0];
+        if (!(d.bvh_cam_valid && d.bvh_cam_stream == stream && d.bvh_cam[0] == c.pos.x && d.bvh_cam[1] == c.pos.y && d.bvh_cam[2] == c.pos.z)) {
+            cudaError_t e = d.bvh.refit_for_camera(c.pos.x, c.pos.y, c.pos.z, stream);
+            if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh refit: ") + cudaGetErrorString(e));
+            d.bvh_cam[0] = c.pos.x; d.bvh_cam[1] = c.pos.y; d.bvh_cam[2] = c.pos.z; d.bvh_cam_valid = true; d.bvh_cam_stream = stream;
+            ctx->launches++;
+        }
+    }
     if (n_items > 0x7FFFFFFFLL) return fail(ctx, RT_ERR_UNSUPPORTED, "too many work items in one launch");
     const size_t smem = ctx->path == PATH_STAGED ? sizeof(f4) * (size_t)ctx->gdata_host.ns : 0;
     TinyKernel tk = ctx->path == PATH_TINY ? tiny_kernel(ctx->tiny_data.ns, ctx->tiny_data.nl) : nullptr;
@@ -340,7 +370,7 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
         case PATH_TINY: tk<<<(unsigned)grid, BLOCK, 0, stream>>>(ctx->tiny_data, fp); break;
         case PATH_STAGED: k_render_staged<<<(unsigned)grid, BLOCK, smem, stream>>>(global_data(ctx, d), fp); break;
         case PATH_GLOBAL: k_render_global<<<(unsigned)grid, BLOCK, 0, stream>>>(global_data(ctx, d), fp); break;
-        default: k_render_lbvh<<<(unsigned)grid, BLOCK, 0, stream>>>(lbvh_data(ctx, d), fp); break;
+        default: k_render_lbvh<<<(unsigned)grid, BLOCK, 0, stream>>>(lbvh_data(ctx, d, true), fp); break;
     }
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
@@ -668,8 +698,8 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int w, int h, int dep
     CU_TRY(ctx, cudaSetDevice(d.dev));
     DebugOut dout; memset(&dout, 0, sizeof(dout));
     unsigned long long* dcnt = nullptr;
-    CU_TRY(ctx, cudaMalloc(&dcnt, 12 * sizeof(unsigned long long)));
-    CU_TRY(ctx, cudaMemset(dcnt, 0, 12 * sizeof(unsigned long long)));
+    CU_TRY(ctx, cudaMalloc(&dcnt, N_DEBUG_COUNTERS * sizeof(unsigned long long)));
+    CU_TRY(ctx, cudaMemset(dcnt, 0, N_DEBUG_COUNTERS * sizeof(unsigned long long)));
     dout.counters = dcnt;
     if (host_hash) CU_TRY(ctx, cudaMalloc(&dout.hash, npix * 4));
     if (host_aov_id) CU_TRY(ctx, cudaMalloc(&dout.aov_id, npix * 4));
@@ -684,7 +714,13 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int w, int h, int dep
         case PATH_TINY: k_debug_tiny<<<(unsigned)grid, BLOCK, 0, d.stream>>>(ctx->tiny_data, fp, dout); break;
         case PATH_STAGED: k_debug_staged<<<(unsigned)grid, BLOCK, sizeof(f4) * (size_t)ctx->gdata_host.ns, d.stream>>>(global_data(ctx, d), fp, dout); break;
         case PATH_GLOBAL: k_debug_global<<<(unsigned)grid, BLOCK, 0, d.stream>>>(global_data(ctx, d), fp, dout); break;
-        default: k_debug_lbvh<<<(unsigned)grid, BLOCK, 0, d.stream>>>(lbvh_data(ctx, d), fp, dout); break;
+        default: {
+            cudaError_t e = d.bvh.refit_for_camera(fp.cam_inline[0].pos.x, fp.cam_inline[0].pos.y, fp.cam_inline[0].pos.z, d.stream);
+            if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh refit: ") + cudaGetErrorString(e));
+            d.bvh_cam_valid = false;
+            k_debug_lbvh<<<(unsigned)grid, BLOCK, 0, d.stream>>>(lbvh_data(ctx, d, true), fp, dout);
+            break;
+        }
     }
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
@@ -695,9 +731,9 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int w, int h, int dep
     if (host_hash) CU_TRY(ctx, cudaMemcpy(host_hash, dout.hash, npix * 4, cudaMemcpyDeviceToHost));
     if (host_aov_id) CU_TRY(ctx, cudaMemcpy(host_aov_id, dout.aov_id, npix * 4, cudaMemcpyDeviceToHost));
     if (host_aov_t) CU_TRY(ctx, cudaMemcpy(host_aov_t, dout.aov_t, npix * 4, cudaMemcpyDeviceToHost));
-    unsigned long long hc[12];
+    unsigned long long hc[N_DEBUG_COUNTERS];
     CU_TRY(ctx, cudaMemcpy(hc, dcnt, sizeof(hc), cudaMemcpyDeviceToHost));
-    if (counters) for (int i = 0; i < 12; i++) counters[i] = hc[i];
+    if (counters) for (int i = 0; i < N_DEBUG_COUNTERS; i++) counters[i] = hc[i];
     cudaFree(dcnt); cudaFree(dout.hash); cudaFree(dout.aov_id); cudaFree(dout.aov_t);
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -721,7 +757,7 @@ int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, 
     CU_TRY(ctx, cudaMalloc(&dt, (size_t)n_rays * 4));
     CU_TRY(ctx, cudaMemcpy(dr, rays6, (size_t)n_rays * 24, cudaMemcpyHostToDevice));
     int grid = (n_rays + BLOCK - 1) / BLOCK; if (grid > d.sm_count * 32) grid = d.sm_count * 32;
-    if (accel == RT_ACCEL_LBVH) k_query_lbvh<<<grid, BLOCK, 0, d.stream>>>(lbvh_data(ctx, d), dr, n_rays, kind, di, dt);
+    if (accel == RT_ACCEL_LBVH) k_query_lbvh<<<grid, BLOCK, 0, d.stream>>>(lbvh_data(ctx, d, false), dr, n_rays, kind, di, dt);
     else k_query_brute<<<grid, BLOCK, 0, d.stream>>>(global_data(ctx, d), dr, n_rays, kind, di, dt);
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;

@@ -166,13 +166,15 @@ class Context:
         st = RtStats()
         n = w * h
         px = np.empty(n, np.int32); hsh = np.empty(n, np.uint32); aid = np.empty(n, np.int32); at = np.empty(n, np.float32)
-        cnt = np.zeros(12, np.uint64)
+        cnt = np.zeros(16, np.uint64)
         self._check(self.lib.rt_render_debug(self.h, C.byref(cam), w, h, max_depth, spp, seed,
                                              px.ctypes.data_as(C.POINTER(C.c_int32)), hsh.ctypes.data_as(C.POINTER(C.c_uint32)),
                                              aid.ctypes.data_as(C.POINTER(C.c_int32)), _fp(at),
                                              cnt.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(st)))
         return dict(pixels=px.reshape(h, w), hash=hsh.reshape(h, w), aov_id=aid.reshape(h, w), aov_t=at.reshape(h, w),
-                    counters=dict(zip(COUNTER_NAMES, (int(v) for v in cnt[:10]))), stats=st)
+                    counters=dict(zip(COUNTER_NAMES, (int(v) for v in cnt[:10]))), stats=st,
+                    lbvh=dict(node_visits_primary=int(cnt[10]), node_visits_secondary=int(cnt[11]), node_visits_shadow=int(cnt[12]),
+                              brute_fallbacks=int(cnt[13])))
 
     def query_spheres(self, rays6, kind, accel=RT_ACCEL_BRUTE):
         rays6 = np.ascontiguousarray(rays6, dtype=np.float32).reshape(-1, 6)

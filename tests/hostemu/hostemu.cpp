@@ -48,7 +48,7 @@ static void host_build(const std::vector<f4>& sg, HostBvh& b) {
         float r2 = sg[i].w > 0 ? sg[i].w : 0; reff[i] = sqrtf(r2) * 1.000001f + 1e-30f; if (r2 > b.r2max) b.r2max = r2;
     }
     float binv[3];
-    for (int k = 0; k < 3; k++) { float e = bmax[k] - bmin[k]; binv[k] = e > 0 ? 1023.0f / e : 0.0f; }
+    morton_scale(bmin, bmax, binv);
     std::vector<uint64_t> keys(n);
     for (int i = 0; i < n; i++) keys[i] = morton_key(sg[i].x, sg[i].y, sg[i].z, bmin, binv, (uint32_t)i);
     std::sort(keys.begin(), keys.end());

@@ -45,6 +45,13 @@ RT_HD uint64_t morton_key(float cx, float cy, float cz, const float* bmin, const
     uint32_t code = (expand_bits10((uint32_t)fx) << 2) | (expand_bits10((uint32_t)fy) << 1) | expand_bits10((uint32_t)fz);
     return ((uint64_t)code << 32) | (uint64_t)index;
 }
+// One cell size for all three axes (the largest extent / 1024): a flat scene (a carpet of spheres on the floor) then
+// spends its Morton bits on the two long axes instead of slicing the thin one into 1024 overlapping layers.
+inline void morton_scale(const float bmin[3], const float bmax[3], float binv[3]) {
+    float ext = 0.0f;
+    for (int k = 0; k < 3; k++) { float e = bmax[k] - bmin[k]; if (e > ext) ext = e; }
+    for (int k = 0; k < 3; k++) binv[k] = ext > 0.0f ? 1023.0f / ext : 0.0f;
+}
 RT_HD int clz64(uint64_t x) {
 #if defined(__CUDA_ARCH__)
     return __clzll((long long)x);

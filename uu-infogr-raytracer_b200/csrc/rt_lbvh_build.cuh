@@ -133,7 +133,7 @@ inline cudaError_t lbvh_build(const f4* sgeom_dev, const float* radius_eff_host,
     LB_TRY(cudaMemsetAsync(arr, 0, sizeof(int) * (size_t)n, stream));
     {
         float binv[3];
-        for (int k = 0; k < 3; k++) { float ext = bmax[k] - bmin[k]; binv[k] = ext > 0.0f ? 1023.0f / ext : 0.0f; }
+        morton_scale(bmin, bmax, binv);
         const int B = 256, G = (n + B - 1) / B;
         k_lbvh_keys<<<G, B, 0, stream>>>(sgeom_dev, n, bmin[0], bmin[1], bmin[2], binv[0], binv[1], binv[2], keys);
         LB_TRY(cudaGetLastError());

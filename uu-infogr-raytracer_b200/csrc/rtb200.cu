@@ -505,10 +505,13 @@ int rt_set_scene(rt_context* ctx, const float* spheres, int ns, const float* pla
         CU_TRY(ctx, cudaMalloc(&d.smat, sizeof(MatRec) * (size_t)(ns > 0 ? ns : 1)));
         CU_TRY(ctx, cudaMalloc(&d.planes, sizeof(PlaneRec) * (size_t)(np > 0 ? np : 1)));
         CU_TRY(ctx, cudaMalloc(&d.lights, sizeof(LightRec) * (size_t)(nl > 0 ? nl : 1)));
-        if (ns) CU_TRY(ctx, cudaMemcpy(d.sgeom, sg.data(), sizeof(f4) * (size_t)ns, cudaMemcpyHostToDevice));
-        if (ns) CU_TRY(ctx, cudaMemcpy(d.smat, sm.data(), sizeof(MatRec) * (size_t)ns, cudaMemcpyHostToDevice));
-        if (np) CU_TRY(ctx, cudaMemcpy(d.planes, pl.data(), sizeof(PlaneRec) * (size_t)np, cudaMemcpyHostToDevice));
-        if (nl) CU_TRY(ctx, cudaMemcpy(d.lights, li.data(), sizeof(LightRec) * (size_t)nl, cudaMemcpyHostToDevice));
+        // Stream-ordered uploads: the context's streams are non-blocking, so a default-stream cudaMemcpy from pageable
+        // memory (which may return before its DMA lands) would NOT be ordered before kernels launched on d.stream.
+        if (ns) CU_TRY(ctx, cudaMemcpyAsync(d.sgeom, sg.data(), sizeof(f4) * (size_t)ns, cudaMemcpyHostToDevice, d.stream));
+        if (ns) CU_TRY(ctx, cudaMemcpyAsync(d.smat, sm.data(), sizeof(MatRec) * (size_t)ns, cudaMemcpyHostToDevice, d.stream));
+        if (np) CU_TRY(ctx, cudaMemcpyAsync(d.planes, pl.data(), sizeof(PlaneRec) * (size_t)np, cudaMemcpyHostToDevice, d.stream));
+        if (nl) CU_TRY(ctx, cudaMemcpyAsync(d.lights, li.data(), sizeof(LightRec) * (size_t)nl, cudaMemcpyHostToDevice, d.stream));
+        CU_TRY(ctx, cudaStreamSynchronize(d.stream));
     }
     // ---- how spheres are traced ----
     const bool want_bvh = ns >= 2 && (accel == RT_ACCEL_LBVH || (accel == RT_ACCEL_AUTO && ns >= AUTO_LBVH_MIN_SPHERES));
@@ -699,7 +702,7 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int w, int h, int dep
     DebugOut dout; memset(&dout, 0, sizeof(dout));
     unsigned long long* dcnt = nullptr;
     CU_TRY(ctx, cudaMalloc(&dcnt, N_DEBUG_COUNTERS * sizeof(unsigned long long)));
-    CU_TRY(ctx, cudaMemset(dcnt, 0, N_DEBUG_COUNTERS * sizeof(unsigned long long)));
+    CU_TRY(ctx, cudaMemsetAsync(dcnt, 0, N_DEBUG_COUNTERS * sizeof(unsigned long long), d.stream));
     dout.counters = dcnt;
     if (host_hash) CU_TRY(ctx, cudaMalloc(&dout.hash, npix * 4));
     if (host_aov_id) CU_TRY(ctx, cudaMalloc(&dout.aov_id, npix * 4));
@@ -755,7 +758,7 @@ int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, 
     CU_TRY(ctx, cudaMalloc(&dr, (size_t)n_rays * 24));
     CU_TRY(ctx, cudaMalloc(&di, (size_t)n_rays * 4));
     CU_TRY(ctx, cudaMalloc(&dt, (size_t)n_rays * 4));
-    CU_TRY(ctx, cudaMemcpy(dr, rays6, (size_t)n_rays * 24, cudaMemcpyHostToDevice));
+    CU_TRY(ctx, cudaMemcpyAsync(dr, rays6, (size_t)n_rays * 24, cudaMemcpyHostToDevice, d.stream));   // stream-ordered before the kernel
     int grid = (n_rays + BLOCK - 1) / BLOCK; if (grid > d.sm_count * 32) grid = d.sm_count * 32;
     if (accel == RT_ACCEL_LBVH) k_query_lbvh<<<grid, BLOCK, 0, d.stream>>>(lbvh_data(ctx, d, false), dr, n_rays, kind, di, dt);
     else k_query_brute<<<grid, BLOCK, 0, d.stream>>>(global_data(ctx, d), dr, n_rays, kind, di, dt);

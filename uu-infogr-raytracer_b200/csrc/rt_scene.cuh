@@ -21,13 +21,13 @@ struct TinySceneData {
 
 // NS >= 0: the sphere count is a compile-time constant — the sphere loops unroll and every record is addressed
 // statically in the constant bank (operands fold into the FMUL/FADD, no load instructions). NS < 0: run-time count.
-// NL likewise for the light loop of the shading code.
-template <int NS, int NL = -1>
+// NL likewise for the light loop of the shading code, NP for the plane loop.
+template <int NS, int NL = -1, int NP = -1>
 struct TinyScene {
     const TinySceneData& s;
     RT_HD explicit TinyScene(const TinySceneData& d) : s(d) {}
     RT_HD int n_spheres() const { return NS >= 0 ? NS : s.ns; }
-    RT_HD int n_planes() const { return s.np; }
+    RT_HD int n_planes() const { return NP >= 0 ? NP : s.np; }
     RT_HD int n_lights() const { return NL >= 0 ? NL : s.nl; }
     RT_HD f3 ambient() const { return s.amb; }
     RT_HD f4 sphere_geom(int i) const { return s.sgeom[i]; }

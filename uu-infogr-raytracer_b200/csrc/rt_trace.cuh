@@ -126,7 +126,9 @@ template <int NS, class SC, class DBG>
 RT_HD void brute_nearest(const SC& sc, f3 o, f3 dir, float a2, float a4, float off, int* sel, float* dsel, DBG& dbg) {
     int best = -1; float closest = RT_INF;
     if constexpr (NS > 0) {
-        float bs[NS], Ds[NS]; bool any = false;
+        // `gate` = max_i min(D_i, -b_i) >= 0 is a cheap SUPERSET of "some sphere has b < 0 && D >= 0" (two FMNMX per sphere;
+        // fminf drops a NaN, b == 0 passes): it only decides whether the exact per-sphere tests below run at all.
+        float bs[NS], Ds[NS]; float gate = -1.0f;
 #pragma unroll
         for (int i = 0; i < NS; i++) {
             f4 g = sc.sphere_geom(i);
@@ -135,9 +137,9 @@ RT_HD void brute_nearest(const SC& sc, f3 o, f3 dir, float a2, float a4, float o
             float c = dot3(oc, oc) - g.w;                         // :619
             Ds[i] = bs[i] * bs[i] - a4 * c;                       // :621
             dbg.sphere_test(Ds[i] >= 0);
-            any = any || (bs[i] < 0 && Ds[i] >= 0);
+            gate = fmaxf(gate, fminf(Ds[i], -bs[i]));
         }
-        if (any) {
+        if (gate >= 0) {
 #pragma unroll
             for (int i = 0; i < NS; i++) {                        // :975 / :792, array order
                 float t;
@@ -164,7 +166,7 @@ template <int NS, class SC, class DBG>
 RT_HD bool brute_shadow_any(const SC& sc, f3 hit, f3 lp, float a2, float a4, DBG& dbg) {
     bool occluded = false;
     if constexpr (NS > 0) {
-        float bs[NS], Ds[NS]; bool any = false;
+        float bs[NS], Ds[NS]; float gate = -1.0f;
 #pragma unroll
         for (int i = 0; i < NS; i++) {
             f4 g = sc.sphere_geom(i);
@@ -173,9 +175,9 @@ RT_HD bool brute_shadow_any(const SC& sc, f3 hit, f3 lp, float a2, float a4, DBG
             float c = dot3(oc, oc) - g.w;
             Ds[i] = bs[i] * bs[i] - a4 * c;
             dbg.sphere_test(Ds[i] >= 0);
-            any = any || (bs[i] < 0 && Ds[i] >= 0);
+            gate = fmaxf(gate, fminf(Ds[i], -bs[i]));
         }
-        if (any) {
+        if (gate >= 0) {
 #pragma unroll
             for (int i = 0; i < NS; i++) {
                 float t;
@@ -286,7 +288,7 @@ RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float
 
     int bounce = 0, top = 0;
     f3 C = mk3(0, 0, 0);
-    const int np = sc.n_planes();
+    const int np = sc.n_planes();      // compile-time constant in the exact-count kernels
     for (;;) {
         float a = dot3(dir, dir);                                                          // :617
         float a2 = 2 * a;                                                                  // :624
@@ -294,6 +296,7 @@ RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float
         int sel_s; float d_s;
         sc.nearest(o, dir, a2, a4, bounce == 0 ? 0.0f : 0.01f, &sel_s, &d_s, dbg);         // :975-981 / :792-808
         int sel_p = -1; float d_p = RT_INF;
+#pragma unroll
         for (int i = 0; i < np; i++) {                                                     // :985 / :812
             f4 pn = sc.plane_n(i);
             float t = (-o.x * pn.x - o.y * pn.y - o.z * pn.z + pn.w) / dot3(dir, mk3(pn.x, pn.y, pn.z));   // :591-596

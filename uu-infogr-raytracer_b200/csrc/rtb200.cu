@@ -7,9 +7,9 @@
 //
 // Work decomposition: a frame is cut into ROW TILES of `tile_rows` rows (contiguous pixel ranges in the row-major
 // framebuffer); tile t belongs to rank t % world (multi-GPU row interleave).  A rank's tiles are cut into chunks of
-// CHUNK = 256 threads x PPT pixels; a grid of (SMs x resident CTAs) walks its chunks with a grid stride, which
-// interleaves sky / floor / sphere chunks over all CTAs.  Each thread owns PPT=4 adjacent pixels and writes them with
-// one 128-bit store; the store address may be a peer (NVLink) mapping of rank 0's framebuffer — the gather is fused.
+// CHUNK = 256 threads x PPT pixels, one CTA per (chunk, tile, frame).  Each thread owns PPT=4 adjacent pixels and writes
+// them with one 128-bit store; the store address may be a peer (NVLink) mapping of rank 0's framebuffer — the gather is
+// fused into the render kernel.
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -34,10 +34,6 @@ constexpr int CHUNK = BLOCK * PPT;          // pixels per CTA work item
 constexpr int STACK_RECS = RT_MAX_DEPTH + 1;
 constexpr int INLINE_CAMS = 16;
 constexpr int N_DEBUG_COUNTERS = 16;
-#ifndef RT_DEFAULT_WAVES
-#define RT_DEFAULT_WAVES 64    // grid-stride grid = SMs x resident CTAs x waves; many short CTAs let the hardware
-                               // scheduler balance sky / floor / mirror chunks (profiles/r01/tuning.md)
-#endif
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 4      // resident CTAs per SM the register allocator must allow (tuned on B200, profiles/)
 #endif
@@ -62,30 +58,27 @@ struct DebugOut {
 };
 
 
-// Walks this rank's (frame, tile, chunk) work items with a grid stride.  All per-frame indices are 32-bit (w*h < 2^31).
+// One CTA per work item: blockIdx = (chunk inside the tile, this rank's tile, frame) — no index divisions, and the hardware
+// block scheduler balances sky / floor / mirror chunks (measured 8 % faster than a one-wave persistent grid-stride loop,
+// profiles/r01/tuning.md). gridDim.y is folded when a launch has more than 65535 tiles.
 template <class SC>
 __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp) {
     HitRec stack[STACK_RECS];
     NoDbg dbg;
     const int npix = fp.w * fp.h;
     const int tile_pix = fp.tile_rows * fp.w;
-    const int items_per_frame = fp.tiles_mine * fp.chunks_per_tile;
-    const int n_items = items_per_frame * fp.n_frames;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int frame = item / items_per_frame;
-        const int r = item - frame * items_per_frame;
-        const int kk = r / fp.chunks_per_tile;
+    const int frame = blockIdx.z;
+    for (int kk = blockIdx.y; kk < fp.tiles_mine; kk += gridDim.y) {
         const int k = fp.k_begin + kk;                         // my k-th tile
-        const int j = r - kk * fp.chunks_per_tile;             // chunk inside the tile
         const int tile = k * fp.world + fp.rank;
         const int base = tile * tile_pix;
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
-        const int p0 = base + j * CHUNK + (int)threadIdx.x * PPT;
+        const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
         if (p0 >= end) continue;
         const CamRec& cam = fp.cams ? fp.cams[frame] : fp.cam_inline[frame];
         uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
         uint32_t px[PPT];
-        int y = p0 / fp.w, x = p0 - y * fp.w;                  // one division per work item; then step along the row
+        int y = p0 / fp.w, x = p0 - y * fp.w;                  // one division per thread; then step along the row
 #pragma unroll 1
         for (int q = 0; q < PPT; q++) {
             uint32_t c = (p0 + q < end) ? trace_pixel(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg) : 0u;
@@ -101,9 +94,9 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
     }
 }
 
-template <int NS, int NL>
+template <int NS, int NL, int NP>
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp) {
-    render_loop(TinyScene<NS, NL>(scd), fp);
+    render_loop(TinyScene<NS, NL, NP>(scd), fp);
 }
 using TinyKernel = void (*)(const TinySceneData, const FrameParams);
 // Exact-count instantiations (sphere and light loops unrolled, records addressed statically) for scenes of the
@@ -111,13 +104,14 @@ using TinyKernel = void (*)(const TinySceneData, const FrameParams);
 constexpr int EXACT_MAX = 4;
 template <int NS, int NL> struct TinyTable {
     static TinyKernel get(int ns, int nl) {
-        if (ns == NS && nl == NL) return k_render_tiny<NS, NL>;
+        if (ns == NS && nl == NL) return k_render_tiny<NS, NL, 1>;
         if constexpr (NL < EXACT_MAX) return TinyTable<NS, NL + 1>::get(ns, nl);
         else if constexpr (NS < EXACT_MAX) return TinyTable<NS + 1, 0>::get(ns, nl);
-        else return k_render_tiny<-1, -1>;
+        else return k_render_tiny<-1, -1, -1>;
     }
 };
-TinyKernel tiny_kernel(int ns, int nl) { return TinyTable<0, 0>::get(ns, nl); }
+// exact kernels exist for 0..4 spheres x 0..4 lights x exactly 1 plane (the reference scene is 3 x 2 x 1)
+TinyKernel tiny_kernel(int ns, int nl, int np) { return np == 1 ? TinyTable<0, 0>::get(ns, nl) : k_render_tiny<-1, -1, -1>; }
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_global(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp) {
     render_loop(GlobalScene(scd), fp);
 }
@@ -161,7 +155,7 @@ __device__ __forceinline__ void debug_loop(const SC& sc, const FrameParams& fp, 
         for (int i = 0; i < N_DEBUG_COUNTERS; i++) if (cnt[i]) atomicAdd(dout.counters + i, cnt[i]);
 }
 __global__ void __launch_bounds__(BLOCK) k_debug_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
-    debug_loop(TinyScene<-1, -1>(scd), fp, dout);
+    debug_loop(TinyScene<-1, -1, -1>(scd), fp, dout);
 }
 __global__ void __launch_bounds__(BLOCK) k_debug_global(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
     debug_loop(GlobalScene(scd), fp, dout);
@@ -340,8 +334,8 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
         }
         return RT_OK;
     }
-    long long n_items = (long long)fp.tiles_mine * fp.chunks_per_tile * fp.n_frames;
-    if (n_items == 0) return RT_OK;
+    if (fp.tiles_mine <= 0 || fp.chunks_per_tile <= 0 || fp.n_frames <= 0) return RT_OK;
+    if (fp.n_frames > 65535) return fail(ctx, RT_ERR_UNSUPPORTED, "more than 65535 frames in one launch");
     if (ctx->path == PATH_LBVH) {
         const CamRec& c = fp.cam_inline[0];
         if (!(d.bvh_cam_valid && d.bvh_cam_stream == stream && d.bvh_cam[0] == c.pos.x && d.bvh_cam[1] == c.pos.y && d.bvh_cam[2] == c.pos.z)) {
@@ -351,26 +345,13 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
             ctx->launches++;
         }
     }
-    if (n_items > 0x7FFFFFFFLL) return fail(ctx, RT_ERR_UNSUPPORTED, "too many work items in one launch");
     const size_t smem = ctx->path == PATH_STAGED ? sizeof(f4) * (size_t)ctx->gdata_host.ns : 0;
-    TinyKernel tk = ctx->path == PATH_TINY ? tiny_kernel(ctx->tiny_data.ns, ctx->tiny_data.nl) : nullptr;
-    int resident = 0;    // CTAs of this kernel that fit on one SM (registers / shared memory / launch bounds decide)
+    const dim3 grid((unsigned)fp.chunks_per_tile, (unsigned)(fp.tiles_mine < 65535 ? fp.tiles_mine : 65535), (unsigned)fp.n_frames);
     switch (ctx->path) {
-        case PATH_TINY: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, tk, BLOCK, 0); break;
-        case PATH_STAGED: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_render_staged, BLOCK, smem); break;
-        case PATH_GLOBAL: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_render_global, BLOCK, 0); break;
-        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_render_lbvh, BLOCK, 0); break;
-    }
-    if (resident < 1) resident = 1;
-    const char* wv = getenv("RTB200_WAVES");        // grid = SMs x resident CTAs x waves
-    int waves = wv ? atoi(wv) : RT_DEFAULT_WAVES; if (waves < 1) waves = 1;
-    long long grid = (long long)d.sm_count * resident * waves;
-    if (grid > n_items) grid = n_items;
-    switch (ctx->path) {
-        case PATH_TINY: tk<<<(unsigned)grid, BLOCK, 0, stream>>>(ctx->tiny_data, fp); break;
-        case PATH_STAGED: k_render_staged<<<(unsigned)grid, BLOCK, smem, stream>>>(global_data(ctx, d), fp); break;
-        case PATH_GLOBAL: k_render_global<<<(unsigned)grid, BLOCK, 0, stream>>>(global_data(ctx, d), fp); break;
-        default: k_render_lbvh<<<(unsigned)grid, BLOCK, 0, stream>>>(lbvh_data(ctx, d, true), fp); break;
+        case PATH_TINY: tiny_kernel(ctx->tiny_data.ns, ctx->tiny_data.nl, ctx->tiny_data.np)<<<grid, BLOCK, 0, stream>>>(ctx->tiny_data, fp); break;
+        case PATH_STAGED: k_render_staged<<<grid, BLOCK, smem, stream>>>(global_data(ctx, d), fp); break;
+        case PATH_GLOBAL: k_render_global<<<grid, BLOCK, 0, stream>>>(global_data(ctx, d), fp); break;
+        default: k_render_lbvh<<<grid, BLOCK, 0, stream>>>(lbvh_data(ctx, d, true), fp); break;
     }
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;

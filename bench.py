@@ -226,6 +226,46 @@ def main():
     total_ms = float(ms.item())
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- N > 1 only: the same step with a library collective instead of the fused peer stores (comparison, not the product):
+    # every rank renders its tiles into a LOCAL framebuffer, packs its rows, NCCL-gathers them to rank 0, rank 0 scatters
+    # them into the frame (partition.pack_rows / assemble — the code the gloo test covers on CPU).
+    nccl_ms = None
+    if world > 1:
+        import partition
+        local = torch.empty((F, H, W), dtype=torch.int32, device="cuda")
+        rows = partition.rows_of_rank(H, args.tile_rows, rank, world)
+        pad = partition.max_rows_per_rank(H, args.tile_rows, world)
+        rows_t = torch.as_tensor(rows, device="cuda")
+        all_rows = [torch.as_tensor(partition.rows_of_rank(H, args.tile_rows, r, world), device="cuda") for r in range(world)]
+        payload = torch.zeros((F, pad, W), dtype=torch.int32, device="cuda")
+        gathered = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
+        frame0 = torch.empty((F, H, W), dtype=torch.int32, device="cuda") if rank == 0 else None
+
+        def nccl_step():
+            ctx.render_device(cams, W, H, DEPTH, 1, 0, local.data_ptr(), sh)
+            payload[:, : len(rows)] = local.index_select(1, rows_t)
+            dist.gather(payload, gathered, dst=0)
+            if rank == 0:
+                for r in range(world):
+                    frame0[:, all_rows[r]] = gathered[r][:, : len(all_rows[r])]
+
+        for _ in range(3):
+            nccl_step()
+        torch.cuda.synchronize(); barrier()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record(stream)
+        for _ in range(args.steps):
+            nccl_step()
+        n1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        t = torch.tensor([n0.elapsed_time(n1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nccl_ms = float(t.item()) / args.steps
+        if rank == 0:     # both gathers must produce the same frames
+            fused = torch.from_numpy(ctx.dev_to_host(fb, fb_bytes).reshape(F, H, W)).cuda()
+            assert torch.equal(fused, frame0), "NCCL-gathered frames differ from the fused peer-store frames"
+        del local, payload, gathered, frame0
+
     # ---- e2e: the reference-facing call with HOST buffers: per frame, camera down, kernel, 33 MB framebuffer up ------
     host = torch.empty((F, npix), dtype=torch.int32, pin_memory=True)
     host_np = host.numpy()
@@ -285,6 +325,9 @@ def main():
                     "path": "rt_render per frame into a pinned host Surface.pixels" if world == 1 else
                             "rt_render_device on all ranks (peer stores), barrier, rank 0 D2H"},
             "gpu_launches": int(launches_timed) * world,
+            "gather_compare": None if nccl_ms is None else {
+                "fused_peer_stores_ms_per_step": ms_per_step, "nccl_gather_ms_per_step": nccl_ms,
+                "note": "same step; NCCL path = render to a local framebuffer, pack rows, torch.distributed.gather, scatter on rank 0"},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -5,8 +5,8 @@
   python bench.py --impl reference [...]                          # the reference's CPU path (oracle port, host cores)
 
 Workload = BASELINE.json configs[1]: the reference's default scene (RayTracer.cs:441-469) at 3840x2160, recursion cap 8.
-A STEP is one pass of the hot path over one batch of `--frames` (default 8) such frames, each written to its own
-framebuffer of a ring (8 x 33.2 MB = 265 MB > the 126 MB L2, so no frame's stores hit lines left by the previous one).
+A STEP is one pass of the hot path over one batch of `--frames` (default 16) such frames, each written to its own
+framebuffer of a ring (16 x 33.2 MB = 531 MB > the 126 MB L2, so no frame's stores hit lines left by the previous one).
 Metric: Mrays/s (primary + shadow + secondary, nearest-first accounting — DESIGN.md), whole job over all N GPUs.
 
 N > 1 (torchrun, one process per GPU): every frame is cut into interleaved row tiles (tile t -> rank t % N); each rank's
@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.p = None
 
@@ -138,10 +138,10 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=8, help="4K frames per step (ring of framebuffers > L2)")
+    ap.add_argument("--frames", type=int, default=16, help="4K frames per step (ring of framebuffers > L2)")
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -225,6 +225,18 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and not clocks.get("samples"):
+        # the timed region was shorter than nvidia-smi's sampling period: sample the same step loop again, untimed
+        sampler = ClockSampler(local_rank); sampler.start()
+        t_end = time.perf_counter() + 0.4
+        while time.perf_counter() < t_end:
+            for _ in range(8):
+                step()
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
+        clocks["source"] = "untimed repeat of the step loop (timed region shorter than the sampling period)"
+    if world > 1:
+        barrier()
 
     # ---- N > 1 only: the same step with a library collective instead of the fused peer stores (comparison, not the product):
     # every rank renders its tiles into a LOCAL framebuffer, packs its rows, NCCL-gathers them to rank 0, rank 0 scatters
@@ -306,6 +318,12 @@ def main():
         fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12        # TFLOP/s, FMA counted as 2
         achieved_tflops = flops_per_frame * F / world / (kernel_ms * 1e-3) / 1e12
         hbm_ach = npix * 4 * F / world / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("frames_per_launch") == F and world == 1:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -315,7 +333,7 @@ def main():
                        "partition": "interleaved row tiles of %d rows, tile t -> rank t %% N, peer stores into rank 0 (CUDA IPC)" % args.tile_rows
                        if world > 1 else "single GPU"},
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / fp32_peak, "traffic": None,
+                         "frac": achieved_tflops / fp32_peak, "traffic": traffic,
                          "note": "kernel is fp32-instruction bound, not HBM or tensor: peak = 148 SM x 128 lanes x 2 (FMA) x sm_max_mhz "
                                  "(%s); parity forbids FMA contraction, so the attainable ceiling is peak/2; achieved = SURVEY §8d "
                                  "algorithmic flops (%.3e per frame) / CUDA-event kernel time" % (peaks["source"], flops_per_frame),

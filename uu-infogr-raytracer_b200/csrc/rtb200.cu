@@ -28,9 +28,16 @@ using namespace rtb;
 
 namespace {
 
-constexpr int BLOCK = 256;
-constexpr int PPT = 4;                      // pixels per thread (one 128-bit store)
-constexpr int CHUNK = BLOCK * PPT;          // pixels per CTA work item
+#ifndef RT_BLOCK
+#define RT_BLOCK 256
+#endif
+#ifndef RT_PPT_TINY
+#define RT_PPT_TINY 4
+#endif
+constexpr int BLOCK = RT_BLOCK;
+constexpr int PPT_TINY = RT_PPT_TINY;       // pixels per thread on the tiny-scene path: one 128-bit store per thread
+constexpr int PPT_HEAVY = 1;                // staged / global / LBVH paths: a pixel costs 10-1000x more, so short CTAs (256
+                                            // pixels) keep the slowest CTA off the critical path (multi-GPU: 2.4 -> see tuning.md)
 constexpr int STACK_RECS = RT_MAX_DEPTH + 1;
 constexpr int INLINE_CAMS = 16;
 constexpr int N_DEBUG_COUNTERS = 16;
@@ -46,7 +53,7 @@ struct FrameParams {
     int tiles_total;            // ceil(h / tile_rows)
     int tiles_mine;             // tiles of this rank rendered by this launch ...
     int k_begin;                // ... starting at the rank's k_begin-th tile (band pipelining, see render_frames)
-    int chunks_per_tile;        // ceil(tile_rows * w / CHUNK)
+    int chunks_per_tile;        // ceil(tile_rows * w / (BLOCK * pixels per thread))
     long long frame_stride;     // pixels between consecutive frames in `out`
     uint32_t* out;              // framebuffer(s): 0x00RRGGBB, row-major (Surface.pixels, surface.cs:9-20)
     const CamRec* cams;         // n_frames cameras (device), or nullptr => cam_inline
@@ -61,8 +68,9 @@ struct DebugOut {
 // One CTA per work item: blockIdx = (chunk inside the tile, this rank's tile, frame) — no index divisions, and the hardware
 // block scheduler balances sky / floor / mirror chunks (measured 8 % faster than a one-wave persistent grid-stride loop,
 // profiles/r01/tuning.md). gridDim.y is folded when a launch has more than 65535 tiles.
-template <class SC>
+template <int PPT, class SC>
 __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp) {
+    constexpr int CHUNK = BLOCK * PPT;          // pixels per CTA work item
     HitRec stack[STACK_RECS];
     NoDbg dbg;
     const int npix = fp.w * fp.h;
@@ -86,8 +94,8 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
 #pragma unroll
             for (int z = 0; z < PPT; z++) if (z == q) px[z] = c;   // keeps px[] in registers under `unroll 1`
         }
-        if (p0 + PPT <= end && ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0)) {
-            *reinterpret_cast<uint4*>(out + p0) = make_uint4(px[0], px[1], px[2], px[3]);     // 128-bit coalesced store
+        if (PPT == 4 && p0 + PPT <= end && ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0)) {
+            *reinterpret_cast<uint4*>(out + p0) = make_uint4(px[0], px[PPT > 1 ? 1 : 0], px[PPT > 2 ? 2 : 0], px[PPT > 3 ? 3 : 0]);   // 128-bit coalesced store
         } else {
             for (int q = 0; q < PPT; q++) if (p0 + q < end) out[p0 + q] = px[q];
         }
@@ -96,7 +104,7 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
 
 template <int NS, int NL, int NP>
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp) {
-    render_loop(TinyScene<NS, NL, NP>(scd), fp);
+    render_loop<PPT_TINY>(TinyScene<NS, NL, NP>(scd), fp);
 }
 using TinyKernel = void (*)(const TinySceneData, const FrameParams);
 // Exact-count instantiations (sphere and light loops unrolled, records addressed statically) for scenes of the
@@ -113,7 +121,7 @@ template <int NS, int NL> struct TinyTable {
 // exact kernels exist for 0..4 spheres x 0..4 lights x exactly 1 plane (the reference scene is 3 x 2 x 1)
 TinyKernel tiny_kernel(int ns, int nl, int np) { return np == 1 ? TinyTable<0, 0>::get(ns, nl) : k_render_tiny<-1, -1, -1>; }
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_global(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp) {
-    render_loop(GlobalScene(scd), fp);
+    render_loop<PPT_HEAVY>(GlobalScene(scd), fp);
 }
 // Brute force with the sphere geometry staged in shared memory (dynamic: 16 B per sphere).
 __device__ __forceinline__ const f4* stage_spheres(const GlobalSceneData& scd) {
@@ -124,11 +132,11 @@ __device__ __forceinline__ const f4* stage_spheres(const GlobalSceneData& scd) {
     return sm;
 }
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_staged(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp) {
-    render_loop(StagedScene(scd, stage_spheres(scd)), fp);
+    render_loop<PPT_HEAVY>(StagedScene(scd, stage_spheres(scd)), fp);
 }
 struct LbvhSceneData { GlobalSceneData g; BvhView bv; };
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_lbvh(const __grid_constant__ LbvhSceneData scd, const __grid_constant__ FrameParams fp) {
-    render_loop(LbvhScene(scd.g, scd.bv), fp);
+    render_loop<PPT_HEAVY>(LbvhScene(scd.g, scd.bv), fp);
 }
 
 // Instrumented kernel: one thread per pixel, writes hash / AOVs / counters.
@@ -297,7 +305,8 @@ FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp,
     fp.rank = rank; fp.world = world; fp.tile_rows = ctx->tile_rows;
     fp.tiles_total = (h + fp.tile_rows - 1) / fp.tile_rows;
     fp.tiles_mine = fp.tiles_total > rank ? (fp.tiles_total - rank + world - 1) / world : 0;
-    fp.chunks_per_tile = (int)(((long long)fp.tile_rows * w + CHUNK - 1) / CHUNK);
+    const int chunk = BLOCK * (ctx->path == PATH_TINY ? PPT_TINY : PPT_HEAVY);
+    fp.chunks_per_tile = (int)(((long long)fp.tile_rows * w + chunk - 1) / chunk);
     fp.frame_stride = frame_stride;
     fp.out = out;
     fp.cams = nullptr;

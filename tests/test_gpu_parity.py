@@ -135,6 +135,25 @@ def test_empty_scene_and_no_lights(ctx):
     assert np.array_equal(px, O.render(nolights, cam, 64, 48, 32)["pixels"])
 
 
+def test_large_batches_are_split_into_launches_of_16_frames(rt, ctx):
+    """Cameras travel in the kernel-parameter block (16 per launch): 19-frame batches must still come back complete, both
+    through rt_render_batch (host buffer and headless) and rt_render_device."""
+    sc = scenes.default_scene()
+    ctx.set_scene(sc)
+    w, h, n = 96, 54, 19
+    cams = np.stack([scenes.make_camera(pos=(0.05 * i, 0.02 * i, -0.1 * i), yaw=0.01 * i, width=w, height=h) for i in range(n)])
+    batch, _ = ctx.render_batch(cams, w, h, 8, headless=False)
+    fb = ctx.dev_alloc(n * w * h * 4)
+    ctx.render_device(cams, w, h, 8, 1, 0, fb); ctx.sync()
+    dev = ctx.dev_to_host(fb, n * w * h * 4).reshape(n, h, w)
+    ctx.dev_free(fb)
+    for i in range(n):
+        ref = O.render(sc, cams[i], w, h, 8)["pixels"]
+        assert np.array_equal(batch[i], ref), i
+        assert np.array_equal(dev[i], ref), i
+    ctx.render_batch(cams, w, h, 8, headless=True)
+
+
 def test_batch_equals_single_frames(ctx):
     sc = scenes.default_scene()
     ctx.set_scene(sc)

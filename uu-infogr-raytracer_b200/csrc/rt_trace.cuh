@@ -255,17 +255,17 @@ RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& d
             float I = occ ? 0.0f : l.intensity;                   // :581
             // ShapePhongShading :665-695
             f3 L = normalize3(sub3(l.p, hit));                    // :667
-            f3 ph = mulf3(m.kd, cs_maxf(0.0f, dot3(N, L)));       // :672-678 (IsDiffuse holds inside this loop)
+            f3 ph = mulf3(m.kd, cs_max0(dot3(N, L)));       // :672-678 (IsDiffuse holds inside this loop)
             if (m.flags & MAT_SPEC) {                             // :682
                 f3 rv = sub3(L, mulf3(N, 2 * dot3(L, N)));        // :683-684
                 float s = dot3(V, normalize3(rv));                // :685-688
-                float pw = spec_pow(cs_maxf(0.0f, s), m.n);       // :691
+                float pw = spec_pow(cs_max0(s), m.n);       // :691
                 ph = add3(ph, mulv3(m.ks, splat3(pw)));           // :690-694
                 dbg.spec();
             }
             float ia = I * att;                                   // (I,I,I) * att
             f3 t = mulf3(mulv3(splat3(ia), ph), tile);            // :868-869 / :774
-            if (is_plane) t = mk3(cs_maxf(t.x, 0.0f), cs_maxf(t.y, 0.0f), cs_maxf(t.z, 0.0f));   // :775 (.Max(0))
+            if (is_plane) t = mk3(cs_max0(t.x), cs_max0(t.y), cs_max0(t.z));   // :775 (.Max(0))
             col = add3(col, t);
         }
     }

@@ -56,8 +56,8 @@ struct FrameParams {
     int chunks_per_tile;        // ceil(tile_rows * w / (BLOCK * pixels per thread))
     long long frame_stride;     // pixels between consecutive frames in `out`
     uint32_t* out;              // framebuffer(s): 0x00RRGGBB, row-major (Surface.pixels, surface.cs:9-20)
-    const CamRec* cams;         // n_frames cameras (device), or nullptr => cam_inline
-    CamRec cam_inline[INLINE_CAMS];   // small batches travel in the parameter block: no upload, no host sync
+    CamRec cam_inline[INLINE_CAMS];   // the launch's cameras travel in the parameter block (constant bank): no upload, no host
+                                      // sync; batches of more than INLINE_CAMS frames are split into several launches
 };
 
 struct DebugOut {
@@ -83,7 +83,7 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
         const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
         if (p0 >= end) continue;
-        const CamRec& cam = fp.cams ? fp.cams[frame] : fp.cam_inline[frame];
+        const CamRec& cam = fp.cam_inline[frame];               // constant bank (LDC); batches > INLINE_CAMS are split on the host
         uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
         uint32_t px[PPT];
         int y = p0 / fp.w, x = p0 - y * fp.w;                  // one division per thread; then step along the row
@@ -92,7 +92,8 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
             uint32_t c = (p0 + q < end) ? trace_pixel(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg) : 0u;
             if (++x == fp.w) { x = 0; ++y; }
 #pragma unroll
-            for (int z = 0; z < PPT; z++) if (z == q) px[z] = c;   // keeps px[] in registers under `unroll 1`
+            for (int z = 0; z + 1 < PPT; z++) px[z] = px[z + 1];   // shift register: after PPT iterations px[] is in pixel order
+            px[PPT - 1] = c;
         }
         if (PPT == 4 && p0 + PPT <= end && ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0)) {
             *reinterpret_cast<uint4*>(out + p0) = make_uint4(px[0], px[PPT > 1 ? 1 : 0], px[PPT > 2 ? 2 : 0], px[PPT > 3 ? 3 : 0]);   // 128-bit coalesced store
@@ -209,7 +210,6 @@ struct DeviceState {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // scene
     f4* sgeom = nullptr; MatRec* smat = nullptr; PlaneRec* planes = nullptr; LightRec* lights = nullptr;
-    CamRec* cams = nullptr; int cams_cap = 0;
     LbvhDevice bvh;
     float bvh_cam[3] = {0, 0, 0}; bool bvh_cam_valid = false;    // camera the nodes_cam copy is currently inflated for ...
     cudaStream_t bvh_cam_stream = nullptr;                        // ... by a refit issued on this stream
@@ -309,7 +309,6 @@ FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp,
     fp.chunks_per_tile = (int)(((long long)fp.tile_rows * w + chunk - 1) / chunk);
     fp.frame_stride = frame_stride;
     fp.out = out;
-    fp.cams = nullptr;
     return fp;
 }
 
@@ -331,12 +330,8 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
         // the camera-inflated BVH copy is per frame: one refit + one launch per frame, back to back on the stream
         for (int f = 0; f < fp.n_frames; f++) {
             FrameParams one = fp;
-            one.n_frames = 1; one.cams = nullptr;
-            if (fp.cams) {
-                cudaError_t e = cudaMemcpyAsync(&one.cam_inline[0], fp.cams + f, sizeof(CamRec), cudaMemcpyDeviceToHost, stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-                if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("camera readback: ") + cudaGetErrorString(e));
-            } else one.cam_inline[0] = fp.cam_inline[f];
+            one.n_frames = 1;
+            one.cam_inline[0] = fp.cam_inline[f];
             one.out = fp.out + (long long)f * fp.frame_stride;
             int rc = launch_render(ctx, d, one, stream);
             if (rc) return rc;
@@ -364,20 +359,6 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
     }
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
-    return RT_OK;
-}
-
-int upload_cams(rt_context* ctx, DeviceState& d, const rt_camera* cams, int n, cudaStream_t stream) {
-    if (d.cams_cap < n) {
-        if (d.cams) CU_TRY(ctx, cudaFree(d.cams));
-        d.cams = nullptr; d.cams_cap = 0;
-        CU_TRY(ctx, cudaMalloc(&d.cams, sizeof(CamRec) * (size_t)n));
-        d.cams_cap = n;
-    }
-    std::vector<CamRec> h((size_t)n);
-    for (int i = 0; i < n; i++) h[i] = to_cam(cams[i]);
-    CU_TRY(ctx, cudaMemcpyAsync(d.cams, h.data(), sizeof(CamRec) * (size_t)n, cudaMemcpyHostToDevice, stream));
-    CU_TRY(ctx, cudaStreamSynchronize(stream));   // h goes out of scope
     return RT_OK;
 }
 
@@ -445,7 +426,7 @@ int rt_destroy(rt_context* ctx) {
         cudaSetDevice(d.dev);
         cudaStreamSynchronize(d.stream);
         free_scene(d);
-        cudaFree(d.cams); cudaFree(d.fb);
+        cudaFree(d.fb);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.evc0) cudaEventDestroy(d.evc0);
@@ -560,10 +541,15 @@ int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int w
     DeviceState& d = ctx->devs[0];
     CU_TRY(ctx, cudaSetDevice(d.dev));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    FrameParams fp = make_params(ctx, w, h, depth, spp, seed, n_frames, ctx->rank, ctx->world, (uint32_t*)dev_pixels, (long long)w * h);
-    if (n_frames <= INLINE_CAMS) for (int i = 0; i < n_frames; i++) fp.cam_inline[i] = to_cam(cams[i]);
-    else { rc = upload_cams(ctx, d, cams, n_frames, st); if (rc) return rc; fp.cams = d.cams; }
-    return launch_render(ctx, d, fp, st);
+    for (int f0 = 0; f0 < n_frames; f0 += INLINE_CAMS) {          // <= INLINE_CAMS frames per launch (cameras in the parameter block)
+        const int nf = n_frames - f0 < INLINE_CAMS ? n_frames - f0 : INLINE_CAMS;
+        FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, ctx->rank, ctx->world,
+                                     (uint32_t*)dev_pixels + (size_t)f0 * w * h, (long long)w * h);
+        for (int i = 0; i < nf; i++) fp.cam_inline[i] = to_cam(cams[f0 + i]);
+        rc = launch_render(ctx, d, fp, st);
+        if (rc) return rc;
+    }
+    return RT_OK;
 }
 
 // Renders n_frames frames into device 0's framebuffer ring and, if host_pixels != NULL, returns them to the host.
@@ -595,7 +581,8 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
     if (band_tiles < world) band_tiles = world;
     n_bands = (tiles_total + band_tiles - 1) / band_tiles;
     const bool pipelined = host_pixels != nullptr;
-    const int n_segments = pipelined ? n_frames * n_bands : 1;
+    const int n_groups = (n_frames + INLINE_CAMS - 1) / INLINE_CAMS;      // headless: one launch per <= INLINE_CAMS frames
+    const int n_segments = pipelined ? n_frames * n_bands : n_groups;
     if (pipelined) {
         for (int g = 0; g < G; g++) {
             DeviceState& d = ctx->devs[(size_t)g];
@@ -609,28 +596,27 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
     for (int g = 0; g < G; g++) {
         DeviceState& d = ctx->devs[(size_t)g];
         CU_TRY(ctx, cudaSetDevice(d.dev));
-        if (!pipelined && n_frames > INLINE_CAMS) { rc = upload_cams(ctx, d, cams, n_frames, d.stream); if (rc) return rc; }
         CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
     }
     const long long tile_pix = (long long)ctx->tile_rows * w;
     bool first_copy = true;
     for (int s = 0; s < n_segments; s++) {
-        const int frame = pipelined ? s / n_bands : 0, band = pipelined ? s % n_bands : 0;
+        const int frame = pipelined ? s / n_bands : s * INLINE_CAMS, band = pipelined ? s % n_bands : 0;
+        const int nf = pipelined ? 1 : (n_frames - frame < INLINE_CAMS ? n_frames - frame : INLINE_CAMS);
         for (int g = 0; g < G; g++) {
             DeviceState& d = ctx->devs[(size_t)g];
             CU_TRY(ctx, cudaSetDevice(d.dev));
             const int rank = G > 1 ? g : ctx->rank;
-            FrameParams fp = make_params(ctx, w, h, depth, spp, seed, pipelined ? 1 : n_frames, rank, world,
-                                         d0.fb + (pipelined ? (size_t)frame * npix : 0), (long long)npix);
+            FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, rank, world, d0.fb + (size_t)frame * npix, (long long)npix);
             if (pipelined) {
                 fp.cam_inline[0] = to_cam(cams[frame]);
                 const int k0 = band * (band_tiles / world), k1 = k0 + band_tiles / world;       // this rank's tiles of the band
                 const int mine = fp.tiles_mine;
                 fp.k_begin = k0 < mine ? k0 : mine;
                 fp.tiles_mine = (k1 < mine ? k1 : mine) - fp.k_begin;
-            } else if (n_frames <= INLINE_CAMS) {
-                for (int i = 0; i < n_frames; i++) fp.cam_inline[i] = to_cam(cams[i]);
-            } else fp.cams = d.cams;
+            } else {
+                for (int i = 0; i < nf; i++) fp.cam_inline[i] = to_cam(cams[frame + i]);
+            }
             rc = launch_render(ctx, d, fp, d.stream); if (rc) return rc;
             if (pipelined) CU_TRY(ctx, cudaEventRecord(d.band_events[(size_t)s], d.stream));
         }

@@ -76,6 +76,12 @@ int rt_create(rt_context** out, const int* device_ids, int n_devices);
 int rt_set_scene(rt_context* ctx, const float* spheres, int n_spheres, const float* planes, int n_planes,
                  const float* lights, int n_lights, const float ambient[3], int accel);
 
+/* Replaces the records of spheres [first, first + count) (same 18-float layout) without rebuilding the acceleration
+ * structure: an LBVH keeps its topology and is refitted bottom-up (results stay exact; traversal slows down if spheres move
+ * far from where they were when rt_set_scene built the tree — call rt_set_scene again to rebuild).  The reference's scene
+ * arrays are readonly (RayTracer.cs:441-465); this is the scene-mutation hook of SURVEY §8(f). */
+int rt_update_spheres(rt_context* ctx, const float* spheres, int first, int count);
+
 /* Renders one frame — the replacement for the loop RayTracer.cs:898-901 (TracePixel for every x,y).
  *   max_depth : the reference's ReflectionRecursionLimit (32)   spp : 1 in the reference; >1 = jittered extension
  *   host_pixels: w*h int32, 0x00RRGGBB, row-major (`Surface.pixels`, surface.cs:9-20; written as :1038); NULL => headless

@@ -132,3 +132,40 @@ def test_config4_100k_lbvh_vs_oracle_subset(rt):
     assert np.array_equal(dbg["hash"].reshape(-1)[idx], ref["hash"])
     assert np.array_equal(dbg["pixels"], px)
     ctx.close()
+
+
+@pytest.mark.parametrize("n,accel_name", [(3, "tiny"), (300, "brute"), (300, "lbvh"), (20000, "lbvh")])
+def test_update_spheres_refit_stays_exact(rt, n, accel_name):
+    """rt_update_spheres (scene mutation + LBVH refit): after moving / resizing / re-materialising spheres the
+    frame must equal the oracle on the new scene and a freshly built context, on every scene path."""
+    accel = {"tiny": rt.RT_ACCEL_AUTO, "brute": rt.RT_ACCEL_BRUTE, "lbvh": rt.RT_ACCEL_LBVH}[accel_name]
+    sc = scenes.default_scene() if n == 3 else scenes.Scene(scenes.random_spheres_scene(n, 77, 30.0, 4.0, 64.0, "m")[0],
+                                                           scenes.default_scene().planes, scenes.config3_scene().lights, scenes.REF_AMBIENT)
+    w, h = 320, 180
+    cam = scenes.make_camera(width=w, height=h, **(dict() if n == 3 else scenes.SCALED_CAMERA))
+    ctx = rt.Context([0]); ctx.set_scene(sc, accel)
+    before, _ = ctx.render(cam, w, h, 8)
+    rng = np.random.default_rng(5)
+    moved = sc.spheres.copy()
+    k = max(1, n // 3)
+    idx0 = n // 4
+    moved[idx0:idx0 + k, 0:3] += rng.normal(size=(k, 3)).astype(np.float32) * np.float32(0.8)     # move
+    moved[idx0:idx0 + k, 3] *= rng.uniform(0.6, 1.5, k).astype(np.float32)                         # resize
+    moved[idx0:idx0 + k, 17] = moved[idx0:idx0 + k, 3] * moved[idx0:idx0 + k, 3]
+    moved[idx0, 4:17] = scenes.mat_mirror((0.8, 0.8, 0.8))                                         # new material
+    ctx.update_spheres(moved[idx0:idx0 + k], first=idx0)
+    sc2 = scenes.Scene(moved, sc.planes, sc.lights, sc.ambient)
+    got, _ = ctx.render(cam, w, h, 8)
+    fresh = rt.Context([0]); fresh.set_scene(sc2, accel)
+    ref_gpu, _ = fresh.render(cam, w, h, 8)
+    fresh.close()
+    assert not np.array_equal(got, before)
+    assert np.array_equal(got, ref_gpu)
+    if n <= 300:
+        assert np.array_equal(got, O.render(sc2, cam, w, h, 8)["pixels"])
+    else:
+        sub = np.random.default_rng(7).choice(w * h, 3000, replace=False).astype(np.int32)
+        assert np.array_equal(got.reshape(-1)[sub], O.render(sc2, cam, w, h, 8, subset=sub)["pixels"])
+    with pytest.raises(rt.RtError):
+        ctx.update_spheres(moved[:2], first=n - 1)          # out of range
+    ctx.close()

@@ -51,11 +51,17 @@ __device__ __forceinline__ void store_child_box_volatile(BvhNode* nd, int which,
     p[0] = b.lox; p[1] = b.loy; p[2] = b.loz; p[4] = b.hix; p[5] = b.hiy; p[6] = b.hiz;
 }
 
-__global__ void k_lbvh_refit(const f4* sorted, const float* radius_eff, const int* orig, int n, BvhNode* nodes,
+// Effective radius of a leaf box: the reference's test only ever sees radiusSquared (:619), so sqrt(r^2) rounded up.
+__device__ __forceinline__ float effective_radius(float r2) { return sqrtf(r2 > 0.0f ? r2 : 0.0f) * 1.000001f + 1e-30f; }
+
+// Bottom-up refit. `sgeom` != nullptr: first re-gather the leaf geometry from the (updated) original-order array.
+__global__ void k_lbvh_refit(f4* sorted, const f4* sgeom, const int* orig, int n, BvhNode* nodes,
                              const int* parent_node, const int* parent_leaf, int* arrivals) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    BvhBox box = sphere_box(sorted[j], radius_eff[orig[j]]);
+    if (sgeom) sorted[j] = sgeom[orig[j]];
+    const f4 g = sorted[j];
+    BvhBox box = sphere_box(g, effective_radius(g.w));
     int enc = parent_leaf[j];
     while (enc >= 0) {
         const int node = enc >> 1, side = enc & 1;
@@ -96,6 +102,15 @@ struct LbvhDevice {
         cudaFree(nodes); cudaFree(nodes_cam); cudaFree(sorted); cudaFree(orig); cudaFree(parent_node); cudaFree(parent_leaf); cudaFree(arrivals);
         nodes = nullptr; nodes_cam = nullptr; sorted = nullptr; orig = nullptr; parent_node = nullptr; parent_leaf = nullptr; arrivals = nullptr; n = 0;
     }
+    // Refit after the sphere records changed (rt_update_spheres): same topology, new leaf geometry and boxes.
+    cudaError_t refit_geometry(const f4* sgeom_dev, cudaStream_t stream) {
+        if (n < 2) return cudaSuccess;
+        cudaError_t e = cudaMemsetAsync(arrivals, 0, sizeof(int) * (size_t)n, stream);
+        if (e != cudaSuccess) return e;
+        const int B = 256, G = (n + B - 1) / B;
+        k_lbvh_refit<<<G, B, 0, stream>>>(sorted, sgeom_dev, orig, n, nodes, parent_node, parent_leaf, arrivals);
+        return cudaGetLastError();
+    }
     // Re-inflates nodes_cam for rays starting at (cx, cy, cz). Asynchronous on `stream`.
     cudaError_t refit_for_camera(float cx, float cy, float cz, cudaStream_t stream) {
         if (n < 2) return cudaSuccess;
@@ -107,20 +122,19 @@ struct LbvhDevice {
     }
 };
 
-// Builds the LBVH on the current device. sgeom_dev: n records (cx,cy,cz,r2) in ORIGINAL order; radius_eff_host: n radii
-// (sqrt of radiusSquared, rounded up); bmin/bmax: bounds of the centres. Returns cudaSuccess or the failing error.
-inline cudaError_t lbvh_build(const f4* sgeom_dev, const float* radius_eff_host, int n, const float bmin[3], const float bmax[3],
+// Builds the LBVH on the current device. sgeom_dev: n records (cx,cy,cz,r2) in ORIGINAL order; bmin/bmax: bounds of the
+// centres. Returns cudaSuccess or the failing error.
+inline cudaError_t lbvh_build(const f4* sgeom_dev, int n, const float bmin[3], const float bmax[3],
                               float r2max, cudaStream_t stream, LbvhDevice* out, uint64_t* launches) {
     out->release();
     if (n < 2) return cudaSuccess;
     cudaError_t e;
-    uint64_t *keys = nullptr, *keys_sorted = nullptr; float* radius = nullptr; int *pn = nullptr, *pl = nullptr, *arr = nullptr;
+    uint64_t *keys = nullptr, *keys_sorted = nullptr; int *pn = nullptr, *pl = nullptr, *arr = nullptr;
     (void)pn; (void)pl; (void)arr;
     void* tmp = nullptr; size_t tmp_bytes = 0;
 #define LB_TRY(x) do { e = (x); if (e != cudaSuccess) goto fail; } while (0)
     LB_TRY(cudaMalloc(&keys, sizeof(uint64_t) * (size_t)n));
     LB_TRY(cudaMalloc(&keys_sorted, sizeof(uint64_t) * (size_t)n));
-    LB_TRY(cudaMalloc(&radius, sizeof(float) * (size_t)n));
     LB_TRY(cudaMalloc(&out->parent_node, sizeof(int) * (size_t)n));
     LB_TRY(cudaMalloc(&out->parent_leaf, sizeof(int) * (size_t)n));
     LB_TRY(cudaMalloc(&out->arrivals, sizeof(int) * (size_t)n));
@@ -129,7 +143,6 @@ inline cudaError_t lbvh_build(const f4* sgeom_dev, const float* radius_eff_host,
     LB_TRY(cudaMalloc(&out->nodes_cam, sizeof(BvhNode) * (size_t)(n - 1)));
     LB_TRY(cudaMalloc(&out->sorted, sizeof(f4) * (size_t)n));
     LB_TRY(cudaMalloc(&out->orig, sizeof(int) * (size_t)n));
-    LB_TRY(cudaMemcpyAsync(radius, radius_eff_host, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, stream));
     LB_TRY(cudaMemsetAsync(arr, 0, sizeof(int) * (size_t)n, stream));
     {
         float binv[3];
@@ -144,7 +157,7 @@ inline cudaError_t lbvh_build(const f4* sgeom_dev, const float* radius_eff_host,
         LB_TRY(cudaGetLastError());
         k_lbvh_karras<<<G, B, 0, stream>>>(keys_sorted, n, out->nodes, pn, pl);
         LB_TRY(cudaGetLastError());
-        k_lbvh_refit<<<G, B, 0, stream>>>(out->sorted, radius, out->orig, n, out->nodes, pn, pl, arr);
+        k_lbvh_refit<<<G, B, 0, stream>>>(out->sorted, nullptr, out->orig, n, out->nodes, pn, pl, arr);
         LB_TRY(cudaGetLastError());
         // the camera copy shares the topology; its boxes are written by refit_for_camera before every frame
         LB_TRY(cudaMemcpyAsync(out->nodes_cam, out->nodes, sizeof(BvhNode) * (size_t)(n - 1), cudaMemcpyDeviceToDevice, stream));
@@ -157,7 +170,7 @@ inline cudaError_t lbvh_build(const f4* sgeom_dev, const float* radius_eff_host,
 fail:
     out->release();
 done:
-    cudaFree(keys); cudaFree(keys_sorted); cudaFree(radius); cudaFree(tmp);
+    cudaFree(keys); cudaFree(keys_sorted); cudaFree(tmp);
 #undef LB_TRY
     return e;
 }

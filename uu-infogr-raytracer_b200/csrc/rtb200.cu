@@ -490,19 +490,16 @@ int rt_set_scene(rt_context* ctx, const float* spheres, int ns, const float* pla
     if (want_bvh) {
         // bounds of the centres, effective radii (the reference's test only ever sees radiusSquared, :619) — O(n) on the host
         float bmin[3] = {sg[0].x, sg[0].y, sg[0].z}, bmax[3] = {sg[0].x, sg[0].y, sg[0].z}, r2max = 0.0f;
-        std::vector<float> reff((size_t)ns);
         for (int i = 0; i < ns; i++) {
             const f4& g = sg[(size_t)i];
             bmin[0] = fminf(bmin[0], g.x); bmin[1] = fminf(bmin[1], g.y); bmin[2] = fminf(bmin[2], g.z);
             bmax[0] = fmaxf(bmax[0], g.x); bmax[1] = fmaxf(bmax[1], g.y); bmax[2] = fmaxf(bmax[2], g.z);
-            float r2 = g.w > 0.0f ? g.w : 0.0f;
-            reff[(size_t)i] = sqrtf(r2) * 1.000001f + 1e-30f;
-            if (r2 > r2max) r2max = r2;
+            if (g.w > r2max) r2max = g.w;
         }
         for (auto& d : ctx->devs) {
             CU_TRY(ctx, cudaSetDevice(d.dev));
             uint64_t nl = 0;
-            cudaError_t e = lbvh_build(d.sgeom, reff.data(), ns, bmin, bmax, r2max, d.stream, &d.bvh, &nl);
+            cudaError_t e = lbvh_build(d.sgeom, ns, bmin, bmax, r2max, d.stream, &d.bvh, &nl);
             if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh_build: ") + cudaGetErrorString(e));
             ctx->launches += nl;
         }
@@ -521,6 +518,38 @@ int rt_set_scene(rt_context* ctx, const float* spheres, int ns, const float* pla
     }
     ctx->accel = accel;
     ctx->has_scene = true;
+    return RT_OK;
+}
+
+int rt_update_spheres(rt_context* ctx, const float* spheres, int first, int count) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_set_scene has not been called");
+    const int ns = ctx->gdata_host.ns;
+    if (count < 0 || first < 0 || first + count > ns || (count > 0 && !spheres)) return fail(ctx, RT_ERR_INVALID, "sphere range out of bounds");
+    if (count == 0) return RT_OK;
+    std::vector<f4> sg((size_t)count); std::vector<MatRec> sm((size_t)count);
+    float r2max = 0.0f;
+    for (int i = 0; i < count; i++) {
+        const float* f = spheres + 18 * (size_t)i;
+        sg[(size_t)i].x = f[0]; sg[(size_t)i].y = f[1]; sg[(size_t)i].z = f[2]; sg[(size_t)i].w = f[17];
+        sm[(size_t)i] = make_mat(f + 4);
+        if (f[17] > r2max) r2max = f[17];
+    }
+    if (ctx->tiny) for (int i = 0; i < count; i++) { ctx->tiny_data.sgeom[first + i] = sg[(size_t)i]; ctx->tiny_data.smat[first + i] = sm[(size_t)i]; }
+    for (auto& d : ctx->devs) {
+        CU_TRY(ctx, cudaSetDevice(d.dev));
+        CU_TRY(ctx, cudaMemcpyAsync(d.sgeom + first, sg.data(), sizeof(f4) * (size_t)count, cudaMemcpyHostToDevice, d.stream));
+        CU_TRY(ctx, cudaMemcpyAsync(d.smat + first, sm.data(), sizeof(MatRec) * (size_t)count, cudaMemcpyHostToDevice, d.stream));
+        if (ctx->has_bvh) {
+            // Same topology, new leaf geometry and boxes (bottom-up refit). The pad bound only ever grows (conservative).
+            if (r2max > d.bvh.r2max) d.bvh.r2max = r2max;
+            cudaError_t e = d.bvh.refit_geometry(d.sgeom, d.stream);
+            if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh refit: ") + cudaGetErrorString(e));
+            d.bvh_cam_valid = false;
+            ctx->launches++;
+        }
+        CU_TRY(ctx, cudaStreamSynchronize(d.stream));     // sg / sm go out of scope; later launches may use another stream
+    }
     return RT_OK;
 }
 

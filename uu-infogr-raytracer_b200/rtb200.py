@@ -25,7 +25,7 @@ COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_
                  "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"]
 
 # every symbol include/rtb200.h declares
-ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_render", "rt_render_batch", "rt_render_debug", "rt_query_spheres",
+ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_update_spheres", "rt_render", "rt_render_batch", "rt_render_debug", "rt_query_spheres",
                "rt_set_partition", "rt_render_device", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_dev_alloc",
                "rt_dev_free", "rt_dev_to_host", "rt_sync", "rt_host_register", "rt_host_unregister", "rt_launch_count", "rt_destroy", "rt_last_error", "rt_abi_version"]
 
@@ -62,6 +62,7 @@ def load_library():
     camp, statp = C.POINTER(RtCamera), C.POINTER(RtStats)
     lib.rt_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
     lib.rt_set_scene.argtypes = [vp, fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, C.c_int]
+    lib.rt_update_spheres.argtypes = [vp, fp, C.c_int, C.c_int]
     lib.rt_render.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, ip, statp]
     lib.rt_render_batch.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, ip, statp]
     lib.rt_render_debug.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, ip, C.POINTER(C.c_uint32), ip, fp,
@@ -137,6 +138,10 @@ class Context:
         self.n_spheres = len(scene.spheres)
         self._check(self.lib.rt_set_scene(self.h, _fp(scene.spheres), len(scene.spheres), _fp(scene.planes), len(scene.planes),
                                           _fp(scene.lights), len(scene.lights), _fp(scene.ambient), accel))
+
+    def update_spheres(self, spheres, first=0):
+        spheres = np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1, 18)
+        self._check(self.lib.rt_update_spheres(self.h, _fp(spheres), first, len(spheres)))
 
     def render(self, cam15, w, h, max_depth=32, spp=1, seed=0, headless=False, out: Optional[np.ndarray] = None):
         """One frame through rt_render (host buffer, D2H inside). Returns (pixels int32[h,w] or None, RtStats)."""

@@ -116,3 +116,18 @@ def test_config3_frame_lbvh_equals_oracle(built):
     b = E.render(sc, cam, w, h, 8, tiny=3, debug=True)
     assert np.array_equal(a["pixels"], b["pixels"]) and np.array_equal(a["hash"], b["hash"])
     assert (a["pixels"] != 0).mean() > 0.5
+
+
+def test_axis_parallel_rays_inside_boxes_straddling_zero(built):
+    """Regression: with an infinite reciprocal direction the FMA slab test gave inf - inf = NaN on one face and +inf on the
+    other for boxes that straddle 0 on an axis the ray is parallel to, culling boxes the origin is inside (caught by the frame
+    test through a light with a zero coordinate, whose position is the shadow ray's direction, RayTracer.cs:574)."""
+    rng = np.random.default_rng(9)
+    sph = np.stack([mk(rng.uniform(-4, 4, 3), rng.uniform(0.2, 0.6)) for _ in range(300)])
+    n = 30000
+    o = rng.uniform(-4, 4, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32) * 5
+    d[: n // 3, 0] = 0; d[n // 3: 2 * n // 3, 1] = 0; d[2 * n // 3:, 2] = 0
+    d[: n // 6, 1] = 0                                   # two zero components
+    d[n // 2: n // 2 + 2000] *= np.float32(1e-20)        # tiny but non-zero components
+    check(sph, np.concatenate([o, d], 1))

@@ -136,25 +136,48 @@ RT_HD float inflated_radius(float r2, float oc2) {
 
 // Entry parameter of the ray into the box inflated by pad (conservative), or +inf when it misses t in [0, tmax].
 // PAD = false: the box is already inflated for this ray origin (nodes_cam).
+// The box test is NOT part of the reference's arithmetic — only its conservativeness matters — so it may use FMA:
+// t = fma(bound, 1/d, -o/d) (noi = -o * inv, per ray). A NaN (inf - inf on an axis with d == 0) is dropped by
+// fminf / fmaxf, i.e. that axis stops constraining: never a false miss.
+RT_HD float rt_fmaf(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
 template <bool PAD>
-RT_HD float box_entry(f3 o, f3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float r2max, float tmax) {
+RT_HD float box_entry(f3 o, f3 inv, f3 noi, float lox, float loy, float loz, float hix, float hiy, float hiz, float r2max, float tmax) {
     float pad = 0.0f;
     if (PAD) {
         float dx = fmaxf(fabsf(lox - o.x), fabsf(hix - o.x));
         float dy = fmaxf(fabsf(loy - o.y), fabsf(hiy - o.y));
         float dz = fmaxf(fabsf(loz - o.z), fabsf(hiz - o.z));
-        pad = BVH_PAD_K * approx_sqrt(dx * dx + dy * dy + dz * dz + r2max);
+        pad = BVH_PAD_K * approx_sqrt(rt_fmaf(dx, dx, rt_fmaf(dy, dy, rt_fmaf(dz, dz, r2max))));
     }
-    float t0x = (lox - pad - o.x) * inv.x, t1x = (hix + pad - o.x) * inv.x;
-    float t0y = (loy - pad - o.y) * inv.y, t1y = (hiy + pad - o.y) * inv.y;
-    float t0z = (loz - pad - o.z) * inv.z, t1z = (hiz + pad - o.z) * inv.z;
-    // fminf/fmaxf drop NaNs (0 * inf when the origin sits exactly on an inflated face of a parallel slab)
+    float t0x = rt_fmaf(lox - pad, inv.x, noi.x), t1x = rt_fmaf(hix + pad, inv.x, noi.x);
+    float t0y = rt_fmaf(loy - pad, inv.y, noi.y), t1y = rt_fmaf(hiy + pad, inv.y, noi.y);
+    float t0z = rt_fmaf(loz - pad, inv.z, noi.z), t1z = rt_fmaf(hiz + pad, inv.z, noi.z);
     float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
     float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
     return (tn <= tf * BVH_T_SLACK) ? tn : RT_INF;
 }
 
-RT_HD f3 safe_inv(f3 d) { return mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
+// Reciprocal direction for the slab test, kept FINITE: a component below 1e-12 of the largest one (incl. exact zeros:
+// axis-parallel rays, e.g. a light with a zero coordinate used as shadow direction, RayTracer.cs:574) is treated as that
+// threshold. With an infinite reciprocal the FMA form fma(bound, inv, -o*inv) yields inf - inf = NaN on one face and +inf on
+// the other, which would cull a box the origin is inside. The substitution only affects culling and stays conservative: it
+// tilts the ray by <= 1e-12 rad, far inside the pad. Directions whose largest component is outside [1e-12, 1e12] (zero
+// vectors, denormal or non-finite directions) do not traverse at all: bvh_* hands them to the brute-force loop.
+RT_HD float dir_scale(f3 d) { return fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fabsf(d.z)); }
+RT_HD bool dir_in_envelope(float m) { return m >= 1e-12f && m <= 1e12f; }      // false for NaN
+RT_HD float finite_rcp(float d, float thr) {
+    float ad = fabsf(d);
+    float r = 1.0f / (ad < thr ? thr : ad);
+    return (f2bits(d) >> 31) ? -r : r;
+}
+RT_HD f3 safe_inv(f3 d, float m) { float thr = m * 1e-12f; return mk3(finite_rcp(d.x, thr), finite_rcp(d.y, thr), finite_rcp(d.z, thr)); }
+RT_HD f3 neg_o_inv(f3 o, f3 inv) { return mk3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z); }
 
 // Nearest fold.  off == 0: primary (:977).  off == 0.01f: secondary (:804-805), exact incl. its order dependence.
 // BRUTE is a callable fallback  void(int* sel, float* t)  running the reference loop.
@@ -162,7 +185,11 @@ template <class DBG, class BRUTE>
 RT_HD void bvh_nearest(const BvhView& bv, f3 o, f3 dir, float a2, float a4, float off, int* sel, float* dsel, DBG& dbg, BRUTE brute) {
     const bool secondary = off != 0.0f;
     const float window = secondary ? BVH_WINDOW : 0.0f;
-    const f3 inv = safe_inv(dir);
+    const float dscale = dir_scale(dir);
+    if (dscale == 0.0f) { *sel = -1; *dsel = RT_INF; return; }      // zero direction: a = 0 -> every test is 0/0 = NaN -> miss
+    if (!dir_in_envelope(dscale)) { dbg.fallback(); brute(sel, dsel); return; }
+    const f3 inv = safe_inv(dir, dscale);
+    const f3 noi = neg_o_inv(o, inv);
     int best = -1; float best_t = RT_INF;                // lexicographic min over (t, original index)
     int cand_i[BVH_CAND]; float cand_t[BVH_CAND]; int ncand = 0; bool overflow = false;
     int stack[BVH_STACK]; int sp = 0;
@@ -177,11 +204,11 @@ RT_HD void bvh_nearest(const BvhView& bv, f3 o, f3 dir, float a2, float a4, floa
         const float bound = (best_t + window) * BVH_T_SLACK;
         float e0, e1;
         if (cam_boxes) {
-            e0 = box_entry<false>(o, inv, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, bound);
-            e1 = box_entry<false>(o, inv, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, bound);
+            e0 = box_entry<false>(o, inv, noi, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, bound);
+            e1 = box_entry<false>(o, inv, noi, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, bound);
         } else {
-            e0 = box_entry<true>(o, inv, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, bound);
-            e1 = box_entry<true>(o, inv, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, bound);
+            e0 = box_entry<true>(o, inv, noi, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, bound);
+            e1 = box_entry<true>(o, inv, noi, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, bound);
         }
         int c0 = nd.c0, c1 = nd.c1;
         if (e1 < e0) { float te = e0; e0 = e1; e1 = te; int tc = c0; c0 = c1; c1 = tc; }   // near child first
@@ -235,17 +262,21 @@ RT_HD void bvh_nearest(const BvhView& bv, f3 o, f3 dir, float a2, float a4, floa
 }
 
 // Shadow any-hit (:573-582): eps = 0.001, unbounded t, boolean result.
-template <class DBG>
-RT_HD bool bvh_shadow_any(const BvhView& bv, f3 hit, f3 lp, float a2, float a4, DBG& dbg) {
-    const f3 inv = safe_inv(lp);
+template <class DBG, class BRUTE>
+RT_HD bool bvh_shadow_any(const BvhView& bv, f3 hit, f3 lp, float a2, float a4, DBG& dbg, BRUTE brute) {
+    const float dscale = dir_scale(lp);
+    if (dscale == 0.0f) return false;                                   // e.g. a light at the origin (:574): never occluded
+    if (!dir_in_envelope(dscale)) { dbg.fallback(); return brute(); }
+    const f3 inv = safe_inv(lp, dscale);
+    const f3 noi = neg_o_inv(hit, inv);
     int stack[BVH_STACK]; int sp = 0;
     int node = 0;
     bool occluded = false;
     for (;;) {
         const BvhNode nd = bv.nodes[node];
         dbg.node_visit(2);
-        float e0 = box_entry<true>(hit, inv, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, RT_INF);
-        float e1 = box_entry<true>(hit, inv, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, RT_INF);
+        float e0 = box_entry<true>(hit, inv, noi, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, RT_INF);
+        float e1 = box_entry<true>(hit, inv, noi, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, RT_INF);
         int next = -1;
 #pragma unroll
         for (int k = 0; k < 2; k++) {

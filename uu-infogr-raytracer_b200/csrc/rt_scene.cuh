@@ -126,7 +126,8 @@ struct LbvhScene : GlobalScene {
                     [&](int* s2, float* t2) { NoDbg nd; brute_nearest<-1>(base, o, d, a2, a4, off, s2, t2, nd); });
     }
     template <class DBG> RT_HD bool shadow_any(f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
-        return bvh_shadow_any(bv, hit, lp, a2, a4, dbg);
+        const GlobalScene& base = *this;
+        return bvh_shadow_any(bv, hit, lp, a2, a4, dbg, [&]() { NoDbg nd; return brute_shadow_any<-1>(base, hit, lp, a2, a4, nd); });
     }
 };
 

@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16, help="4K frames per step (ring of framebuffers > L2)")
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compaction", type=int, default=0, help="1: opt-in warp-ballot compaction kernel variant (tuning)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,6 +175,8 @@ def main():
     ctx = rtb200.Context([local_rank])
     ctx.set_scene(sc)
     ctx.set_partition(rank, world, args.tile_rows)
+    if args.compaction:
+        ctx.set_option(rtb200.RT_OPT_COMPACTION, 1)
 
     # ray / flop accounting from the instrumented kernel (not timed); identical on every rank
     dbg = ctx.render_debug(cam, W, H, DEPTH)

@@ -110,6 +110,11 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int width, int height
  *   accel: RT_ACCEL_BRUTE or RT_ACCEL_LBVH */
 int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, int accel, int32_t* out_id, float* out_t);
 
+/* Tuning options. RT_OPT_COMPACTION (default 0): tiny-scene kernel variant that parks rays needing a third or later bounce in a
+ * shared-memory queue (warp-ballot compaction) and finishes them in fully populated warps; identical pixels, spp == 1 only. */
+#define RT_OPT_COMPACTION 1
+int rt_set_option(rt_context* ctx, int option, int value);
+
 /* ---- device-pointer / multi-process interface (torchrun: one process per GPU) --------------------------------- */
 
 /* Row-tile partition of this context inside a `world` of cooperating contexts (default rank 0 of 1). Tile t of

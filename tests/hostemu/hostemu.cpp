@@ -71,6 +71,21 @@ static uint32_t dispatch(int use_tiny, const TinySceneData& t, const GlobalScene
     if (use_tiny == 0) return px_of(GlobalScene(g), cam, x, y, w, h, d, spp, seed, st, dbg);
     if (use_tiny == 3) return px_of(LbvhScene(g, g_bvh->view()), cam, x, y, w, h, d, spp, seed, st, dbg);
     if (use_tiny == 4) return px_of(StagedScene(g, g.sgeom), cam, x, y, w, h, d, spp, seed, st, dbg);
+    if (use_tiny == 5) {
+        // park / resume (the compacting kernel's two passes, sequentially): trace to the second hit, copy the state out the
+        // way k_render_tiny_compact parks it, wipe the stack, restore, finish. spp == 1 only.
+        TinyScene<-1, -1, -1> sc(t);
+        f3 o, dir, C; int bounce = 0, top = 0;
+        primary_ray(cam, (float)x, (float)y, (float)w, (float)h, &o, &dir);
+        if (!trace_chain(sc, d, o, dir, bounce, top, st, 2, &C, dbg)) {
+            struct { int bounce; f3 o, dir; HitRec rec[2]; } e = {bounce, o, dir, {st[0], st[1]}};
+            for (int i = 0; i < 33; i++) memset(&st[i], 0xCD, sizeof(HitRec));
+            o = e.o; dir = e.dir; bounce = e.bounce; top = 2; st[0] = e.rec[0]; st[1] = e.rec[1];
+            bool done = trace_chain(sc, d, o, dir, bounce, top, st, -1, &C, dbg);
+            if (!done) return 0xDEADBEEFu;
+        }
+        return pack_color(C);
+    }
     if (use_tiny == 2) {
         switch (t.ns) {
             case 0: return px_of(TinyScene<0>(t), cam, x, y, w, h, d, spp, seed, st, dbg);
@@ -113,7 +128,7 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         g_bvh = &bvh;
     }
     TinySceneData t; memset(&t, 0, sizeof(t));
-    if (use_tiny == 1 || use_tiny == 2) {
+    if (use_tiny == 1 || use_tiny == 2 || use_tiny == 5) {
         if (ns > TINY_MAX_SPHERES || np > TINY_MAX_PLANES || nl > TINY_MAX_LIGHTS) return -1;
         t.ns = ns; t.np = np; t.nl = nl; t.amb = g.amb;
         for (int i = 0; i < ns; i++) { t.sgeom[i] = sg[i]; t.smat[i] = sm[i]; }

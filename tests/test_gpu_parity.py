@@ -273,3 +273,25 @@ def test_cpp_host_mirror_demo(built, tmp_path):
     cam = app.camera(); app.close()
     ref = O.render(scenes.default_scene(), cam, 320, 180, 32)["pixels"]
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("n,seed", [(3, 0), (12, 1), (16, 2), (2, 7)])
+def test_compaction_variant_is_identical(rt, n, seed):
+    """RT_OPT_COMPACTION: the kernel that parks deep mirror chains in a shared-memory queue (warp-ballot compaction) and
+    finishes them in full warps must produce exactly the default kernel's frames — full frames, odd sizes, partitions."""
+    sc = scenes.default_scene() if n == 3 else scenes.small_random_scene(n, seed)
+    ctx = rt.Context([0]); ctx.set_scene(sc)
+    for (w, h, camkw, depth) in [(1280, 720, dict(), 32), (640, 360, dict(pos=(-2.0, 1.2, 5.0), yaw=-0.3, pitch=0.2), 8),
+                                 (333, 77, dict(pos=(0, 0.4, 2.0)), 3), (37, 23, dict(), 8)]:
+        cam = scenes.make_camera(width=w, height=h, **camkw)
+        ctx.set_option(rt.RT_OPT_COMPACTION, 0)
+        ref, _ = ctx.render(cam, w, h, depth)
+        ctx.set_option(rt.RT_OPT_COMPACTION, 1)
+        got, _ = ctx.render(cam, w, h, depth)
+        assert np.array_equal(got, ref), (w, h)
+        got16, _ = ctx.render(cam, w, h, depth, spp=4, seed=3)          # spp > 1 takes the default kernel
+        ctx.set_option(rt.RT_OPT_COMPACTION, 0)
+        assert np.array_equal(got16, ctx.render(cam, w, h, depth, spp=4, seed=3)[0])
+    cam = scenes.make_camera(width=640, height=360)
+    assert np.array_equal(ctx.render(cam, 640, 360, 8)[0], O.render(sc, cam, 640, 360, 8)["pixels"])
+    ctx.close()

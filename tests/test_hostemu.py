@@ -63,3 +63,18 @@ def test_golden(built, name):
                  tiny=len(sc.spheres) <= 16, debug=True)
     assert np.array_equal(r["pixels"], g["pixels"])
     assert np.array_equal(r["hash"], g["hash"])
+
+
+@pytest.mark.parametrize("camkw,depth", [(dict(), 32), (dict(pos=(-2.0, 1.2, 5.0), yaw=-0.3, pitch=0.2), 8), (dict(pos=(0, 0.4, 2.0)), 2)])
+def test_chain_park_and_resume(built, camkw, depth):
+    """trace_chain is resumable: parking a chain at its third ray and finishing it later (what the compacting kernel does with
+    deep mirror chains) gives the same pixels, hashes and counters as following it in one go."""
+    sc = scenes.default_scene()
+    cam = scenes.make_camera(width=240, height=135, **camkw)
+    a = O.render(sc, cam, 240, 135, depth, want_hash=True)
+    b = E.render(sc, cam, 240, 135, depth, tiny=5, debug=True)
+    assert np.array_equal(a["pixels"], b["pixels"]) and np.array_equal(a["hash"], b["hash"])
+    assert [a["counters"][k] for k in O.COUNTER_NAMES[:10]] == b["counters"]
+    sc2 = scenes.small_random_scene(12, 1)        # several mirror classes incl. DiffuseMirror
+    cam2 = scenes.make_camera(pos=(0, 1.5, -4.0), pitch=0.1, width=160, height=100)
+    assert np.array_equal(O.render(sc2, cam2, 160, 100, 8)["pixels"], E.render(sc2, cam2, 160, 100, 8, tiny=5)["pixels"])

@@ -274,22 +274,26 @@ RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& d
 
 // ---------------------------------------------------------------------------------------------------------
 // One sample: TracePixel RayTracer.cs:962-1002 with (fx, fy) in place of (x, y).
-// `stack` must hold cap+1 records.
 // ---------------------------------------------------------------------------------------------------------
-template <class SC, class DBG>
-RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float fw, float fh, int cap,
-                      HitRec* stack, DBG& dbg) {
+RT_HD void primary_ray(const CamRec& cam, float fx, float fy, float fw, float fh, f3* o, f3* dir) {
     float u = fx / fw - 0.5f;                                                              // :964
     float v = fy / fh - 0.5f;
     f3 local = mulv3(mk3(u, v, 1.0f), cam.view);                                           // :965
     f3 vp = add3(add3(add3(cam.pos, mulf3(cam.right, local.x)), mulf3(cam.up, local.y)), mulf3(cam.fwd, local.z));   // :967-969
-    f3 o = cam.pos;
-    f3 dir = normalize3(sub3(vp, cam.pos));                                                // :971
+    *o = cam.pos;
+    *dir = normalize3(sub3(vp, cam.pos));                                                  // :971
+}
 
-    int bounce = 0, top = 0;
+// The ray chain of one sample, resumable.  Continues the descent from the state (o, dir, bounce, top; stack[0..top) filled);
+// when the chain ends it unwinds the whole stack, stores the colour in *C and returns true.  If defer_at >= 0 and the chain is
+// about to trace the ray of level `defer_at` it returns false instead, leaving the state ready for a later call (used by the
+// compacting kernel to hand deep mirror chains to fully populated warps).  `stack` must hold cap+1 records.
+template <class SC, class DBG>
+RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& top, HitRec* stack, int defer_at, f3* Cout, DBG& dbg) {
     f3 C = mk3(0, 0, 0);
     const int np = sc.n_planes();      // compile-time constant in the exact-count kernels
     for (;;) {
+        if (top == defer_at) return false;
         float a = dot3(dir, dir);                                                          // :617
         float a2 = 2 * a;                                                                  // :624
         float a4 = 4 * a;                                                                  // :621
@@ -330,6 +334,17 @@ RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float
         --top;
         C = shade_hit(sc, stack[top], C, (uint32_t)top, dbg);
     }
+    *Cout = C;
+    return true;
+}
+
+template <class SC, class DBG>
+RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float fw, float fh, int cap,
+                      HitRec* stack, DBG& dbg) {
+    f3 o, dir, C;
+    primary_ray(cam, fx, fy, fw, fh, &o, &dir);
+    int bounce = 0, top = 0;
+    trace_chain(sc, cap, o, dir, bounce, top, stack, -1, &C, dbg);
     return C;
 }
 

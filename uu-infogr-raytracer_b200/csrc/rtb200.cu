@@ -107,6 +107,109 @@ template <int NS, int NL, int NP>
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp) {
     render_loop<PPT_TINY>(TinyScene<NS, NL, NP>(scd), fp);
 }
+// ---------------------------------------------------------------------------------------------------------------------
+// Opt-in variant (rt_set_option(RT_OPT_COMPACTION, 1)): warp-ballot ray compaction between bounces.
+// Pass 1 traces every pixel of the chunk up to its second hit. A chain that goes on (a mirror seen in a mirror) is not followed by
+// its lane: the lanes that want to continue are counted with __ballot_sync / __popc, one lane per warp reserves that many slots
+// of a per-CTA shared-memory queue, and each parks its ray state there (ray, bounce count, the two hit records needed for the
+// exact back-to-front colour sum). After the barrier pass 2 hands the parked rays to the first threads of the CTA, so deep chains
+// run in fully populated warps instead of one or two lanes of many. Both passes go through ONE call site of trace_chain (a
+// second inlined copy would double the kernel and push it out of the instruction cache). Pixels are identical to the default
+// kernel's (tests/test_gpu_parity.py::test_compaction_variant_is_identical); measured speed: profiles/r01/tuning.md.
+// spp == 1 only (a parked sample could not be averaged in order); other launches take the default kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+struct ParkedRay { int p; int bounce; f3 o; f3 dir; HitRec rec[2]; };     // 96 B
+constexpr int PARK_CAP = 128;          // per CTA; a full queue simply makes further lanes follow their chain inline
+constexpr int DEFER_LEVEL = 2;
+
+template <int NS, int NL, int NP>
+__global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_compact(const __grid_constant__ TinySceneData scd,
+                                                                              const __grid_constant__ FrameParams fp) {
+    constexpr int PPT = PPT_TINY, CHUNK = BLOCK * PPT;
+    __shared__ ParkedRay queue[PARK_CAP];
+    __shared__ int qcount;
+    TinyScene<NS, NL, NP> sc(scd);
+    HitRec stack[STACK_RECS];
+    NoDbg dbg;
+    if (threadIdx.x == 0) qcount = 0;
+    __syncthreads();
+    const int npix = fp.w * fp.h;
+    const int tile_pix = fp.tile_rows * fp.w;
+    const int frame = blockIdx.z;
+    const int lane = threadIdx.x & 31;
+    const CamRec& cam = fp.cam_inline[frame];
+    uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
+    const float fw = (float)fp.w, fh = (float)fp.h;
+    for (int kk = blockIdx.y; kk < fp.tiles_mine; kk += gridDim.y) {       // uniform per CTA
+        const int k = fp.k_begin + kk;
+        const int tile = k * fp.world + fp.rank;
+        const int base = tile * tile_pix;
+        int end = base + tile_pix; if (end > npix || end < base) end = npix;
+        const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
+        uint32_t px[PPT];
+        int y = p0 / fp.w, x = p0 - y * fp.w;
+#pragma unroll 1
+        for (int it = 0; it <= PPT; it++) {                                // it < PPT: my pixels; it == PPT: parked rays
+            if (it == PPT) __syncthreads();
+            bool active; int p, bounce, top, defer_at; f3 o, dir;
+            if (it < PPT) {
+                p = p0 + it; active = p < end; bounce = 0; top = 0; defer_at = DEFER_LEVEL;
+                if (active) primary_ray(cam, (float)x, (float)y, fw, fh, &o, &dir);
+                if (++x == fp.w) { x = 0; ++y; }
+            } else {
+                const int n = qcount < PARK_CAP ? qcount : PARK_CAP;
+                active = (int)threadIdx.x < n; defer_at = -1; top = DEFER_LEVEL; p = 0; bounce = 0;
+                if (active) {
+                    const ParkedRay& e = queue[threadIdx.x];
+                    p = e.p; bounce = e.bounce; o = e.o; dir = e.dir; stack[0] = e.rec[0]; stack[1] = e.rec[1];
+                }
+            }
+            f3 C = mk3(0, 0, 0);
+            bool done = !active, parked = false;
+#pragma unroll 1
+            for (int attempt = 0; attempt < 2; attempt++) {
+                if (active && !done) done = trace_chain(sc, fp.cap, o, dir, bounce, top, stack, defer_at, &C, dbg);
+                if (attempt == 0 && it < PPT) {                            // every lane of the warp is here: convergent ballot
+                    const bool want = active && !done;
+                    const unsigned m = __ballot_sync(0xffffffffu, want);
+                    if (m) {
+                        const int leader = __ffs((int)m) - 1;
+                        int slot0 = 0;
+                        if (lane == leader) slot0 = atomicAdd(&qcount, __popc(m));
+                        slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+                        const int slot = slot0 + __popc(m & ((1u << lane) - 1u));
+                        if (want && slot < PARK_CAP) {
+                            ParkedRay& e = queue[slot];
+                            e.p = p; e.bounce = bounce; e.o = o; e.dir = dir; e.rec[0] = stack[0]; e.rec[1] = stack[1];
+                            parked = true;
+                        }
+                    }
+                }
+                if (done || parked || !active) break;
+                defer_at = -1;                                             // queue full: follow the chain inline
+            }
+            if (it < PPT) {
+                const uint32_t c = (active && done) ? pack_color(C) : 0u;  // parked pixels are written by pass 2
+#pragma unroll
+                for (int z = 0; z + 1 < PPT; z++) px[z] = px[z + 1];
+                px[PPT - 1] = c;
+                if (it == PPT - 1 && p0 < end) {
+                    if (p0 + PPT <= end && ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0)) {
+                        *reinterpret_cast<uint4*>(out + p0) = make_uint4(px[0], px[PPT > 1 ? 1 : 0], px[PPT > 2 ? 2 : 0], px[PPT > 3 ? 3 : 0]);
+                    } else {
+                        for (int q = 0; q < PPT; q++) if (p0 + q < end) out[p0 + q] = px[q];
+                    }
+                }
+            } else if (active) {
+                out[p] = pack_color(C);                                    // after the barrier: overwrites the placeholder
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) qcount = 0;
+        __syncthreads();
+    }
+}
+
 using TinyKernel = void (*)(const TinySceneData, const FrameParams);
 // Exact-count instantiations (sphere and light loops unrolled, records addressed statically) for scenes of the
 // reference's size; everything else up to the TINY_MAX_* limits takes the run-time-count instantiation.
@@ -121,6 +224,10 @@ template <int NS, int NL> struct TinyTable {
 };
 // exact kernels exist for 0..4 spheres x 0..4 lights x exactly 1 plane (the reference scene is 3 x 2 x 1)
 TinyKernel tiny_kernel(int ns, int nl, int np) { return np == 1 ? TinyTable<0, 0>::get(ns, nl) : k_render_tiny<-1, -1, -1>; }
+// compacting variant: exact instantiation for the reference scene's shape, run-time counts otherwise
+TinyKernel tiny_kernel_compact(int ns, int nl, int np) {
+    return (ns == 3 && nl == 2 && np == 1) ? k_render_tiny_compact<3, 2, 1> : k_render_tiny_compact<-1, -1, -1>;
+}
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_global(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp) {
     render_loop<PPT_HEAVY>(GlobalScene(scd), fp);
 }
@@ -238,6 +345,7 @@ struct rt_context {
     GlobalSceneData gdata_host;     // counts + ambient (pointers per device filled at launch)
     int accel = RT_ACCEL_BRUTE;
     int rank = 0, world = 1, tile_rows = 8;
+    bool compaction = false;        // RT_OPT_COMPACTION
     bool peer_ok = false;
     std::atomic<uint64_t> launches{0};
 };
@@ -352,7 +460,12 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
     const size_t smem = ctx->path == PATH_STAGED ? sizeof(f4) * (size_t)ctx->gdata_host.ns : 0;
     const dim3 grid((unsigned)fp.chunks_per_tile, (unsigned)(fp.tiles_mine < 65535 ? fp.tiles_mine : 65535), (unsigned)fp.n_frames);
     switch (ctx->path) {
-        case PATH_TINY: tiny_kernel(ctx->tiny_data.ns, ctx->tiny_data.nl, ctx->tiny_data.np)<<<grid, BLOCK, 0, stream>>>(ctx->tiny_data, fp); break;
+        case PATH_TINY: {
+            const TinySceneData& t = ctx->tiny_data;
+            TinyKernel kern = (ctx->compaction && fp.spp == 1) ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np);
+            kern<<<grid, BLOCK, 0, stream>>>(t, fp);
+            break;
+        }
         case PATH_STAGED: k_render_staged<<<grid, BLOCK, smem, stream>>>(global_data(ctx, d), fp); break;
         case PATH_GLOBAL: k_render_global<<<grid, BLOCK, 0, stream>>>(global_data(ctx, d), fp); break;
         default: k_render_lbvh<<<grid, BLOCK, 0, stream>>>(lbvh_data(ctx, d, true), fp); break;
@@ -551,6 +664,14 @@ int rt_update_spheres(rt_context* ctx, const float* spheres, int first, int coun
         CU_TRY(ctx, cudaStreamSynchronize(d.stream));     // sg / sm go out of scope; later launches may use another stream
     }
     return RT_OK;
+}
+
+int rt_set_option(rt_context* ctx, int option, int value) {
+    if (!ctx) return RT_ERR_INVALID;
+    switch (option) {
+        case RT_OPT_COMPACTION: ctx->compaction = value != 0; return RT_OK;
+        default: return fail(ctx, RT_ERR_INVALID, "unknown option");
+    }
 }
 
 int rt_set_partition(rt_context* ctx, int rank, int world, int tile_rows) {

@@ -21,12 +21,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RTB200_LIB", os.path.join(_HERE, "librtb200.so"))   # RTB200_LIB: tuning variants only
 
 RT_ACCEL_AUTO, RT_ACCEL_BRUTE, RT_ACCEL_LBVH = 0, 1, 2
+RT_OPT_COMPACTION = 1
 COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_pos", "plane_tests",
                  "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"]
 
 # every symbol include/rtb200.h declares
 ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_update_spheres", "rt_render", "rt_render_batch", "rt_render_debug", "rt_query_spheres",
-               "rt_set_partition", "rt_render_device", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_dev_alloc",
+               "rt_set_option", "rt_set_partition", "rt_render_device", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_dev_alloc",
                "rt_dev_free", "rt_dev_to_host", "rt_sync", "rt_host_register", "rt_host_unregister", "rt_launch_count", "rt_destroy", "rt_last_error", "rt_abi_version"]
 
 
@@ -68,6 +69,7 @@ def load_library():
     lib.rt_render_debug.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, ip, C.POINTER(C.c_uint32), ip, fp,
                                     C.POINTER(C.c_uint64), statp]
     lib.rt_query_spheres.argtypes = [vp, fp, C.c_int, C.c_int, C.c_int, ip, fp]
+    lib.rt_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.rt_set_partition.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.rt_render_device.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, vp, vp]
     lib.rt_ipc_export.argtypes = [vp, vp, vp]
@@ -187,6 +189,9 @@ class Context:
         ids = np.empty(n, np.int32); ts = np.empty(n, np.float32)
         self._check(self.lib.rt_query_spheres(self.h, _fp(rays6), n, kind, accel, ids.ctypes.data_as(C.POINTER(C.c_int32)), _fp(ts)))
         return ids, ts
+
+    def set_option(self, option, value):
+        self._check(self.lib.rt_set_option(self.h, option, value))
 
     # ---- device-pointer / multi-process interface --------------------------------------------------------
     def set_partition(self, rank, world, tile_rows=8):

@@ -113,6 +113,9 @@ int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, 
 /* Tuning options. RT_OPT_COMPACTION (default 0): tiny-scene kernel variant that parks rays needing a third or later bounce in a
  * shared-memory queue (warp-ballot compaction) and finishes them in fully populated warps; identical pixels, spp == 1 only. */
 #define RT_OPT_COMPACTION 1
+/* RT_OPT_HOST_VIA_GPU0 (default 0): multi-device contexts normally send each device's row tiles to the host over that device's
+ * own PCIe link; 1 = gather the frame on device 0 first (NVLink peer stores) and copy it from there. */
+#define RT_OPT_HOST_VIA_GPU0 2
 int rt_set_option(rt_context* ctx, int option, int value);
 
 /* ---- device-pointer / multi-process interface (torchrun: one process per GPU) --------------------------------- */

@@ -58,6 +58,37 @@ def test_in_library_multi_device_equals_single(rt, g):
         one.close()
 
 
+@need2
+@pytest.mark.parametrize("w,h,tile_rows", [(1280, 723, 8), (640, 97, 16), (96, 5, 8)])
+def test_multi_device_host_output_paths(rt, w, h, tile_rows):
+    """Host output from a multi-device context: (a) default — every device sends its own row tiles over its own PCIe link
+    (strided 2-D copies, incl. a short last tile), (b) RT_OPT_HOST_VIA_GPU0 — gather on device 0, then copy. Both must equal the
+    single-device frame, into pageable and into page-locked host memory."""
+    g = min(N_GPUS, 4) if N_GPUS >= 4 else 2
+    sc = scenes.default_scene()
+    cam = scenes.make_camera(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15, width=w, height=h)
+    one = rt.Context([0]); one.set_scene(sc)
+    ref, _ = one.render(cam, w, h, 8)
+    one.close()
+    multi = rt.Context(list(range(g))); multi.set_scene(sc); multi.set_partition(0, 1, tile_rows)
+    for via0 in (0, 1):
+        multi.set_option(rt.RT_OPT_HOST_VIA_GPU0, via0)
+        got, st = multi.render(cam, w, h, 8)
+        assert np.array_equal(got, ref), via0
+        pinned = np.full((h, w), 0x55555555, dtype=np.int32)
+        multi.host_register(pinned)
+        multi.render(cam, w, h, 8, out=pinned)
+        multi.host_unregister(pinned)
+        assert np.array_equal(pinned, ref), via0
+        cams = np.stack([scenes.make_camera(pos=(0.1 * i, 0.4, -1.0), yaw=0.05 * i, width=w, height=h) for i in range(3)])
+        batch, _ = multi.render_batch(cams, w, h, 8, headless=False)
+        for i in range(3):
+            one = rt.Context([0]); one.set_scene(sc)
+            assert np.array_equal(batch[i], one.render(cams[i], w, h, 8)[0])
+            one.close()
+    multi.close()
+
+
 def _ipc_worker(rank, world, w, h, tile_rows, q_handle, q_done, q_go):
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, os.path.join(os.path.dirname(here), "uu-infogr-raytracer_b200"))

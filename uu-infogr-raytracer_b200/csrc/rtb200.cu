@@ -346,6 +346,7 @@ struct rt_context {
     int accel = RT_ACCEL_BRUTE;
     int rank = 0, world = 1, tile_rows = 8;
     bool compaction = false;        // RT_OPT_COMPACTION
+    bool host_via_gpu0 = false;     // RT_OPT_HOST_VIA_GPU0
     bool peer_ok = false;
     std::atomic<uint64_t> launches{0};
 };
@@ -375,8 +376,8 @@ void free_scene(DeviceState& d) {
     d.sgeom = nullptr; d.smat = nullptr; d.planes = nullptr; d.lights = nullptr;
 }
 
-int ensure_fb(rt_context* ctx, size_t pixels) {
-    DeviceState& d0 = ctx->devs[0];
+int ensure_fb(rt_context* ctx, size_t pixels, int dev_index = 0) {
+    DeviceState& d0 = ctx->devs[(size_t)dev_index];
     if (d0.fb_pixels >= pixels) return RT_OK;
     CU_TRY(ctx, cudaSetDevice(d0.dev));
     if (d0.fb) CU_TRY(ctx, cudaFree(d0.fb));
@@ -670,6 +671,7 @@ int rt_set_option(rt_context* ctx, int option, int value) {
     if (!ctx) return RT_ERR_INVALID;
     switch (option) {
         case RT_OPT_COMPACTION: ctx->compaction = value != 0; return RT_OK;
+        case RT_OPT_HOST_VIA_GPU0: ctx->host_via_gpu0 = value != 0; return RT_OK;
         default: return fail(ctx, RT_ERR_INVALID, "unknown option");
     }
 }
@@ -702,19 +704,25 @@ int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int w
     return RT_OK;
 }
 
-// Renders n_frames frames into device 0's framebuffer ring and, if host_pixels != NULL, returns them to the host.
-//  * headless: ONE launch per device covers all frames (work items = frame x tile x chunk).
+// Renders n_frames frames and, if host_pixels != NULL, returns them to the host.
+//  * headless: ONE launch per device covers (up to 16) frames; with several devices every device stores its row tiles straight
+//    into device 0's framebuffer ring (peer stores over NVLink: the gather is fused into the kernel).
 //  * with a host buffer: every frame is cut into BANDS of row tiles; band s+1 is rendered while band s crosses PCIe on a
 //    separate copy stream, so the device->host copy (33 MB per 4K frame, ~0.6 ms) hides the kernel instead of following it.
 //    Bands are multiples of `world` tiles so that every device owns the same share of each band.
+//    With several devices the frame is NOT gathered on device 0 first: each device renders into a local framebuffer and sends
+//    its own tiles to the host over ITS OWN PCIe link (one strided 2-D copy per band), so host bandwidth scales with the device
+//    count. rt_set_option(RT_OPT_HOST_VIA_GPU0, 1) restores gather-on-GPU-0-then-copy.
 static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, int w, int h, int depth, int spp, uint32_t seed,
                          int32_t* host_pixels, rt_stats* stats) {
     int rc = check_frame_args(ctx, cams, w, h, depth, spp);
     if (rc) return rc;
     if (n_frames < 1) return fail(ctx, RT_ERR_INVALID, "n_frames");
     const size_t npix = (size_t)w * h;
-    rc = ensure_fb(ctx, npix * (size_t)n_frames); if (rc) return rc;
     const int G = (int)ctx->devs.size();
+    const bool direct = host_pixels != nullptr && G > 1 && !ctx->host_via_gpu0;     // per-device D2H of own tiles
+    rc = ensure_fb(ctx, npix * (size_t)n_frames); if (rc) return rc;
+    if (direct) for (int g = 1; g < G; g++) { rc = ensure_fb(ctx, npix * (size_t)n_frames, g); if (rc) return rc; }
     DeviceState& d0 = ctx->devs[0];
     const int world = G > 1 ? G : ctx->world;
     const int tiles_total = (h + ctx->tile_rows - 1) / ctx->tile_rows;
@@ -750,6 +758,7 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
     }
     const long long tile_pix = (long long)ctx->tile_rows * w;
     bool first_copy = true;
+    std::vector<char> first_copy_dev((size_t)G, 1);
     for (int s = 0; s < n_segments; s++) {
         const int frame = pipelined ? s / n_bands : s * INLINE_CAMS, band = pipelined ? s % n_bands : 0;
         const int nf = pipelined ? 1 : (n_frames - frame < INLINE_CAMS ? n_frames - frame : INLINE_CAMS);
@@ -757,7 +766,7 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             DeviceState& d = ctx->devs[(size_t)g];
             CU_TRY(ctx, cudaSetDevice(d.dev));
             const int rank = G > 1 ? g : ctx->rank;
-            FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, rank, world, d0.fb + (size_t)frame * npix, (long long)npix);
+            FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, rank, world, (direct ? d.fb : d0.fb) + (size_t)frame * npix, (long long)npix);
             if (pipelined) {
                 fp.cam_inline[0] = to_cam(cams[frame]);
                 const int k0 = band * (band_tiles / world), k1 = k0 + band_tiles / world;       // this rank's tiles of the band
@@ -769,8 +778,26 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             }
             rc = launch_render(ctx, d, fp, d.stream); if (rc) return rc;
             if (pipelined) CU_TRY(ctx, cudaEventRecord(d.band_events[(size_t)s], d.stream));
+            if (direct && fp.tiles_mine > 0) {
+                // this device's tiles of the band: tile k*world + g for k in [k_begin, k_begin + tiles_mine), i.e. blocks of
+                // tile_pix pixels every world*tile_pix pixels -> one strided 2-D copy (+ a 1-D copy if the frame's last tile is short)
+                CU_TRY(ctx, cudaStreamWaitEvent(d.copy_stream, d.band_events[(size_t)s], 0));
+                if (first_copy_dev[(size_t)g]) { CU_TRY(ctx, cudaEventRecord(d.evc0, d.copy_stream)); first_copy_dev[(size_t)g] = 0; }
+                const long long first_px = ((long long)fp.k_begin * world + g) * tile_pix;
+                const long long last_tile = ((long long)(fp.k_begin + fp.tiles_mine - 1)) * world + g;
+                const bool last_short = (last_tile + 1) * tile_pix > (long long)npix;
+                const int full = fp.tiles_mine - (last_short ? 1 : 0);
+                uint32_t* src = d.fb + (size_t)frame * npix; int32_t* dst = host_pixels + (size_t)frame * npix;
+                if (full > 0)
+                    CU_TRY(ctx, cudaMemcpy2DAsync(dst + first_px, (size_t)world * tile_pix * 4, src + first_px, (size_t)world * tile_pix * 4,
+                                                  (size_t)tile_pix * 4, (size_t)full, cudaMemcpyDeviceToHost, d.copy_stream));
+                if (last_short) {
+                    const long long p0 = last_tile * tile_pix;
+                    CU_TRY(ctx, cudaMemcpyAsync(dst + p0, src + p0, (size_t)((long long)npix - p0) * 4, cudaMemcpyDeviceToHost, d.copy_stream));
+                }
+            }
         }
-        if (pipelined) {
+        if (pipelined && !direct) {
             CU_TRY(ctx, cudaSetDevice(d0.dev));
             for (int g = 0; g < G; g++) CU_TRY(ctx, cudaStreamWaitEvent(d0.copy_stream, ctx->devs[(size_t)g].band_events[(size_t)s], 0));
             if (first_copy) { CU_TRY(ctx, cudaEventRecord(d0.evc0, d0.copy_stream)); first_copy = false; }
@@ -795,11 +822,23 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         CU_TRY(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
         if (ms > kernel_ms) kernel_ms = ms;
     }
-    if (pipelined) {
+    if (pipelined && !direct) {
         CU_TRY(ctx, cudaSetDevice(d0.dev));
         CU_TRY(ctx, cudaEventRecord(d0.evc1, d0.copy_stream));
         CU_TRY(ctx, cudaStreamSynchronize(d0.copy_stream));
         CU_TRY(ctx, cudaEventElapsedTime(&d2h_ms, d0.evc0, d0.evc1));
+    }
+    if (direct) {
+        for (int g = 0; g < G; g++) {
+            DeviceState& d = ctx->devs[(size_t)g];
+            if (first_copy_dev[(size_t)g]) continue;             // this device owned no tile
+            CU_TRY(ctx, cudaSetDevice(d.dev));
+            CU_TRY(ctx, cudaEventRecord(d.evc1, d.copy_stream));
+            CU_TRY(ctx, cudaStreamSynchronize(d.copy_stream));
+            float ms = 0.0f;
+            CU_TRY(ctx, cudaEventElapsedTime(&ms, d.evc0, d.evc1));
+            if (ms > d2h_ms) d2h_ms = ms;
+        }
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));

@@ -350,10 +350,12 @@ RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float
 
 // One pixel: spp == 1 is the reference; spp > 1 is the jittered extension (BASELINE.json configs[4]).
 // A single call site of trace_sample: with spp == 1 the jitter is +0.0f and the average is *1.0f, both exact.
-template <class SC, class DBG>
+// SPP1 = true: compile-time single sample (the reference): no sample loop, no jitter, no average.
+template <bool SPP1 = false, class SC, class DBG>
 RT_HD uint32_t trace_pixel(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int cap, int spp, uint32_t seed,
                            HitRec* stack, DBG& dbg) {
     const float fw = (float)w, fh = (float)h;
+    if (SPP1) return pack_color(trace_sample(sc, cam, (float)x, (float)y, fw, fh, cap, stack, dbg));   // :1000 -> :1038
     f3 acc = mk3(0, 0, 0);
     for (int s = 0; s < spp; s++) {
         float jx = 0.0f, jy = 0.0f;

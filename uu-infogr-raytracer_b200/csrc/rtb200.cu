@@ -68,7 +68,7 @@ struct DebugOut {
 // One CTA per work item: blockIdx = (chunk inside the tile, this rank's tile, frame) — no index divisions, and the hardware
 // block scheduler balances sky / floor / mirror chunks (measured 8 % faster than a one-wave persistent grid-stride loop,
 // profiles/r01/tuning.md). gridDim.y is folded when a launch has more than 65535 tiles.
-template <int PPT, class SC>
+template <int PPT, bool SPP1 = false, class SC>
 __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp) {
     constexpr int CHUNK = BLOCK * PPT;          // pixels per CTA work item
     HitRec stack[STACK_RECS];
@@ -89,7 +89,7 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
         int y = p0 / fp.w, x = p0 - y * fp.w;                  // one division per thread; then step along the row
 #pragma unroll 1
         for (int q = 0; q < PPT; q++) {
-            uint32_t c = (p0 + q < end) ? trace_pixel(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg) : 0u;
+            uint32_t c = (p0 + q < end) ? trace_pixel<SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg) : 0u;
             if (++x == fp.w) { x = 0; ++y; }
 #pragma unroll
             for (int z = 0; z + 1 < PPT; z++) px[z] = px[z + 1];   // shift register: after PPT iterations px[] is in pixel order
@@ -103,9 +103,9 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
     }
 }
 
-template <int NS, int NL, int NP>
+template <int NS, int NL, int NP, bool SPP1>
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp) {
-    render_loop<PPT_TINY>(TinyScene<NS, NL, NP>(scd), fp);
+    render_loop<PPT_TINY, SPP1>(TinyScene<NS, NL, NP>(scd), fp);
 }
 // ---------------------------------------------------------------------------------------------------------------------
 // Opt-in variant (rt_set_option(RT_OPT_COMPACTION, 1)): warp-ballot ray compaction between bounces.
@@ -216,14 +216,18 @@ using TinyKernel = void (*)(const TinySceneData, const FrameParams);
 constexpr int EXACT_MAX = 4;
 template <int NS, int NL> struct TinyTable {
     static TinyKernel get(int ns, int nl) {
-        if (ns == NS && nl == NL) return k_render_tiny<NS, NL, 1>;
+        if (ns == NS && nl == NL) return k_render_tiny<NS, NL, 1, true>;
         if constexpr (NL < EXACT_MAX) return TinyTable<NS, NL + 1>::get(ns, nl);
         else if constexpr (NS < EXACT_MAX) return TinyTable<NS + 1, 0>::get(ns, nl);
-        else return k_render_tiny<-1, -1, -1>;
+        else return k_render_tiny<-1, -1, -1, true>;
     }
 };
-// exact kernels exist for 0..4 spheres x 0..4 lights x exactly 1 plane (the reference scene is 3 x 2 x 1)
-TinyKernel tiny_kernel(int ns, int nl, int np) { return np == 1 ? TinyTable<0, 0>::get(ns, nl) : k_render_tiny<-1, -1, -1>; }
+// Exact kernels exist for 0..4 spheres x 0..4 lights x exactly 1 plane x one sample per pixel (the reference is 3 x 2 x 1 x 1).
+// Supersampled frames (extension) take the reference scene's own multi-sample instantiation or the run-time-count kernel.
+TinyKernel tiny_kernel(int ns, int nl, int np, int spp) {
+    if (spp == 1) return np == 1 ? TinyTable<0, 0>::get(ns, nl) : k_render_tiny<-1, -1, -1, true>;
+    return (ns == 3 && nl == 2 && np == 1) ? k_render_tiny<3, 2, 1, false> : k_render_tiny<-1, -1, -1, false>;
+}
 // compacting variant: exact instantiation for the reference scene's shape, run-time counts otherwise
 TinyKernel tiny_kernel_compact(int ns, int nl, int np) {
     return (ns == 3 && nl == 2 && np == 1) ? k_render_tiny_compact<3, 2, 1> : k_render_tiny_compact<-1, -1, -1>;
@@ -463,7 +467,7 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
     switch (ctx->path) {
         case PATH_TINY: {
             const TinySceneData& t = ctx->tiny_data;
-            TinyKernel kern = (ctx->compaction && fp.spp == 1) ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np);
+            TinyKernel kern = (ctx->compaction && fp.spp == 1) ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np, fp.spp);
             kern<<<grid, BLOCK, 0, stream>>>(t, fp);
             break;
         }
@@ -730,7 +734,8 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
     int n_bands = 1;
     if (host_pixels) {
         const char* be = getenv("RTB200_BANDS");
-        n_bands = be ? atoi(be) : (int)((npix * 4 + (4u << 20) - 1) / (4u << 20));    // ~4 MB per band
+        const size_t link_bytes = npix * 4 / (size_t)(direct ? G : 1);               // bytes one PCIe link carries per frame
+        n_bands = be ? atoi(be) : (int)((link_bytes + (4u << 20) - 1) / (4u << 20));  // ~4 MB per band and link
         if (n_bands > 16) n_bands = 16;
         if (n_bands < 1) n_bands = 1;
     }

@@ -30,3 +30,5 @@ for l in sys.stdin:
 "
   fi
 done
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_all.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu_all.log; tail -3 gpurun_out/pytest_gpu_all.log
+python profiles/e2e_multi.py $MAXG | tee gpurun_out/e2e_multi.txt

@@ -295,3 +295,25 @@ def test_compaction_variant_is_identical(rt, n, seed):
     cam = scenes.make_camera(width=640, height=360)
     assert np.array_equal(ctx.render(cam, 640, 360, 8)[0], O.render(sc, cam, 640, 360, 8)["pixels"])
     ctx.close()
+
+
+@pytest.mark.parametrize("accel_name", ["auto", "brute", "lbvh"])
+def test_degenerate_scene(rt, accel_name):
+    """IEEE corner cases (scenes.degenerate_scene) on the tiny, and via replication of the spheres, staged and LBVH paths:
+    geometry must stay exact (chain hashes), colours within tolerance (general Math.Pow exponents: f64 pow of CUDA vs glibc)."""
+    sc = scenes.degenerate_scene()
+    accel = {"auto": rt.RT_ACCEL_AUTO, "brute": rt.RT_ACCEL_BRUTE, "lbvh": rt.RT_ACCEL_LBVH}[accel_name]
+    if accel_name == "brute":        # > 16 spheres -> shared-memory staged path: pad with far-away invisible spheres
+        pad = np.stack([scenes.sphere((1000.0 + i, -500.0, -1000.0), 0.1, scenes.mat_diffuse((1, 1, 1))) for i in range(20)])
+        sc = scenes.Scene(np.concatenate([sc.spheres, pad]), sc.planes, sc.lights, sc.ambient)
+    ctx = rt.Context([0]); ctx.set_scene(sc, accel)
+    for camkw in (dict(), dict(pos=(0.0, 0.0, 6.0)), dict(pos=(0.5, -1.0, 2.0), yaw=0.1, pitch=-0.2), dict(pos=(-3, 2, 1), yaw=0.5, pitch=0.3)):
+        w, h = 320, 180
+        cam = scenes.make_camera(width=w, height=h, **camkw)
+        ref = O.render(sc, cam, w, h, 8, want_hash=True)
+        got = ctx.render_debug(cam, w, h, 8)
+        assert np.array_equal(got["hash"], ref["hash"])
+        px, _ = ctx.render(cam, w, h, 8)
+        assert_image_parity(px, ref["pixels"], "degenerate " + accel_name)
+        assert np.array_equal(px, got["pixels"])
+    ctx.close()

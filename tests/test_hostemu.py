@@ -78,3 +78,17 @@ def test_chain_park_and_resume(built, camkw, depth):
     sc2 = scenes.small_random_scene(12, 1)        # several mirror classes incl. DiffuseMirror
     cam2 = scenes.make_camera(pos=(0, 1.5, -4.0), pitch=0.1, width=160, height=100)
     assert np.array_equal(O.render(sc2, cam2, 160, 100, 8)["pixels"], E.render(sc2, cam2, 160, 100, 8, tiny=5)["pixels"])
+
+
+@pytest.mark.parametrize("policy", [0, 1, 3, 4, 5])
+@pytest.mark.parametrize("camkw", [dict(), dict(pos=(0.0, 0.0, 6.0)), dict(pos=(0.5, -1.0, 2.0), yaw=0.1, pitch=-0.2)])
+def test_degenerate_scene(built, policy, camkw):
+    """scenes.degenerate_scene(): zero / negative radiusSquared, light at the origin, zero-normal plane, camera inside a sphere
+    and on the floor, negative colours, general pow exponents, far sphere, overlapping spheres — every scene policy."""
+    sc = scenes.degenerate_scene()
+    w, h = 160, 96
+    cam = scenes.make_camera(width=w, height=h, **camkw)
+    a = O.render(sc, cam, w, h, 8, want_hash=True)
+    assert np.array_equal(a["pixels"], O.render(sc, cam, w, h, 8, mode="faithful")["pixels"])
+    b = E.render(sc, cam, w, h, 8, tiny=policy, debug=True)
+    assert np.array_equal(a["pixels"], b["pixels"]) and np.array_equal(a["hash"], b["hash"])

@@ -208,3 +208,28 @@ def small_random_scene(n: int, seed: int) -> Scene:
 
 
 SCALED_CAMERA = dict(pos=(0.0, 3.0, -6.0), yaw=0.0, pitch=0.25)      # configs 3/4 camera
+
+
+def degenerate_scene() -> Scene:
+    """Parity edge cases the reference handles "by accident of IEEE": zero / negative radiusSquared, a light at the origin
+    (shadow direction = zero vector, RayTracer.cs:574), a light inside a sphere, a plane with a zero normal (0/0 = NaN: never
+    hit), a non-unit plane normal (used as given, :743), negative and > 1 colours, tiny and large specular exponents, a sphere
+    far away (fp32 noise regime), overlapping spheres < 0.01 apart (order-dependent secondary fold, :804)."""
+    s = [
+        sphere((0.0, 0.0, 6.0), 1.0, mat_mirror((1.2, 0.9, 0.8))),
+        sphere((0.004, 0.0, 6.003), 1.0, mat_plastic((0.2, 0.7, 1.5), 64.0)),          # overlaps the mirror within 0.01
+        sphere((-2.5, 0.2, 5.0), 0.8, mat_metal((0.9, -0.3, 0.4), 0.001)),             # negative colour, tiny exponent
+        sphere((2.5, 0.0, 5.0), 0.0, mat_diffuse((1, 1, 1))),                           # radius 0
+        sphere((1.5, 1.5, 4.0), 0.5, mat_diffuse_mirror((0.3, 0.3, 0.3), (0.5, 0.5, 0.5))),
+        sphere((400.0, 30.0, 900.0), 0.3, mat_diffuse((1, 1, 0))),                      # far: discriminant noise > r^2
+        sphere((-1.0, 3.0, 7.0), 0.7, mat_plastic((0.5, 0.5, 0.5), 3.5)),               # general Math.Pow exponent
+    ]
+    s = np.stack(s)
+    s[3, 17] = -0.25                                                                    # negative radiusSquared
+    planes = np.stack([
+        reference_plane(),
+        plane((0, 0, 0), (0, 0, 0), mat_diffuse((1, 1, 1))),                            # zero normal
+        plane((0, 0, 30.0), (0.0, 0.5, -3.0), material((0.4, 0.4, 0.9), (0.3, 0.3, 0.3), (0.2, 0.2, 0.2), 2.0, (0.3, 0.3, 0.3))),
+    ])
+    lights = np.stack([light((0, 0, 0), 1.0), light((0.0, 0.1, 6.0), 2.0), light((-4, 5, 0), 1.0), light((0, 8, 10), 0.5)])
+    return Scene(s, planes, lights, REF_AMBIENT.copy(), "degenerate")

@@ -65,11 +65,17 @@ static uint32_t px_of(const SC& sc, const CamRec& cam, int x, int y, int w, int 
 // use_tiny: 0 global-memory policy, 1 TinyScene<-1> (run-time count), 2 TinyScene<NS> with the exact compile-time count,
 //           3 LBVH policy, 4 shared-memory-staged policy (here: an ordinary host array)
 static const HostBvh* g_bvh = nullptr;
+static ShadowGridsHost g_sgh;
+static ShadowGridsView sg_view() {
+    ShadowGridsView v; memset(&v, 0, sizeof(v));
+    if (!g_sgh.empty() && !g_sgh.cell_start.empty()) { v.grids = g_sgh.grids.data(); v.cell_start = g_sgh.cell_start.data(); v.items = g_sgh.items.data(); v.lo = g_sgh.lo; v.hi = g_sgh.hi; }
+    return v;
+}
 template <class DBG>
 static uint32_t dispatch(int use_tiny, const TinySceneData& t, const GlobalSceneData& g, const CamRec& cam, int x, int y, int w, int h,
                          int d, int spp, uint32_t seed, HitRec* st, DBG& dbg) {
     if (use_tiny == 0) return px_of(GlobalScene(g), cam, x, y, w, h, d, spp, seed, st, dbg);
-    if (use_tiny == 3) return px_of(LbvhScene(g, g_bvh->view()), cam, x, y, w, h, d, spp, seed, st, dbg);
+    if (use_tiny == 3) return px_of(LbvhScene(g, g_bvh->view(), sg_view()), cam, x, y, w, h, d, spp, seed, st, dbg);
     if (use_tiny == 4) return px_of(StagedScene(g, g.sgeom), cam, x, y, w, h, d, spp, seed, st, dbg);
     if (use_tiny == 5) {
         // park / resume (the compacting kernel's two passes, sequentially): trace to the second hit, copy the state out the
@@ -126,6 +132,9 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         bvh.nodes_cam = bvh.nodes;
         host_refit_cam(bvh, mk3(cam15[0], cam15[1], cam15[2]), 0);
         g_bvh = &bvh;
+        std::vector<f3> lp((size_t)nl);
+        for (int i = 0; i < nl; i++) lp[i] = li[i].p;
+        shadow_grids_build(sg, lp, &g_sgh);
     }
     TinySceneData t; memset(&t, 0, sizeof(t));
     if (use_tiny == 1 || use_tiny == 2 || use_tiny == 5) {
@@ -190,9 +199,10 @@ extern "C" int emu_query(const float* spheres, int ns, const float* rays6, int n
         auto run = [&](auto sc) {
             if (kind == 0) { sc.nearest(o, d, a2, a4, 0.0f, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
             else if (kind == 1) { sc.nearest(o, d, a2, a4, 0.01f, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
-            else { sel = sc.shadow_any(o, d, a2, a4, dbg) ? 1 : 0; t = 0.0f; }
+            else { sel = sc.shadow_any(-1, o, d, a2, a4, dbg) ? 1 : 0; t = 0.0f; }
         };
-        if (accel == 2) run(LbvhScene(g, bv)); else run(GlobalScene(g));
+        ShadowGridsView nosg; memset(&nosg, 0, sizeof(nosg));
+        if (accel == 2) run(LbvhScene(g, bv, nosg)); else run(GlobalScene(g));
         out_id[r] = sel; out_t[r] = t;
     }
     return 0;

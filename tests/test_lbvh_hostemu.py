@@ -131,3 +131,23 @@ def test_axis_parallel_rays_inside_boxes_straddling_zero(built):
     d[: n // 6, 1] = 0                                   # two zero components
     d[n // 2: n // 2 + 2000] *= np.float32(1e-20)        # tiny but non-zero components
     check(sph, np.concatenate([o, d], 1))
+
+
+def test_shadow_bins_in_the_fp_noise_regime(built):
+    """Per-light projected shadow bins (rt_shadow_grid.cuh): small spheres spread over ~1 km, so shadow rays start up to
+    ~1000 units from the spheres they graze and the reference reports noise hits well outside the exact discs; plus far floor
+    points outside the bins' validity box (LBVH fallback). Frame and chain hashes must equal the oracle's brute force."""
+    rng = np.random.default_rng(21)
+    sph = np.stack([scenes.sphere((rng.uniform(-400, 400), rng.uniform(-0.8, 6), rng.uniform(20, 700)), rng.uniform(0.05, 0.35),
+                                  [scenes.mat_diffuse, scenes.mat_plastic, lambda c: scenes.mat_mirror((0.8, 0.8, 0.8))][i % 3]((0.9, 0.6, 0.3)))
+                    for i in range(1500)])
+    lights = np.stack([scenes.light((-300, 40, 100), 1.0), scenes.light((0, 500, 0), 1.0), scenes.light((250, 3, 650), 1.0)])
+    sc = scenes.Scene(sph, scenes.reference_plane()[None], lights, scenes.REF_AMBIENT)
+    for camkw in (dict(pos=(0, 8, -5), pitch=0.12), dict(pos=(-350, 3, 300), yaw=1.3, pitch=0.05)):
+        w, h = 200, 112
+        cam = scenes.make_camera(width=w, height=h, **camkw)
+        a = O.render(sc, cam, w, h, 4, want_hash=True)
+        b = E.render(sc, cam, w, h, 4, tiny=3, debug=True)
+        assert np.array_equal(a["hash"], b["hash"]), "%d hashes differ" % (a["hash"] != b["hash"]).sum()
+        assert np.array_equal(a["pixels"], b["pixels"])
+        assert a["counters"]["shadow"] > 10000

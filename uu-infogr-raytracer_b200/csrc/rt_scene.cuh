@@ -5,6 +5,7 @@
 #pragma once
 #include "rt_trace.cuh"
 #include "rt_lbvh.cuh"
+#include "rt_shadow_grid.cuh"
 
 namespace rtb {
 
@@ -42,7 +43,7 @@ struct TinyScene {
     template <class DBG> RT_HD void nearest(f3 o, f3 d, float a2, float a4, float off, int* sel, float* t, DBG& dbg) const {
         brute_nearest<NS>(*this, o, d, a2, a4, off, sel, t, dbg);
     }
-    template <class DBG> RT_HD bool shadow_any(f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
+    template <class DBG> RT_HD bool shadow_any(int, f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
         return brute_shadow_any<NS>(*this, hit, lp, a2, a4, dbg);
     }
 };
@@ -97,7 +98,7 @@ struct GlobalScene {
     template <class DBG> RT_HD void nearest(f3 o, f3 d, float a2, float a4, float off, int* sel, float* t, DBG& dbg) const {
         brute_nearest<-1>(*this, o, d, a2, a4, off, sel, t, dbg);
     }
-    template <class DBG> RT_HD bool shadow_any(f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
+    template <class DBG> RT_HD bool shadow_any(int, f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
         return brute_shadow_any<-1>(*this, hit, lp, a2, a4, dbg);
     }
 };
@@ -111,21 +112,26 @@ struct StagedScene : GlobalScene {
     template <class DBG> RT_HD void nearest(f3 o, f3 d, float a2, float a4, float off, int* sel, float* t, DBG& dbg) const {
         brute_nearest<-1>(*this, o, d, a2, a4, off, sel, t, dbg);
     }
-    template <class DBG> RT_HD bool shadow_any(f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
+    template <class DBG> RT_HD bool shadow_any(int, f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
         return brute_shadow_any<-1>(*this, hit, lp, a2, a4, dbg);
     }
 };
 
-// LBVH over the spheres (rt_lbvh.cuh); planes stay in the brute-force side list (they are infinite).
+// LBVH over the spheres (rt_lbvh.cuh) for nearest-hit queries, per-light projected bins (rt_shadow_grid.cuh) for shadow rays;
+// planes stay in the brute-force side list (they are infinite).
 struct LbvhScene : GlobalScene {
     BvhView bv;
-    RT_HD LbvhScene(const GlobalSceneData& d, const BvhView& v) : GlobalScene(d), bv(v) {}
+    ShadowGridsView sg;
+    RT_HD LbvhScene(const GlobalSceneData& d, const BvhView& v, const ShadowGridsView& g) : GlobalScene(d), bv(v), sg(g) {}
     template <class DBG> RT_HD void nearest(f3 o, f3 d, float a2, float a4, float off, int* sel, float* t, DBG& dbg) const {
         const GlobalScene& base = *this;
         bvh_nearest(bv, o, d, a2, a4, off, sel, t, dbg,
                     [&](int* s2, float* t2) { NoDbg nd; brute_nearest<-1>(base, o, d, a2, a4, off, s2, t2, nd); });
     }
-    template <class DBG> RT_HD bool shadow_any(f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
+    template <class DBG> RT_HD bool shadow_any(int li, f3 hit, f3 lp, float a2, float a4, DBG& dbg) const {
+        bool decided;
+        const bool occ = shadow_grid_any(sg, li, hit, lp, a2, a4, &decided, dbg);
+        if (decided) return occ;
         const GlobalScene& base = *this;
         return bvh_shadow_any(bv, hit, lp, a2, a4, dbg, [&]() { NoDbg nd; return brute_shadow_any<-1>(base, hit, lp, a2, a4, nd); });
     }

@@ -15,7 +15,7 @@
 //   PlaneRec access: plane_n(i) (normal + Dot(center,normal)), plane_e1/e2(i), plane_mat(i), plane_flags(i)
 //   LightRec light(i)
 //   void nearest   (o, dir, a2, a4, off, &sel, &d, dbg)   RayTracer.cs:975-981 (off = 0) / :792-808 (off = 0.01f)
-//   bool shadow_any(hit, light, dbg)                       RayTracer.cs:573-582
+//   bool shadow_any(li, hit, lp, a2, a4, dbg)              RayTracer.cs:573-582 (li = light index, -1 for free queries)
 #pragma once
 #include "rt_math.cuh"
 
@@ -250,7 +250,7 @@ RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& d
 #pragma unroll
         for (int li = 0; li < nl; li++) {                         // :863 / :751
             const LightRec l = sc.light(li);
-            bool occ = sc.shadow_any(hit, l.p, l.a2, l.a4, dbg);  // :864 / :752
+            bool occ = sc.shadow_any(li, hit, l.p, l.a2, l.a4, dbg);  // :864 / :752
             dbg.shadow(level, (uint32_t)li, occ);
             float I = occ ? 0.0f : l.intensity;                   // :581
             // ShapePhongShading :665-695

@@ -246,9 +246,9 @@ __device__ __forceinline__ const f4* stage_spheres(const GlobalSceneData& scd) {
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_staged(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp) {
     render_loop<PPT_HEAVY>(StagedScene(scd, stage_spheres(scd)), fp);
 }
-struct LbvhSceneData { GlobalSceneData g; BvhView bv; };
+struct LbvhSceneData { GlobalSceneData g; BvhView bv; ShadowGridsView sg; };
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_lbvh(const __grid_constant__ LbvhSceneData scd, const __grid_constant__ FrameParams fp) {
-    render_loop<PPT_HEAVY>(LbvhScene(scd.g, scd.bv), fp);
+    render_loop<PPT_HEAVY>(LbvhScene(scd.g, scd.bv, scd.sg), fp);
 }
 
 // Instrumented kernel: one thread per pixel, writes hash / AOVs / counters.
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(BLOCK) k_debug_staged(const __grid_constant__ 
     debug_loop(StagedScene(scd, stage_spheres(scd)), fp, dout);
 }
 __global__ void __launch_bounds__(BLOCK) k_debug_lbvh(const __grid_constant__ LbvhSceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
-    debug_loop(LbvhScene(scd.g, scd.bv), fp, dout);
+    debug_loop(LbvhScene(scd.g, scd.bv, scd.sg), fp, dout);
 }
 
 // Sphere-query kernels (LBVH == brute equality harness, rt_query_spheres).
@@ -298,7 +298,7 @@ __device__ __forceinline__ void query_loop(const SC& sc, const float* rays6, int
         int sel = -1; float t = 0.0f;
         if (kind == 0) { sc.nearest(o, d, a2, a4, 0.0f, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
         else if (kind == 1) { sc.nearest(o, d, a2, a4, 0.01f, &sel, &t, dbg); if (sel < 0) t = 0.0f; }
-        else { sel = sc.shadow_any(o, d, a2, a4, dbg) ? 1 : 0; t = 0.0f; }
+        else { sel = sc.shadow_any(-1, o, d, a2, a4, dbg) ? 1 : 0; t = 0.0f; }
         out_id[r] = sel; out_t[r] = t;
     }
 }
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(BLOCK) k_query_brute(const __grid_constant__ G
 }
 __global__ void __launch_bounds__(BLOCK) k_query_lbvh(const __grid_constant__ LbvhSceneData scd, const float* rays6, int n, int kind,
                                                        int32_t* out_id, float* out_t) {
-    query_loop(LbvhScene(scd.g, scd.bv), rays6, n, kind, out_id, out_t);
+    query_loop(LbvhScene(scd.g, scd.bv, scd.sg), rays6, n, kind, out_id, out_t);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -322,6 +322,7 @@ struct DeviceState {
     // scene
     f4* sgeom = nullptr; MatRec* smat = nullptr; PlaneRec* planes = nullptr; LightRec* lights = nullptr;
     LbvhDevice bvh;
+    ShadowGrid* sg_grids = nullptr; int* sg_cells = nullptr; f4* sg_items = nullptr;      // per-light shadow bins (rt_shadow_grid.cuh)
     float bvh_cam[3] = {0, 0, 0}; bool bvh_cam_valid = false;    // camera the nodes_cam copy is currently inflated for ...
     cudaStream_t bvh_cam_stream = nullptr;                        // ... by a refit issued on this stream
     // framebuffer ring (device 0 of the context only, unless partitioned multi-process)
@@ -345,6 +346,9 @@ struct rt_context {
     bool tiny = false;              // scene fits the kernel-parameter block (TinySceneData)
     int path = PATH_TINY;           // how rt_render traces spheres
     bool has_bvh = false;
+    bool has_shadow_grids = false;
+    std::vector<f4> host_sgeom; std::vector<f3> host_lights;     // kept for rt_update_spheres (shadow bins are rebuilt on the host)
+    f3 sg_lo, sg_hi;
     TinySceneData tiny_data;
     GlobalSceneData gdata_host;     // counts + ambient (pointers per device filled at launch)
     int accel = RT_ACCEL_BRUTE;
@@ -376,6 +380,8 @@ int fail(rt_context* ctx, int code, const std::string& msg) {
 void free_scene(DeviceState& d) {
     cudaSetDevice(d.dev);
     d.bvh.release(); d.bvh_cam_valid = false;
+    cudaFree(d.sg_grids); cudaFree(d.sg_cells); cudaFree(d.sg_items);
+    d.sg_grids = nullptr; d.sg_cells = nullptr; d.sg_items = nullptr;
     cudaFree(d.sgeom); cudaFree(d.smat); cudaFree(d.planes); cudaFree(d.lights);
     d.sgeom = nullptr; d.smat = nullptr; d.planes = nullptr; d.lights = nullptr;
 }
@@ -423,6 +429,31 @@ FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp,
     fp.frame_stride = frame_stride;
     fp.out = out;
     return fp;
+}
+
+// (Re)builds the per-light shadow bins on the host from ctx->host_sgeom / host_lights and uploads them to every device.
+int upload_shadow_grids(rt_context* ctx) {
+    ctx->has_shadow_grids = false;
+    if (!ctx->has_bvh || getenv("RTB200_NO_SHADOW_GRID")) return RT_OK;
+    ShadowGridsHost h;
+    shadow_grids_build(ctx->host_sgeom, ctx->host_lights, &h);
+    if (h.empty() || h.cell_start.empty()) return RT_OK;
+    for (auto& d : ctx->devs) {
+        CU_TRY(ctx, cudaSetDevice(d.dev));
+        cudaFree(d.sg_grids); cudaFree(d.sg_cells); cudaFree(d.sg_items);
+        d.sg_grids = nullptr; d.sg_cells = nullptr; d.sg_items = nullptr;
+        CU_TRY(ctx, cudaMalloc(&d.sg_grids, sizeof(ShadowGrid) * h.grids.size()));
+        CU_TRY(ctx, cudaMalloc(&d.sg_cells, sizeof(int) * h.cell_start.size()));
+        CU_TRY(ctx, cudaMalloc(&d.sg_items, sizeof(f4) * (h.items.empty() ? 1 : h.items.size())));
+        CU_TRY(ctx, cudaMemcpyAsync(d.sg_grids, h.grids.data(), sizeof(ShadowGrid) * h.grids.size(), cudaMemcpyHostToDevice, d.stream));
+        CU_TRY(ctx, cudaMemcpyAsync(d.sg_cells, h.cell_start.data(), sizeof(int) * h.cell_start.size(), cudaMemcpyHostToDevice, d.stream));
+        if (!h.items.empty())
+            CU_TRY(ctx, cudaMemcpyAsync(d.sg_items, h.items.data(), sizeof(f4) * h.items.size(), cudaMemcpyHostToDevice, d.stream));
+        CU_TRY(ctx, cudaStreamSynchronize(d.stream));
+    }
+    ctx->sg_lo = h.lo; ctx->sg_hi = h.hi;
+    ctx->has_shadow_grids = true;
+    return RT_OK;
 }
 
 GlobalSceneData global_data(const rt_context* ctx, const DeviceState& d) {
@@ -623,6 +654,10 @@ int rt_set_scene(rt_context* ctx, const float* spheres, int ns, const float* pla
         }
         ctx->has_bvh = true;
     }
+    ctx->host_sgeom = sg;
+    ctx->host_lights.resize((size_t)nl);
+    for (int i = 0; i < nl; i++) ctx->host_lights[(size_t)i] = li[(size_t)i].p;
+    { int rc = upload_shadow_grids(ctx); if (rc) return rc; }
     if (ctx->has_bvh) ctx->path = PATH_LBVH;
     else if (ctx->tiny) ctx->path = PATH_TINY;
     else if (ns <= STAGED_MAX_SPHERES) ctx->path = PATH_STAGED;
@@ -654,6 +689,7 @@ int rt_update_spheres(rt_context* ctx, const float* spheres, int first, int coun
         if (f[17] > r2max) r2max = f[17];
     }
     if (ctx->tiny) for (int i = 0; i < count; i++) { ctx->tiny_data.sgeom[first + i] = sg[(size_t)i]; ctx->tiny_data.smat[first + i] = sm[(size_t)i]; }
+    for (int i = 0; i < count; i++) ctx->host_sgeom[(size_t)(first + i)] = sg[(size_t)i];
     for (auto& d : ctx->devs) {
         CU_TRY(ctx, cudaSetDevice(d.dev));
         CU_TRY(ctx, cudaMemcpyAsync(d.sgeom + first, sg.data(), sizeof(f4) * (size_t)count, cudaMemcpyHostToDevice, d.stream));
@@ -668,7 +704,7 @@ int rt_update_spheres(rt_context* ctx, const float* spheres, int first, int coun
         }
         CU_TRY(ctx, cudaStreamSynchronize(d.stream));     // sg / sm go out of scope; later launches may use another stream
     }
-    return RT_OK;
+    return upload_shadow_grids(ctx);                       // the bins depend on the sphere positions: rebuilt on the host
 }
 
 int rt_set_option(rt_context* ctx, int option, int value) {

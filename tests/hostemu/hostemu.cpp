@@ -144,12 +144,12 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         for (int i = 0; i < np; i++) t.planes[i] = pl[i];
         for (int i = 0; i < nl; i++) t.lights[i] = li[i];
     }
-    uint64_t cnt[10] = {0};
+    uint64_t cnt[14] = {0};
     const bool dbg_mode = hash || aov_id || aov_t || counters;
 #pragma omp parallel
     {
         HitRec stack[33];
-        uint64_t lc[10] = {0};
+        uint64_t lc[14] = {0};
 #pragma omp for schedule(dynamic, 4)
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++) {
@@ -164,6 +164,7 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
                     lc[0] += dbg.primary; lc[1] += dbg.n_shadow; lc[2] += dbg.secondary; lc[3] += dbg.sphere_tests;
                     lc[4] += dbg.sphere_disc_pos; lc[5] += dbg.plane_tests; lc[6] += dbg.shade_diffuse; lc[7] += dbg.shade_specular;
                     lc[8] += dbg.shade_mirror; lc[9] += dbg.shaded_hits;
+                    lc[10] += dbg.node_visits[0]; lc[11] += dbg.node_visits[1]; lc[12] += dbg.node_visits[2]; lc[13] += dbg.fallbacks;
                 } else {
                     NoDbg dbg;
                     uint32_t c = dispatch(use_tiny, t, g, cam, x, y, w, h, max_depth, spp, seed, stack, dbg);
@@ -171,9 +172,9 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
                 }
             }
 #pragma omp critical
-        for (int i = 0; i < 10; i++) cnt[i] += lc[i];
+        for (int i = 0; i < 14; i++) cnt[i] += lc[i];
     }
-    if (counters) for (int i = 0; i < 10; i++) counters[i] = cnt[i];
+    if (counters) for (int i = 0; i < 14; i++) counters[i] = cnt[i];
     return 0;
 }
 

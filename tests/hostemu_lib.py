@@ -32,7 +32,7 @@ def render(scene, cam, w, h, max_depth=32, spp=1, seed=0, tiny=0, debug=False):
     lib = load()
     n = w * h
     px = np.zeros(n, np.int32)
-    hsh = np.zeros(n, np.uint32); aid = np.zeros(n, np.int32); at = np.zeros(n, np.float32); cnt = np.zeros(10, np.uint64)
+    hsh = np.zeros(n, np.uint32); aid = np.zeros(n, np.int32); at = np.zeros(n, np.float32); cnt = np.zeros(14, np.uint64)
     cam = np.ascontiguousarray(cam, np.float32)
     rc = lib.emu_render(_fp(scene.spheres), len(scene.spheres), _fp(scene.planes), len(scene.planes), _fp(scene.lights),
                         len(scene.lights), _fp(scene.ambient), _fp(cam), w, h, max_depth, spp, seed, int(tiny),
@@ -42,7 +42,7 @@ def render(scene, cam, w, h, max_depth=32, spp=1, seed=0, tiny=0, debug=False):
                         cnt.ctypes.data_as(C.POINTER(C.c_uint64)) if debug else None)
     assert rc == 0
     return dict(pixels=px.reshape(h, w), hash=hsh.reshape(h, w), aov_id=aid.reshape(h, w), aov_t=at.reshape(h, w),
-                counters=[int(v) for v in cnt])
+                counters=[int(v) for v in cnt[:10]], lbvh=[int(v) for v in cnt[10:]])
 
 
 def query(spheres, rays6, kind, accel):

@@ -463,8 +463,12 @@ GlobalSceneData global_data(const rt_context* ctx, const DeviceState& d) {
 }
 LbvhSceneData lbvh_data(const rt_context* ctx, const DeviceState& d, bool with_cam_boxes) {
     LbvhSceneData l;
+    memset(&l, 0, sizeof(l));
     l.g = global_data(ctx, d);
     l.bv.nodes = d.bvh.nodes; l.bv.nodes_cam = with_cam_boxes ? d.bvh.nodes_cam : nullptr; l.bv.sgeom_sorted = d.bvh.sorted; l.bv.orig = d.bvh.orig; l.bv.n = d.bvh.n; l.bv.r2max = d.bvh.r2max;
+    const bool grids = ctx->has_shadow_grids && with_cam_boxes;      // free single-ray queries always traverse
+    l.sg.grids = grids ? d.sg_grids : nullptr; l.sg.cell_start = d.sg_cells; l.sg.items = d.sg_items;
+    l.sg.lo = ctx->sg_lo; l.sg.hi = ctx->sg_hi;
     return l;
 }
 

@@ -199,6 +199,9 @@ RT_HD bool brute_shadow_any(const SC& sc, f3 hit, f3 lp, float a2, float a4, DBG
 // (float)Math.Pow((double)base, (double)n) — RayTracer.cs:691.  pow(x,1) == x exactly; pow(x,.5) rounds as sqrtf(x)
 // (SURVEY A.12); everything else takes the f64 pow.
 RT_HD float spec_pow(float base, float n) {
+    // base comes from cs_max0: +0 whenever the highlight faces away. pow(+0, n) = +0 for every n > 0 (HasSpecularity, :93) —
+    // answering it here also keeps sqrtf(0) out of its slow path (0.6 % of all instructions on the default scene).
+    if (base == 0.0f) return 0.0f;
     if (n == 1.0f) return base;
     if (n == 0.5f) return sqrtf(base);
 #if defined(__CUDA_ARCH__)
@@ -303,9 +306,15 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
 #pragma unroll
         for (int i = 0; i < np; i++) {                                                     // :985 / :812
             f4 pn = sc.plane_n(i);
-            float t = (-o.x * pn.x - o.y * pn.y - o.z * pn.z + pn.w) / dot3(dir, mk3(pn.x, pn.y, pn.z));   // :591-596
+            float num = -o.x * pn.x - o.y * pn.y - o.z * pn.z + pn.w;                       // :591-594
             dbg.plane_test();
-            if (t > 0 && t < d_p) { d_p = t; sel_p = i; }                                  // :598 + :987 / :819
+            // num == 0 (a ray leaving the plane it starts on: every floor reflection re-tests the floor) gives
+            // t = 0/den = +-0 or NaN: never `> 0`. Skipping the division is exact and avoids the IEEE-divide slow path that a zero
+            // numerator takes (2.4 % of all instructions on the default scene).
+            if (num != 0.0f) {
+                float t = num / dot3(dir, mk3(pn.x, pn.y, pn.z));                          // :595-596
+                if (t > 0 && t < d_p) { d_p = t; sel_p = i; }                              // :598 + :987 / :819
+            }
         }
         bool pick_s = d_s < d_p;                                                           // :993 / :825
         bool none = !pick_s && sel_p < 0;

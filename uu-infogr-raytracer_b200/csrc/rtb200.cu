@@ -29,7 +29,7 @@ using namespace rtb;
 namespace {
 
 #ifndef RT_BLOCK
-#define RT_BLOCK 256
+#define RT_BLOCK 128              // 128-thread CTAs (512 / 128 pixels per CTA): +2.4 % over 256 on B200 (profiles/r01/tuning.md)
 #endif
 #ifndef RT_PPT_TINY
 #define RT_PPT_TINY 4
@@ -42,7 +42,7 @@ constexpr int STACK_RECS = RT_MAX_DEPTH + 1;
 constexpr int INLINE_CAMS = 16;
 constexpr int N_DEBUG_COUNTERS = 16;
 #ifndef RT_MIN_BLOCKS
-#define RT_MIN_BLOCKS 4      // resident CTAs per SM the register allocator must allow (tuned on B200, profiles/)
+#define RT_MIN_BLOCKS 8      // resident CTAs per SM the register allocator must allow (tuned on B200, profiles/)
 #endif
 
 struct FrameParams {

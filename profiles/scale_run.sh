@@ -21,7 +21,7 @@ for l in open("gpurun_out/scale.jsonl"):
 PY
 for n in 1 2 4 8; do
   if [ $n -le $MAXG ]; then
-    python profiles/run_configs.py gpurun_out/configs45_n$n.json --only45 --devices=$n 2>>gpurun_out/scale.err | python -c "
+    python profiles/run_configs.py gpurun_out/configs45_n$n.json --skip-brute3 --devices=$n 2>>gpurun_out/scale.err | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)

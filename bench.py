@@ -59,7 +59,9 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.p = None
-        self.idx = gpu_index
+        # nvidia-smi numbers physical GPUs; map the CUDA ordinal through CUDA_VISIBLE_DEVICES (indices or UUIDs) if it is set
+        vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        self.idx = vis[gpu_index] if gpu_index < len(vis) else gpu_index
 
     def start(self):
         try:

@@ -13,6 +13,9 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -339,9 +342,43 @@ constexpr int AUTO_LBVH_MIN_SPHERES = 48;      // below this the brute-force loo
 
 }  // namespace
 
+// One enqueue worker per extra device: a multi-device frame needs ~5 runtime calls per device (refit, launch, events, copies);
+// issued from one thread they skew the last device's start by ~20 us per device. The workers issue them concurrently.
+struct DeviceWorkers {
+    struct W { std::thread th; std::mutex m; std::condition_variable cv; std::function<int()> job; bool has_job = false, quit = false; int rc = 0; };
+    std::vector<W*> ws;
+    void start(int n) {
+        for (int i = 0; i < n; i++) {
+            W* w = new W();
+            w->th = std::thread([w]() {
+                std::unique_lock<std::mutex> lk(w->m);
+                for (;;) {
+                    w->cv.wait(lk, [w] { return w->has_job || w->quit; });
+                    if (w->quit) return;
+                    std::function<int()> j = std::move(w->job);
+                    lk.unlock();
+                    int rc = j();
+                    lk.lock();
+                    w->rc = rc; w->has_job = false;
+                    w->cv.notify_all();
+                }
+            });
+            ws.push_back(w);
+        }
+    }
+    void post(int i, std::function<int()> j) { W* w = ws[(size_t)i]; { std::lock_guard<std::mutex> lk(w->m); w->job = std::move(j); w->has_job = true; } w->cv.notify_all(); }
+    int wait(int i) { W* w = ws[(size_t)i]; std::unique_lock<std::mutex> lk(w->m); w->cv.wait(lk, [w] { return !w->has_job; }); return w->rc; }
+    void stop() {
+        for (W* w : ws) { { std::lock_guard<std::mutex> lk(w->m); w->quit = true; } w->cv.notify_all(); w->th.join(); delete w; }
+        ws.clear();
+    }
+};
+
 struct rt_context {
     std::vector<DeviceState> devs;
     std::string err;
+    std::mutex err_mu;              // fail() may be called from the enqueue workers
+    DeviceWorkers workers;          // devs.size() - 1 threads (device 0 is served by the calling thread)
     bool has_scene = false;
     bool tiny = false;              // scene fits the kernel-parameter block (TinySceneData)
     int path = PATH_TINY;           // how rt_render traces spheres
@@ -365,7 +402,7 @@ std::string g_create_err;
 std::mutex g_err_mu;
 
 int fail(rt_context* ctx, int code, const std::string& msg) {
-    if (ctx) ctx->err = msg;
+    if (ctx) { std::lock_guard<std::mutex> lk(ctx->err_mu); ctx->err = msg; }
     else { std::lock_guard<std::mutex> lk(g_err_mu); g_create_err = msg; }
     if (getenv("RT_LOG")) fprintf(stderr, "[rtb200] error %d: %s\n", code, msg.c_str());
     return code;
@@ -569,12 +606,14 @@ int rt_create(rt_context** out, const int* device_ids, int n_devices) {
         cudaGetLastError();
     }
     if (n_devices > 1 && !ctx->peer_ok) { delete ctx; return fail(nullptr, RT_ERR_PEER, "peer access to device 0 unavailable"); }
+    if (n_devices > 1) ctx->workers.start(n_devices - 1);
     *out = ctx;
     return RT_OK;
 }
 
 int rt_destroy(rt_context* ctx) {
     if (!ctx) return RT_ERR_INVALID;
+    ctx->workers.stop();
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.dev);
         cudaStreamSynchronize(d.stream);
@@ -796,67 +835,89 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             }
         }
     }
-    for (int g = 0; g < G; g++) {
-        DeviceState& d = ctx->devs[(size_t)g];
-        CU_TRY(ctx, cudaSetDevice(d.dev));
-        CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
-    }
     const long long tile_pix = (long long)ctx->tile_rows * w;
-    bool first_copy = true;
     std::vector<char> first_copy_dev((size_t)G, 1);
-    for (int s = 0; s < n_segments; s++) {
+    // Everything device g has to enqueue for segment s (its launch, its band event, and in `direct` mode its own D2H copies).
+    auto enqueue = [&](int g, int s) -> int {
+        DeviceState& d = ctx->devs[(size_t)g];
         const int frame = pipelined ? s / n_bands : s * INLINE_CAMS, band = pipelined ? s % n_bands : 0;
         const int nf = pipelined ? 1 : (n_frames - frame < INLINE_CAMS ? n_frames - frame : INLINE_CAMS);
+        const int rank = G > 1 ? g : ctx->rank;
+        FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, rank, world, (direct ? d.fb : d0.fb) + (size_t)frame * npix, (long long)npix);
+        if (pipelined) {
+            fp.cam_inline[0] = to_cam(cams[frame]);
+            const int k0 = band * (band_tiles / world), k1 = k0 + band_tiles / world;       // this rank's tiles of the band
+            const int mine = fp.tiles_mine;
+            fp.k_begin = k0 < mine ? k0 : mine;
+            fp.tiles_mine = (k1 < mine ? k1 : mine) - fp.k_begin;
+        } else {
+            for (int i = 0; i < nf; i++) fp.cam_inline[i] = to_cam(cams[frame + i]);
+        }
+        int rc2 = launch_render(ctx, d, fp, d.stream); if (rc2) return rc2;
+        if (pipelined) CU_TRY(ctx, cudaEventRecord(d.band_events[(size_t)s], d.stream));
+        if (direct && fp.tiles_mine > 0) {
+            // this device's tiles of the band: tile k*world + g for k in [k_begin, k_begin + tiles_mine), i.e. blocks of
+            // tile_pix pixels every world*tile_pix pixels -> one strided 2-D copy (+ a 1-D copy if the frame's last tile is short)
+            CU_TRY(ctx, cudaStreamWaitEvent(d.copy_stream, d.band_events[(size_t)s], 0));
+            if (first_copy_dev[(size_t)g]) { CU_TRY(ctx, cudaEventRecord(d.evc0, d.copy_stream)); first_copy_dev[(size_t)g] = 0; }
+            const long long first_px = ((long long)fp.k_begin * world + g) * tile_pix;
+            const long long last_tile = ((long long)(fp.k_begin + fp.tiles_mine - 1)) * world + g;
+            const bool last_short = (last_tile + 1) * tile_pix > (long long)npix;
+            const int full = fp.tiles_mine - (last_short ? 1 : 0);
+            uint32_t* src = d.fb + (size_t)frame * npix; int32_t* dst = host_pixels + (size_t)frame * npix;
+            if (full > 0)
+                CU_TRY(ctx, cudaMemcpy2DAsync(dst + first_px, (size_t)world * tile_pix * 4, src + first_px, (size_t)world * tile_pix * 4,
+                                              (size_t)tile_pix * 4, (size_t)full, cudaMemcpyDeviceToHost, d.copy_stream));
+            if (last_short) {
+                const long long p0 = last_tile * tile_pix;
+                CU_TRY(ctx, cudaMemcpyAsync(dst + p0, src + p0, (size_t)((long long)npix - p0) * 4, cudaMemcpyDeviceToHost, d.copy_stream));
+            }
+        }
+        return RT_OK;
+    };
+    if (G > 1 && (direct || !pipelined)) {
+        // No cross-device dependency at enqueue time: every device's whole frame (all segments) is issued by its own thread.
+        auto device_job = [&](int g) -> int {
+            DeviceState& d = ctx->devs[(size_t)g];
+            CU_TRY(ctx, cudaSetDevice(d.dev));
+            CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
+            for (int s = 0; s < n_segments; s++) { int rc2 = enqueue(g, s); if (rc2) return rc2; }
+            CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
+            return RT_OK;
+        };
+        for (int g = 1; g < G; g++) ctx->workers.post(g - 1, [&device_job, g]() { return device_job(g); });
+        rc = device_job(0);
+        for (int g = 1; g < G; g++) { int rc2 = ctx->workers.wait(g - 1); if (!rc) rc = rc2; }
+        if (rc) return rc;
+    } else {
         for (int g = 0; g < G; g++) {
             DeviceState& d = ctx->devs[(size_t)g];
             CU_TRY(ctx, cudaSetDevice(d.dev));
-            const int rank = G > 1 ? g : ctx->rank;
-            FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, rank, world, (direct ? d.fb : d0.fb) + (size_t)frame * npix, (long long)npix);
-            if (pipelined) {
-                fp.cam_inline[0] = to_cam(cams[frame]);
-                const int k0 = band * (band_tiles / world), k1 = k0 + band_tiles / world;       // this rank's tiles of the band
-                const int mine = fp.tiles_mine;
-                fp.k_begin = k0 < mine ? k0 : mine;
-                fp.tiles_mine = (k1 < mine ? k1 : mine) - fp.k_begin;
-            } else {
-                for (int i = 0; i < nf; i++) fp.cam_inline[i] = to_cam(cams[frame + i]);
+            CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
+        }
+        bool first_copy = true;
+        for (int s = 0; s < n_segments; s++) {
+            const int frame = pipelined ? s / n_bands : s * INLINE_CAMS, band = pipelined ? s % n_bands : 0;
+            for (int g = 0; g < G; g++) {
+                CU_TRY(ctx, cudaSetDevice(ctx->devs[(size_t)g].dev));
+                rc = enqueue(g, s); if (rc) return rc;
             }
-            rc = launch_render(ctx, d, fp, d.stream); if (rc) return rc;
-            if (pipelined) CU_TRY(ctx, cudaEventRecord(d.band_events[(size_t)s], d.stream));
-            if (direct && fp.tiles_mine > 0) {
-                // this device's tiles of the band: tile k*world + g for k in [k_begin, k_begin + tiles_mine), i.e. blocks of
-                // tile_pix pixels every world*tile_pix pixels -> one strided 2-D copy (+ a 1-D copy if the frame's last tile is short)
-                CU_TRY(ctx, cudaStreamWaitEvent(d.copy_stream, d.band_events[(size_t)s], 0));
-                if (first_copy_dev[(size_t)g]) { CU_TRY(ctx, cudaEventRecord(d.evc0, d.copy_stream)); first_copy_dev[(size_t)g] = 0; }
-                const long long first_px = ((long long)fp.k_begin * world + g) * tile_pix;
-                const long long last_tile = ((long long)(fp.k_begin + fp.tiles_mine - 1)) * world + g;
-                const bool last_short = (last_tile + 1) * tile_pix > (long long)npix;
-                const int full = fp.tiles_mine - (last_short ? 1 : 0);
-                uint32_t* src = d.fb + (size_t)frame * npix; int32_t* dst = host_pixels + (size_t)frame * npix;
-                if (full > 0)
-                    CU_TRY(ctx, cudaMemcpy2DAsync(dst + first_px, (size_t)world * tile_pix * 4, src + first_px, (size_t)world * tile_pix * 4,
-                                                  (size_t)tile_pix * 4, (size_t)full, cudaMemcpyDeviceToHost, d.copy_stream));
-                if (last_short) {
-                    const long long p0 = last_tile * tile_pix;
-                    CU_TRY(ctx, cudaMemcpyAsync(dst + p0, src + p0, (size_t)((long long)npix - p0) * 4, cudaMemcpyDeviceToHost, d.copy_stream));
-                }
+            if (pipelined && !direct) {       // gather-on-GPU-0 path: device 0's copy stream waits for every device's band
+                CU_TRY(ctx, cudaSetDevice(d0.dev));
+                for (int g = 0; g < G; g++) CU_TRY(ctx, cudaStreamWaitEvent(d0.copy_stream, ctx->devs[(size_t)g].band_events[(size_t)s], 0));
+                if (first_copy) { CU_TRY(ctx, cudaEventRecord(d0.evc0, d0.copy_stream)); first_copy = false; }
+                long long p0 = (long long)band * band_tiles * tile_pix, p1 = p0 + (long long)band_tiles * tile_pix;
+                if (p1 > (long long)npix) p1 = (long long)npix;
+                if (p1 > p0)
+                    CU_TRY(ctx, cudaMemcpyAsync(host_pixels + (size_t)frame * npix + p0, d0.fb + (size_t)frame * npix + p0,
+                                                (size_t)(p1 - p0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, d0.copy_stream));
             }
         }
-        if (pipelined && !direct) {
-            CU_TRY(ctx, cudaSetDevice(d0.dev));
-            for (int g = 0; g < G; g++) CU_TRY(ctx, cudaStreamWaitEvent(d0.copy_stream, ctx->devs[(size_t)g].band_events[(size_t)s], 0));
-            if (first_copy) { CU_TRY(ctx, cudaEventRecord(d0.evc0, d0.copy_stream)); first_copy = false; }
-            long long p0 = (long long)band * band_tiles * tile_pix, p1 = p0 + (long long)band_tiles * tile_pix;
-            if (p1 > (long long)npix) p1 = (long long)npix;
-            if (p1 > p0)
-                CU_TRY(ctx, cudaMemcpyAsync(host_pixels + (size_t)frame * npix + p0, d0.fb + (size_t)frame * npix + p0,
-                                            (size_t)(p1 - p0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, d0.copy_stream));
+        for (int g = 0; g < G; g++) {
+            DeviceState& d = ctx->devs[(size_t)g];
+            CU_TRY(ctx, cudaSetDevice(d.dev));
+            CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
         }
-    }
-    for (int g = 0; g < G; g++) {
-        DeviceState& d = ctx->devs[(size_t)g];
-        CU_TRY(ctx, cudaSetDevice(d.dev));
-        CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
     }
     float kernel_ms = 0.0f, d2h_ms = 0.0f;
     for (int g = 0; g < G; g++) {

@@ -761,7 +761,7 @@ int rt_set_option(rt_context* ctx, int option, int value) {
 
 int rt_set_partition(rt_context* ctx, int rank, int world, int tile_rows) {
     if (!ctx) return RT_ERR_INVALID;
-    if (world < 1 || rank < 0 || rank >= world || tile_rows < 1) return fail(ctx, RT_ERR_INVALID, "bad partition");
+    if (world < 1 || rank < 0 || rank >= world || tile_rows < 1 || tile_rows > 65536) return fail(ctx, RT_ERR_INVALID, "bad partition");
     if (ctx->devs.size() != 1 && world != 1) return fail(ctx, RT_ERR_INVALID, "rt_set_partition needs a single-device context");
     ctx->rank = rank; ctx->world = world; ctx->tile_rows = tile_rows;
     return RT_OK;

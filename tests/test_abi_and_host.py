@@ -100,3 +100,21 @@ def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu(built, tmp_path):
     r = subprocess.run([exe, str(tmp_path / "x.ppm"), "32", "18"], capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
     assert not (tmp_path / "x.ppm").exists()
+
+
+def test_sass_has_packed_fp32_but_no_packed_fma(built):
+    """The exact-count kernels use Blackwell's packed fp32 instructions (FADD2 / FMUL2) for two spheres at a time, but a
+    packed FMA must never appear: ptxas contracts packed mul+add into FFMA2 even under --fmad=false, which would round dot
+    products and discriminants once instead of twice (csrc/rt_trace.cuh). Scalar FFMA only comes from IEEE div / sqrt sequences."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "uu-infogr-raytracer_b200", "librtb200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert sass.count("FFMA2") == 0
+    assert sass.count("FADD2") > 0 and sass.count("FMUL2") > 0
+    assert "STG.E.128" in sass                      # 128-bit framebuffer stores
+    for mnem in ("HMMA", "UTCHMMA", "UTCQMMA"):      # no tensor cores on this path (north_star)
+        assert mnem not in sass

@@ -90,7 +90,7 @@ def test_golden_fixtures(ctx, name):
     assert np.array_equal(px, g["pixels"])
 
 
-@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (12, 1), (16, 2), (17, 9), (40, 3), (200, 4)])
+@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (2, 7), (4, 9), (5, 3), (8, 6), (9, 2), (12, 1), (17, 9), (40, 3), (200, 4)])
 def test_random_scenes(ctx, n, seed):
     """tiny (kernel-parameter) and global-memory scene paths, every material class, 2 planes, 3 lights."""
     sc = scenes.small_random_scene(n, seed)
@@ -275,7 +275,7 @@ def test_cpp_host_mirror_demo(built, tmp_path):
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("n,seed", [(3, 0), (12, 1), (16, 2), (2, 7)])
+@pytest.mark.parametrize("n,seed", [(3, 0), (8, 1), (5, 2), (2, 7)])
 def test_compaction_variant_is_identical(rt, n, seed):
     """RT_OPT_COMPACTION: the kernel that parks deep mirror chains in a shared-memory queue (warp-ballot compaction) and
     finishes them in full warps must produce exactly the default kernel's frames — full frames, odd sizes, partitions."""

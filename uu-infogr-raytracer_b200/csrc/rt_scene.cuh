@@ -9,11 +9,16 @@
 
 namespace rtb {
 
-enum { TINY_MAX_SPHERES = 16, TINY_MAX_PLANES = 4, TINY_MAX_LIGHTS = 8 };
+enum { TINY_MAX_SPHERES = 8, TINY_MAX_PLANES = 4, TINY_MAX_LIGHTS = 8 };
 
+// Sphere geometry of spheres 2k and 2k+1 side by side, NEGATED (o - c == o + (-c) and x - r^2 == x + (-r^2) exactly), so that one
+// packed-fp32 instruction (Blackwell FADD2 / FMUL2, rt_trace.cuh) serves both spheres with a 64-bit constant-bank operand.
+// An odd sphere count is padded with a sphere that can never pass the exact test (-r^2 = +1e30).
+struct SpherePair { float ncx[2], ncy[2], ncz[2], nr2[2]; };
 struct TinySceneData {
     int ns, np, nl, pad;
     f3 amb; float pad1;
+    SpherePair pairs[TINY_MAX_SPHERES / 2];
     f4 sgeom[TINY_MAX_SPHERES];
     MatRec smat[TINY_MAX_SPHERES];
     PlaneRec planes[TINY_MAX_PLANES];
@@ -32,6 +37,8 @@ struct TinyScene {
     RT_HD int n_lights() const { return NL >= 0 ? NL : s.nl; }
     RT_HD f3 ambient() const { return s.amb; }
     RT_HD f4 sphere_geom(int i) const { return s.sgeom[i]; }
+    RT_HD const SpherePair& sphere_pair(int k) const { return s.pairs[k]; }
+    static constexpr bool has_pairs = true;
     RT_HD MatRec sphere_mat(int i) const { return s.smat[i]; }
     RT_HD uint32_t sphere_flags(int i) const { return s.smat[i].flags; }
     RT_HD f4 plane_n(int i) const { f4 r; r.x = s.planes[i].n.x; r.y = s.planes[i].n.y; r.z = s.planes[i].n.z; r.w = s.planes[i].cn; return r; }
@@ -136,6 +143,16 @@ struct LbvhScene : GlobalScene {
         return bvh_shadow_any(bv, hit, lp, a2, a4, dbg, [&]() { NoDbg nd; return brute_shadow_any<-1>(base, hit, lp, a2, a4, nd); });
     }
 };
+
+inline void tiny_fill_pairs(TinySceneData& t) {
+    for (int k = 0; k < TINY_MAX_SPHERES / 2; k++)
+        for (int h = 0; h < 2; h++) {
+            const int i = 2 * k + h;
+            SpherePair& p = t.pairs[k];
+            if (i < t.ns) { p.ncx[h] = -t.sgeom[i].x; p.ncy[h] = -t.sgeom[i].y; p.ncz[h] = -t.sgeom[i].z; p.nr2[h] = -t.sgeom[i].w; }
+            else { p.ncx[h] = 0.0f; p.ncy[h] = 0.0f; p.ncz[h] = 0.0f; p.nr2[h] = 1e30f; }
+        }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Upload-time record construction (host, strict fp32: this file is compiled with -ffp-contract=off on the host side)

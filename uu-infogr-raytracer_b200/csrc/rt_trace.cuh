@@ -116,6 +116,47 @@ RT_HD bool sphere_root(float b, float D, float a2, float eps, float* t) {
     return true;
 }
 
+// b and the discriminant of spheres i0 and i0+1 in one pass of packed-fp32 instructions (sm_100 FADD2 / FMUL2: two IEEE
+// round-to-nearest fp32 operations per lane per instruction — bit-identical to the scalar sequence, half the issue slots; the
+// kernel is issue-bound with the FMA pipe ~35 % busy). Operation order per element is exactly :614-621.
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+#define RT_HAVE_F32X2 1
+// ptxas contracts a packed multiply that feeds a packed add into FFMA2 — even with explicit .rn, with --fmad=false, and when
+// the two are written as fma(a,b,-0) / fma(a,1,c) (it canonicalises and re-fuses; seen in SASS). A fused dot product or
+// discriminant rounds once instead of twice and breaks bit-exactness, so packed instructions are used only where no product
+// feeds an add directly: the three o + (-c) additions, all six products, 2*(.), the - r^2 addition and the two products of the
+// discriminant are packed; the sums of products stay scalar FADDs on the register halves (scalar contraction IS off under
+// -fmad=false). 13 packed + 10 scalar instructions per sphere pair instead of 36 scalar ones.
+__device__ __forceinline__ float2 rt_add2(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 rt_mul2(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+template <class PAIR>
+__device__ __forceinline__ void sphere_pair_bd(const PAIR& p, float2 ox, float2 oy, float2 oz, float2 dx, float2 dy, float2 dz,
+                                               float2 na4, float* b_out, float* D_out) {
+    const float2 ocx = rt_add2(ox, make_float2(p.ncx[0], p.ncx[1]));                      // :614  o - c
+    const float2 ocy = rt_add2(oy, make_float2(p.ncy[0], p.ncy[1]));
+    const float2 ocz = rt_add2(oz, make_float2(p.ncz[0], p.ncz[1]));
+    const float2 px = rt_mul2(ocx, dx), py = rt_mul2(ocy, dy), pz = rt_mul2(ocz, dz);
+    const float2 qx = rt_mul2(ocx, ocx), qy = rt_mul2(ocy, ocy), qz = rt_mul2(ocz, ocz);
+    const float2 bd = make_float2((px.x + py.x) + pz.x, (px.y + py.y) + pz.y);            // Dot: scalar adds (see above)
+    const float2 cd = make_float2((qx.x + qy.x) + qz.x, (qx.y + qy.y) + qz.y);
+    const float2 b = rt_mul2(make_float2(2.0f, 2.0f), bd);                                // :618
+    const float2 c = rt_add2(cd, make_float2(p.nr2[0], p.nr2[1]));                        // :619  dot - r^2
+    const float2 bb = rt_mul2(b, b), ac = rt_mul2(na4, c);
+    const float2 D = make_float2(bb.x + ac.x, bb.y + ac.y);                               // :621  b*b - (4a)*c
+    b_out[0] = b.x; b_out[1] = b.y; D_out[0] = D.x; D_out[1] = D.y;
+}
+#endif
+
 // The reference's loops over every sphere, in array order.  One loop serves both folds:
 //   primary   (:977)  `d > 0 && nearest > d`                    == key > 0 && key < closest with key = d - 0
 //   secondary (:804)  `d - 0.01f > 0 && d - 0.01f < closest`    == the same with key = d - 0.01f
@@ -128,16 +169,35 @@ RT_HD void brute_nearest(const SC& sc, f3 o, f3 dir, float a2, float a4, float o
     if constexpr (NS > 0) {
         // `gate` = max_i min(D_i, -b_i) >= 0 is a cheap SUPERSET of "some sphere has b < 0 && D >= 0" (two FMNMX per sphere;
         // fminf drops a NaN, b == 0 passes): it only decides whether the exact per-sphere tests below run at all.
-        float bs[NS], Ds[NS]; float gate = -1.0f;
+        float bs[NS + 1], Ds[NS + 1]; float gate = -1.0f;
+#if defined(RT_HAVE_F32X2)
+        if constexpr (SC::has_pairs && NS >= 2 && !DBG::enabled) {
+            const float2 ox = make_float2(o.x, o.x), oy = make_float2(o.y, o.y), oz = make_float2(o.z, o.z);
+            const float2 dx = make_float2(dir.x, dir.x), dy = make_float2(dir.y, dir.y), dz = make_float2(dir.z, dir.z);
+            const float2 na4 = make_float2(-a4, -a4);
 #pragma unroll
-        for (int i = 0; i < NS; i++) {
-            f4 g = sc.sphere_geom(i);
-            f3 oc = sub3(o, mk3(g.x, g.y, g.z));                  // :614
-            bs[i] = 2 * dot3(oc, dir);                            // :618
-            float c = dot3(oc, oc) - g.w;                         // :619
-            Ds[i] = bs[i] * bs[i] - a4 * c;                       // :621
-            dbg.sphere_test(Ds[i] >= 0);
-            gate = fmaxf(gate, fminf(Ds[i], -bs[i]));
+            for (int k = 0; k < NS / 2; k++) sphere_pair_bd(sc.sphere_pair(k), ox, oy, oz, dx, dy, dz, na4, bs + 2 * k, Ds + 2 * k);
+            if (NS & 1) {                                         // odd one out: scalar
+                f4 g = sc.sphere_geom(NS - 1);
+                f3 oc = sub3(o, mk3(g.x, g.y, g.z));
+                bs[NS - 1] = 2 * dot3(oc, dir);
+                Ds[NS - 1] = bs[NS - 1] * bs[NS - 1] - a4 * (dot3(oc, oc) - g.w);
+            }
+#pragma unroll
+            for (int i = 0; i < NS; i++) gate = fmaxf(gate, fminf(Ds[i], -bs[i]));
+        } else
+#endif
+        {
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                f4 g = sc.sphere_geom(i);
+                f3 oc = sub3(o, mk3(g.x, g.y, g.z));              // :614
+                bs[i] = 2 * dot3(oc, dir);                        // :618
+                float c = dot3(oc, oc) - g.w;                     // :619
+                Ds[i] = bs[i] * bs[i] - a4 * c;                   // :621
+                dbg.sphere_test(Ds[i] >= 0);
+                gate = fmaxf(gate, fminf(Ds[i], -bs[i]));
+            }
         }
         if (gate >= 0) {
 #pragma unroll
@@ -166,16 +226,35 @@ template <int NS, class SC, class DBG>
 RT_HD bool brute_shadow_any(const SC& sc, f3 hit, f3 lp, float a2, float a4, DBG& dbg) {
     bool occluded = false;
     if constexpr (NS > 0) {
-        float bs[NS], Ds[NS]; float gate = -1.0f;
+        float bs[NS + 1], Ds[NS + 1]; float gate = -1.0f;
+#if defined(RT_HAVE_F32X2)
+        if constexpr (SC::has_pairs && NS >= 2 && !DBG::enabled) {
+            const float2 ox = make_float2(hit.x, hit.x), oy = make_float2(hit.y, hit.y), oz = make_float2(hit.z, hit.z);
+            const float2 dx = make_float2(lp.x, lp.x), dy = make_float2(lp.y, lp.y), dz = make_float2(lp.z, lp.z);
+            const float2 na4 = make_float2(-a4, -a4);
 #pragma unroll
-        for (int i = 0; i < NS; i++) {
-            f4 g = sc.sphere_geom(i);
-            f3 oc = sub3(hit, mk3(g.x, g.y, g.z));
-            bs[i] = 2 * dot3(oc, lp);
-            float c = dot3(oc, oc) - g.w;
-            Ds[i] = bs[i] * bs[i] - a4 * c;
-            dbg.sphere_test(Ds[i] >= 0);
-            gate = fmaxf(gate, fminf(Ds[i], -bs[i]));
+            for (int k = 0; k < NS / 2; k++) sphere_pair_bd(sc.sphere_pair(k), ox, oy, oz, dx, dy, dz, na4, bs + 2 * k, Ds + 2 * k);
+            if (NS & 1) {                                         // odd one out: scalar
+                f4 g = sc.sphere_geom(NS - 1);
+                f3 oc = sub3(hit, mk3(g.x, g.y, g.z));
+                bs[NS - 1] = 2 * dot3(oc, lp);
+                Ds[NS - 1] = bs[NS - 1] * bs[NS - 1] - a4 * (dot3(oc, oc) - g.w);
+            }
+#pragma unroll
+            for (int i = 0; i < NS; i++) gate = fmaxf(gate, fminf(Ds[i], -bs[i]));
+        } else
+#endif
+        {
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                f4 g = sc.sphere_geom(i);
+                f3 oc = sub3(hit, mk3(g.x, g.y, g.z));
+                bs[i] = 2 * dot3(oc, lp);
+                float c = dot3(oc, oc) - g.w;
+                Ds[i] = bs[i] * bs[i] - a4 * c;
+                dbg.sphere_test(Ds[i] >= 0);
+                gate = fmaxf(gate, fminf(Ds[i], -bs[i]));
+            }
         }
         if (gate >= 0) {
 #pragma unroll

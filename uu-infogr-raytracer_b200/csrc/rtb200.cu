@@ -656,6 +656,7 @@ int rt_set_scene(rt_context* ctx, const float* spheres, int ns, const float* pla
         for (int i = 0; i < ns; i++) { t.sgeom[i] = sg[(size_t)i]; t.smat[i] = sm[(size_t)i]; }
         for (int i = 0; i < np; i++) t.planes[i] = pl[(size_t)i];
         for (int i = 0; i < nl; i++) t.lights[i] = li[(size_t)i];
+        tiny_fill_pairs(t);
     }
     memset(&ctx->gdata_host, 0, sizeof(ctx->gdata_host));
     ctx->gdata_host.ns = ns; ctx->gdata_host.np = np; ctx->gdata_host.nl = nl;
@@ -731,7 +732,10 @@ int rt_update_spheres(rt_context* ctx, const float* spheres, int first, int coun
         sm[(size_t)i] = make_mat(f + 4);
         if (f[17] > r2max) r2max = f[17];
     }
-    if (ctx->tiny) for (int i = 0; i < count; i++) { ctx->tiny_data.sgeom[first + i] = sg[(size_t)i]; ctx->tiny_data.smat[first + i] = sm[(size_t)i]; }
+    if (ctx->tiny) {
+        for (int i = 0; i < count; i++) { ctx->tiny_data.sgeom[first + i] = sg[(size_t)i]; ctx->tiny_data.smat[first + i] = sm[(size_t)i]; }
+        tiny_fill_pairs(ctx->tiny_data);
+    }
     for (int i = 0; i < count; i++) ctx->host_sgeom[(size_t)(first + i)] = sg[(size_t)i];
     for (auto& d : ctx->devs) {
         CU_TRY(ctx, cudaSetDevice(d.dev));

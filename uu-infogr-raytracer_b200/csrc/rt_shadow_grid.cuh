@@ -26,10 +26,14 @@ struct ShadowGrid {             // one per light
     float inv_cell; int dim_s, dim_t, cell_base;   // 1 / cell size; grid dimensions; offset of this light in cell_start
     int valid, pad0, pad1, pad2;                   // 0: no grid (zero / out-of-envelope light vector) -> LBVH traversal
 };
+// Cell lists hold spheres two at a time in the negated pair layout of rt_scene.cuh (SpherePair semantics: -cx[2], -cy[2], -cz[2],
+// -r^2[2]; an odd list is padded with a sphere that cannot pass the exact test), so that the query tests two spheres per pass of
+// packed fp32 instructions (sphere_pair_bd).
+struct GridPair { float ncx[2], ncy[2], ncz[2], nr2[2]; };
 struct ShadowGridsView {
     const ShadowGrid* grids;    // n_lights records, or nullptr
-    const int* cell_start;      // per light dim_s*dim_t + 1 offsets into items
-    const f4* items;            // (cx, cy, cz, r^2) per (cell, sphere) pair
+    const int* cell_start;      // per light dim_s*dim_t + 1 offsets into items (in pairs)
+    const GridPair* items;      // sphere pairs per cell
     f3 lo, hi;                  // query points inside this box may use the grids
 };
 
@@ -47,20 +51,37 @@ RT_HD bool shadow_grid_any(const ShadowGridsView& sg, int li, f3 hit, f3 lp, flo
     const int cell = g.cell_base + (int)ft * g.dim_s + (int)fs;
     const int b = sg.cell_start[cell], e = sg.cell_start[cell + 1];
     bool occluded = false;
+#if defined(RT_HAVE_F32X2)
+    const float2 ox = make_float2(hit.x, hit.x), oy = make_float2(hit.y, hit.y), oz = make_float2(hit.z, hit.z);
+    const float2 dx = make_float2(lp.x, lp.x), dy = make_float2(lp.y, lp.y), dz = make_float2(lp.z, lp.z);
+    const float2 na4 = make_float2(-a4, -a4);
+#endif
     for (int k = b; k < e; k++) {
-        const f4 s = sg.items[k];
-        float t;
-        if (sphere_hit(sub3(hit, mk3(s.x, s.y, s.z)), lp, s.w, a2, a4, 0.001f, &t, dbg)) {   // RayTracer.cs:578
-            occluded = true;
-            if (!DBG::enabled) break;       // boolean OR
+        float bs[2], Ds[2];
+#if defined(RT_HAVE_F32X2)
+        sphere_pair_bd(sg.items[k], ox, oy, oz, dx, dy, dz, na4, bs, Ds);                   // RayTracer.cs:614-621, two spheres
+        dbg.sphere_test(Ds[0] >= 0); dbg.sphere_test(Ds[1] >= 0);
+#else
+        const GridPair p = sg.items[k];
+        for (int h = 0; h < 2; h++) {
+            const f3 oc = mk3(hit.x + p.ncx[h], hit.y + p.ncy[h], hit.z + p.ncz[h]);       // o - c == o + (-c)
+            bs[h] = 2 * dot3(oc, lp);
+            Ds[h] = bs[h] * bs[h] - a4 * (dot3(oc, oc) + p.nr2[h]);                        // x - r^2 == x + (-r^2)
+            dbg.sphere_test(Ds[h] >= 0);
         }
+#endif
+        for (int h = 0; h < 2; h++) {
+            float t;
+            if (bs[h] < 0 && Ds[h] >= 0 && sphere_root(bs[h], Ds[h], a2, 0.001f, &t)) occluded = true;   // :622-635 (:578)
+        }
+        if (occluded && !DBG::enabled) break;       // boolean OR
     }
     return occluded;
 }
 
 // Host-side build (scene upload). sg: sphere geometry in original order; lights: n x (px, py, pz).
 struct ShadowGridsHost {
-    std::vector<ShadowGrid> grids; std::vector<int> cell_start; std::vector<f4> items; f3 lo, hi;
+    std::vector<ShadowGrid> grids; std::vector<int> cell_start; std::vector<GridPair> items; f3 lo, hi;
     bool empty() const { return grids.empty(); }
 };
 inline void shadow_grids_build(const std::vector<f4>& sg, const std::vector<f3>& lights, ShadowGridsHost* out) {
@@ -132,15 +153,23 @@ inline void shadow_grids_build(const std::vector<f4>& sg, const std::vector<f3>&
             int x0, x1, y0, y1; range(cs[(size_t)i], R[(size_t)i], s0, g.dim_s, &x0, &x1); range(ct[(size_t)i], R[(size_t)i], t0, g.dim_t, &y0, &y1);
             for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) count[(size_t)(y * g.dim_s + x) + 1]++;
         }
-        for (int c = 0; c < ncell; c++) count[(size_t)c + 1] += count[(size_t)c];
+        // per-cell sphere counts -> pair counts -> offsets (in pairs)
+        std::vector<int> pstart((size_t)ncell + 1, 0);
+        for (int c = 0; c < ncell; c++) pstart[(size_t)c + 1] = pstart[(size_t)c] + (count[(size_t)c + 1] + 1) / 2;
         const int item_base = (int)out->items.size();
-        out->items.resize((size_t)item_base + (size_t)count[(size_t)ncell]);
-        std::vector<int> fill(count.begin(), count.end() - 1);
+        GridPair never; for (int h = 0; h < 2; h++) { never.ncx[h] = 0.0f; never.ncy[h] = 0.0f; never.ncz[h] = 0.0f; never.nr2[h] = 1e30f; }
+        out->items.resize((size_t)item_base + (size_t)pstart[(size_t)ncell], never);
+        std::vector<int> fill((size_t)ncell, 0);
         for (int i = 0; i < n; i++) {
             int x0, x1, y0, y1; range(cs[(size_t)i], R[(size_t)i], s0, g.dim_s, &x0, &x1); range(ct[(size_t)i], R[(size_t)i], t0, g.dim_t, &y0, &y1);
-            for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) out->items[(size_t)item_base + (size_t)fill[(size_t)(y * g.dim_s + x)]++] = sg[(size_t)i];
+            for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) {
+                const int c = y * g.dim_s + x, slot = fill[(size_t)c]++;
+                GridPair& p = out->items[(size_t)item_base + (size_t)pstart[(size_t)c] + (size_t)(slot / 2)];
+                const int hh = slot & 1;
+                p.ncx[hh] = -sg[(size_t)i].x; p.ncy[hh] = -sg[(size_t)i].y; p.ncz[hh] = -sg[(size_t)i].z; p.nr2[hh] = -sg[(size_t)i].w;
+            }
         }
-        for (int c = 0; c <= ncell; c++) out->cell_start.push_back(item_base + count[(size_t)c]);
+        for (int c = 0; c <= ncell; c++) out->cell_start.push_back(item_base + pstart[(size_t)c]);
         g.valid = 1;
     }
 }

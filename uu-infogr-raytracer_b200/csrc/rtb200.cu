@@ -325,7 +325,7 @@ struct DeviceState {
     // scene
     f4* sgeom = nullptr; MatRec* smat = nullptr; PlaneRec* planes = nullptr; LightRec* lights = nullptr;
     LbvhDevice bvh;
-    ShadowGrid* sg_grids = nullptr; int* sg_cells = nullptr; f4* sg_items = nullptr;      // per-light shadow bins (rt_shadow_grid.cuh)
+    ShadowGrid* sg_grids = nullptr; int* sg_cells = nullptr; GridPair* sg_items = nullptr;      // per-light shadow bins (rt_shadow_grid.cuh)
     float bvh_cam[3] = {0, 0, 0}; bool bvh_cam_valid = false;    // camera the nodes_cam copy is currently inflated for ...
     cudaStream_t bvh_cam_stream = nullptr;                        // ... by a refit issued on this stream
     // framebuffer ring (device 0 of the context only, unless partitioned multi-process)
@@ -481,11 +481,11 @@ int upload_shadow_grids(rt_context* ctx) {
         d.sg_grids = nullptr; d.sg_cells = nullptr; d.sg_items = nullptr;
         CU_TRY(ctx, cudaMalloc(&d.sg_grids, sizeof(ShadowGrid) * h.grids.size()));
         CU_TRY(ctx, cudaMalloc(&d.sg_cells, sizeof(int) * h.cell_start.size()));
-        CU_TRY(ctx, cudaMalloc(&d.sg_items, sizeof(f4) * (h.items.empty() ? 1 : h.items.size())));
+        CU_TRY(ctx, cudaMalloc(&d.sg_items, sizeof(GridPair) * (h.items.empty() ? 1 : h.items.size())));
         CU_TRY(ctx, cudaMemcpyAsync(d.sg_grids, h.grids.data(), sizeof(ShadowGrid) * h.grids.size(), cudaMemcpyHostToDevice, d.stream));
         CU_TRY(ctx, cudaMemcpyAsync(d.sg_cells, h.cell_start.data(), sizeof(int) * h.cell_start.size(), cudaMemcpyHostToDevice, d.stream));
         if (!h.items.empty())
-            CU_TRY(ctx, cudaMemcpyAsync(d.sg_items, h.items.data(), sizeof(f4) * h.items.size(), cudaMemcpyHostToDevice, d.stream));
+            CU_TRY(ctx, cudaMemcpyAsync(d.sg_items, h.items.data(), sizeof(GridPair) * h.items.size(), cudaMemcpyHostToDevice, d.stream));
         CU_TRY(ctx, cudaStreamSynchronize(d.stream));
     }
     ctx->sg_lo = h.lo; ctx->sg_hi = h.hi;

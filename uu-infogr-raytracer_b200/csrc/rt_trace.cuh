@@ -119,26 +119,7 @@ RT_HD bool sphere_root(float b, float D, float a2, float eps, float* t) {
 // b and the discriminant of spheres i0 and i0+1 in one pass of packed-fp32 instructions (sm_100 FADD2 / FMUL2: two IEEE
 // round-to-nearest fp32 operations per lane per instruction — bit-identical to the scalar sequence, half the issue slots; the
 // kernel is issue-bound with the FMA pipe ~35 % busy). Operation order per element is exactly :614-621.
-#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
-#define RT_HAVE_F32X2 1
-// ptxas contracts a packed multiply that feeds a packed add into FFMA2 — even with explicit .rn, with --fmad=false, and when
-// the two are written as fma(a,b,-0) / fma(a,1,c) (it canonicalises and re-fuses; seen in SASS). A fused dot product or
-// discriminant rounds once instead of twice and breaks bit-exactness, so packed instructions are used only where no product
-// feeds an add directly: the three o + (-c) additions, all six products, 2*(.), the - r^2 addition and the two products of the
-// discriminant are packed; the sums of products stay scalar FADDs on the register halves (scalar contraction IS off under
-// -fmad=false). 13 packed + 10 scalar instructions per sphere pair instead of 36 scalar ones.
-__device__ __forceinline__ float2 rt_add2(float2 a, float2 b) {
-    float2 r;
-    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
-__device__ __forceinline__ float2 rt_mul2(float2 a, float2 b) {
-    float2 r;
-    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
+#if defined(RT_HAVE_F32X2)
 template <class PAIR>
 __device__ __forceinline__ void sphere_pair_bd(const PAIR& p, float2 ox, float2 oy, float2 oz, float2 dx, float2 dy, float2 dz,
                                                float2 na4, float* b_out, float* D_out) {

@@ -110,6 +110,33 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int width, int height
  *   accel: RT_ACCEL_BRUTE or RT_ACCEL_LBVH */
 int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, int accel, int32_t* out_id, float* out_t);
 
+/* Ray log — the data behind the reference's DEBUG_ENABLE overlay: `TracedRay` RayTracer.cs:424-435, filled at :601, :639, :801 and
+ * drawn (a random sample of 500) at :914-933. One record per RAY of the nearest-first chain of each listed pixel (spp = 1):
+ *   kind      RayKind :343-362: 0 primary, 1 secondary, 2 shadow
+ *   origin, direction   Ray.origin / Ray.direction (shadow rays: direction = the light POSITION, :574)
+ *   hit       primary / secondary: the selected hit — sphere index, n_spheres + plane index, -1 none;
+ *             shadow: the nearest occluding sphere (eps 0.001, lowest index on ties), -1 if the light is visible
+ *   distance  of that hit, 0 when hit = -1;   hit_point = origin + direction * distance (TracedRay.hitPoint)
+ *   pixel     y * width + x;   level = bounce level of the surface point the ray starts from / was cast for;   light = light index
+ * Records are grouped by pixel in the order of `pixels`; within a pixel: the rays of the chain, then the shadow rays deepest
+ * level first (the order the reference's recursion creates them). Always computed by brute force on device 0. */
+typedef struct rt_ray_record {
+    float origin[3];
+    float direction[3];
+    float hit_point[3];
+    float distance;
+    int32_t hit;
+    uint32_t kind;
+    uint32_t pixel;
+    uint32_t level;
+    uint32_t light;
+    uint32_t reserved;
+} rt_ray_record;   /* 64 bytes */
+/* pixels: n_pixels linear indices (< width*height). out: room for max_records records (may be NULL with max_records = 0 to
+ * size the log). *n_records receives the number of records the pixels produce; at most max_records of them are written. */
+int rt_ray_log(rt_context* ctx, const rt_camera* cam, int width, int height, int max_depth, const uint32_t* pixels, int n_pixels,
+               rt_ray_record* out, int max_records, int* n_records);
+
 /* Tuning options. RT_OPT_COMPACTION (default 0): tiny-scene kernel variant that parks rays needing a third or later bounce in a
  * shared-memory queue (warp-ballot compaction) and finishes them in fully populated warps; identical pixels, spp == 1 only. */
 #define RT_OPT_COMPACTION 1

@@ -139,7 +139,16 @@ static inline uint32_t event_hash(uint32_t level, uint32_t kind, uint32_t a, uin
 }
 static inline uint32_t fbits(float f) { uint32_t b; std::memcpy(&b, &f, 4); return b; }
 
+// One record per ray of the nearest-first chain: the per-ray digest of the reference's DEBUG_ENABLE TracedRay log (:424-435,
+// filled per intersection test at :601, :639, :801). Same layout as rt_ray_record (include/rtb200.h).
+struct RayRecord {
+    float origin[3], direction[3], hit_point[3], distance;
+    int32_t hit; uint32_t kind, pixel, level, light, reserved;
+};
+static_assert(sizeof(RayRecord) == 64, "RayRecord layout");
+
 struct Ctx {            // per-thread trace context
+    std::vector<RayRecord>* log = nullptr; uint32_t log_pixel = 0;    // orc_ray_log only
     const Scene* sc; Counters cnt; uint32_t hash;
     bool faithful;      // true: shade-all-then-select exactly as written; false: select-then-shade (A.11)
     bool count_chain;   // == !faithful: chain counters / hash are only meaningful in nearest-first mode
@@ -178,6 +187,26 @@ static Isect intersect_plane(Ctx& cx, const Ray& ray, const Plane& p) {
     if (cx.count_chain) cx.cnt.plane_tests++;
     Isect r; r.hit = t > 0; r.d = r.hit ? t : 0.0f;                                       // :598
     return r;
+}
+
+static void log_ray(Ctx& cx, uint32_t kind, uint32_t level, uint32_t light, int32_t hit, V3 o, V3 d, float dist) {
+    if (!cx.log) return;
+    V3 hp = add(o, mulf(d, dist));                                                        // TracedRay.hitPoint :601 / :639
+    RayRecord r = {{o.x, o.y, o.z}, {d.x, d.y, d.z}, {hp.x, hp.y, hp.z}, dist, hit, kind, cx.log_pixel, level, light, 0u};
+    cx.log->push_back(r);
+}
+// Shadow-ray record: the nearest colliding sphere of IntersectShadowLight's loop (:577-579), lowest index on ties.
+static void log_shadow(Ctx& cx, uint32_t level, uint32_t li, V3 hit, const Light& l) {
+    if (!cx.log) return;
+    const bool cc = cx.count_chain; cx.count_chain = false;                               // do not disturb the counters
+    Ray ray = {hit, l.p};
+    int sel = -1; float best = INFINITY;
+    for (int i = 0; i < (int)cx.sc->spheres.size(); i++) {
+        Isect is = intersects_sphere(cx, ray, cx.sc->spheres[i], 0.001f);
+        if (is.hit && is.d < best) { best = is.d; sel = i; }
+    }
+    cx.count_chain = cc;
+    log_ray(cx, 2, level, li, sel, hit, l.p, sel >= 0 ? best : 0.0f);
 }
 
 // IntersectShadowLight :573-582 — direction is the light POSITION, spheres only, no early-out, unbounded t.
@@ -239,6 +268,7 @@ static Trace shade_sphere(Ctx& cx, const Ray& ray, const Sphere& s, Isect is, in
             cx.cnt.faithful_shadow++;
             float I = intersect_shadow_light(cx, hit, l);                                 // :864
             if (on_chain) cx.hash += event_hash(level, 3, li, I == 0.0f ? 1u : 0u);
+            if (on_chain) log_shadow(cx, level, li, hit, l);
             V3 irgb = splat(I);                                                           // :865
             float att = 1 / is.d * is.d;                                                  // :866 ((1/d)*d)
             V3 n = normalize(sub(hit, s.c));                                              // :706
@@ -273,6 +303,7 @@ static Trace shade_plane(Ctx& cx, const Ray& ray, const Plane& p, Isect is, int 
             cx.cnt.faithful_shadow++;
             float I = intersect_shadow_light(cx, hit, l);                                 // :752
             if (on_chain) cx.hash += event_hash(level, 3, li, I == 0.0f ? 1u : 0u);
+            if (on_chain) log_shadow(cx, level, li, hit, l);
             V3 irgb = splat(I);                                                           // :753
             float att = (float)(1 / std::pow((double)is.d, 2.0));                         // :754
             V3 tile = v3(1, 1, 1);                                                        // :756
@@ -326,6 +357,7 @@ static V3 trace_secondary(Ctx& cx, V3 origin, V3 dir, int bounce, uint32_t level
     uint32_t code = pick_s ? (uint32_t)sel_s : (sel_p >= 0 ? (uint32_t)(sc.spheres.size() + sel_p) : 0xFFFFFFFFu);
     float dsel = pick_s ? closest_s : (sel_p >= 0 ? closest_p : 0.0f);
     cx.hash += event_hash(level, 2, code, fbits(dsel));
+    log_ray(cx, 1, level, 0, (int32_t)code, origin, dir, dsel);
     if (pick_s) return shade_sphere(cx, ray, sc.spheres[sel_s], is_s, bounce, level).col;
     if (sel_p >= 0) return shade_plane(cx, ray, sc.planes[sel_p], is_p, bounce, level).col;
     return v3(0, 0, 0);
@@ -383,6 +415,7 @@ static V3 trace_sample(Ctx& cx, const Camera& cam, float fx, float fy, int w, in
     if (aov_t) *aov_t = dsel;
     if (cx.faithful) return pick_s ? col_s : col_p;
     cx.hash += event_hash(0, 1, code, fbits(dsel));
+    log_ray(cx, 0, 0, 0, (int32_t)code, ray.o, ray.d, dsel);
     if (pick_s) return shade_sphere(cx, ray, sc.spheres[sel_s], is_s, 0, 0).col;
     if (sel_p >= 0) return shade_plane(cx, ray, sc.planes[sel_p], is_p, 0, 0).col;
     return v3(0, 0, 0);
@@ -548,6 +581,27 @@ int orc_query_spheres(const float* spheres, int ns, const float* rays6, int n_ra
         out_id[r] = sel; out_t[r] = (sel >= 0 && kind != 2) ? best : 0.0f;
     }
     return 0;
+}
+
+// Ray log of the listed pixels (nearest-first mode, spp = 1): the checker of rt_ray_log. Records grouped by pixel in list
+// order; within a pixel in creation order of the recursion. Returns the number of records; writes at most max_records.
+int orc_ray_log(const float* spheres, int ns, const float* planes, int np, const float* lights, int nl,
+                const float* ambient, const float* cam15, int w, int h, int max_depth,
+                const uint32_t* pixels, int n_pixels, void* out_records, int max_records) {
+    if (w <= 0 || h <= 0 || n_pixels < 0 || (n_pixels && !pixels)) return -1;
+    Scene sc = build_scene(spheres, ns, planes, np, lights, nl, ambient, max_depth);
+    Camera cam = load_cam(cam15);
+    std::vector<RayRecord> log;
+    Ctx cx; cx.sc = &sc; cx.hash = 0; cx.faithful = false; cx.count_chain = true; cx.log = &log;
+    for (int i = 0; i < n_pixels; i++) {
+        uint32_t p = pixels[i];
+        if (p >= (uint32_t)w * (uint32_t)h) return -1;
+        cx.log_pixel = p;
+        trace_sample(cx, cam, (float)(p % (uint32_t)w), (float)(p / (uint32_t)w), w, h, nullptr, nullptr);
+    }
+    size_t take = log.size() < (size_t)max_records ? log.size() : (size_t)max_records;
+    if (take && out_records) std::memcpy(out_records, log.data(), take * sizeof(RayRecord));
+    return (int)log.size();
 }
 
 int orc_pack_color(float r, float g, float b) { return shift_color(v3(r, g, b)); }

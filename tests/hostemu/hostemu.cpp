@@ -178,6 +178,43 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
     return 0;
 }
 
+// The body of k_ray_log (rtb200.cu) on the host: LogDbg + the global-memory scene policy, one listed pixel after the other.
+extern "C" int emu_ray_log(const float* spheres, int ns, const float* planes, int np, const float* lights, int nl,
+                           const float* ambient, const float* cam15, int w, int h, int max_depth,
+                           const uint32_t* pixels, int n_pixels, void* out_records, int max_records) {
+    std::vector<f4> sg((size_t)ns); std::vector<MatRec> sm((size_t)ns);
+    std::vector<PlaneRec> pl((size_t)np); std::vector<LightRec> li((size_t)nl);
+    for (int i = 0; i < ns; i++) {
+        const float* f = spheres + 18 * (size_t)i;
+        sg[i].x = f[0]; sg[i].y = f[1]; sg[i].z = f[2]; sg[i].w = f[17];
+        sm[i] = make_mat(f + 4);
+    }
+    for (int i = 0; i < np; i++) pl[i] = make_plane(planes + 20 * (size_t)i);
+    for (int i = 0; i < nl; i++) li[i] = make_light(lights + 4 * (size_t)i);
+    CamRec cam;
+    cam.pos = mk3(cam15[0], cam15[1], cam15[2]); cam.right = mk3(cam15[3], cam15[4], cam15[5]);
+    cam.up = mk3(cam15[6], cam15[7], cam15[8]); cam.fwd = mk3(cam15[9], cam15[10], cam15[11]);
+    cam.view = mk3(cam15[12], cam15[13], cam15[14]);
+    GlobalSceneData g; memset(&g, 0, sizeof(g));
+    g.ns = ns; g.np = np; g.nl = nl; g.amb = mk3(ambient[0], ambient[1], ambient[2]);
+    g.sgeom = sg.data(); g.smat = sm.data(); g.planes = pl.data(); g.lights = li.data();
+    const int slots = (max_depth + 2) + (max_depth + 1) * nl;
+    std::vector<RayRec> buf((size_t)slots);
+    HitRec stack[33];
+    RayRec* out = (RayRec*)out_records;
+    long long total = 0;
+    for (int i = 0; i < n_pixels; i++) {
+        const uint32_t p = pixels[i];
+        LogDbg dbg; dbg.out = buf.data(); dbg.cap = (uint32_t)slots; dbg.pixel = p;
+        const int y = (int)(p / (uint32_t)w), x = (int)(p - (uint32_t)y * (uint32_t)w);
+        trace_pixel<true>(GlobalScene(g), cam, x, y, w, h, max_depth, 1, 0u, stack, dbg);
+        if (dbg.n > (uint32_t)slots) return -3;                    // the slot bound rt_ray_log relies on
+        for (uint32_t k = 0; k < dbg.n; k++, total++)
+            if (total < max_records) out[total] = buf[k];
+    }
+    return (int)total;
+}
+
 // Single-ray sphere queries through the device query code: accel 1 brute, 2 LBVH (same semantics as rt_query_spheres).
 extern "C" int emu_query(const float* spheres, int ns, const float* rays6, int n_rays, int kind, int accel, int32_t* out_id, float* out_t) {
     std::vector<f4> sg((size_t)ns); std::vector<MatRec> sm((size_t)ns);

@@ -20,6 +20,9 @@ def load():
         _lib.emu_render.restype = C.c_int
         _lib.emu_query.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), fp]
         _lib.emu_query.restype = C.c_int
+        _lib.emu_ray_log.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_uint32), C.c_int, C.c_void_p, C.c_int]
+        _lib.emu_ray_log.restype = C.c_int
     return _lib
 
 
@@ -54,3 +57,20 @@ def query(spheres, rays6, kind, accel):
     rc = lib.emu_query(_fp(spheres), len(spheres), _fp(rays6), n, kind, accel, ids.ctypes.data_as(C.POINTER(C.c_int32)), _fp(ts))
     assert rc == 0, rc
     return ids, ts
+
+
+def ray_log(scene, cam, w, h, max_depth, pixels):
+    """The device ray-log code (LogDbg + GlobalScene, the body of k_ray_log) on the host."""
+    from oracle_lib import RAY_RECORD
+    lib = load()
+    pixels = np.ascontiguousarray(pixels, dtype=np.uint32).reshape(-1)
+    cam = np.ascontiguousarray(cam, np.float32)
+    args = (_fp(scene.spheres), len(scene.spheres), _fp(scene.planes), len(scene.planes), _fp(scene.lights), len(scene.lights),
+            _fp(scene.ambient), _fp(cam), w, h, max_depth, pixels.ctypes.data_as(C.POINTER(C.c_uint32)) if len(pixels) else None, len(pixels))
+    n = lib.emu_ray_log(*args, None, 0)
+    if n < 0:
+        raise RuntimeError("emu_ray_log failed rc=%d" % n)
+    out = np.zeros(n, dtype=RAY_RECORD)
+    if n:
+        lib.emu_ray_log(*args, C.c_void_p(out.ctypes.data), n)
+    return out

@@ -38,6 +38,9 @@ def load(variant: str = ""):
     lib.orc_render.restype = C.c_int
     lib.orc_query_spheres.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_int32), fp]
     lib.orc_query_spheres.restype = C.c_int
+    lib.orc_ray_log.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int,
+                                C.POINTER(C.c_uint32), C.c_int, C.c_void_p, C.c_int]
+    lib.orc_ray_log.restype = C.c_int
     lib.orc_pack_color.argtypes = [C.c_float, C.c_float, C.c_float]
     lib.orc_pack_color.restype = C.c_int
     lib.orc_max_threads.restype = C.c_int
@@ -85,6 +88,27 @@ def query_spheres(spheres, rays6, kind):
     ts = np.zeros(n, dtype=np.float32)
     lib.orc_query_spheres(_fp(spheres), len(spheres), _fp(rays6), n, kind, ids.ctypes.data_as(C.POINTER(C.c_int32)), _fp(ts))
     return ids, ts
+
+
+RAY_RECORD = np.dtype([("origin", np.float32, 3), ("direction", np.float32, 3), ("hit_point", np.float32, 3), ("distance", np.float32),
+                       ("hit", np.int32), ("kind", np.uint32), ("pixel", np.uint32), ("level", np.uint32), ("light", np.uint32),
+                       ("reserved", np.uint32)])
+
+
+def ray_log(scene, cam, w, h, max_depth, pixels):
+    """Oracle ray log of the listed pixels (nearest-first chain, one record per ray): the checker of rt_ray_log."""
+    lib = load()
+    pixels = np.ascontiguousarray(pixels, dtype=np.uint32).reshape(-1)
+    cam = np.ascontiguousarray(cam, dtype=np.float32)
+    args = (_fp(scene.spheres), len(scene.spheres), _fp(scene.planes), len(scene.planes), _fp(scene.lights), len(scene.lights),
+            _fp(scene.ambient), _fp(cam), w, h, max_depth, pixels.ctypes.data_as(C.POINTER(C.c_uint32)) if len(pixels) else None, len(pixels))
+    n = lib.orc_ray_log(*args, None, 0)
+    if n < 0:
+        raise RuntimeError("orc_ray_log failed rc=%d" % n)
+    out = np.zeros(n, dtype=RAY_RECORD)
+    if n:
+        lib.orc_ray_log(*args, C.c_void_p(out.ctypes.data), n)
+    return out
 
 
 def pack_color(r, g, b):

@@ -32,6 +32,17 @@ internal sealed unsafe class NativeRayTracer : IDisposable {
                                                             float* lights, int nLights, float* ambient, int accel);
     [DllImport(Lib)] private static extern int rt_render(IntPtr ctx, ref RtCamera cam, int width, int height, int maxDepth, int spp,
                                                          uint seed, int* hostPixels, out RtStats stats);
+    [StructLayout(LayoutKind.Sequential)]
+    public struct RtRayRecord {              // include/rtb200.h: rt_ray_record (64 bytes) — one TracedRay (RayTracer.cs:424-435) per ray
+        public Vector3 origin, direction, hitPoint;
+        public float distance;
+        public int hit;                      // sphere index, spheres.Length + plane index, -1 none (shadow: nearest occluder)
+        public uint kind;                    // (uint)RayKind: 0 Primary, 1 Secondary, 2 Shadow (:343-362)
+        public uint pixel, level, light, reserved;
+    }
+
+    [DllImport(Lib)] private static extern int rt_ray_log(IntPtr ctx, ref RtCamera cam, int width, int height, int maxDepth, uint* pixels,
+                                                          int nPixels, RtRayRecord* records, int maxRecords, out int nRecords);
     [DllImport(Lib)] private static extern int rt_host_register(IntPtr ctx, void* hostPtr, ulong bytes);
     [DllImport(Lib)] private static extern int rt_host_unregister(IntPtr ctx, void* hostPtr);
     [DllImport(Lib)] private static extern int rt_destroy(IntPtr ctx);
@@ -83,6 +94,20 @@ internal sealed unsafe class NativeRayTracer : IDisposable {
         RtCamera cam = new() { pos = position, right = right, up = up, forward = forward, viewParams = viewParams };
         Check(rt_render(_ctx, ref cam, width, height, maxDepth, 1, 0u, _pixels, out RtStats stats));
         return stats;
+    }
+
+    /// <summary>Ray records of the listed pixels (y * width + x) — the data the DEBUG_ENABLE overlay draws (RayTracer.cs:914-933):
+    /// pick ~500 random pixels outside the debug view, then draw origin -> hitPoint per record, coloured by kind.</summary>
+    public RtRayRecord[] RayLog(Vector3 position, Vector3 right, Vector3 up, Vector3 forward, Vector3 viewParams,
+                                int width, int height, int maxDepth, uint[] pixels) {
+        RtCamera cam = new() { pos = position, right = right, up = up, forward = forward, viewParams = viewParams };
+        fixed (uint* px = pixels) {
+            Check(rt_ray_log(_ctx, ref cam, width, height, maxDepth, px, pixels.Length, null, 0, out int n));
+            RtRayRecord[] records = new RtRayRecord[n];
+            fixed (RtRayRecord* r = records)
+                Check(rt_ray_log(_ctx, ref cam, width, height, maxDepth, px, pixels.Length, r, n, out n));
+            return records;
+        }
     }
 
     public void Dispose() {

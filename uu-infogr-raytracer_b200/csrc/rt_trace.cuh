@@ -61,6 +61,8 @@ struct NoDbg {
     RT_HD void primary_aov(int, float) {}
     RT_HD void node_visit(int) {}
     RT_HD void fallback() {}
+    template <class SC> RT_HD void ray_geom(const SC&, uint32_t, uint32_t, uint32_t, f3, f3, float) {}
+    template <class SC> RT_HD void shadow_geom(const SC&, uint32_t, uint32_t, f3, f3, float, float, bool) {}
 };
 struct FullDbg {
     static constexpr bool enabled = true;
@@ -83,6 +85,8 @@ struct FullDbg {
     RT_HD void primary_aov(int id, float t) { if (!aov_set) { aov_id = id; aov_t = t; aov_set = true; } }
     RT_HD void node_visit(int kind) { node_visits[kind]++; }
     RT_HD void fallback() { fallbacks++; }
+    template <class SC> RT_HD void ray_geom(const SC&, uint32_t, uint32_t, uint32_t, f3, f3, float) {}
+    template <class SC> RT_HD void shadow_geom(const SC&, uint32_t, uint32_t, f3, f3, float, float, bool) {}
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -115,6 +119,61 @@ RT_HD bool sphere_root(float b, float D, float a2, float eps, float* t) {
     *t = t1;
     return true;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Ray log (rt_ray_log): the GPU-side counterpart of the reference's DEBUG_ENABLE TracedRay log, RayTracer.cs:424-435 — one
+// record per RAY of the nearest-first chain (the reference logs one per intersection TEST, :601, :639, :801, and then draws a
+// random sample of them, :914-933). Layout == rt_ray_record (include/rtb200.h).
+//   primary / secondary: the selected hit (prim = sphere index, n_spheres + plane index or -1; d = its distance, 0 on a miss)
+//   shadow: the NEAREST occluding sphere (lowest index on ties) by a brute-force pass with the shadow epsilon, or -1 / d = 0
+//   hit = o + dir * d in every case (TracedRay.hitPoint).
+// Record order within a pixel: the rays of the descent, then the shadow rays deepest level first — the order in which the
+// reference's recursion creates them (the mirror term :857/:746 is evaluated before the light loop :863/:751).
+// ---------------------------------------------------------------------------------------------------------
+struct RayRec {
+    float o[3], dir[3], hit[3], d;
+    int32_t prim;
+    uint32_t kind, pixel, level, light, reserved;
+};
+static_assert(sizeof(RayRec) == 64, "RayRec layout");
+
+struct LogDbg {
+    static constexpr bool enabled = true;
+    RayRec* out = nullptr; uint32_t cap = 0, n = 0, pixel = 0;
+    RT_HD void sphere_test(bool) {}
+    RT_HD void plane_test() {}
+    RT_HD void ray(uint32_t, uint32_t, uint32_t, float) {}
+    RT_HD void shadow(uint32_t, uint32_t, bool) {}
+    RT_HD void shaded(bool) {}
+    RT_HD void spec() {}
+    RT_HD void primary_aov(int, float) {}
+    RT_HD void node_visit(int) {}
+    RT_HD void fallback() {}
+    RT_HD void push(uint32_t kind, uint32_t level, uint32_t light, int32_t prim, f3 o, f3 dir, float d) {
+        if (n < cap) {
+            RayRec& r = out[n];
+            f3 h = add3(o, mulf3(dir, d));                        // :601 / :639 / :801
+            r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z; r.dir[0] = dir.x; r.dir[1] = dir.y; r.dir[2] = dir.z;
+            r.hit[0] = h.x; r.hit[1] = h.y; r.hit[2] = h.z; r.d = d; r.prim = prim;
+            r.kind = kind; r.pixel = pixel; r.level = level; r.light = light; r.reserved = 0;
+        }
+        n++;                                                      // keeps counting past cap: the caller sees the overflow
+    }
+    template <class SC> RT_HD void ray_geom(const SC&, uint32_t level, uint32_t kind, uint32_t code, f3 o, f3 dir, float d) {
+        push(kind, level, 0, (int32_t)code, o, dir, d);
+    }
+    template <class SC> RT_HD void shadow_geom(const SC& sc, uint32_t level, uint32_t li, f3 hit, f3 lp, float a2, float a4, bool) {
+        NoDbg nd;
+        int sel = -1; float best = RT_INF;
+        const int ns = sc.n_spheres();
+        for (int i = 0; i < ns; i++) {                            // :577, keeping the nearest collision instead of a flag
+            f4 g = sc.sphere_geom(i);
+            float t;
+            if (sphere_hit(sub3(hit, mk3(g.x, g.y, g.z)), lp, g.w, a2, a4, 0.001f, &t, nd) && t < best) { best = t; sel = i; }
+        }
+        push(2, level, li, sel, hit, lp, sel >= 0 ? best : 0.0f);
+    }
+};
 
 // b and the discriminant of spheres i0 and i0+1 in one pass of packed-fp32 instructions (sm_100 FADD2 / FMUL2: two IEEE
 // round-to-nearest fp32 operations per lane per instruction — bit-identical to the scalar sequence, half the issue slots; the
@@ -315,6 +374,7 @@ RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& d
             const LightRec l = sc.light(li);
             bool occ = sc.shadow_any(li, hit, l.p, l.a2, l.a4, dbg);  // :864 / :752
             dbg.shadow(level, (uint32_t)li, occ);
+            dbg.shadow_geom(sc, level, (uint32_t)li, hit, l.p, l.a2, l.a4, occ);
             float I = occ ? 0.0f : l.intensity;                   // :581
             // ShapePhongShading :665-695
             f3 L = normalize3(sub3(l.p, hit));                    // :667
@@ -382,6 +442,7 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
         if (DBG::enabled) {
             uint32_t code = pick_s ? (uint32_t)sel_s : (none ? 0xFFFFFFFFu : (uint32_t)(sc.n_spheres() + sel_p));
             dbg.ray((uint32_t)top, bounce == 0 ? 1u : 2u, code, d);
+            dbg.ray_geom(sc, (uint32_t)top, bounce == 0 ? 0u : 1u, code, o, dir, d);
             if (bounce == 0) dbg.primary_aov((int)code, d);
         }
         if (none) break;                                                                   // nothing hit: black

@@ -314,6 +314,21 @@ __global__ void __launch_bounds__(BLOCK) k_query_lbvh(const __grid_constant__ Lb
     query_loop(LbvhScene(scd.g, scd.bv, scd.sg), rays6, n, kind, out_id, out_t);
 }
 
+// Ray-log kernel (rt_ray_log): one thread per listed pixel, `slots` records reserved per pixel, count[i] = records produced.
+static_assert(sizeof(RayRec) == sizeof(rt_ray_record), "RayRec must mirror rt_ray_record");
+__global__ void __launch_bounds__(BLOCK) k_ray_log(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp,
+                                                    const uint32_t* pixels, int n_pixels, int slots, RayRec* recs, uint32_t* count) {
+    HitRec stack[STACK_RECS];
+    GlobalScene sc(scd);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += gridDim.x * blockDim.x) {
+        const uint32_t p = pixels[i];
+        LogDbg dbg; dbg.out = recs + (size_t)i * slots; dbg.cap = (uint32_t)slots; dbg.pixel = p;
+        const int y = (int)(p / (uint32_t)fp.w), x = (int)(p - (uint32_t)y * (uint32_t)fp.w);
+        trace_pixel<true>(sc, fp.cam_inline[0], x, y, fp.w, fp.h, fp.cap, 1, 0u, stack, dbg);
+        count[i] = dbg.n;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------------
@@ -1043,6 +1058,53 @@ int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, 
     CU_TRY(ctx, cudaMemcpy(out_id, di, (size_t)n_rays * 4, cudaMemcpyDeviceToHost));
     CU_TRY(ctx, cudaMemcpy(out_t, dt, (size_t)n_rays * 4, cudaMemcpyDeviceToHost));
     cudaFree(dr); cudaFree(di); cudaFree(dt);
+    return RT_OK;
+}
+
+int rt_ray_log(rt_context* ctx, const rt_camera* cam, int w, int h, int depth, const uint32_t* pixels, int n_pixels,
+               rt_ray_record* out, int max_records, int* n_records) {
+    int rc = check_frame_args(ctx, cam, w, h, depth, 1);
+    if (rc) return rc;
+    if (n_pixels < 0 || max_records < 0 || !n_records || (n_pixels > 0 && !pixels) || (max_records > 0 && !out))
+        return fail(ctx, RT_ERR_INVALID, "bad ray-log args");
+    const uint64_t npix = (uint64_t)w * (uint64_t)h;
+    for (int i = 0; i < n_pixels; i++)
+        if (pixels[i] >= npix) return fail(ctx, RT_ERR_INVALID, "ray-log pixel index outside the frame");
+    *n_records = 0;
+    if (n_pixels == 0) return RT_OK;
+    // a chain has at most depth + 2 rays and depth + 1 shaded hits, each casting one shadow ray per light
+    const int slots = (depth + 2) + (depth + 1) * ctx->gdata_host.nl;
+    if ((uint64_t)slots * (uint64_t)n_pixels * sizeof(RayRec) > (1ull << 31))
+        return fail(ctx, RT_ERR_UNSUPPORTED, "ray log too large: list fewer pixels per call");
+    DeviceState& d = ctx->devs[0];
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    uint32_t* dpix = nullptr; uint32_t* dcount = nullptr; RayRec* drecs = nullptr;
+    CU_TRY(ctx, cudaMalloc(&dpix, (size_t)n_pixels * 4));
+    CU_TRY(ctx, cudaMalloc(&dcount, (size_t)n_pixels * 4));
+    CU_TRY(ctx, cudaMalloc(&drecs, (size_t)n_pixels * slots * sizeof(RayRec)));
+    CU_TRY(ctx, cudaMemcpyAsync(dpix, pixels, (size_t)n_pixels * 4, cudaMemcpyHostToDevice, d.stream));
+    FrameParams fp = make_params(ctx, w, h, depth, 1, 0u, 1, 0, 1, nullptr, (long long)npix);
+    fp.cam_inline[0] = to_cam(*cam);
+    int grid = (n_pixels + BLOCK - 1) / BLOCK; if (grid > d.sm_count * 32) grid = d.sm_count * 32;
+    k_ray_log<<<grid, BLOCK, 0, d.stream>>>(global_data(ctx, d), fp, dpix, n_pixels, slots, drecs, dcount);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    CU_TRY(ctx, cudaStreamSynchronize(d.stream));
+    std::vector<uint32_t> hcount((size_t)n_pixels);
+    CU_TRY(ctx, cudaMemcpy(hcount.data(), dcount, (size_t)n_pixels * 4, cudaMemcpyDeviceToHost));
+    long long total = 0, written = 0;
+    for (int i = 0; i < n_pixels; i++) {
+        const uint32_t c = hcount[(size_t)i];
+        if (c > (uint32_t)slots) { cudaFree(dpix); cudaFree(dcount); cudaFree(drecs); return fail(ctx, RT_ERR_CUDA, "ray log: slot bound violated"); }
+        const long long room = (long long)max_records - written;
+        const long long take = (long long)c < room ? (long long)c : (room > 0 ? room : 0);
+        if (take > 0)
+            CU_TRY(ctx, cudaMemcpy(out + written, drecs + (size_t)i * slots, (size_t)take * sizeof(RayRec), cudaMemcpyDeviceToHost));
+        written += take; total += c;
+    }
+    cudaFree(dpix); cudaFree(dcount); cudaFree(drecs);
+    if (total > 0x7fffffffLL) return fail(ctx, RT_ERR_UNSUPPORTED, "ray log: record count overflows int");
+    *n_records = (int)total;
     return RT_OK;
 }
 

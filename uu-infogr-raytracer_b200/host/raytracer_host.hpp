@@ -123,8 +123,7 @@ public:
     }
     void OnMouseMove(float deltaX, float deltaY) { _yaw += deltaX / 360; _pitch += deltaY / 360; }               // :1058-1061
 
-    void Tick() {                                                                                                // :886-901
-        // screen.Clear(0) (:890) is subsumed: the backend writes every pixel.
+    rt_camera FrameCamera() const {                                                                              // :892-896
         const float degToRad = 3.14159274f / 180.0f;                                  // MathHelper.DegreesToRadians (OpenTK)
         float planeHeight = NearClip * (float)std::tan((double)(FieldOfView * 0.5f * degToRad)) * 2;               // :892
         float aspectRatio = (float)screen.width / screen.height;                                                  // :893
@@ -133,8 +132,26 @@ public:
         Put(cam.pos, _cameraPosition); Put(cam.right, CameraRightDirection()); Put(cam.up, CameraUpDirection());
         Put(cam.forward, CameraForwardDirection());
         cam.view_params[0] = planeWidth; cam.view_params[1] = planeHeight; cam.view_params[2] = NearClip;         // :896
+        return cam;
+    }
+
+    void Tick() {                                                                                                // :886-901
+        // screen.Clear(0) (:890) is subsumed: the backend writes every pixel.
+        rt_camera cam = FrameCamera();
         // for (x) Parallel.For(y => TracePixel(x, y, viewParams))  (:898-901)  ==>
         Check(rt_render(_ctx, &cam, screen.width, screen.height, ReflectionRecursionLimit, 1, 0u, screen.pixels.data(), &last_stats));
+    }
+
+    // The data of the DEBUG_ENABLE overlay: one TracedRay (:424-435) per ray of the listed pixels' chains (:914-933 draws a sample).
+    std::vector<rt_ray_record> TracedRays(const std::vector<uint32_t>& pixelIndices) {
+        rt_camera cam = FrameCamera();
+        int n = 0;
+        Check(rt_ray_log(_ctx, &cam, screen.width, screen.height, ReflectionRecursionLimit, pixelIndices.data(), (int)pixelIndices.size(),
+                         nullptr, 0, &n));
+        std::vector<rt_ray_record> recs((size_t)n);
+        if (n) Check(rt_ray_log(_ctx, &cam, screen.width, screen.height, ReflectionRecursionLimit, pixelIndices.data(),
+                                (int)pixelIndices.size(), recs.data(), n, &n));
+        return recs;
     }
 
 private:

@@ -1,6 +1,7 @@
 // rt_demo — headless stand-in for the reference's window loop (template.cs:175-213): N ticks of the C++ host mirror,
 // a few simulated key presses / mouse moves, last frame written as a binary PPM.
-//   rt_demo out.ppm [width height [ticks [n_devices]]]
+//   rt_demo out.ppm [width height [ticks [n_devices [raylog.csv]]]]
+// raylog.csv: the rays of 500 pseudo-random pixels of the last frame (the sample the DEBUG_ENABLE overlay draws, RayTracer.cs:914-933).
 #include <cstdio>
 #include <cstdlib>
 
@@ -26,6 +27,20 @@ int main(int argc, char** argv) {
             fwrite(rgb, 1, 3, f);
         }
         fclose(f);
+        if (argc > 6) {
+            std::vector<uint32_t> px(500);                                              // debugNumRays :916
+            uint32_t st = 12345u;
+            for (auto& p : px) { st = st * 747796405u + 2891336453u; p = (st >> 8) % (uint32_t)(w * h); }
+            std::vector<rt_ray_record> recs = app.TracedRays(px);
+            FILE* g = fopen(argv[6], "w");
+            if (!g) { perror(argv[6]); return 2; }
+            fprintf(g, "pixel,kind,level,light,hit,distance,ox,oy,oz,hx,hy,hz\n");
+            for (const rt_ray_record& r : recs)
+                fprintf(g, "%u,%u,%u,%u,%d,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g\n", r.pixel, r.kind, r.level, r.light, r.hit, r.distance,
+                        r.origin[0], r.origin[1], r.origin[2], r.hit_point[0], r.hit_point[1], r.hit_point[2]);
+            fclose(g);
+            fprintf(stderr, "ray log: %zu records of %zu pixels -> %s\n", recs.size(), px.size(), argv[6]);
+        }
     } catch (const std::exception& e) {
         fprintf(stderr, "rt_demo: %s\n", e.what());
         return 1;

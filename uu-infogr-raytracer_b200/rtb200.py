@@ -27,7 +27,7 @@ COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_
                  "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"]
 
 # every symbol include/rtb200.h declares
-ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_update_spheres", "rt_render", "rt_render_batch", "rt_render_debug", "rt_query_spheres",
+ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_update_spheres", "rt_render", "rt_render_batch", "rt_render_debug", "rt_query_spheres", "rt_ray_log",
                "rt_set_option", "rt_set_partition", "rt_render_device", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_dev_alloc",
                "rt_dev_free", "rt_dev_to_host", "rt_sync", "rt_host_register", "rt_host_unregister", "rt_launch_count", "rt_destroy", "rt_last_error", "rt_abi_version"]
 
@@ -35,6 +35,14 @@ ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_update_spheres", "rt_render", "r
 class RtCamera(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("right", C.c_float * 3), ("up", C.c_float * 3), ("forward", C.c_float * 3),
                 ("view_params", C.c_float * 3)]
+
+
+# rt_ray_record (include/rtb200.h) as a numpy record type: one entry per ray, TracedRay RayTracer.cs:424-435
+RAY_RECORD = np.dtype([("origin", np.float32, 3), ("direction", np.float32, 3), ("hit_point", np.float32, 3), ("distance", np.float32),
+                       ("hit", np.int32), ("kind", np.uint32), ("pixel", np.uint32), ("level", np.uint32), ("light", np.uint32),
+                       ("reserved", np.uint32)])
+assert RAY_RECORD.itemsize == 64
+RAY_PRIMARY, RAY_SECONDARY, RAY_SHADOW = 0, 1, 2      # RayKind RayTracer.cs:343-362
 
 
 class RtStats(C.Structure):
@@ -70,6 +78,7 @@ def load_library():
     lib.rt_render_debug.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, ip, C.POINTER(C.c_uint32), ip, fp,
                                     C.POINTER(C.c_uint64), statp]
     lib.rt_query_spheres.argtypes = [vp, fp, C.c_int, C.c_int, C.c_int, ip, fp]
+    lib.rt_ray_log.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
     lib.rt_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.rt_set_partition.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.rt_render_device.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, vp, vp]
@@ -136,6 +145,13 @@ class Context:
         except Exception:
             pass
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def set_scene(self, scene, accel=RT_ACCEL_AUTO):
         self._scene = scene
         self.n_spheres = len(scene.spheres)
@@ -190,6 +206,18 @@ class Context:
         ids = np.empty(n, np.int32); ts = np.empty(n, np.float32)
         self._check(self.lib.rt_query_spheres(self.h, _fp(rays6), n, kind, accel, ids.ctypes.data_as(C.POINTER(C.c_int32)), _fp(ts)))
         return ids, ts
+
+    def ray_log(self, cam15, w, h, max_depth, pixels):
+        """Ray records (RAY_RECORD array) of the listed pixels (linear indices y*w+x) — the data of the reference's debug overlay."""
+        pixels = np.ascontiguousarray(pixels, dtype=np.uint32).reshape(-1)
+        cam = to_rt_camera(cam15)
+        n = C.c_int(0)
+        pp = pixels.ctypes.data_as(C.POINTER(C.c_uint32)) if len(pixels) else None
+        self._check(self.lib.rt_ray_log(self.h, C.byref(cam), w, h, max_depth, pp, len(pixels), None, 0, C.byref(n)))    # size it
+        out = np.zeros(n.value, dtype=RAY_RECORD)
+        if n.value:
+            self._check(self.lib.rt_ray_log(self.h, C.byref(cam), w, h, max_depth, pp, len(pixels), C.c_void_p(out.ctypes.data), n.value, C.byref(n)))
+        return out
 
     def set_option(self, option, value):
         self._check(self.lib.rt_set_option(self.h, option, value))

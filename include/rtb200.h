@@ -137,6 +137,17 @@ typedef struct rt_ray_record {
 int rt_ray_log(rt_context* ctx, const rt_camera* cam, int width, int height, int max_depth, const uint32_t* pixels, int n_pixels,
                rt_ray_record* out, int max_records, int* n_records);
 
+/* Device self-test of the library's hand-scheduled fp32 sequences against the compiler's IEEE code, exhaustive over their domain:
+ *   RT_SELFTEST_INV_LEN    1/sqrt as two correctly rounded operations (OpenTK Vector3.Normalize, used at RayTracer.cs:667, :668,
+ *                          :687, :706, :854, :971): every float in [2^-65, 2^65)
+ *   RT_SELFTEST_PIXEL_DIV  x / w (:964) for every integer 0 <= x < w <= 16384
+ *   RT_SELFTEST_INV_LEN_RSQ_SEED  a rejected cheaper variant, kept to document WHY it is rejected (it has mismatches)
+ * n_mismatch must come back 0 for the first two. */
+#define RT_SELFTEST_INV_LEN 0
+#define RT_SELFTEST_PIXEL_DIV 1
+#define RT_SELFTEST_INV_LEN_RSQ_SEED 2
+int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mismatch);
+
 /* Tuning options. RT_OPT_COMPACTION (default 0): tiny-scene kernel variant that parks rays needing a third or later bounce in a
  * shared-memory queue (warp-ballot compaction) and finishes them in fully populated warps; identical pixels, spp == 1 only. */
 #define RT_OPT_COMPACTION 1

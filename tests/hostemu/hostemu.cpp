@@ -82,7 +82,7 @@ static uint32_t dispatch(int use_tiny, const TinySceneData& t, const GlobalScene
         // way k_render_tiny_compact parks it, wipe the stack, restore, finish. spp == 1 only.
         TinyScene<-1, -1, -1> sc(t);
         f3 o, dir, C; int bounce = 0, top = 0;
-        primary_ray(cam, (float)x, (float)y, (float)w, (float)h, &o, &dir);
+        primary_ray(cam, (float)x, (float)y, (float)w, (float)h, 0.0f, 0.0f, &o, &dir);
         if (!trace_chain(sc, d, o, dir, bounce, top, st, 2, &C, dbg)) {
             struct { int bounce; f3 o, dir; HitRec rec[2]; } e = {bounce, o, dir, {st[0], st[1]}};
             for (int i = 0; i < 33; i++) memset(&st[i], 0xCD, sizeof(HitRec));

@@ -398,9 +398,18 @@ RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& d
 // ---------------------------------------------------------------------------------------------------------
 // One sample: TracePixel RayTracer.cs:962-1002 with (fx, fy) in place of (x, y).
 // ---------------------------------------------------------------------------------------------------------
-RT_HD void primary_ray(const CamRec& cam, float fx, float fy, float fw, float fh, f3* o, f3* dir) {
+// FASTDIV (device, single-sample kernels, frame sides <= RT_FASTDIV_MAX): rw = 1/fw, rh = 1/fh correctly rounded on the host,
+// the two divisions become rt_div_rcp — same bits (rt_math.cuh), a quarter of the instructions.
+template <bool FASTDIV = false>
+RT_HD void primary_ray(const CamRec& cam, float fx, float fy, float fw, float fh, float rw, float rh, f3* o, f3* dir) {
+#if defined(__CUDA_ARCH__)
+    float u = (FASTDIV ? rt_div_rcp(fx, fw, rw) : fx / fw) - 0.5f;                         // :964
+    float v = (FASTDIV ? rt_div_rcp(fy, fh, rh) : fy / fh) - 0.5f;
+#else
+    (void)rw; (void)rh;
     float u = fx / fw - 0.5f;                                                              // :964
     float v = fy / fh - 0.5f;
+#endif
     f3 local = mulv3(mk3(u, v, 1.0f), cam.view);                                           // :965
     f3 vp = add3(add3(add3(cam.pos, mulf3(cam.right, local.x)), mulf3(cam.up, local.y)), mulf3(cam.fwd, local.z));   // :967-969
     *o = cam.pos;
@@ -468,11 +477,11 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
     return true;
 }
 
-template <class SC, class DBG>
-RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float fw, float fh, int cap,
+template <bool FASTDIV = false, class SC, class DBG>
+RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float fw, float fh, float rw, float rh, int cap,
                       HitRec* stack, DBG& dbg) {
     f3 o, dir, C;
-    primary_ray(cam, fx, fy, fw, fh, &o, &dir);
+    primary_ray<FASTDIV>(cam, fx, fy, fw, fh, rw, rh, &o, &dir);
     int bounce = 0, top = 0;
     trace_chain(sc, cap, o, dir, bounce, top, stack, -1, &C, dbg);
     return C;
@@ -481,11 +490,12 @@ RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float
 // One pixel: spp == 1 is the reference; spp > 1 is the jittered extension (BASELINE.json configs[4]).
 // A single call site of trace_sample: with spp == 1 the jitter is +0.0f and the average is *1.0f, both exact.
 // SPP1 = true: compile-time single sample (the reference): no sample loop, no jitter, no average.
-template <bool SPP1 = false, class SC, class DBG>
+// FASTDIV (only with SPP1, w and h <= RT_FASTDIV_MAX): rw / rh = correctly rounded 1/w, 1/h; see primary_ray.
+template <bool SPP1 = false, bool FASTDIV = false, class SC, class DBG>
 RT_HD uint32_t trace_pixel(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int cap, int spp, uint32_t seed,
-                           HitRec* stack, DBG& dbg) {
+                           HitRec* stack, DBG& dbg, float rw = 0.0f, float rh = 0.0f) {
     const float fw = (float)w, fh = (float)h;
-    if (SPP1) return pack_color(trace_sample(sc, cam, (float)x, (float)y, fw, fh, cap, stack, dbg));   // :1000 -> :1038
+    if (SPP1) return pack_color(trace_sample<FASTDIV>(sc, cam, (float)x, (float)y, fw, fh, rw, rh, cap, stack, dbg));   // :1000 -> :1038
     f3 acc = mk3(0, 0, 0);
     for (int s = 0; s < spp; s++) {
         float jx = 0.0f, jy = 0.0f;
@@ -495,7 +505,7 @@ RT_HD uint32_t trace_pixel(const SC& sc, const CamRec& cam, int x, int y, int w,
             jx = (float)(h1 >> 8) * 5.9604644775390625e-08f;
             jy = (float)(h2 >> 8) * 5.9604644775390625e-08f;
         }
-        acc = add3(acc, trace_sample(sc, cam, (float)x + jx, (float)y + jy, fw, fh, cap, stack, dbg));
+        acc = add3(acc, trace_sample(sc, cam, (float)x + jx, (float)y + jy, fw, fh, 0.0f, 0.0f, cap, stack, dbg));
     }
     return pack_color(mulf3(acc, 1.0f / (float)spp));                                      // :1000 -> :1038, :1046-1052
 }

@@ -57,6 +57,7 @@ struct FrameParams {
     int tiles_mine;             // tiles of this rank rendered by this launch ...
     int k_begin;                // ... starting at the rank's k_begin-th tile (band pipelining, see render_frames)
     int chunks_per_tile;        // ceil(tile_rows * w / (BLOCK * pixels per thread))
+    float rcp_w, rcp_h;         // 1/w, 1/h correctly rounded (host): pixel-coordinate divisions of the single-sample kernels (rt_div_rcp)
     long long frame_stride;     // pixels between consecutive frames in `out`
     uint32_t* out;              // framebuffer(s): 0x00RRGGBB, row-major (Surface.pixels, surface.cs:9-20)
     CamRec cam_inline[INLINE_CAMS];   // the launch's cameras travel in the parameter block (constant bank): no upload, no host
@@ -92,7 +93,7 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
         int y = p0 / fp.w, x = p0 - y * fp.w;                  // one division per thread; then step along the row
 #pragma unroll 1
         for (int q = 0; q < PPT; q++) {
-            uint32_t c = (p0 + q < end) ? trace_pixel<SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg) : 0u;
+            uint32_t c = (p0 + q < end) ? trace_pixel<SPP1, SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg, fp.rcp_w, fp.rcp_h) : 0u;
             if (++x == fp.w) { x = 0; ++y; }
 #pragma unroll
             for (int z = 0; z + 1 < PPT; z++) px[z] = px[z + 1];   // shift register: after PPT iterations px[] is in pixel order
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_compact(co
             bool active; int p, bounce, top, defer_at; f3 o, dir;
             if (it < PPT) {
                 p = p0 + it; active = p < end; bounce = 0; top = 0; defer_at = DEFER_LEVEL;
-                if (active) primary_ray(cam, (float)x, (float)y, fw, fh, &o, &dir);
+                if (active) primary_ray<true>(cam, (float)x, (float)y, fw, fh, fp.rcp_w, fp.rcp_h, &o, &dir);
                 if (++x == fp.w) { x = 0; ++y; }
             } else {
                 const int n = qcount < PARK_CAP ? qcount : PARK_CAP;
@@ -227,8 +228,10 @@ template <int NS, int NL> struct TinyTable {
 };
 // Exact kernels exist for 0..4 spheres x 0..4 lights x exactly 1 plane x one sample per pixel (the reference is 3 x 2 x 1 x 1).
 // Supersampled frames (extension) take the reference scene's own multi-sample instantiation or the run-time-count kernel.
-TinyKernel tiny_kernel(int ns, int nl, int np, int spp) {
-    if (spp == 1) return np == 1 ? TinyTable<0, 0>::get(ns, nl) : k_render_tiny<-1, -1, -1, true>;
+// Frames with a side above RT_FASTDIV_MAX (outside the exhaustively verified range of rt_div_rcp) also take the multi-sample kernels,
+// which divide with the IEEE sequence.
+TinyKernel tiny_kernel(int ns, int nl, int np, int spp, bool fastdiv_ok) {
+    if (spp == 1 && fastdiv_ok) return np == 1 ? TinyTable<0, 0>::get(ns, nl) : k_render_tiny<-1, -1, -1, true>;
     return (ns == 3 && nl == 2 && np == 1) ? k_render_tiny<3, 2, 1, false> : k_render_tiny<-1, -1, -1, false>;
 }
 // compacting variant: exact instantiation for the reference scene's shape, run-time counts otherwise
@@ -312,6 +315,35 @@ __global__ void __launch_bounds__(BLOCK) k_query_brute(const __grid_constant__ G
 __global__ void __launch_bounds__(BLOCK) k_query_lbvh(const __grid_constant__ LbvhSceneData scd, const float* rays6, int n, int kind,
                                                        int32_t* out_id, float* out_t) {
     query_loop(LbvhScene(scd.g, scd.bv, scd.sg), rays6, n, kind, out_id, out_t);
+}
+
+// Self-test kernels (rt_selftest): the hand-scheduled fp32 sequences of rt_math.cuh against the compiler's IEEE code, exhaustively.
+__global__ void __launch_bounds__(256) k_selftest_inv_len(uint32_t first_bits, uint32_t count, int variant, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const float s = __uint_as_float(first_bits + i);
+        float got;
+        if (variant == 0) got = rt_inv_len(s);
+        else {                                                 // experiment: reuse the rsqrt estimate as the reciprocal seed
+            float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+            const float g = __fmul_rn(s, y), h = __fmul_rn(y, 0.5f);
+            const float len = __fmaf_rn(__fmaf_rn(-g, g, s), h, g);
+            got = __fmaf_rn(y, __fmaf_rn(-len, y, 1.0f), y);
+        }
+        if (__float_as_uint(got) != __float_as_uint(rt_inv_len_ieee(s))) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+__global__ void __launch_bounds__(256) k_selftest_pixel_div(int max_side, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (int w = 1 + blockIdx.x; w <= max_side; w += gridDim.x) {
+        const float fw = (float)w, rw = 1.0f / fw;
+        for (int x = threadIdx.x; x < w; x += blockDim.x) {
+            const float fx = (float)x;
+            if (__float_as_uint(rt_div_rcp(fx, fw, rw)) != __float_as_uint(fx / fw)) bad++;
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // Ray-log kernel (rt_ray_log): one thread per listed pixel, `slots` records reserved per pixel, count[i] = records produced.
@@ -478,6 +510,7 @@ FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp,
     fp.tiles_mine = fp.tiles_total > rank ? (fp.tiles_total - rank + world - 1) / world : 0;
     const int chunk = BLOCK * (ctx->path == PATH_TINY ? PPT_TINY : PPT_HEAVY);
     fp.chunks_per_tile = (int)(((long long)fp.tile_rows * w + chunk - 1) / chunk);
+    fp.rcp_w = 1.0f / (float)w; fp.rcp_h = 1.0f / (float)h;      // host fp32 division: IEEE
     fp.frame_stride = frame_stride;
     fp.out = out;
     return fp;
@@ -554,7 +587,8 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
     switch (ctx->path) {
         case PATH_TINY: {
             const TinySceneData& t = ctx->tiny_data;
-            TinyKernel kern = (ctx->compaction && fp.spp == 1) ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np, fp.spp);
+            const bool fastdiv_ok = fp.w <= RT_FASTDIV_MAX && fp.h <= RT_FASTDIV_MAX;
+            TinyKernel kern = (ctx->compaction && fp.spp == 1 && fastdiv_ok) ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np, fp.spp, fastdiv_ok);
             kern<<<grid, BLOCK, 0, stream>>>(t, fp);
             break;
         }
@@ -1058,6 +1092,37 @@ int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, 
     CU_TRY(ctx, cudaMemcpy(out_id, di, (size_t)n_rays * 4, cudaMemcpyDeviceToHost));
     CU_TRY(ctx, cudaMemcpy(out_t, dt, (size_t)n_rays * 4, cudaMemcpyDeviceToHost));
     cudaFree(dr); cudaFree(di); cudaFree(dt);
+    return RT_OK;
+}
+
+int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mismatch) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!n_checked || !n_mismatch) return fail(ctx, RT_ERR_INVALID, "bad selftest args");
+    DeviceState& d = ctx->devs[0];
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    unsigned long long* dbad = nullptr;
+    CU_TRY(ctx, cudaMalloc(&dbad, sizeof(unsigned long long)));
+    CU_TRY(ctx, cudaMemsetAsync(dbad, 0, sizeof(unsigned long long), d.stream));
+    uint64_t checked = 0;
+    if (test == RT_SELFTEST_INV_LEN || test == RT_SELFTEST_INV_LEN_RSQ_SEED) {
+        // every float of the fast path's range [2^-64, 2^64) plus a binade on either side (those take the IEEE branch)
+        const uint32_t first = 0x1F000000u, count = 0x41000000u;
+        k_selftest_inv_len<<<d.sm_count * 16, 256, 0, d.stream>>>(first, count, test == RT_SELFTEST_INV_LEN ? 0 : 1, dbad);
+        checked = count;
+    } else if (test == RT_SELFTEST_PIXEL_DIV) {
+        k_selftest_pixel_div<<<d.sm_count * 8, 256, 0, d.stream>>>(RT_FASTDIV_MAX, dbad);
+        checked = (uint64_t)RT_FASTDIV_MAX * (RT_FASTDIV_MAX + 1) / 2;
+    } else {
+        cudaFree(dbad);
+        return fail(ctx, RT_ERR_INVALID, "unknown selftest");
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    CU_TRY(ctx, cudaStreamSynchronize(d.stream));
+    unsigned long long bad = 0;
+    CU_TRY(ctx, cudaMemcpy(&bad, dbad, sizeof(bad), cudaMemcpyDeviceToHost));
+    cudaFree(dbad);
+    *n_checked = checked; *n_mismatch = bad;
     return RT_OK;
 }
 

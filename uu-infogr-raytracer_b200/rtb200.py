@@ -27,7 +27,7 @@ COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_
                  "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"]
 
 # every symbol include/rtb200.h declares
-ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_update_spheres", "rt_render", "rt_render_batch", "rt_render_debug", "rt_query_spheres", "rt_ray_log",
+ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_update_spheres", "rt_render", "rt_render_batch", "rt_render_debug", "rt_query_spheres", "rt_ray_log", "rt_selftest",
                "rt_set_option", "rt_set_partition", "rt_render_device", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_dev_alloc",
                "rt_dev_free", "rt_dev_to_host", "rt_sync", "rt_host_register", "rt_host_unregister", "rt_launch_count", "rt_destroy", "rt_last_error", "rt_abi_version"]
 
@@ -42,6 +42,7 @@ RAY_RECORD = np.dtype([("origin", np.float32, 3), ("direction", np.float32, 3), 
                        ("hit", np.int32), ("kind", np.uint32), ("pixel", np.uint32), ("level", np.uint32), ("light", np.uint32),
                        ("reserved", np.uint32)])
 assert RAY_RECORD.itemsize == 64
+RT_SELFTEST_INV_LEN, RT_SELFTEST_PIXEL_DIV, RT_SELFTEST_INV_LEN_RSQ_SEED = 0, 1, 2
 RAY_PRIMARY, RAY_SECONDARY, RAY_SHADOW = 0, 1, 2      # RayKind RayTracer.cs:343-362
 
 
@@ -79,6 +80,7 @@ def load_library():
                                     C.POINTER(C.c_uint64), statp]
     lib.rt_query_spheres.argtypes = [vp, fp, C.c_int, C.c_int, C.c_int, ip, fp]
     lib.rt_ray_log.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
+    lib.rt_selftest.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.rt_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.rt_set_partition.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.rt_render_device.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, vp, vp]
@@ -218,6 +220,12 @@ class Context:
         if n.value:
             self._check(self.lib.rt_ray_log(self.h, C.byref(cam), w, h, max_depth, pp, len(pixels), C.c_void_p(out.ctypes.data), n.value, C.byref(n)))
         return out
+
+    def selftest(self, test):
+        """(n_checked, n_mismatch) of one exhaustive device self-test (RT_SELFTEST_*)."""
+        n, bad = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.rt_selftest(self.h, test, C.byref(n), C.byref(bad)))
+        return n.value, bad.value
 
     def set_option(self, option, value):
         self._check(self.lib.rt_set_option(self.h, option, value))

@@ -154,6 +154,9 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
 /* RT_OPT_HOST_VIA_GPU0 (default 0): multi-device contexts normally send each device's row tiles to the host over that device's
  * own PCIe link; 1 = gather the frame on device 0 first (NVLink peer stores) and copy it from there. */
 #define RT_OPT_HOST_VIA_GPU0 2
+/* RT_OPT_PRIMARY_GATE (default 1): tiny-scene kernels skip the sphere loop of primary rays (RayTracer.cs:975-981) for pixels outside
+ * a per-frame rectangle the host proves no sphere can be hit in (csrc/rt_gate.cuh); 0 = test every sphere for every pixel. Same pixels. */
+#define RT_OPT_PRIMARY_GATE 3
 int rt_set_option(rt_context* ctx, int option, int value);
 
 /* ---- device-pointer / multi-process interface (torchrun: one process per GPU) --------------------------------- */

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <vector>
 #include "../../uu-infogr-raytracer_b200/csrc/rt_scene.cuh"
+#include "../../uu-infogr-raytracer_b200/csrc/rt_gate.cuh"
 
 using namespace rtb;
 
@@ -58,8 +59,14 @@ static void host_build(const std::vector<f4>& sg, HostBvh& b) {
     host_refit(b, reff, 0);
 }
 
+// The uninstrumented tiny-scene path at one sample per pixel runs like the single-sample kernels: with the host's primary-ray gate.
+static bool g_gate_on = false;
+static GateRect g_gate = {0, 0, 0, 0};
 template <class SC, class DBG>
 static uint32_t px_of(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int d, int spp, uint32_t seed, HitRec* st, DBG& dbg) {
+    if constexpr (!DBG::enabled) {
+        if (g_gate_on) return trace_pixel<true>(sc, cam, x, y, w, h, d, 1, seed, st, dbg, 0.0f, 0.0f, gate_skips(g_gate, x, y));
+    }
     return trace_pixel(sc, cam, x, y, w, h, d, spp, seed, st, dbg);
 }
 // use_tiny: 0 global-memory policy, 1 TinyScene<-1> (run-time count), 2 TinyScene<NS> with the exact compile-time count,
@@ -144,6 +151,8 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         for (int i = 0; i < np; i++) t.planes[i] = pl[i];
         for (int i = 0; i < nl; i++) t.lights[i] = li[i];
     }
+    g_gate_on = (use_tiny == 1 || use_tiny == 2) && spp == 1;
+    if (g_gate_on) g_gate = primary_gate_rect(cam, w, h, sg.data(), ns);
     uint64_t cnt[14] = {0};
     const bool dbg_mode = hash || aov_id || aov_t || counters;
 #pragma omp parallel
@@ -175,6 +184,19 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         for (int i = 0; i < 14; i++) cnt[i] += lc[i];
     }
     if (counters) for (int i = 0; i < 14; i++) counters[i] = cnt[i];
+    return 0;
+}
+
+// The host's primary-ray gate (rt_gate.cuh) for a camera: rect[4] = x0, y0, x1, y1 (inclusive; empty = {w, h, w, h}).
+extern "C" int emu_gate_rect(const float* spheres, int ns, const float* cam15, int w, int h, int* rect) {
+    std::vector<f4> sg((size_t)ns);
+    for (int i = 0; i < ns; i++) { const float* f = spheres + 18 * (size_t)i; sg[i].x = f[0]; sg[i].y = f[1]; sg[i].z = f[2]; sg[i].w = f[17]; }
+    CamRec cam;
+    cam.pos = mk3(cam15[0], cam15[1], cam15[2]); cam.right = mk3(cam15[3], cam15[4], cam15[5]);
+    cam.up = mk3(cam15[6], cam15[7], cam15[8]); cam.fwd = mk3(cam15[9], cam15[10], cam15[11]);
+    cam.view = mk3(cam15[12], cam15[13], cam15[14]);
+    GateRect g = primary_gate_rect(cam, w, h, sg.data(), ns);
+    rect[0] = g.x0; rect[1] = g.y0; rect[2] = g.x1; rect[3] = g.y1;
     return 0;
 }
 

@@ -23,6 +23,8 @@ def load():
         _lib.emu_ray_log.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int,
                                      C.POINTER(C.c_uint32), C.c_int, C.c_void_p, C.c_int]
         _lib.emu_ray_log.restype = C.c_int
+        _lib.emu_gate_rect.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        _lib.emu_gate_rect.restype = C.c_int
     return _lib
 
 
@@ -74,3 +76,12 @@ def ray_log(scene, cam, w, h, max_depth, pixels):
     if n:
         lib.emu_ray_log(*args, C.c_void_p(out.ctypes.data), n)
     return out
+
+
+def gate_rect(scene, cam, w, h):
+    """The host's primary-ray sphere gate (csrc/rt_gate.cuh): (x0, y0, x1, y1) inclusive; empty = (w, h, w, h)."""
+    lib = load()
+    cam = np.ascontiguousarray(cam, np.float32)
+    r = (C.c_int * 4)()
+    lib.emu_gate_rect(_fp(scene.spheres), len(scene.spheres), _fp(cam), w, h, r)
+    return tuple(int(v) for v in r)

@@ -1,0 +1,82 @@
+"""The host's primary-ray sphere gate (csrc/rt_gate.cuh): outside its rectangle the kernels skip the sphere loop of primary rays,
+so the rectangle must contain EVERY pixel whose primary ray the oracle reports as hitting a sphere — for any camera — and it
+must degrade to the full frame whenever its derivation does not apply."""
+import numpy as np
+import pytest
+
+import hostemu_lib as E
+import oracle_lib as O
+import scenes
+
+
+def _sphere_hit_mask(sc, cam, w, h):
+    a = O.render(sc, cam, w, h, 0, want_aov=True)
+    return (a["aov_id"] >= 0) & (a["aov_id"] < len(sc.spheres))
+
+
+def _check(sc, cam, w, h):
+    x0, y0, x1, y1 = E.gate_rect(sc, cam, w, h)
+    m = _sphere_hit_mask(sc, cam, w, h)
+    ys, xs = np.nonzero(m)
+    if len(xs):
+        assert x0 <= xs.min() and xs.max() <= x1 and y0 <= ys.min() and ys.max() <= y1, ((x0, y0, x1, y1), (xs.min(), ys.min(), xs.max(), ys.max()))
+    return (x0, y0, x1, y1), m
+
+
+def test_default_scene_rect_is_tight():
+    sc = scenes.default_scene()
+    w, h = 640, 360
+    (x0, y0, x1, y1), m = _check(sc, scenes.make_camera(width=w, height=h), w, h)
+    ys, xs = np.nonzero(m)
+    assert xs.min() - x0 <= 4 and x1 - xs.max() <= 4 and ys.min() - y0 <= 4 and y1 - ys.max() <= 4
+    assert (x1 - x0 + 1) * (y1 - y0 + 1) < 0.35 * w * h
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_cameras_contain_every_sphere_hit(built, seed):
+    rng = np.random.default_rng(seed)
+    sc = scenes.default_scene() if seed % 3 == 0 else scenes.small_random_scene(int(rng.integers(1, 9)), seed)
+    w, h = 200, 120
+    for _ in range(6):
+        pos = tuple(rng.uniform(-6, 6, 3) * np.array([1, 0.5, 1]) + np.array([0, 1.0, -3]))
+        cam = scenes.make_camera(pos=pos, yaw=float(rng.uniform(-3.2, 3.2)), pitch=float(rng.uniform(-1.2, 1.2)), width=w, height=h)
+        _check(sc, cam, w, h)
+
+
+def test_far_camera_large_coordinates(built):
+    """|P| ~ 1e4: the fp32 primary directions are coarse (vp - P cancels); the gate must widen accordingly or give up."""
+    sc = scenes.default_scene()
+    sc.spheres[:, 0:3] += np.float32([10000.0, 0.0, 10000.0])
+    w, h = 240, 135
+    cam = scenes.make_camera(pos=(10000.0, 0.0, 10000.0), width=w, height=h)
+    _check(sc, cam, w, h)
+
+
+def test_degenerate_inputs_disable_the_gate(built):
+    sc = scenes.default_scene()
+    w, h = 64, 48
+    full = (0, 0, w - 1, h - 1)
+    cam = scenes.make_camera(width=w, height=h)
+    inside = np.array(cam, np.float32); inside[0:3] = sc.spheres[0, 0:3]                   # camera inside a sphere
+    assert E.gate_rect(sc, inside, w, h) == full
+    skew = np.array(cam, np.float32); skew[3:6] = (1.0, 0.2, 0.0)                          # basis not orthonormal
+    assert E.gate_rect(sc, skew, w, h) == full
+    nan = np.array(cam, np.float32); nan[1] = np.nan
+    assert E.gate_rect(sc, nan, w, h) == full
+    flat = np.array(cam, np.float32); flat[12] = 0.0                                       # zero-width view plane
+    assert E.gate_rect(sc, flat, w, h) == full
+    behind = scenes.make_camera(yaw=3.14159, width=w, height=h)                            # every sphere behind the camera
+    assert E.gate_rect(sc, behind, w, h) == (w, h, w, h)
+    assert E.gate_rect(scenes.small_random_scene(0, 1), cam, w, h) == (w, h, w, h)         # no spheres: always skip
+    for c in (inside, skew, behind):                                                       # and rendering stays exact either way
+        a = O.render(sc, c, w, h, 4)
+        b = E.render(sc, c, w, h, 4, tiny=2)
+        assert np.array_equal(a["pixels"], b["pixels"])
+
+
+def test_crossing_camera_plane_is_full(built):
+    sc = scenes.default_scene()
+    w, h = 64, 48
+    cam = scenes.make_camera(pos=(2.5, 0.0, 7.5), yaw=1.5708, width=w, height=h)            # sphere 0 straddles the camera plane
+    r = E.gate_rect(sc, cam, w, h)
+    assert r == (0, 0, w - 1, h - 1)

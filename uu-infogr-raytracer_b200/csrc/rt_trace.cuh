@@ -421,7 +421,8 @@ RT_HD void primary_ray(const CamRec& cam, float fx, float fy, float fw, float fh
 // about to trace the ray of level `defer_at` it returns false instead, leaving the state ready for a later call (used by the
 // compacting kernel to hand deep mirror chains to fully populated warps).  `stack` must hold cap+1 records.
 template <class SC, class DBG>
-RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& top, HitRec* stack, int defer_at, f3* Cout, DBG& dbg) {
+RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& top, HitRec* stack, int defer_at, f3* Cout, DBG& dbg,
+                       bool skip0 = false) {
     f3 C = mk3(0, 0, 0);
     const int np = sc.n_planes();      // compile-time constant in the exact-count kernels
     for (;;) {
@@ -429,8 +430,10 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
         float a = dot3(dir, dir);                                                          // :617
         float a2 = 2 * a;                                                                  // :624
         float a4 = 4 * a;                                                                  // :621
-        int sel_s; float d_s;
-        sc.nearest(o, dir, a2, a4, bounce == 0 ? 0.0f : 0.01f, &sel_s, &d_s, dbg);         // :975-981 / :792-808
+        // skip0: the host proved that this pixel's primary ray cannot be reported as hitting any sphere (rt_gate.cuh)
+        int sel_s = -1; float d_s = RT_INF;
+        if (!(skip0 && bounce == 0))
+            sc.nearest(o, dir, a2, a4, bounce == 0 ? 0.0f : 0.01f, &sel_s, &d_s, dbg);     // :975-981 / :792-808
         int sel_p = -1; float d_p = RT_INF;
 #pragma unroll
         for (int i = 0; i < np; i++) {                                                     // :985 / :812
@@ -479,11 +482,11 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
 
 template <bool FASTDIV = false, class SC, class DBG>
 RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float fw, float fh, float rw, float rh, int cap,
-                      HitRec* stack, DBG& dbg) {
+                      HitRec* stack, DBG& dbg, bool skip0 = false) {
     f3 o, dir, C;
     primary_ray<FASTDIV>(cam, fx, fy, fw, fh, rw, rh, &o, &dir);
     int bounce = 0, top = 0;
-    trace_chain(sc, cap, o, dir, bounce, top, stack, -1, &C, dbg);
+    trace_chain(sc, cap, o, dir, bounce, top, stack, -1, &C, dbg, skip0);
     return C;
 }
 
@@ -493,9 +496,9 @@ RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float
 // FASTDIV (only with SPP1, w and h <= RT_FASTDIV_MAX): rw / rh = correctly rounded 1/w, 1/h; see primary_ray.
 template <bool SPP1 = false, bool FASTDIV = false, class SC, class DBG>
 RT_HD uint32_t trace_pixel(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int cap, int spp, uint32_t seed,
-                           HitRec* stack, DBG& dbg, float rw = 0.0f, float rh = 0.0f) {
+                           HitRec* stack, DBG& dbg, float rw = 0.0f, float rh = 0.0f, bool skip0 = false) {
     const float fw = (float)w, fh = (float)h;
-    if (SPP1) return pack_color(trace_sample<FASTDIV>(sc, cam, (float)x, (float)y, fw, fh, rw, rh, cap, stack, dbg));   // :1000 -> :1038
+    if (SPP1) return pack_color(trace_sample<FASTDIV>(sc, cam, (float)x, (float)y, fw, fh, rw, rh, cap, stack, dbg, skip0));   // :1000 -> :1038
     f3 acc = mk3(0, 0, 0);
     for (int s = 0; s < spp; s++) {
         float jx = 0.0f, jy = 0.0f;

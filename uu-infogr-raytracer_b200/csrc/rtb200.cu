@@ -26,6 +26,7 @@
 #include "../../include/rtb200.h"
 #include "rt_scene.cuh"
 #include "rt_lbvh_build.cuh"
+#include "rt_gate.cuh"
 
 using namespace rtb;
 
@@ -60,6 +61,7 @@ struct FrameParams {
     float rcp_w, rcp_h;         // 1/w, 1/h correctly rounded (host): pixel-coordinate divisions of the single-sample kernels (rt_div_rcp)
     long long frame_stride;     // pixels between consecutive frames in `out`
     uint32_t* out;              // framebuffer(s): 0x00RRGGBB, row-major (Surface.pixels, surface.cs:9-20)
+    GateRect gate[INLINE_CAMS];       // per frame: pixels outside may skip the primary rays' sphere loop (rt_gate.cuh; tiny single-sample kernels)
     CamRec cam_inline[INLINE_CAMS];   // the launch's cameras travel in the parameter block (constant bank): no upload, no host
                                       // sync; batches of more than INLINE_CAMS frames are split into several launches
 };
@@ -88,12 +90,13 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
         const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
         if (p0 >= end) continue;
         const CamRec& cam = fp.cam_inline[frame];               // constant bank (LDC); batches > INLINE_CAMS are split on the host
+        const GateRect& gate = fp.gate[frame];
         uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
         uint32_t px[PPT];
         int y = p0 / fp.w, x = p0 - y * fp.w;                  // one division per thread; then step along the row
 #pragma unroll 1
         for (int q = 0; q < PPT; q++) {
-            uint32_t c = (p0 + q < end) ? trace_pixel<SPP1, SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg, fp.rcp_w, fp.rcp_h) : 0u;
+            uint32_t c = (p0 + q < end) ? trace_pixel<SPP1, SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg, fp.rcp_w, fp.rcp_h, SPP1 && gate_skips(gate, x, y)) : 0u;
             if (++x == fp.w) { x = 0; ++y; }
 #pragma unroll
             for (int z = 0; z + 1 < PPT; z++) px[z] = px[z + 1];   // shift register: after PPT iterations px[] is in pixel order
@@ -439,6 +442,7 @@ struct rt_context {
     int rank = 0, world = 1, tile_rows = 8;
     bool compaction = false;        // RT_OPT_COMPACTION
     bool host_via_gpu0 = false;     // RT_OPT_HOST_VIA_GPU0
+    bool primary_gate = true;       // RT_OPT_PRIMARY_GATE
     bool peer_ok = false;
     std::atomic<uint64_t> launches{0};
 };
@@ -588,8 +592,11 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
         case PATH_TINY: {
             const TinySceneData& t = ctx->tiny_data;
             const bool fastdiv_ok = fp.w <= RT_FASTDIV_MAX && fp.h <= RT_FASTDIV_MAX;
+            FrameParams gp = fp;                      // + per-frame primary-ray sphere gate (a few hundred host flops per frame)
+            for (int f = 0; f < fp.n_frames; f++)
+                gp.gate[f] = ctx->primary_gate ? primary_gate_rect(fp.cam_inline[f], fp.w, fp.h, t.sgeom, t.ns) : gate_full(fp.w, fp.h);
             TinyKernel kern = (ctx->compaction && fp.spp == 1 && fastdiv_ok) ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np, fp.spp, fastdiv_ok);
-            kern<<<grid, BLOCK, 0, stream>>>(t, fp);
+            kern<<<grid, BLOCK, 0, stream>>>(t, gp);
             break;
         }
         case PATH_STAGED: k_render_staged<<<grid, BLOCK, smem, stream>>>(global_data(ctx, d), fp); break;
@@ -808,6 +815,7 @@ int rt_set_option(rt_context* ctx, int option, int value) {
     switch (option) {
         case RT_OPT_COMPACTION: ctx->compaction = value != 0; return RT_OK;
         case RT_OPT_HOST_VIA_GPU0: ctx->host_via_gpu0 = value != 0; return RT_OK;
+        case RT_OPT_PRIMARY_GATE: ctx->primary_gate = value != 0; return RT_OK;
         default: return fail(ctx, RT_ERR_INVALID, "unknown option");
     }
 }

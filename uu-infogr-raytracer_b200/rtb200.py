@@ -23,6 +23,7 @@ LIB_PATH = os.environ.get("RTB200_LIB", os.path.join(_HERE, "librtb200.so"))   #
 RT_ACCEL_AUTO, RT_ACCEL_BRUTE, RT_ACCEL_LBVH = 0, 1, 2
 RT_OPT_COMPACTION = 1
 RT_OPT_HOST_VIA_GPU0 = 2
+RT_OPT_PRIMARY_GATE = 3
 COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_pos", "plane_tests",
                  "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"]
 

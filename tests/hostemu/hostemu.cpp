@@ -62,10 +62,15 @@ static void host_build(const std::vector<f4>& sg, HostBvh& b) {
 // The uninstrumented tiny-scene path at one sample per pixel runs like the single-sample kernels: with the host's primary-ray gate.
 static bool g_gate_on = false;
 static GateRect g_gate = {0, 0, 0, 0};
+static SkyGate g_sky = {-1.0f, 0.0f, 0.0f};
 template <class SC, class DBG>
 static uint32_t px_of(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int d, int spp, uint32_t seed, HitRec* st, DBG& dbg) {
     if constexpr (!DBG::enabled) {
-        if (g_gate_on) return trace_pixel<true>(sc, cam, x, y, w, h, d, 1, seed, st, dbg, 0.0f, 0.0f, gate_skips(g_gate, x, y));
+        if (g_gate_on) {
+            const bool skip0 = gate_skips(g_gate, x, y);
+            if (skip0 && sky_skips(g_sky, (float)x, (float)y)) return 0u;
+            return trace_pixel<true>(sc, cam, x, y, w, h, d, 1, seed, st, dbg, 0.0f, 0.0f, skip0);
+        }
     }
     return trace_pixel(sc, cam, x, y, w, h, d, spp, seed, st, dbg);
 }
@@ -152,7 +157,7 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         for (int i = 0; i < nl; i++) t.lights[i] = li[i];
     }
     g_gate_on = (use_tiny == 1 || use_tiny == 2) && spp == 1;
-    if (g_gate_on) g_gate = primary_gate_rect(cam, w, h, sg.data(), ns);
+    if (g_gate_on) { g_gate = primary_gate_rect(cam, w, h, sg.data(), ns); g_sky = primary_sky_gate(cam, w, h, pl.data(), np); }
     uint64_t cnt[14] = {0};
     const bool dbg_mode = hash || aov_id || aov_t || counters;
 #pragma omp parallel
@@ -197,6 +202,19 @@ extern "C" int emu_gate_rect(const float* spheres, int ns, const float* cam15, i
     cam.view = mk3(cam15[12], cam15[13], cam15[14]);
     GateRect g = primary_gate_rect(cam, w, h, sg.data(), ns);
     rect[0] = g.x0; rect[1] = g.y0; rect[2] = g.x1; rect[3] = g.y1;
+    return 0;
+}
+// sky mask of a frame: out[y*w+x] = 1 where the host's sky gate says the (single) plane cannot be hit by the pixel's primary ray
+extern "C" int emu_sky_mask(const float* planes, int np, const float* cam15, int w, int h, unsigned char* out, float* coeff) {
+    std::vector<PlaneRec> pl((size_t)np);
+    for (int i = 0; i < np; i++) pl[i] = make_plane(planes + 20 * (size_t)i);
+    CamRec cam;
+    cam.pos = mk3(cam15[0], cam15[1], cam15[2]); cam.right = mk3(cam15[3], cam15[4], cam15[5]);
+    cam.up = mk3(cam15[6], cam15[7], cam15[8]); cam.fwd = mk3(cam15[9], cam15[10], cam15[11]);
+    cam.view = mk3(cam15[12], cam15[13], cam15[14]);
+    SkyGate g = primary_sky_gate(cam, w, h, pl.data(), np);
+    if (coeff) { coeff[0] = g.ga; coeff[1] = g.gx; coeff[2] = g.gy; }
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) out[(size_t)y * w + x] = sky_skips(g, (float)x, (float)y) ? 1 : 0;
     return 0;
 }
 

@@ -25,6 +25,8 @@ def load():
         _lib.emu_ray_log.restype = C.c_int
         _lib.emu_gate_rect.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_int)]
         _lib.emu_gate_rect.restype = C.c_int
+        _lib.emu_sky_mask.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), fp]
+        _lib.emu_sky_mask.restype = C.c_int
     return _lib
 
 
@@ -85,3 +87,12 @@ def gate_rect(scene, cam, w, h):
     r = (C.c_int * 4)()
     lib.emu_gate_rect(_fp(scene.spheres), len(scene.spheres), _fp(cam), w, h, r)
     return tuple(int(v) for v in r)
+
+
+def sky_mask(scene, cam, w, h):
+    """(mask bool[h,w], (ga, gx, gy)): where the host's sky gate (csrc/rt_gate.cuh) says the plane cannot be hit."""
+    lib = load()
+    cam = np.ascontiguousarray(cam, np.float32)
+    out = np.zeros(w * h, np.uint8); co = np.zeros(3, np.float32)
+    lib.emu_sky_mask(_fp(scene.planes), len(scene.planes), _fp(cam), w, h, out.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(co))
+    return out.reshape(h, w).astype(bool), tuple(float(v) for v in co)

@@ -317,3 +317,29 @@ def test_degenerate_scene(rt, accel_name):
         assert_image_parity(px, ref["pixels"], "degenerate " + accel_name)
         assert np.array_equal(px, got["pixels"])
     ctx.close()
+
+
+def test_primary_gate_on_off_identical(ctx, rt):
+    """RT_OPT_PRIMARY_GATE only skips sphere loops the host proved fruitless (csrc/rt_gate.cuh): frames must not change, for
+    cameras anywhere — far away, inside a sphere, looking away, rolled basis included."""
+    rng = np.random.default_rng(42)
+    w, h = 480, 270
+    for k in range(24):
+        sc = scenes.default_scene() if k % 2 == 0 else scenes.small_random_scene(int(rng.integers(1, 9)), 100 + k)
+        ctx.set_scene(sc)
+        if k == 3:
+            pos = tuple(sc.spheres[0, 0:3] + np.float32([0.2, 0.1, -0.3]))               # inside sphere 0
+        elif k == 5:
+            pos = (800.0, 3.0, -900.0)                                                      # coarse fp32 directions
+        else:
+            pos = tuple(rng.uniform(-6, 6, 3) * np.array([1, 0.4, 1]) + np.array([0, 1.2, -2]))
+        cam = scenes.make_camera(pos=pos, yaw=float(rng.uniform(-3.2, 3.2)), pitch=float(rng.uniform(-1.3, 1.3)), width=w, height=h)
+        ctx.set_option(rt.RT_OPT_PRIMARY_GATE, 1)
+        on, _ = ctx.render(cam, w, h, 6, 1, 0)
+        ctx.set_option(rt.RT_OPT_PRIMARY_GATE, 0)
+        off, _ = ctx.render(cam, w, h, 6, 1, 0)
+        ctx.set_option(rt.RT_OPT_PRIMARY_GATE, 1)
+        assert np.array_equal(on, off), "camera %d: %d pixels differ" % (k, (on != off).sum())
+        if k % 6 == 0:
+            ref = O.render(sc, cam, w, h, 6)
+            assert_image_parity(on.reshape(h, w), ref["pixels"], "gated frame")

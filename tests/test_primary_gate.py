@@ -80,3 +80,73 @@ def test_crossing_camera_plane_is_full(built):
     cam = scenes.make_camera(pos=(2.5, 0.0, 7.5), yaw=1.5708, width=w, height=h)            # sphere 0 straddles the camera plane
     r = E.gate_rect(sc, cam, w, h)
     assert r == (0, 0, w - 1, h - 1)
+
+
+# ---- sky gate: the side of the plane's horizon on which no primary ray can hit the plane ----------------------------------
+
+def _plane_hit_mask(sc, cam, w, h):
+    import copy
+    bare = copy.copy(sc)
+    bare.spheres = sc.spheres[:0]
+    a = O.render(bare, cam, w, h, 0, want_aov=True)
+    return a["aov_id"] >= 0
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_sky_gate_never_claims_a_plane_hit(built, seed):
+    rng = np.random.default_rng(1000 + seed)
+    sc = scenes.default_scene()
+    w, h = 200, 120
+    claimed = missed = 0
+    for k in range(8):
+        pos = tuple(rng.uniform(-6, 6, 3) * np.array([1, 0.6, 1]) + np.array([0, 0.5, -3]))      # above and below the floor
+        cam = scenes.make_camera(pos=pos, yaw=float(rng.uniform(-3.2, 3.2)), pitch=float(rng.uniform(-1.5, 1.5)), width=w, height=h)
+        sky, _ = E.sky_mask(sc, cam, w, h)
+        hit = _plane_hit_mask(sc, cam, w, h)
+        assert not (sky & hit).any(), "camera %d: %d plane hits inside the sky mask" % (k, (sky & hit).sum())
+        claimed += int(sky.sum()); missed += int((~hit).sum())
+    assert claimed > 0.9 * missed       # and it is tight: it claims > 90 % of the pixels that really miss the plane
+
+
+def test_sky_gate_tilted_plane_and_rolled_camera(built):
+    """A plane whose normal is not axis-aligned (and not unit length) seen by a rolled camera: the horizon is an oblique line."""
+    sc = scenes.default_scene()
+    sc.planes[0, 3:6] = np.float32([0.3, 1.7, -0.4])
+    w, h = 160, 120
+    for roll in (0.0, 0.4, -1.1, 2.5):
+        cam = np.array(scenes.make_camera(pos=(0.5, 1.0, -2.0), yaw=0.3, pitch=0.2, width=w, height=h), np.float32)
+        r, u = cam[3:6].copy(), cam[6:9].copy()
+        cam[3:6] = np.float32(np.cos(roll) * r + np.sin(roll) * u)
+        cam[6:9] = np.float32(-np.sin(roll) * r + np.cos(roll) * u)
+        sky, co = E.sky_mask(sc, cam, w, h)
+        hit = _plane_hit_mask(sc, cam, w, h)
+        assert not (sky & hit).any()
+        a = O.render(sc, cam, w, h, 4)
+        b = E.render(sc, cam, w, h, 4, tiny=2)
+        assert np.array_equal(a["pixels"], b["pixels"])
+    assert sky.any() and co[1] != 0.0 and co[2] != 0.0
+
+
+def test_sky_gate_degenerate_cases(built):
+    sc = scenes.default_scene()
+    w, h = 64, 48
+    cam = scenes.make_camera(width=w, height=h)
+    two = scenes.default_scene()
+    two.planes = np.concatenate([sc.planes, sc.planes]); two.planes[1, 1] = 5.0; two.planes[1, 4] = -1.0     # a ceiling: 2 planes
+    sky, co = E.sky_mask(two, cam, w, h)
+    assert not sky.any() and co[0] < 0                                     # more than one plane: the gate is off
+    a = O.render(two, cam, w, h, 3); b = E.render(two, cam, w, h, 3, tiny=1)
+    assert np.array_equal(a["pixels"], b["pixels"])
+    none = scenes.default_scene(); none.planes = sc.planes[:0]
+    sky, _ = E.sky_mask(none, cam, w, h)
+    assert sky.all()                                                       # no plane: nothing to hit
+    a = O.render(none, cam, w, h, 3); b = E.render(none, cam, w, h, 3, tiny=1)
+    assert np.array_equal(a["pixels"], b["pixels"])
+    on_plane = scenes.make_camera(pos=(0.0, -1.0, 0.0), width=w, height=h)                                  # camera ON the floor: num == 0
+    sky, _ = E.sky_mask(sc, on_plane, w, h)
+    assert sky.all() and not _plane_hit_mask(sc, on_plane, w, h).any()
+    a = O.render(sc, on_plane, w, h, 3); b = E.render(sc, on_plane, w, h, 3, tiny=2)
+    assert np.array_equal(a["pixels"], b["pixels"])
+    skew = np.array(cam, np.float32); skew[3:6] = (1.0, 0.2, 0.0)
+    sky, _ = E.sky_mask(sc, skew, w, h)
+    assert not sky.any()

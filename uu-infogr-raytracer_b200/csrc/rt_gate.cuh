@@ -25,30 +25,51 @@ namespace rtb {
 
 struct GateRect { int x0, y0, x1, y1; };      // inclusive pixel ranges; empty (no primary ray can hit a sphere) = {w, h, w, h}
 
+// Second gate, same spirit: the side of the (single) plane's horizon on which no primary ray can hit the plane. All primary rays
+// share the origin, so the numerator of IntersectPlane (:591-594) is one number per frame (evaluated here with the kernel's own
+// fp32 expression, plane_num); `t = num / den > 0` (:598) then needs den = Dot(direction, normal) to have num's sign, and
+// den(x, y) is — up to the direction error eps and the rounding of the dot product — an affine function of the pixel
+// coordinates. sky(x, y) = fma(gx, x, fma(gy, y, ga)) > 0  ==>  the plane cannot be hit by pixel (x, y)'s primary ray.
+// A pixel that is outside the sphere rectangle AND on the sky side hits nothing: its colour is 0x00000000 (:993, :1000) without
+// tracing. More than one plane, or anything unusual: ga = -1, gx = gy = 0 (never skips). No plane or num == 0: ga = +1.
+struct SkyGate { float ga, gx, gy; };
+
 inline GateRect gate_full(int w, int h) { GateRect g = {0, 0, w - 1, h - 1}; return g; }
+
+// Bound on the angle between the fp32 primary direction of any pixel and its ideal direction (header), or -1 when the camera is
+// not one the gates are derived for.
+inline double primary_dir_eps(const CamRec& cam) {
+    const double P[3] = {cam.pos.x, cam.pos.y, cam.pos.z};
+    const double R[3] = {cam.right.x, cam.right.y, cam.right.z}, U[3] = {cam.up.x, cam.up.y, cam.up.z}, F[3] = {cam.fwd.x, cam.fwd.y, cam.fwd.z};
+    const double pw = cam.view.x, ph = cam.view.y, nearp = cam.view.z;
+    auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    auto finite3 = [](const double* a) { return std::isfinite(a[0]) && std::isfinite(a[1]) && std::isfinite(a[2]); };
+    if (!finite3(P) || !finite3(R) || !finite3(U) || !finite3(F) || !std::isfinite(pw) || !std::isfinite(ph) || !std::isfinite(nearp)) return -1;
+    if (!(pw > 1e-6) || !(ph > 1e-6) || !(nearp > 1e-6) || pw > 1e6 || ph > 1e6 || nearp > 1e6) return -1;
+    const double tol = 1e-5;
+    if (std::fabs(dot(R, R) - 1) > tol || std::fabs(dot(U, U) - 1) > tol || std::fabs(dot(F, F) - 1) > tol ||
+        std::fabs(dot(R, U)) > tol || std::fabs(dot(R, F)) > tol || std::fabs(dot(U, F)) > tol) return -1;
+    // rounding of u, v, of the three scaled basis vectors and of the running sum (scales with |P|), with a factor 2 in hand
+    const double u32 = 5.9604644775390625e-08;           // 2^-24
+    const double pmax = std::fmax(std::fabs(P[0]), std::fmax(std::fabs(P[1]), std::fabs(P[2])));
+    const double L = 0.5 * pw + 0.5 * ph + nearp;
+    const double E = u32 * (8.0 * (pmax + L) + 4.0 * (pw + ph));
+    const double eps = 2.0 * (2.0 * std::sqrt(3.0) * E / nearp + 1e-6) + 4e-5;
+    return eps < 1e-2 ? eps : -1;
+}
 
 inline GateRect primary_gate_rect(const CamRec& cam, int w, int h, const f4* sgeom, int ns) {
     const GateRect full = gate_full(w, h);
     const GateRect empty = {w, h, w, h};
     GateRect out = {w, h, -1, -1};
     if (ns <= 0) return empty;
+    const double eps = primary_dir_eps(cam);
+    if (eps < 0) return full;
     const double P[3] = {cam.pos.x, cam.pos.y, cam.pos.z};
     const double R[3] = {cam.right.x, cam.right.y, cam.right.z}, U[3] = {cam.up.x, cam.up.y, cam.up.z}, F[3] = {cam.fwd.x, cam.fwd.y, cam.fwd.z};
     const double pw = cam.view.x, ph = cam.view.y, nearp = cam.view.z;
     auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
     auto finite3 = [](const double* a) { return std::isfinite(a[0]) && std::isfinite(a[1]) && std::isfinite(a[2]); };
-    if (!finite3(P) || !finite3(R) || !finite3(U) || !finite3(F) || !std::isfinite(pw) || !std::isfinite(ph) || !std::isfinite(nearp)) return full;
-    if (!(pw > 1e-6) || !(ph > 1e-6) || !(nearp > 1e-6) || pw > 1e6 || ph > 1e6 || nearp > 1e6) return full;
-    const double tol = 1e-5;
-    if (std::fabs(dot(R, R) - 1) > tol || std::fabs(dot(U, U) - 1) > tol || std::fabs(dot(F, F) - 1) > tol ||
-        std::fabs(dot(R, U)) > tol || std::fabs(dot(R, F)) > tol || std::fabs(dot(U, F)) > tol) return full;
-    // angular error of the fp32 primary direction against the ideal one (see header), with a factor 2 in hand
-    const double u32 = 5.9604644775390625e-08;           // 2^-24
-    const double pmax = std::fmax(std::fabs(P[0]), std::fmax(std::fabs(P[1]), std::fabs(P[2])));
-    const double L = 0.5 * pw + 0.5 * ph + nearp;
-    const double E = u32 * (8.0 * (pmax + L) + 4.0 * (pw + ph));
-    const double eps = 2.0 * (2.0 * std::sqrt(3.0) * E / nearp + 1e-6) + 4e-5;
-    if (!(eps < 1e-2)) return full;
     const double K = (double)RT_BVH_PAD_K;
     for (int i = 0; i < ns; i++) {
         const double c[3] = {sgeom[i].x, sgeom[i].y, sgeom[i].z};
@@ -87,6 +108,42 @@ inline GateRect primary_gate_rect(const CamRec& cam, int w, int h, const f4* sge
     if (out.x1 < out.x0 || out.y1 < out.y0) return empty;
     return out;
 }
+
+// planes: PlaneRec array of the scene (n, cn as uploaded). See SkyGate.
+inline SkyGate primary_sky_gate(const CamRec& cam, int w, int h, const PlaneRec* planes, int np) {
+    const SkyGate never = {-1.0f, 0.0f, 0.0f}, always = {1.0f, 0.0f, 0.0f};
+    if (np <= 0) return always;
+    if (np > 1) return never;
+    const double eps = primary_dir_eps(cam);
+    if (eps < 0) return never;
+    const PlaneRec& pl = planes[0];
+    f4 pn; pn.x = pl.n.x; pn.y = pl.n.y; pn.z = pl.n.z; pn.w = pl.cn;
+    const float num = plane_num(cam.pos, pn);            // the kernel's own fp32 value (same expression, no contraction)
+    if (!(num == num)) return never;
+    if (num == 0.0f) return always;                      // 0 / den is never > 0 (:598)
+    const double n[3] = {pl.n.x, pl.n.y, pl.n.z};
+    const double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (!std::isfinite(nl) || !(nl > 0)) return never;
+    const double R[3] = {cam.right.x, cam.right.y, cam.right.z}, U[3] = {cam.up.x, cam.up.y, cam.up.z}, F[3] = {cam.fwd.x, cam.fwd.y, cam.fwd.z};
+    const double pw = cam.view.x, ph = cam.view.y, nearp = cam.view.z;
+    auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    // ideal direction of pixel (x, y): D = A + x Bx + y By;  den has the sign of D . n up to the margin below
+    const double Rn = dot(R, n), Un = dot(U, n), Fn = dot(F, n);
+    const double a = -0.5 * pw * Rn - 0.5 * ph * Un + nearp * Fn, bx = pw * Rn / w, by = ph * Un / h;
+    const double sgn = num > 0 ? -1.0 : 1.0;              // sky side: den of the opposite sign to num (or zero)
+    const double u32 = 5.9604644775390625e-08;
+    const double Dmax = std::sqrt(nearp * nearp + 0.25 * pw * pw + 0.25 * ph * ph) * 1.0001;
+    const double margin = 2.0 * (eps + 24.0 * u32) * std::sqrt(3.0) * nl * Dmax;
+    const double S = std::fabs(a) + std::fabs(bx) * w + std::fabs(by) * h;
+    SkyGate g;
+    g.gx = (float)(sgn * bx); g.gy = (float)(sgn * by);
+    g.ga = (float)(sgn * a - margin - 16.0 * u32 * S);
+    // the float conversion of ga may round up by half an ulp: step it down once more
+    g.ga = std::nextafter(g.ga, -INFINITY);
+    if (!std::isfinite(g.ga) || !std::isfinite(g.gx) || !std::isfinite(g.gy)) return never;
+    return g;
+}
+RT_HD bool sky_skips(const SkyGate& g, float fx, float fy) { return rt_fmaf(g.gx, fx, rt_fmaf(g.gy, fy, g.ga)) > 0.0f; }
 
 // true: the pixel's primary ray may skip the sphere loop
 RT_HD bool gate_skips(const GateRect& g, int x, int y) {

@@ -416,6 +416,9 @@ RT_HD void primary_ray(const CamRec& cam, float fx, float fy, float fw, float fh
     *dir = normalize3(sub3(vp, cam.pos));                                                  // :971
 }
 
+// Numerator of IntersectPlane (:591-594) — also evaluated on the host for the primary rays' common origin (rt_gate.cuh).
+RT_HD float plane_num(f3 o, f4 pn) { return -o.x * pn.x - o.y * pn.y - o.z * pn.z + pn.w; }
+
 // The ray chain of one sample, resumable.  Continues the descent from the state (o, dir, bounce, top; stack[0..top) filled);
 // when the chain ends it unwinds the whole stack, stores the colour in *C and returns true.  If defer_at >= 0 and the chain is
 // about to trace the ray of level `defer_at` it returns false instead, leaving the state ready for a later call (used by the
@@ -438,7 +441,7 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
 #pragma unroll
         for (int i = 0; i < np; i++) {                                                     // :985 / :812
             f4 pn = sc.plane_n(i);
-            float num = -o.x * pn.x - o.y * pn.y - o.z * pn.z + pn.w;                       // :591-594
+            float num = plane_num(o, pn);                                                  // :591-594
             dbg.plane_test();
             // num == 0 (a ray leaving the plane it starts on: every floor reflection re-tests the floor) gives
             // t = 0/den = +-0 or NaN: never `> 0`. Skipping the division is exact and avoids the IEEE-divide slow path that a zero

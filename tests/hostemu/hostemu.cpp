@@ -61,15 +61,20 @@ static void host_build(const std::vector<f4>& sg, HostBvh& b) {
 
 // The uninstrumented tiny-scene path at one sample per pixel runs like the single-sample kernels: with the host's primary-ray gate.
 static bool g_gate_on = false;
-static GateRect g_gate = {0, 0, 0, 0};
-static SkyGate g_sky = {-1.0f, 0.0f, 0.0f};
+static FrameGates g_gates;
 template <class SC, class DBG>
 static uint32_t px_of(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int d, int spp, uint32_t seed, HitRec* st, DBG& dbg) {
     if constexpr (!DBG::enabled) {
         if (g_gate_on) {
-            const bool skip0 = gate_skips(g_gate, x, y);
-            if (skip0 && sky_skips(g_sky, (float)x, (float)y)) return 0u;
-            return trace_pixel<true>(sc, cam, x, y, w, h, d, 1, seed, st, dbg, 0.0f, 0.0f, skip0);
+            // as render_loop (rtb200.cu): gates per span of 4 consecutive pixels (linear index aligned to 4), only inside one row
+            const int p = y * w + x, ps = p & ~3, ys = ps / w, xs = ps - ys * w;
+            uint32_t bits = 0u;
+            if (xs + 4 <= w && ps + 4 <= w * h) {
+                bool black = false;
+                bits = gate_bits_span(g_gates, xs, xs + 3, ys, sc.n_lights(), &black);
+                if (black) return 0u;
+            }
+            return trace_pixel<true>(sc, cam, x, y, w, h, d, 1, seed, st, dbg, 0.0f, 0.0f, bits);
         }
     }
     return trace_pixel(sc, cam, x, y, w, h, d, spp, seed, st, dbg);
@@ -157,7 +162,7 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         for (int i = 0; i < nl; i++) t.lights[i] = li[i];
     }
     g_gate_on = (use_tiny == 1 || use_tiny == 2) && spp == 1;
-    if (g_gate_on) { g_gate = primary_gate_rect(cam, w, h, sg.data(), ns); g_sky = primary_sky_gate(cam, w, h, pl.data(), np); }
+    if (g_gate_on) g_gates = compute_frame_gates(cam, w, h, sg.data(), ns, pl.data(), np, li.data(), nl);
     uint64_t cnt[14] = {0};
     const bool dbg_mode = hash || aov_id || aov_t || counters;
 #pragma omp parallel
@@ -192,29 +197,28 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
     return 0;
 }
 
-// The host's primary-ray gate (rt_gate.cuh) for a camera: rect[4] = x0, y0, x1, y1 (inclusive; empty = {w, h, w, h}).
-extern "C" int emu_gate_rect(const float* spheres, int ns, const float* cam15, int w, int h, int* rect) {
-    std::vector<f4> sg((size_t)ns);
+// The host's frame gates (rt_gate.cuh) for a scene and camera. rects: 6 x 4 ints (spheres, mirror, shadow[0..3]), inclusive,
+// empty = {w, h, w, h}; affine: 2 x 3 floats (sky, deep); bits (nullable): w*h bytes = gate_bits() per pixel, bit 7 = black.
+extern "C" int emu_gates(const float* spheres, int ns, const float* planes, int np, const float* lights, int nl, const float* cam15,
+                         int w, int h, int* rects, float* affine, unsigned char* bits) {
+    std::vector<f4> sg((size_t)ns); std::vector<PlaneRec> pl((size_t)np); std::vector<LightRec> li((size_t)nl);
     for (int i = 0; i < ns; i++) { const float* f = spheres + 18 * (size_t)i; sg[i].x = f[0]; sg[i].y = f[1]; sg[i].z = f[2]; sg[i].w = f[17]; }
-    CamRec cam;
-    cam.pos = mk3(cam15[0], cam15[1], cam15[2]); cam.right = mk3(cam15[3], cam15[4], cam15[5]);
-    cam.up = mk3(cam15[6], cam15[7], cam15[8]); cam.fwd = mk3(cam15[9], cam15[10], cam15[11]);
-    cam.view = mk3(cam15[12], cam15[13], cam15[14]);
-    GateRect g = primary_gate_rect(cam, w, h, sg.data(), ns);
-    rect[0] = g.x0; rect[1] = g.y0; rect[2] = g.x1; rect[3] = g.y1;
-    return 0;
-}
-// sky mask of a frame: out[y*w+x] = 1 where the host's sky gate says the (single) plane cannot be hit by the pixel's primary ray
-extern "C" int emu_sky_mask(const float* planes, int np, const float* cam15, int w, int h, unsigned char* out, float* coeff) {
-    std::vector<PlaneRec> pl((size_t)np);
     for (int i = 0; i < np; i++) pl[i] = make_plane(planes + 20 * (size_t)i);
+    for (int i = 0; i < nl; i++) li[i] = make_light(lights + 4 * (size_t)i);
     CamRec cam;
     cam.pos = mk3(cam15[0], cam15[1], cam15[2]); cam.right = mk3(cam15[3], cam15[4], cam15[5]);
     cam.up = mk3(cam15[6], cam15[7], cam15[8]); cam.fwd = mk3(cam15[9], cam15[10], cam15[11]);
     cam.view = mk3(cam15[12], cam15[13], cam15[14]);
-    SkyGate g = primary_sky_gate(cam, w, h, pl.data(), np);
-    if (coeff) { coeff[0] = g.ga; coeff[1] = g.gx; coeff[2] = g.gy; }
-    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) out[(size_t)y * w + x] = sky_skips(g, (float)x, (float)y) ? 1 : 0;
+    const FrameGates g = compute_frame_gates(cam, w, h, sg.data(), ns, pl.data(), np, li.data(), nl);
+    const GateRect* rs[6] = {&g.spheres, &g.mirror, &g.shadow[0], &g.shadow[1], &g.shadow[2], &g.shadow[3]};
+    for (int i = 0; i < 6; i++) { rects[4 * i] = rs[i]->x0; rects[4 * i + 1] = rs[i]->y0; rects[4 * i + 2] = rs[i]->x1; rects[4 * i + 3] = rs[i]->y1; }
+    affine[0] = g.sky.a; affine[1] = g.sky.bx; affine[2] = g.sky.by; affine[3] = g.deep.a; affine[4] = g.deep.bx; affine[5] = g.deep.by;
+    if (bits)
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+            bool black = false;
+            const uint32_t b = gate_bits(g, x, y, &black);
+            bits[(size_t)y * w + x] = (unsigned char)(b | (black ? 0x80u : 0u));
+        }
     return 0;
 }
 

@@ -23,10 +23,8 @@ def load():
         _lib.emu_ray_log.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int,
                                      C.POINTER(C.c_uint32), C.c_int, C.c_void_p, C.c_int]
         _lib.emu_ray_log.restype = C.c_int
-        _lib.emu_gate_rect.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_int)]
-        _lib.emu_gate_rect.restype = C.c_int
-        _lib.emu_sky_mask.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), fp]
-        _lib.emu_sky_mask.restype = C.c_int
+        _lib.emu_gates.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_int), fp, C.POINTER(C.c_ubyte)]
+        _lib.emu_gates.restype = C.c_int
     return _lib
 
 
@@ -80,19 +78,33 @@ def ray_log(scene, cam, w, h, max_depth, pixels):
     return out
 
 
-def gate_rect(scene, cam, w, h):
-    """The host's primary-ray sphere gate (csrc/rt_gate.cuh): (x0, y0, x1, y1) inclusive; empty = (w, h, w, h)."""
+GATE_SPHERES, GATE_MIRROR, GATE_SHADOW0, GATE_BLACK = 1, 2, 4, 0x80
+
+
+def gates(scene, cam, w, h, want_bits=True):
+    """The host's frame gates (csrc/rt_gate.cuh): dict(spheres, mirror, shadow[4] rects (x0, y0, x1, y1) inclusive, empty =
+    (w, h, w, h); sky, deep affine (a, bx, by); bits uint8[h, w] = per-pixel skip bits, 0x80 = black untraced)."""
     lib = load()
     cam = np.ascontiguousarray(cam, np.float32)
-    r = (C.c_int * 4)()
-    lib.emu_gate_rect(_fp(scene.spheres), len(scene.spheres), _fp(cam), w, h, r)
-    return tuple(int(v) for v in r)
+    r = (C.c_int * 24)(); aff = np.zeros(6, np.float32)
+    bits = np.zeros(w * h, np.uint8) if want_bits else None
+    lib.emu_gates(_fp(scene.spheres), len(scene.spheres), _fp(scene.planes), len(scene.planes), _fp(scene.lights), len(scene.lights),
+                  _fp(cam), w, h, r, _fp(aff), bits.ctypes.data_as(C.POINTER(C.c_ubyte)) if want_bits else None)
+    rr = [tuple(int(v) for v in r[4 * i:4 * i + 4]) for i in range(6)]
+    return dict(spheres=rr[0], mirror=rr[1], shadow=rr[2:6], sky=tuple(float(v) for v in aff[0:3]), deep=tuple(float(v) for v in aff[3:6]),
+                bits=bits.reshape(h, w) if want_bits else None)
+
+
+def gate_rect(scene, cam, w, h):
+    return gates(scene, cam, w, h, want_bits=False)["spheres"]
 
 
 def sky_mask(scene, cam, w, h):
-    """(mask bool[h,w], (ga, gx, gy)): where the host's sky gate (csrc/rt_gate.cuh) says the plane cannot be hit."""
-    lib = load()
-    cam = np.ascontiguousarray(cam, np.float32)
-    out = np.zeros(w * h, np.uint8); co = np.zeros(3, np.float32)
-    lib.emu_sky_mask(_fp(scene.planes), len(scene.planes), _fp(cam), w, h, out.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(co))
-    return out.reshape(h, w).astype(bool), tuple(float(v) for v in co)
+    """(mask bool[h,w], (a, bx, by)): where the sky gate says the plane cannot be hit by the pixel's primary ray."""
+    g = gates(scene, cam, w, h, want_bits=False)
+    a, bx, by = (np.float32(v) for v in g["sky"])
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.float64), np.arange(w, dtype=np.float64), indexing="ij")
+    # fma(bx, x, fma(by, y, a)) evaluated exactly (float64 holds the float32 products and sums of these magnitudes to within 2^-53)
+    inner = np.float32(np.float64(by) * ys + np.float64(a))
+    val = np.float32(np.float64(bx) * xs + np.float64(inner))
+    return val > 0, g["sky"]

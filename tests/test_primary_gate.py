@@ -150,3 +150,86 @@ def test_sky_gate_degenerate_cases(built):
     skew = np.array(cam, np.float32); skew[3:6] = (1.0, 0.2, 0.0)
     sky, _ = E.sky_mask(sc, skew, w, h)
     assert not sky.any()
+
+
+# ---- all gates against the oracle's ray log: every skipped piece of work must be one the oracle finds fruitless --------------
+
+def _check_bits_against_log(sc, cam, w, h, depth=3):
+    g = E.gates(sc, cam, w, h)
+    bits = g["bits"].reshape(-1)
+    ns = len(sc.spheres)
+    log = O.ray_log(sc, cam, w, h, depth, np.arange(w * h, dtype=np.uint32))
+    prim = log[log["kind"] == 0]
+    assert np.array_equal(prim["pixel"], np.arange(w * h))
+    phit = prim["hit"]
+    on_plane = phit >= ns                                                       # primary ray hit the plane
+    assert (phit[(bits & E.GATE_BLACK) != 0] == -1).all()
+    assert not ((phit >= 0) & (phit < ns))[(bits & E.GATE_SPHERES) != 0].any()
+    # mirror bit: the reflection ray of a primary plane hit contributes nothing
+    sec = log[(log["kind"] == 1) & (log["level"] == 1)]
+    sel = ((bits[sec["pixel"]] & E.GATE_MIRROR) != 0) & on_plane[sec["pixel"]]
+    s = sec[sel]
+    fruitless = (s["hit"] == -1) | ((s["hit"] >= ns) & (s["distance"] - np.float32(0.01) <= 0))
+    assert fruitless.all(), "%d reflection rays the mirror gate would skip do hit something" % (~fruitless).sum()
+    # shadow bits: the shadow ray of light l from the primary plane hit is unoccluded
+    sh = log[(log["kind"] == 2) & (log["level"] == 0)]
+    for l in range(min(4, len(sc.lights))):
+        q = sh[(sh["light"] == l)]
+        sel = ((bits[q["pixel"]] & (E.GATE_SHADOW0 << l)) != 0) & on_plane[q["pixel"]]
+        assert (q["hit"][sel] == -1).all(), "light %d: %d occluded shadow rays inside the gate" % (l, (q["hit"][sel] != -1).sum())
+    return g, bits, on_plane, sec, sh
+
+
+def test_default_scene_gates_are_sound_and_effective(built):
+    sc = scenes.default_scene()
+    w, h = 384, 216
+    g, bits, on_plane, sec, sh = _check_bits_against_log(sc, scenes.make_camera(width=w, height=h), w, h)
+    floor = on_plane.mean()
+    assert ((bits & E.GATE_BLACK) != 0).mean() > 0.30
+    assert ((bits & E.GATE_MIRROR) != 0).mean() > 0.35 * floor
+    assert ((bits & E.GATE_SHADOW0) != 0).mean() > 0.75 * floor
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_cameras_and_scenes_all_gates(built, seed):
+    rng = np.random.default_rng(500 + seed)
+    sc = scenes.default_scene() if seed % 4 == 0 else scenes.small_random_scene(int(rng.integers(1, 9)), 700 + seed)
+    if seed % 4 == 3:                                                           # a tilted (but unit-normal) mirror floor
+        n = np.float32([0.2, 1.0, -0.1]); n = (n / np.float32(np.linalg.norm(n))).astype(np.float32)
+        sc.planes[0, 3:6] = n
+    w, h = 144, 96
+    for _ in range(4):
+        pos = tuple(rng.uniform(-6, 6, 3) * np.array([1, 0.5, 1]) + np.array([0, 1.0, -3]))
+        cam = scenes.make_camera(pos=pos, yaw=float(rng.uniform(-3.2, 3.2)), pitch=float(rng.uniform(-1.4, 1.4)), width=w, height=h)
+        _check_bits_against_log(sc, cam, w, h)
+        a = O.render(sc, cam, w, h, 5)
+        b = E.render(sc, cam, w, h, 5, tiny=1 if len(sc.spheres) > 4 else 2)
+        assert np.array_equal(a["pixels"], b["pixels"])
+
+
+def test_high_camera_and_grazing_light(built):
+    """A camera high above the floor (long primary rays: the self-hit bound must raise sin_min or drop the mirror gate) and a light
+    almost in the plane (unbounded shadows: that light's gate must stay off)."""
+    sc = scenes.default_scene()
+    sc.lights[1, 0:3] = np.float32([40.0, 0.0001, 5.0])
+    w, h = 160, 120
+    for pos, pitch in (((0.0, 60.0, -20.0), 1.0), ((3.0, 400.0, 2.0), 1.5), ((0.0, 0.2, 0.0), 0.05)):
+        cam = scenes.make_camera(pos=pos, pitch=pitch, width=w, height=h)
+        g, *_ = _check_bits_against_log(sc, cam, w, h)
+        assert g["shadow"][1] == (0, 0, w - 1, h - 1)
+        a = O.render(sc, cam, w, h, 5)
+        b = E.render(sc, cam, w, h, 5, tiny=2)
+        assert np.array_equal(a["pixels"], b["pixels"])
+
+
+def test_non_unit_normal_disables_only_the_mirror_gate(built):
+    sc = scenes.default_scene()
+    sc.planes[0, 3:6] = np.float32([0.0, 2.0, 0.0])          # :741-744 reflects about the normal AS GIVEN: not a mirror image
+    w, h = 160, 90
+    cam = scenes.make_camera(width=w, height=h)
+    g, bits, *_ = _check_bits_against_log(sc, cam, w, h)
+    assert g["mirror"] == (0, 0, w - 1, h - 1) and not (bits & E.GATE_MIRROR).any()
+    assert (bits & E.GATE_SHADOW0).any()
+    a = O.render(sc, cam, w, h, 5)
+    b = E.render(sc, cam, w, h, 5, tiny=2)
+    assert np.array_equal(a["pixels"], b["pixels"])

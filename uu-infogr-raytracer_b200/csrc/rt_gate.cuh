@@ -1,20 +1,39 @@
-// rt_gate.cuh — host-side, per frame: the pixel rectangle outside of which NO primary ray can be reported as hitting ANY sphere by
-// the reference's test (RayTracer.cs:613-642), so the kernel may skip the sphere loop of those primary rays (:975-981) and keep
-// the exact result `no sphere` (the plane loop still runs). Only conservativeness matters here, none of this is reference
-// arithmetic; everything is evaluated in double.
+// rt_gate.cuh — per-frame, host-side "gates": pixel-space regions outside of which a part of the reference's per-pixel work
+// is PROVEN to find nothing, so the single-sample tiny-scene kernels skip it and keep the exact result. None of this is
+// reference arithmetic — only conservativeness matters — and everything here is evaluated in double on the host (a few
+// microseconds per frame). Any doubt (odd camera, several planes, unbounded projection, non-finite input) yields the gate that
+// never skips. rt_set_option(RT_OPT_PRIMARY_GATE, 0) turns all of them off; frames are identical either way (tests).
 //
-// Why a rectangle exists.  All primary rays start at the camera position P.  The reference's fp32 discriminant can only be >= 0
-// for a ray whose exact line passes within R' = sqrt(r^2 + K^2 (|oc|^2 + r^2)) of the centre (K = RT_BVH_PAD_K, the bound the
-// LBVH boxes use — derivation in rt_lbvh.cuh / DESIGN.md §5), and a sphere wholly behind the camera plane gives b >= 0.  The
-// directions that pass within R' of a centre form a cone; its projection on the view plane is bounded, per axis, by the two planes
-// through the camera's other axis that touch the ball: with the centre at (X, Y, Z) in camera coordinates the slopes k = x/z of
-// those planes solve  k^2 (Z^2 - R^2) - 2 X Z k + (X^2 - R^2) = 0.
-// What the fp32 pipeline adds.  The direction the kernel really uses is normalize(fl(vp - P)) with vp accumulated in fp32
-// (:964-971); its angle to the ideal direction of the pixel is bounded by eps below (rounding of u, v, of the three scaled basis
-// vectors and of the running sum, which scales with |P|), plus 4e-5 for a basis that is orthonormal only to 1e-5. A ray that is
-// off by eps passes at most eps (|oc| + R') further from the centre, so R' grows by that much. Then +-2 pixels.
-// Anything unusual (basis not orthonormal, non-positive view-plane sizes, camera inside an inflated ball, a ball crossing the
-// camera plane, eps > 1e-2, non-finite numbers) returns the full frame: the gate then never skips anything.
+// Facts used.
+//  (F1) Sphere test, RayTracer.cs:613-642: the fp32 discriminant b^2 - 4ac can only be >= 0 for a ray whose exact line passes
+//       within R' = sqrt(r^2 + K^2 (|oc|^2 + r^2)) of the centre, K = RT_BVH_PAD_K (derivation: rt_lbvh.cuh, DESIGN.md §5 — the
+//       bound the LBVH boxes rely on), |oc| = distance from the ray origin to the centre.
+//  (F2) All primary rays start at the camera position P, and the direction the kernel really uses, normalize(fl(vp - P))
+//       (:964-971), is within an angle eps of the ideal direction D(x, y) = R (x/w - .5) pw + U (y/h - .5) ph + F near of its
+//       pixel (primary_dir_eps: rounding of u, v, the scaled basis vectors and the running sum, which grows with |P|; the basis
+//       must be orthonormal to 1e-5).
+//  (F3) Plane test, :590-604: t = num / den > 0 with num = plane_num(origin) — ONE fp32 number per frame for primary rays,
+//       evaluated here with the kernel's own expression — and den = Dot(direction, normal), whose sign is that of D . n outside
+//       a margin. D . n is affine in (x, y).
+//
+// Gates (FrameGates), for pixel (x, y):
+//  spheres  rectangle. Outside: no sphere can be hit by the primary ray -> the sphere loop :975-981 is skipped.
+//           [cone of directions within R'' of a centre, R'' = R' + eps (|oc| + R'), projected per axis by the tangent planes
+//            k^2 (Z^2 - R^2) - 2 X Z k + (X^2 - R^2) = 0, +-2 pixels]
+//  sky      affine, > 0: den has the wrong sign -> the plane cannot be hit (single plane only). Outside `spheres` AND sky:
+//           the pixel is 0x00000000 (:993, :1000) without tracing.
+//  deep     affine, > 0: the primary ray meets the plane at a slope >= sin_min, hence within dmax = H / sin_min of P (H = distance
+//           of P from the plane). Precondition of the two gates below, which concern a primary ray that HIT the plane
+//           (checked at run time).
+//  mirror   rectangle. deep AND outside: the reflection ray of the plane hit (:741-746) hits nothing, so the mirror term is
+//           (0,0,0) and the ray is not traced. [the exact reflection of the primary line passes through the mirror image P' of P:
+//           the spheres seen from P', inflated by the fp32 deviations of the hit point and of the reflected direction; and the
+//           reflection cannot re-hit its own plane beyond the 0.01 cut-off :731 — t_self bound below; needs |n| = 1 to 1e-6]
+//  shadow[l] rectangle. deep AND outside: the shadow ray of light l from the plane hit (:752, direction = light POSITION :574)
+//           meets no sphere -> unoccluded, IntersectShadowLight is not evaluated. [the points of the plane whose shadow line
+//           passes within R'' of a centre form an ellipse (cylinder around the line centre + s * light, cut by the plane); a
+//           circumscribed polygon of it, clipped to the front of the camera, is projected to pixels; + the pixel margin that
+//           covers eps]
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -23,131 +42,324 @@
 
 namespace rtb {
 
-struct GateRect { int x0, y0, x1, y1; };      // inclusive pixel ranges; empty (no primary ray can hit a sphere) = {w, h, w, h}
+constexpr int RT_GATE_LIGHTS = (int)RT_GATE_MAX_LIGHTS;   // shadow gates exist for the first 4 lights; further lights are always tested
 
-// Second gate, same spirit: the side of the (single) plane's horizon on which no primary ray can hit the plane. All primary rays
-// share the origin, so the numerator of IntersectPlane (:591-594) is one number per frame (evaluated here with the kernel's own
-// fp32 expression, plane_num); `t = num / den > 0` (:598) then needs den = Dot(direction, normal) to have num's sign, and
-// den(x, y) is — up to the direction error eps and the rounding of the dot product — an affine function of the pixel
-// coordinates. sky(x, y) = fma(gx, x, fma(gy, y, ga)) > 0  ==>  the plane cannot be hit by pixel (x, y)'s primary ray.
-// A pixel that is outside the sphere rectangle AND on the sky side hits nothing: its colour is 0x00000000 (:993, :1000) without
-// tracing. More than one plane, or anything unusual: ga = -1, gx = gy = 0 (never skips). No plane or num == 0: ga = +1.
-struct SkyGate { float ga, gx, gy; };
+struct GateRect { int x0, y0, x1, y1; };      // inclusive pixel ranges; empty = {w, h, w, h}
+struct GateAffine { float a, bx, by; };       // value(x, y) = fma(bx, x, fma(by, y, a)); "never" = {-1, 0, 0}, "always" = {+1, 0, 0}
+struct FrameGates {
+    GateRect spheres;
+    GateAffine sky;
+    GateAffine deep;
+    GateRect mirror;
+    GateRect shadow[RT_GATE_LIGHTS];
+};
+enum : uint32_t { GATE_SKIP_SPHERES = RT_GATE_SPHERES, GATE_SKIP_MIRROR = RT_GATE_MIRROR, GATE_SKIP_SHADOW0 = 1u << RT_GATE_SHADOW_SHIFT };   // bits of gate_bits() (rt_trace.cuh)
 
 inline GateRect gate_full(int w, int h) { GateRect g = {0, 0, w - 1, h - 1}; return g; }
+inline GateRect gate_empty(int w, int h) { GateRect g = {w, h, w, h}; return g; }
+inline FrameGates gates_off(int w, int h) {
+    FrameGates g;
+    g.spheres = gate_full(w, h); g.mirror = gate_full(w, h);
+    for (int i = 0; i < RT_GATE_LIGHTS; i++) g.shadow[i] = gate_full(w, h);
+    g.sky.a = -1.0f; g.sky.bx = 0.0f; g.sky.by = 0.0f; g.deep = g.sky;
+    return g;
+}
 
-// Bound on the angle between the fp32 primary direction of any pixel and its ideal direction (header), or -1 when the camera is
-// not one the gates are derived for.
-inline double primary_dir_eps(const CamRec& cam) {
-    const double P[3] = {cam.pos.x, cam.pos.y, cam.pos.z};
-    const double R[3] = {cam.right.x, cam.right.y, cam.right.z}, U[3] = {cam.up.x, cam.up.y, cam.up.z}, F[3] = {cam.fwd.x, cam.fwd.y, cam.fwd.z};
-    const double pw = cam.view.x, ph = cam.view.y, nearp = cam.view.z;
-    auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
-    auto finite3 = [](const double* a) { return std::isfinite(a[0]) && std::isfinite(a[1]) && std::isfinite(a[2]); };
-    if (!finite3(P) || !finite3(R) || !finite3(U) || !finite3(F) || !std::isfinite(pw) || !std::isfinite(ph) || !std::isfinite(nearp)) return -1;
-    if (!(pw > 1e-6) || !(ph > 1e-6) || !(nearp > 1e-6) || pw > 1e6 || ph > 1e6 || nearp > 1e6) return -1;
+namespace gate_detail {
+
+constexpr double U32 = 5.9604644775390625e-08;          // 2^-24
+constexpr double PI = 3.14159265358979323846;
+inline double dot3d(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+inline bool finite3d(const double* a) { return std::isfinite(a[0]) && std::isfinite(a[1]) && std::isfinite(a[2]); }
+
+struct Cam {                 // a pinhole in double: position, orthonormal basis, view-plane size, frame size
+    double P[3], R[3], U[3], F[3], pw, ph, nearp;
+    int w, h;
+};
+inline Cam load_cam(const CamRec& c, int w, int h) {
+    Cam k = {{c.pos.x, c.pos.y, c.pos.z}, {c.right.x, c.right.y, c.right.z}, {c.up.x, c.up.y, c.up.z}, {c.fwd.x, c.fwd.y, c.fwd.z},
+             c.view.x, c.view.y, c.view.z, w, h};
+    return k;
+}
+
+// (F2) bound on the angle between the fp32 primary direction and the ideal one, or -1 if the camera is not one the gates
+// are derived for.
+inline double primary_dir_eps(const Cam& c) {
+    if (!finite3d(c.P) || !finite3d(c.R) || !finite3d(c.U) || !finite3d(c.F) || !std::isfinite(c.pw) || !std::isfinite(c.ph) || !std::isfinite(c.nearp)) return -1;
+    if (!(c.pw > 1e-6) || !(c.ph > 1e-6) || !(c.nearp > 1e-6) || c.pw > 1e6 || c.ph > 1e6 || c.nearp > 1e6) return -1;
     const double tol = 1e-5;
-    if (std::fabs(dot(R, R) - 1) > tol || std::fabs(dot(U, U) - 1) > tol || std::fabs(dot(F, F) - 1) > tol ||
-        std::fabs(dot(R, U)) > tol || std::fabs(dot(R, F)) > tol || std::fabs(dot(U, F)) > tol) return -1;
-    // rounding of u, v, of the three scaled basis vectors and of the running sum (scales with |P|), with a factor 2 in hand
-    const double u32 = 5.9604644775390625e-08;           // 2^-24
-    const double pmax = std::fmax(std::fabs(P[0]), std::fmax(std::fabs(P[1]), std::fabs(P[2])));
-    const double L = 0.5 * pw + 0.5 * ph + nearp;
-    const double E = u32 * (8.0 * (pmax + L) + 4.0 * (pw + ph));
-    const double eps = 2.0 * (2.0 * std::sqrt(3.0) * E / nearp + 1e-6) + 4e-5;
+    if (std::fabs(dot3d(c.R, c.R) - 1) > tol || std::fabs(dot3d(c.U, c.U) - 1) > tol || std::fabs(dot3d(c.F, c.F) - 1) > tol ||
+        std::fabs(dot3d(c.R, c.U)) > tol || std::fabs(dot3d(c.R, c.F)) > tol || std::fabs(dot3d(c.U, c.F)) > tol) return -1;
+    const double pmax = std::fmax(std::fabs(c.P[0]), std::fmax(std::fabs(c.P[1]), std::fabs(c.P[2])));
+    const double L = 0.5 * c.pw + 0.5 * c.ph + c.nearp;
+    const double E = U32 * (8.0 * (pmax + L) + 4.0 * (c.pw + c.ph));          // per-component error of fl(vp - P), factor 2 in hand
+    const double eps = 2.0 * (2.0 * std::sqrt(3.0) * E / c.nearp + 1e-6) + 4e-5;   // + normalisation, + basis tolerance
     return eps < 1e-2 ? eps : -1;
 }
 
-inline GateRect primary_gate_rect(const CamRec& cam, int w, int h, const f4* sgeom, int ns) {
-    const GateRect full = gate_full(w, h);
-    const GateRect empty = {w, h, w, h};
-    GateRect out = {w, h, -1, -1};
-    if (ns <= 0) return empty;
-    const double eps = primary_dir_eps(cam);
-    if (eps < 0) return full;
-    const double P[3] = {cam.pos.x, cam.pos.y, cam.pos.z};
-    const double R[3] = {cam.right.x, cam.right.y, cam.right.z}, U[3] = {cam.up.x, cam.up.y, cam.up.z}, F[3] = {cam.fwd.x, cam.fwd.y, cam.fwd.z};
-    const double pw = cam.view.x, ph = cam.view.y, nearp = cam.view.z;
-    auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
-    auto finite3 = [](const double* a) { return std::isfinite(a[0]) && std::isfinite(a[1]) && std::isfinite(a[2]); };
-    const double K = (double)RT_BVH_PAD_K;
-    for (int i = 0; i < ns; i++) {
-        const double c[3] = {sgeom[i].x, sgeom[i].y, sgeom[i].z};
-        const double r2 = sgeom[i].w > 0.0f ? (double)sgeom[i].w : 0.0;
-        if (!finite3(c) || !std::isfinite((double)sgeom[i].w)) return full;
-        const double oc[3] = {c[0] - P[0], c[1] - P[1], c[2] - P[2]};
-        const double oc2 = dot(oc, oc), ocl = std::sqrt(oc2);
-        const double Rp = std::sqrt(r2 + K * K * (oc2 + r2)) * (1.0 + 1e-6) + 1e-30;
-        const double Rg = Rp + eps * (ocl + Rp);
-        if (!(ocl > Rg * 1.001)) return full;             // camera inside (or on) the inflated ball
-        const double X = dot(oc, R), Y = dot(oc, U), Z = dot(oc, F);
-        if (Z < -Rg * 1.001) continue;                    // wholly behind the camera plane: b >= 0 for every primary ray
-        if (!(Z > Rg * 1.001)) return full;               // crosses the camera plane: the projection is unbounded
-        const double den = Z * Z - Rg * Rg;
-        int lim[2][2];
-        const double ctr[2] = {X, Y}, size[2] = {pw, ph};
-        const int npx[2] = {w, h};
-        for (int a = 0; a < 2; a++) {
-            const double A = ctr[a];
-            const double disc = A * A + Z * Z - Rg * Rg;  // > 0 because Z > Rg
-            const double root = Rg * std::sqrt(disc);
-            const double k1 = (A * Z - root) / den, k2 = (A * Z + root) / den;
-            // slope k <-> pixel: (x / w - 0.5) * pw = k * near
-            const double p1 = (k1 * nearp / size[a] + 0.5) * npx[a], p2 = (k2 * nearp / size[a] + 0.5) * npx[a];
-            if (!std::isfinite(p1) || !std::isfinite(p2)) return full;
-            const double lo = std::floor(std::fmin(p1, p2)) - 2.0, hi = std::ceil(std::fmax(p1, p2)) + 2.0;
-            lim[a][0] = lo < 0 ? 0 : (lo > npx[a] ? npx[a] : (int)lo);
-            lim[a][1] = hi > npx[a] - 1 ? npx[a] - 1 : (hi < -1 ? -1 : (int)hi);
-        }
-        if (lim[0][1] < lim[0][0] || lim[1][1] < lim[1][0]) continue;      // projects outside the frame
-        if (lim[0][0] < out.x0) out.x0 = lim[0][0];
-        if (lim[1][0] < out.y0) out.y0 = lim[1][0];
-        if (lim[0][1] > out.x1) out.x1 = lim[0][1];
-        if (lim[1][1] > out.y1) out.y1 = lim[1][1];
-    }
-    if (out.x1 < out.x0 || out.y1 < out.y0) return empty;
-    return out;
+// an angle `ang` moves a pixel by at most ang * sec^2 * (pixels per unit of slope); + 2 pixels
+inline double pixel_margin(const Cam& c, double ang) {
+    const double sec2 = 1.0 + 0.25 * (c.pw * c.pw + c.ph * c.ph) / (c.nearp * c.nearp);
+    const double ppu = std::fmax(c.w * c.nearp / c.pw, c.h * c.nearp / c.ph);
+    return std::ceil(ang * sec2 * ppu) + 2.0;
 }
 
-// planes: PlaneRec array of the scene (n, cn as uploaded). See SkyGate.
-inline SkyGate primary_sky_gate(const CamRec& cam, int w, int h, const PlaneRec* planes, int np) {
-    const SkyGate never = {-1.0f, 0.0f, 0.0f}, always = {1.0f, 0.0f, 0.0f};
-    if (np <= 0) return always;
-    if (np > 1) return never;
-    const double eps = primary_dir_eps(cam);
-    if (eps < 0) return never;
-    const PlaneRec& pl = planes[0];
-    f4 pn; pn.x = pl.n.x; pn.y = pl.n.y; pn.z = pl.n.z; pn.w = pl.cn;
-    const float num = plane_num(cam.pos, pn);            // the kernel's own fp32 value (same expression, no contraction)
-    if (!(num == num)) return never;
-    if (num == 0.0f) return always;                      // 0 / den is never > 0 (:598)
-    const double n[3] = {pl.n.x, pl.n.y, pl.n.z};
-    const double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-    if (!std::isfinite(nl) || !(nl > 0)) return never;
-    const double R[3] = {cam.right.x, cam.right.y, cam.right.z}, U[3] = {cam.up.x, cam.up.y, cam.up.z}, F[3] = {cam.fwd.x, cam.fwd.y, cam.fwd.z};
-    const double pw = cam.view.x, ph = cam.view.y, nearp = cam.view.z;
-    auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
-    // ideal direction of pixel (x, y): D = A + x Bx + y By;  den has the sign of D . n up to the margin below
-    const double Rn = dot(R, n), Un = dot(U, n), Fn = dot(F, n);
-    const double a = -0.5 * pw * Rn - 0.5 * ph * Un + nearp * Fn, bx = pw * Rn / w, by = ph * Un / h;
-    const double sgn = num > 0 ? -1.0 : 1.0;              // sky side: den of the opposite sign to num (or zero)
-    const double u32 = 5.9604644775390625e-08;
-    const double Dmax = std::sqrt(nearp * nearp + 0.25 * pw * pw + 0.25 * ph * ph) * 1.0001;
-    const double margin = 2.0 * (eps + 24.0 * u32) * std::sqrt(3.0) * nl * Dmax;
+// Accumulates into `out` (init {w, h, -1, -1}) the pixel bounds of the directions from c.P that pass within Rg of `ctr`.
+// Returns false when the projection is unbounded / undefined (caller must fall back to the full frame).
+inline bool add_ball_rect(const Cam& c, const double* ctr, double Rg, double margin_px, GateRect* out) {
+    const double oc[3] = {ctr[0] - c.P[0], ctr[1] - c.P[1], ctr[2] - c.P[2]};
+    const double ocl = std::sqrt(dot3d(oc, oc));
+    if (!std::isfinite(ocl) || !std::isfinite(Rg)) return false;
+    if (!(ocl > Rg * 1.001)) return false;                  // eye inside (or on) the ball
+    const double X = dot3d(oc, c.R), Y = dot3d(oc, c.U), Z = dot3d(oc, c.F);
+    if (Z < -Rg * 1.001) return true;                       // wholly behind the eye plane: every ray of the frame has z > 0
+    if (!(Z > Rg * 1.001)) return false;                    // crosses the eye plane: unbounded projection
+    const double den = Z * Z - Rg * Rg;
+    int lim[2][2];
+    const double ctr2[2] = {X, Y}, size[2] = {c.pw, c.ph};
+    const int npx[2] = {c.w, c.h};
+    for (int a = 0; a < 2; a++) {
+        const double A = ctr2[a];
+        const double root = Rg * std::sqrt(A * A + Z * Z - Rg * Rg);
+        const double k1 = (A * Z - root) / den, k2 = (A * Z + root) / den;
+        const double p1 = (k1 * c.nearp / size[a] + 0.5) * npx[a], p2 = (k2 * c.nearp / size[a] + 0.5) * npx[a];   // (x/w - .5) pw = k near
+        if (!std::isfinite(p1) || !std::isfinite(p2)) return false;
+        const double lo = std::floor(std::fmin(p1, p2)) - margin_px, hi = std::ceil(std::fmax(p1, p2)) + margin_px;
+        lim[a][0] = lo < 0 ? 0 : (lo > npx[a] ? npx[a] : (int)lo);
+        lim[a][1] = hi > npx[a] - 1 ? npx[a] - 1 : (hi < -1 ? -1 : (int)hi);
+    }
+    if (lim[0][1] < lim[0][0] || lim[1][1] < lim[1][0]) return true;       // projects outside the frame
+    if (lim[0][0] < out->x0) out->x0 = lim[0][0];
+    if (lim[1][0] < out->y0) out->y0 = lim[1][0];
+    if (lim[0][1] > out->x1) out->x1 = lim[0][1];
+    if (lim[1][1] > out->y1) out->y1 = lim[1][1];
+    return true;
+}
+inline GateRect finish_rect(const GateRect& acc, int w, int h) {
+    if (acc.x1 < acc.x0 || acc.y1 < acc.y0) return gate_empty(w, h);
+    return acc;
+}
+inline double inflated(double r2, double oc_max) {          // (F1)
+    const double K = (double)RT_BVH_PAD_K;
+    return std::sqrt(r2 + K * K * (oc_max * oc_max + r2)) * (1.0 + 1e-6) + 1e-30;
+}
+
+// float coefficients of an affine gate that is > 0 only where sgn * (a + bx x + by y) > margin, with the evaluation error
+// of the two device FMAs and of the double -> float conversions folded in
+inline GateAffine make_affine(double sgn, double a, double bx, double by, double margin, int w, int h) {
     const double S = std::fabs(a) + std::fabs(bx) * w + std::fabs(by) * h;
-    SkyGate g;
-    g.gx = (float)(sgn * bx); g.gy = (float)(sgn * by);
-    g.ga = (float)(sgn * a - margin - 16.0 * u32 * S);
-    // the float conversion of ga may round up by half an ulp: step it down once more
-    g.ga = std::nextafter(g.ga, -INFINITY);
-    if (!std::isfinite(g.ga) || !std::isfinite(g.gx) || !std::isfinite(g.gy)) return never;
+    GateAffine g;
+    g.bx = (float)(sgn * bx); g.by = (float)(sgn * by);
+    g.a = std::nextafter((float)(sgn * a - margin - 16.0 * U32 * S), -INFINITY);
+    if (!std::isfinite(g.a) || !std::isfinite(g.bx) || !std::isfinite(g.by)) { g.a = -1.0f; g.bx = 0.0f; g.by = 0.0f; }
     return g;
 }
-RT_HD bool sky_skips(const SkyGate& g, float fx, float fy) { return rt_fmaf(g.gx, fx, rt_fmaf(g.gy, fy, g.ga)) > 0.0f; }
 
-// true: the pixel's primary ray may skip the sphere loop
-RT_HD bool gate_skips(const GateRect& g, int x, int y) {
-    return (unsigned)(x - g.x0) > (unsigned)(g.x1 - g.x0) || (unsigned)(y - g.y0) > (unsigned)(g.y1 - g.y0);
+}  // namespace gate_detail
+
+// All gates of one frame. planes: PlaneRec as uploaded (n, cn); lights: LightRec (p).
+inline FrameGates compute_frame_gates(const CamRec& camrec, int w, int h, const f4* sgeom, int ns, const PlaneRec* planes, int np,
+                                      const LightRec* lights, int nl) {
+    using namespace gate_detail;
+    FrameGates g = gates_off(w, h);
+    const Cam c = load_cam(camrec, w, h);
+    const double eps = primary_dir_eps(c);
+    if (eps < 0) { if (ns <= 0) g.spheres = gate_empty(w, h); return g; }
+    for (int i = 0; i < ns; i++) {
+        const double ctr[3] = {sgeom[i].x, sgeom[i].y, sgeom[i].z};
+        if (!finite3d(ctr) || !std::isfinite((double)sgeom[i].w)) return g;
+    }
+    // ---- spheres --------------------------------------------------------------------------------------------------------
+    {
+        GateRect acc = {w, h, -1, -1};
+        bool ok = true;
+        for (int i = 0; i < ns && ok; i++) {
+            const double ctr[3] = {sgeom[i].x, sgeom[i].y, sgeom[i].z};
+            const double r2 = sgeom[i].w > 0.0f ? (double)sgeom[i].w : 0.0;
+            const double oc[3] = {ctr[0] - c.P[0], ctr[1] - c.P[1], ctr[2] - c.P[2]};
+            const double ocl = std::sqrt(dot3d(oc, oc));
+            const double Rp = inflated(r2, ocl);
+            ok = add_ball_rect(c, ctr, Rp + eps * (ocl + Rp), 2.0, &acc);
+        }
+        g.spheres = ok ? finish_rect(acc, w, h) : gate_full(w, h);
+    }
+    // ---- the plane ------------------------------------------------------------------------------------------------------
+    if (np <= 0) { g.sky.a = 1.0f; return g; }                   // nothing but spheres can be hit
+    if (np > 1) return g;
+    const PlaneRec& pl = planes[0];
+    f4 pn; pn.x = pl.n.x; pn.y = pl.n.y; pn.z = pl.n.z; pn.w = pl.cn;
+    const float num = plane_num(camrec.pos, pn);                 // (F3) the kernel's own fp32 value (same expression, no contraction)
+    if (!(num == num)) return g;
+    if (num == 0.0f) { g.sky.a = 1.0f; return g; }               // 0 / den is never > 0 (:598)
+    const double n[3] = {pl.n.x, pl.n.y, pl.n.z};
+    const double nlen = std::sqrt(dot3d(n, n));
+    if (!std::isfinite(nlen) || !(nlen > 1e-12) || !std::isfinite((double)pl.cn)) return g;
+    const double nh[3] = {n[0] / nlen, n[1] / nlen, n[2] / nlen};
+    // ideal D . n_hat = a + bx x + by y
+    const double Rn = dot3d(c.R, nh), Un = dot3d(c.U, nh), Fn = dot3d(c.F, nh);
+    const double a = -0.5 * c.pw * Rn - 0.5 * c.ph * Un + c.nearp * Fn, bx = c.pw * Rn / w, by = c.ph * Un / h;
+    const double Dmax = std::sqrt(c.nearp * c.nearp + 0.25 * c.pw * c.pw + 0.25 * c.ph * c.ph) * 1.0001;
+    const double away = num > 0 ? -1.0 : 1.0;                    // sign of D . n for which den has the wrong sign (or is zero)
+    const double den_margin = 2.0 * (eps + 24.0 * U32) * std::sqrt(3.0);          // |den_fp / |n| - D_hat . n_hat| is below this
+    g.sky = make_affine(away, a, bx, by, den_margin * Dmax, w, h);
+    // ---- deep: bounded plane hits ---------------------------------------------------------------------------------------
+    const double c0 = (double)pl.cn / nlen;                      // plane: x . n_hat = c0
+    const double hP = dot3d(c.P, nh) - c0;                       // signed distance of the eye
+    const double H = std::fabs(hP);
+    if (!(H > 1e-3) || !(eps < 2e-3)) return g;
+    int kmax = 0;
+    for (int k = 1; k < 3; k++) if (std::fabs(nh[k]) > std::fabs(nh[kmax])) kmax = k;
+    double T = 0;                                                // sum of the non-dominant |n_hat| components (0 if axis-aligned)
+    for (int k = 0; k < 3; k++) if (k != kmax) T += std::fabs(nh[k]);
+    const double Pl = std::sqrt(dot3d(c.P, c.P));
+    double PnAbs = 0;
+    for (int k = 0; k < 3; k++) PnAbs += std::fabs(c.P[k] * nh[k]);
+    double sin_min = 0.02, dmax = 0, delta_h = 0;
+    bool mirror_ok = std::fabs(nlen - 1.0) < 1e-6;               // :741-744 reflects with the normal as given: a mirror only if unit
+    for (;; sin_min *= 2.0) {
+        if (sin_min > 0.5) { mirror_ok = false; sin_min = 0.02; }
+        const double s_lo = sin_min - den_margin;                // slope the fp32 direction is guaranteed to have
+        dmax = H / s_lo * 1.001;
+        // relative error of d = num / den: cancellation in num, rounding of den (only the non-dominant normal components add
+        // absolute error), the division
+        const double rel_d = 4.0 * U32 * (PnAbs + std::fabs(c0)) / H + 3.0 * U32 * (1.0 + 2.0 * T / s_lo) + 2.0 * U32;
+        // |h_k| bounds: within dmax of P; along the dominant normal axis the plane equation pins it
+        double hk[3], side = 0;
+        for (int k = 0; k < 3; k++) { hk[k] = std::fabs(c.P[k]) + dmax; if (k != kmax) side += std::fabs(nh[k]) * hk[k]; }
+        hk[kmax] = std::fmin(hk[kmax], (std::fabs(c0) + side + 1e-3) / std::fabs(nh[kmax]));
+        double Bnd = 0;
+        for (int k = 0; k < 3; k++) Bnd += std::fabs(nh[k]) * hk[k];
+        // displacement of the fp32 hit point from the exact plane hit of the fp32 primary line
+        delta_h = 2.0 * U32 * std::sqrt(3.0) * (Pl + dmax) + dmax * rel_d;
+        if (!mirror_ok) break;
+        // the reflection re-tests its own plane (:812-819): |num_self| / |n| <= off-plane distance of the fp32 hit point
+        // + rounding of the expression; den_self / |n| >= s_lo - 1e-5. It must stay below the 0.01 cut-off (:731) with room.
+        const double off_plane = H * rel_d + 2.0 * U32 * Bnd;
+        const double num_self = off_plane + 4.0 * U32 * (Bnd + std::fabs(c0));
+        const double t_self = 2.0 * num_self / (s_lo - 1e-5);
+        if (t_self < 0.004) break;
+    }
+    g.deep = make_affine(-away, a, bx, by, sin_min * Dmax, w, h);      // toward the plane: -away * D_hat . n_hat >= sin_min (|D| <= Dmax)
+    const double mpx = pixel_margin(c, eps);
+    // ---- mirror: spheres seen from the mirror image of the eye --------------------------------------------------------------
+    if (mirror_ok) {
+        Cam m = c;
+        for (int k = 0; k < 3; k++) {
+            m.P[k] = c.P[k] - 2.0 * hP * nh[k];
+            m.R[k] = c.R[k] - 2.0 * Rn * nh[k]; m.U[k] = c.U[k] - 2.0 * Un * nh[k]; m.F[k] = c.F[k] - 2.0 * Fn * nh[k];
+        }
+        const double eps_r = 5e-6 + 8.0 * U32;                   // |n| = 1 to 1e-6, rounding of the reflection formula
+        GateRect acc = {w, h, -1, -1};
+        bool ok = true;
+        for (int i = 0; i < ns && ok; i++) {
+            const double ctr[3] = {sgeom[i].x, sgeom[i].y, sgeom[i].z};
+            const double r2 = sgeom[i].w > 0.0f ? (double)sgeom[i].w : 0.0;
+            const double pc[3] = {ctr[0] - c.P[0], ctr[1] - c.P[1], ctr[2] - c.P[2]};
+            const double mc[3] = {ctr[0] - m.P[0], ctr[1] - m.P[1], ctr[2] - m.P[2]};
+            const double Rp = inflated(r2, std::sqrt(dot3d(pc, pc)) + dmax);          // |oc| of the reflection ray <= |P c| + dmax
+            const double ml = std::sqrt(dot3d(mc, mc));
+            const double Rg = Rp + (eps + 2.0 * eps_r) * (ml + Rp) + 2.0 * delta_h;
+            ok = add_ball_rect(m, ctr, Rg, 2.0, &acc);
+        }
+        g.mirror = ok ? finish_rect(acc, w, h) : gate_full(w, h);
+    }
+    // ---- shadow[l]: shadow ellipses on the plane, seen from the eye ---------------------------------------------------------
+    for (int l = 0; l < nl && l < RT_GATE_LIGHTS; l++) {
+        const double lp[3] = {lights[l].p.x, lights[l].p.y, lights[l].p.z};
+        const double ll = std::sqrt(dot3d(lp, lp));
+        if (!finite3d(lp) || !(ll > 1e-12) || !std::isfinite(ll)) continue;                 // stays "full": always tested
+        const double lh[3] = {lp[0] / ll, lp[1] / ll, lp[2] / ll};
+        const double ln = dot3d(lh, nh);
+        if (std::fabs(ln) < 1e-3) continue;                      // light direction (almost) in the plane: unbounded shadows
+        // in-plane axes: e1 along the projected light direction (long axis), e2 across
+        double e1[3], e2[3];
+        for (int k = 0; k < 3; k++) e1[k] = lh[k] - ln * nh[k];
+        const double e1l = std::sqrt(dot3d(e1, e1));
+        if (e1l < 1e-9) {                                        // light along the normal: a circle; any in-plane basis
+            const double t[3] = {std::fabs(nh[0]) < 0.9 ? 1.0 : 0.0, std::fabs(nh[0]) < 0.9 ? 0.0 : 1.0, 0.0};
+            const double tn = dot3d(t, nh);
+            for (int k = 0; k < 3; k++) e1[k] = t[k] - tn * nh[k];
+            const double l1 = std::sqrt(dot3d(e1, e1));
+            for (int k = 0; k < 3; k++) e1[k] /= l1;
+        } else {
+            for (int k = 0; k < 3; k++) e1[k] /= e1l;
+        }
+        e2[0] = nh[1] * e1[2] - nh[2] * e1[1]; e2[1] = nh[2] * e1[0] - nh[0] * e1[2]; e2[2] = nh[0] * e1[1] - nh[1] * e1[0];
+        GateRect acc = {w, h, -1, -1};
+        bool ok = true;
+        constexpr int M = 64;
+        const double circ = 1.0 / std::cos(PI / M);              // circumscribed polygon
+        const double zc = 1e-4 * c.nearp;
+        auto project = [&](double x, double y, double z) {
+            const double px = (x / z * c.nearp / c.pw + 0.5) * w, py = (y / z * c.nearp / c.ph + 0.5) * h;
+            const double cx = std::fmax(-1e6, std::fmin(1e6, px)), cy = std::fmax(-1e6, std::fmin(1e6, py));   // before the int conversion
+            const int x0 = (int)std::floor(cx - mpx), x1 = (int)std::ceil(cx + mpx), y0 = (int)std::floor(cy - mpx), y1 = (int)std::ceil(cy + mpx);
+            if (x0 < acc.x0) acc.x0 = x0;
+            if (y0 < acc.y0) acc.y0 = y0;
+            if (x1 > acc.x1) acc.x1 = x1;
+            if (y1 > acc.y1) acc.y1 = y1;
+        };
+        for (int i = 0; i < ns && ok; i++) {
+            const double ctr[3] = {sgeom[i].x, sgeom[i].y, sgeom[i].z};
+            const double r2 = sgeom[i].w > 0.0f ? (double)sgeom[i].w : 0.0;
+            const double pc[3] = {ctr[0] - c.P[0], ctr[1] - c.P[1], ctr[2] - c.P[2]};
+            const double Rg = (inflated(r2, std::sqrt(dot3d(pc, pc)) + dmax) + 2.0 * delta_h) * 1.0001;
+            const double s0 = (dot3d(ctr, nh) - c0) / ln;        // ctr - s0 * l_hat lies on the plane
+            double e0[3];
+            for (int k = 0; k < 3; k++) e0[k] = ctr[k] - s0 * lh[k];
+            const double ax1 = Rg / std::fabs(ln) * circ, ax2 = Rg * circ;
+            if (!std::isfinite(ax1) || !finite3d(e0)) { ok = false; break; }
+            double X[M], Y[M], Z[M];                             // polygon vertices in eye coordinates
+            for (int v = 0; v < M; v++) {
+                const double ang = 2.0 * PI * v / M, cs = std::cos(ang), sn = std::sin(ang);
+                double q[3];
+                for (int k = 0; k < 3; k++) q[k] = e0[k] + ax1 * cs * e1[k] + ax2 * sn * e2[k] - c.P[k];
+                X[v] = dot3d(q, c.R); Y[v] = dot3d(q, c.U); Z[v] = dot3d(q, c.F);
+                if (!std::isfinite(X[v]) || !std::isfinite(Y[v]) || !std::isfinite(Z[v])) ok = false;
+            }
+            if (!ok) break;
+            for (int v = 0; v < M; v++) {                        // clipped to z >= zc, projected
+                const int u2 = (v + 1) % M;
+                if (Z[v] >= zc) project(X[v], Y[v], Z[v]);
+                if ((Z[v] >= zc) != (Z[u2] >= zc)) {             // the edge crosses the clip plane: add the crossing point
+                    const double t = (zc - Z[v]) / (Z[u2] - Z[v]);
+                    project(X[v] + t * (X[u2] - X[v]), Y[v] + t * (Y[u2] - Y[v]), zc);
+                }
+            }
+        }
+        if (!ok) continue;
+        if (acc.x1 < acc.x0 || acc.y1 < acc.y0) { g.shadow[l] = gate_empty(w, h); continue; }
+        GateRect r = {acc.x0 < 0 ? 0 : acc.x0, acc.y0 < 0 ? 0 : acc.y0, acc.x1 > w - 1 ? w - 1 : acc.x1, acc.y1 > h - 1 ? h - 1 : acc.y1};
+        g.shadow[l] = (r.x1 < r.x0 || r.y1 < r.y0) ? gate_empty(w, h) : r;
+    }
+    return g;
 }
+
+// ---- device side ------------------------------------------------------------------------------------------------------------
+// Gates are evaluated once per SPAN of consecutive pixels of one row, xa..xb (the pixels one thread renders): a skip bit is set
+// only if it holds for every pixel of the span. Regions are large, so little is lost at their borders, and the per-pixel cost
+// of the gates (each rectangle is four constant-bank loads and four integer instructions) is divided by the span length.
+RT_HD bool span_outside(const GateRect& g, int xa, int xb, int y) {
+    return xb < g.x0 || xa > g.x1 || (unsigned)(y - g.y0) > (unsigned)(g.y1 - g.y0);
+}
+RT_HD bool span_positive(const GateAffine& g, float fxa, float fxb, float fy) {     // affine: extreme at an end of the span
+    const float base = rt_fmaf(g.by, fy, g.a);
+    return rt_fmaf(g.bx, fxa, base) > 0.0f && rt_fmaf(g.bx, fxb, base) > 0.0f;
+}
+// The skip bits (RT_GATE_*, rt_trace.cuh) common to pixels (xa..xb, y), nl = number of lights; *black: all of them are
+// 0x00000000 without tracing.
+RT_HD uint32_t gate_bits_span(const FrameGates& g, int xa, int xb, int y, int nl, bool* black) {
+    const float fxa = (float)xa, fxb = (float)xb, fy = (float)y;
+    uint32_t bits = span_outside(g.spheres, xa, xb, y) ? (uint32_t)GATE_SKIP_SPHERES : 0u;
+    *black = bits != 0u && span_positive(g.sky, fxa, fxb, fy);
+    if (!*black && span_positive(g.deep, fxa, fxb, fy)) {
+        if (span_outside(g.mirror, xa, xb, y)) bits |= GATE_SKIP_MIRROR;
+#pragma unroll
+        for (int l = 0; l < RT_GATE_LIGHTS; l++)
+            if (l < nl && span_outside(g.shadow[l], xa, xb, y)) bits |= (uint32_t)GATE_SKIP_SHADOW0 << l;
+    }
+    return bits;
+}
+RT_HD uint32_t gate_bits(const FrameGates& g, int x, int y, bool* black) { return gate_bits_span(g, x, x, y, RT_GATE_LIGHTS, black); }
 
 }  // namespace rtb

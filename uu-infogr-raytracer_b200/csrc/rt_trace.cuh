@@ -22,6 +22,8 @@
 namespace rtb {
 
 enum { MAT_MIRROR = 1u, MAT_DIFFUSE = 2u, MAT_SPEC = 4u };
+// per-pixel proof bits computed from the host's frame gates (rt_gate.cuh); 0 = nothing proven, trace everything
+enum : uint32_t { RT_GATE_SPHERES = 1u, RT_GATE_MIRROR = 2u, RT_GATE_SHADOW_SHIFT = 2u, RT_GATE_MAX_LIGHTS = 4u };
 
 struct MatRec {            // 16 words; Material RayTracer.cs:60-93
     f3 kd; float n;        // diffuseColor, specularity
@@ -342,7 +344,7 @@ RT_HD float spec_pow(float base, float n) {
 // `x * tile` with tile = (1,1,1) is exact, so spheres run the plane expression with tile = 1 and skip only the Max.
 // ---------------------------------------------------------------------------------------------------------
 template <class SC, class DBG>
-RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& dbg) {
+RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& dbg, uint32_t gates = 0u) {
     const f3 hit = add3(h.o, mulf3(h.dir, h.d));                  // :846 / :736
     const bool is_plane = h.prim < 0;
     MatRec m; f3 N; float att, tile;
@@ -372,7 +374,9 @@ RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& d
 #pragma unroll
         for (int li = 0; li < nl; li++) {                         // :863 / :751
             const LightRec l = sc.light(li);
-            bool occ = sc.shadow_any(li, hit, l.p, l.a2, l.a4, dbg);  // :864 / :752
+            // gates bit 2 + li: the shadow ray of light li from the PRIMARY hit on the (single) plane meets no sphere (rt_gate.cuh)
+            const bool proven_clear = li < (int)RT_GATE_MAX_LIGHTS && ((gates >> (RT_GATE_SHADOW_SHIFT + li)) & 1u) && level == 0 && is_plane;
+            bool occ = proven_clear ? false : sc.shadow_any(li, hit, l.p, l.a2, l.a4, dbg);  // :864 / :752
             dbg.shadow(level, (uint32_t)li, occ);
             dbg.shadow_geom(sc, level, (uint32_t)li, hit, l.p, l.a2, l.a4, occ);
             float I = occ ? 0.0f : l.intensity;                   // :581
@@ -425,7 +429,7 @@ RT_HD float plane_num(f3 o, f4 pn) { return -o.x * pn.x - o.y * pn.y - o.z * pn.
 // compacting kernel to hand deep mirror chains to fully populated warps).  `stack` must hold cap+1 records.
 template <class SC, class DBG>
 RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& top, HitRec* stack, int defer_at, f3* Cout, DBG& dbg,
-                       bool skip0 = false) {
+                       uint32_t gates = 0u) {
     f3 C = mk3(0, 0, 0);
     const int np = sc.n_planes();      // compile-time constant in the exact-count kernels
     for (;;) {
@@ -433,9 +437,10 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
         float a = dot3(dir, dir);                                                          // :617
         float a2 = 2 * a;                                                                  // :624
         float a4 = 4 * a;                                                                  // :621
-        // skip0: the host proved that this pixel's primary ray cannot be reported as hitting any sphere (rt_gate.cuh)
+        // gates (rt_gate.cuh, bits RT_GATE_*): what the host PROVED about this pixel. Bit 0: its primary ray cannot be reported
+        // as hitting any sphere.
         int sel_s = -1; float d_s = RT_INF;
-        if (!(skip0 && bounce == 0))
+        if (!((gates & RT_GATE_SPHERES) && bounce == 0))
             sc.nearest(o, dir, a2, a4, bounce == 0 ? 0.0f : 0.01f, &sel_s, &d_s, dbg);     // :975-981 / :792-808
         int sel_p = -1; float d_p = RT_INF;
 #pragma unroll
@@ -467,6 +472,8 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
         h.o = o; h.dir = dir; h.d = d; h.prim = pick_s ? sel_s : ~sel_p;
         uint32_t flags = pick_s ? sc.sphere_flags(sel_s) : sc.plane_flags(sel_p);
         if (!(flags & MAT_MIRROR)) break;                                                  // :850 / :739
+        // Bit 1: if the primary ray hit the (single) plane, its reflection ray hits nothing — the mirror term is (0,0,0), C as is.
+        if ((gates & RT_GATE_MIRROR) && bounce == 0 && !pick_s) break;
         bounce++;                                                                          // :851 / :740
         f3 hit = add3(o, mulf3(dir, d));                                                   // :846 / :736
         f3 N;
@@ -477,7 +484,7 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
     }
     while (top > 0) {
         --top;
-        C = shade_hit(sc, stack[top], C, (uint32_t)top, dbg);
+        C = shade_hit(sc, stack[top], C, (uint32_t)top, dbg, gates);
     }
     *Cout = C;
     return true;
@@ -485,11 +492,11 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
 
 template <bool FASTDIV = false, class SC, class DBG>
 RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float fw, float fh, float rw, float rh, int cap,
-                      HitRec* stack, DBG& dbg, bool skip0 = false) {
+                      HitRec* stack, DBG& dbg, uint32_t gates = 0u) {
     f3 o, dir, C;
     primary_ray<FASTDIV>(cam, fx, fy, fw, fh, rw, rh, &o, &dir);
     int bounce = 0, top = 0;
-    trace_chain(sc, cap, o, dir, bounce, top, stack, -1, &C, dbg, skip0);
+    trace_chain(sc, cap, o, dir, bounce, top, stack, -1, &C, dbg, gates);
     return C;
 }
 
@@ -499,9 +506,9 @@ RT_HD f3 trace_sample(const SC& sc, const CamRec& cam, float fx, float fy, float
 // FASTDIV (only with SPP1, w and h <= RT_FASTDIV_MAX): rw / rh = correctly rounded 1/w, 1/h; see primary_ray.
 template <bool SPP1 = false, bool FASTDIV = false, class SC, class DBG>
 RT_HD uint32_t trace_pixel(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int cap, int spp, uint32_t seed,
-                           HitRec* stack, DBG& dbg, float rw = 0.0f, float rh = 0.0f, bool skip0 = false) {
+                           HitRec* stack, DBG& dbg, float rw = 0.0f, float rh = 0.0f, uint32_t gates = 0u) {
     const float fw = (float)w, fh = (float)h;
-    if (SPP1) return pack_color(trace_sample<FASTDIV>(sc, cam, (float)x, (float)y, fw, fh, rw, rh, cap, stack, dbg, skip0));   // :1000 -> :1038
+    if (SPP1) return pack_color(trace_sample<FASTDIV>(sc, cam, (float)x, (float)y, fw, fh, rw, rh, cap, stack, dbg, gates));   // :1000 -> :1038
     f3 acc = mk3(0, 0, 0);
     for (int s = 0; s < spp; s++) {
         float jx = 0.0f, jy = 0.0f;

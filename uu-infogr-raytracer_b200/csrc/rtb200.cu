@@ -61,8 +61,7 @@ struct FrameParams {
     float rcp_w, rcp_h;         // 1/w, 1/h correctly rounded (host): pixel-coordinate divisions of the single-sample kernels (rt_div_rcp)
     long long frame_stride;     // pixels between consecutive frames in `out`
     uint32_t* out;              // framebuffer(s): 0x00RRGGBB, row-major (Surface.pixels, surface.cs:9-20)
-    SkyGate sky[INLINE_CAMS];         // per frame: pixels on the sky side of the plane's horizon AND outside `gate` are black untraced
-    GateRect gate[INLINE_CAMS];       // per frame: pixels outside may skip the primary rays' sphere loop (rt_gate.cuh; tiny single-sample kernels)
+    FrameGates gates[INLINE_CAMS];    // per frame: what the host proved pixel regions cannot hit (rt_gate.cuh; tiny single-sample kernels)
     CamRec cam_inline[INLINE_CAMS];   // the launch's cameras travel in the parameter block (constant bank): no upload, no host
                                       // sync; batches of more than INLINE_CAMS frames are split into several launches
 };
@@ -91,17 +90,26 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
         const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
         if (p0 >= end) continue;
         const CamRec& cam = fp.cam_inline[frame];               // constant bank (LDC); batches > INLINE_CAMS are split on the host
-        const GateRect& gate = fp.gate[frame];
-        const SkyGate& sky = fp.sky[frame];
+        const FrameGates& gates = fp.gates[frame];
         uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
         uint32_t px[PPT];
         int y = p0 / fp.w, x = p0 - y * fp.w;                  // one division per thread; then step along the row
+        // What the host proved about this thread's span of pixels (rt_gate.cuh): evaluated once, for spans inside one row.
+        uint32_t bits = 0u;
+        if (SPP1 && x + PPT <= fp.w && p0 + PPT <= end) {
+            bool black = false;
+            bits = gate_bits_span(gates, x, x + PPT - 1, y, sc.n_lights(), &black);
+            if (black) {                                       // nothing can be hit anywhere in the span: 0x00000000 (:993) untraced
+                if (PPT == 4 && ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0)) *reinterpret_cast<uint4*>(out + p0) = make_uint4(0u, 0u, 0u, 0u);
+                else for (int q = 0; q < PPT; q++) out[p0 + q] = 0u;
+                continue;
+            }
+        }
 #pragma unroll 1
         for (int q = 0; q < PPT; q++) {
-            const bool skip0 = SPP1 && gate_skips(gate, x, y);               // no sphere can be hit by this primary ray
-            uint32_t c = 0u;                                                  // ... and no plane either: nothing hit, black (:993)
-            if (p0 + q < end && !(skip0 && sky_skips(sky, (float)x, (float)y)))
-                c = trace_pixel<SPP1, SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg, fp.rcp_w, fp.rcp_h, skip0);
+            uint32_t c = 0u;
+            if (p0 + q < end)
+                c = trace_pixel<SPP1, SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg, fp.rcp_w, fp.rcp_h, bits);
             if (++x == fp.w) { x = 0; ++y; }
 #pragma unroll
             for (int z = 0; z + 1 < PPT; z++) px[z] = px[z + 1];   // shift register: after PPT iterations px[] is in pixel order
@@ -598,11 +606,9 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
             const TinySceneData& t = ctx->tiny_data;
             const bool fastdiv_ok = fp.w <= RT_FASTDIV_MAX && fp.h <= RT_FASTDIV_MAX;
             FrameParams gp = fp;                      // + per-frame primary-ray sphere gate (a few hundred host flops per frame)
-            for (int f = 0; f < fp.n_frames; f++) {
-                gp.gate[f] = ctx->primary_gate ? primary_gate_rect(fp.cam_inline[f], fp.w, fp.h, t.sgeom, t.ns) : gate_full(fp.w, fp.h);
-                const SkyGate never = {-1.0f, 0.0f, 0.0f};
-                gp.sky[f] = ctx->primary_gate ? primary_sky_gate(fp.cam_inline[f], fp.w, fp.h, t.planes, t.np) : never;
-            }
+            for (int f = 0; f < fp.n_frames; f++)
+                gp.gates[f] = ctx->primary_gate ? compute_frame_gates(fp.cam_inline[f], fp.w, fp.h, t.sgeom, t.ns, t.planes, t.np, t.lights, t.nl)
+                                                : gates_off(fp.w, fp.h);
             TinyKernel kern = (ctx->compaction && fp.spp == 1 && fastdiv_ok) ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np, fp.spp, fastdiv_ok);
             kern<<<grid, BLOCK, 0, stream>>>(t, gp);
             break;

@@ -343,3 +343,22 @@ def test_primary_gate_on_off_identical(ctx, rt):
         if k % 6 == 0:
             ref = O.render(sc, cam, w, h, 6)
             assert_image_parity(on.reshape(h, w), ref["pixels"], "gated frame")
+
+
+def test_gates_follow_scene_updates(ctx):
+    """The frame gates are cached per camera: rt_update_spheres must invalidate them (same camera, a sphere moved out of the old
+    gate rectangles must still be rendered)."""
+    import copy
+    sc = scenes.default_scene()
+    w, h = 640, 360
+    cam = scenes.make_camera(width=w, height=h)
+    ctx.set_scene(sc)
+    a, _ = ctx.render(cam, w, h, 8, 1, 0)
+    assert_image_parity(a.reshape(h, w), O.render(sc, cam, w, h, 8)["pixels"], "before the update")
+    moved = copy.deepcopy(sc)
+    moved.spheres[0, 0:3] = np.float32([-1.5, 2.5, 4.0])                 # sphere 0 up into the former sky, over the other side
+    ctx.update_spheres(moved.spheres[0:1], 0)
+    b, _ = ctx.render(cam, w, h, 8, 1, 0)
+    ref = O.render(moved, cam, w, h, 8)["pixels"]
+    assert_image_parity(b.reshape(h, w), ref, "after the update")
+    assert (b.reshape(h, w) != a.reshape(h, w)).sum() > 1000

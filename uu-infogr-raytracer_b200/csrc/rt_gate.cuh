@@ -144,6 +144,19 @@ inline double inflated(double r2, double oc_max) {          // (F1)
     return std::sqrt(r2 + K * K * (oc_max * oc_max + r2)) * (1.0 + 1e-6) + 1e-30;
 }
 
+// unit circle sampled for the circumscribed shadow polygons (built once)
+constexpr int GATE_POLY = 32;
+struct PolyTable { double cs[GATE_POLY], sn[GATE_POLY], circ; };
+inline const PolyTable& poly_table() {
+    static const PolyTable t = [] {
+        PolyTable p;
+        for (int v = 0; v < GATE_POLY; v++) { p.cs[v] = std::cos(2.0 * PI * v / GATE_POLY); p.sn[v] = std::sin(2.0 * PI * v / GATE_POLY); }
+        p.circ = 1.0 / std::cos(PI / GATE_POLY);
+        return p;
+    }();
+    return t;
+}
+
 // float coefficients of an affine gate that is > 0 only where sgn * (a + bx x + by y) > margin, with the evaluation error
 // of the two device FMAs and of the double -> float conversions folded in
 inline GateAffine make_affine(double sgn, double a, double bx, double by, double margin, int w, int h) {
@@ -287,8 +300,9 @@ inline FrameGates compute_frame_gates(const CamRec& camrec, int w, int h, const 
         e2[0] = nh[1] * e1[2] - nh[2] * e1[1]; e2[1] = nh[2] * e1[0] - nh[0] * e1[2]; e2[2] = nh[0] * e1[1] - nh[1] * e1[0];
         GateRect acc = {w, h, -1, -1};
         bool ok = true;
-        constexpr int M = 64;
-        const double circ = 1.0 / std::cos(PI / M);              // circumscribed polygon
+        constexpr int M = GATE_POLY;
+        const PolyTable& tab = poly_table();
+        const double circ = tab.circ;                            // circumscribed polygon
         const double zc = 1e-4 * c.nearp;
         auto project = [&](double x, double y, double z) {
             const double px = (x / z * c.nearp / c.pw + 0.5) * w, py = (y / z * c.nearp / c.ph + 0.5) * h;
@@ -311,7 +325,7 @@ inline FrameGates compute_frame_gates(const CamRec& camrec, int w, int h, const 
             if (!std::isfinite(ax1) || !finite3d(e0)) { ok = false; break; }
             double X[M], Y[M], Z[M];                             // polygon vertices in eye coordinates
             for (int v = 0; v < M; v++) {
-                const double ang = 2.0 * PI * v / M, cs = std::cos(ang), sn = std::sin(ang);
+                const double cs = tab.cs[v], sn = tab.sn[v];
                 double q[3];
                 for (int k = 0; k < 3; k++) q[k] = e0[k] + ax1 * cs * e1[k] + ax2 * sn * e2[k] - c.P[k];
                 X[v] = dot3d(q, c.R); Y[v] = dot3d(q, c.U); Z[v] = dot3d(q, c.F);

@@ -456,6 +456,8 @@ struct rt_context {
     bool compaction = false;        // RT_OPT_COMPACTION
     bool host_via_gpu0 = false;     // RT_OPT_HOST_VIA_GPU0
     bool primary_gate = true;       // RT_OPT_PRIMARY_GATE
+    // last frame gates computed (a camera that does not move, batches of equal cameras): guarded, launches may come from workers
+    std::mutex gate_mutex; bool gate_valid = false; CamRec gate_cam; int gate_w = 0, gate_h = 0; FrameGates gate_last;
     bool peer_ok = false;
     std::atomic<uint64_t> launches{0};
 };
@@ -606,9 +608,15 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
             const TinySceneData& t = ctx->tiny_data;
             const bool fastdiv_ok = fp.w <= RT_FASTDIV_MAX && fp.h <= RT_FASTDIV_MAX;
             FrameParams gp = fp;                      // + per-frame primary-ray sphere gate (a few hundred host flops per frame)
-            for (int f = 0; f < fp.n_frames; f++)
-                gp.gates[f] = ctx->primary_gate ? compute_frame_gates(fp.cam_inline[f], fp.w, fp.h, t.sgeom, t.ns, t.planes, t.np, t.lights, t.nl)
-                                                : gates_off(fp.w, fp.h);
+            for (int f = 0; f < fp.n_frames; f++) {
+                if (!ctx->primary_gate || fp.spp != 1) { gp.gates[f] = gates_off(fp.w, fp.h); continue; }
+                std::lock_guard<std::mutex> lock(ctx->gate_mutex);
+                if (!(ctx->gate_valid && ctx->gate_w == fp.w && ctx->gate_h == fp.h && memcmp(&ctx->gate_cam, &fp.cam_inline[f], sizeof(CamRec)) == 0)) {
+                    ctx->gate_last = compute_frame_gates(fp.cam_inline[f], fp.w, fp.h, t.sgeom, t.ns, t.planes, t.np, t.lights, t.nl);
+                    ctx->gate_cam = fp.cam_inline[f]; ctx->gate_w = fp.w; ctx->gate_h = fp.h; ctx->gate_valid = true;
+                }
+                gp.gates[f] = ctx->gate_last;
+            }
             TinyKernel kern = (ctx->compaction && fp.spp == 1 && fastdiv_ok) ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np, fp.spp, fastdiv_ok);
             kern<<<grid, BLOCK, 0, stream>>>(t, gp);
             break;
@@ -785,6 +793,7 @@ int rt_set_scene(rt_context* ctx, const float* spheres, int ns, const float* pla
     }
     ctx->accel = accel;
     ctx->has_scene = true;
+    { std::lock_guard<std::mutex> lock(ctx->gate_mutex); ctx->gate_valid = false; }
     return RT_OK;
 }
 
@@ -821,6 +830,7 @@ int rt_update_spheres(rt_context* ctx, const float* spheres, int first, int coun
         }
         CU_TRY(ctx, cudaStreamSynchronize(d.stream));     // sg / sm go out of scope; later launches may use another stream
     }
+    { std::lock_guard<std::mutex> lock(ctx->gate_mutex); ctx->gate_valid = false; }
     return upload_shadow_grids(ctx);                       // the bins depend on the sphere positions: rebuilt on the host
 }
 

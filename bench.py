@@ -341,7 +341,8 @@ def main():
                          "frac": achieved_tflops / fp32_peak, "traffic": traffic,
                          "note": "kernel is fp32-instruction bound, not HBM or tensor: peak = 148 SM x 128 lanes x 2 (FMA) x sm_max_mhz "
                                  "(%s); parity forbids FMA contraction, so the attainable ceiling is peak/2; achieved = SURVEY §8d "
-                                 "algorithmic flops (%.3e per frame) / CUDA-event kernel time" % (peaks["source"], flops_per_frame),
+                                 "algorithmic flops (%.3e per frame: every ray tests every sphere, as the reference does) / CUDA-event kernel time; the "
+                                 "kernel skips tests the host's frame gates prove fruitless (csrc/rt_gate.cuh), so it executes fewer" % (peaks["source"], flops_per_frame),
                          "hbm_write": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"]}},
             "e2e": {"value": rays_step * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 60 * F,
                     "d2h_bytes_per_step": fb_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3,

@@ -205,6 +205,15 @@ def main():
         if world > 1:
             dist.barrier()
 
+    if world > 1:
+        # all ranks store into rank 0's framebuffer: spans the frame gates prove black are not sent over NVLink, rank 0 zero-fills
+        # them locally (RT_OPT_SHARED_TARGET). The ring is poisoned first so that a span nobody writes would show up in the
+        # frame comparisons below.
+        ctx.set_option(rtb200.RT_OPT_SHARED_TARGET, 1)
+        if rank == 0:
+            ctx.dev_memset(fb, 0x5A, fb_bytes)
+        barrier()
+
     def step():
         ctx.render_device(cams, W, H, DEPTH, 1, 0, fb, sh)
 
@@ -258,6 +267,8 @@ def main():
         gathered = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
         frame0 = torch.empty((F, H, W), dtype=torch.int32, device="cuda") if rank == 0 else None
 
+        ctx.set_option(rtb200.RT_OPT_SHARED_TARGET, 0)       # separate local framebuffers: every rank writes all of its tiles
+
         def nccl_step():
             ctx.render_device(cams, W, H, DEPTH, 1, 0, local.data_ptr(), sh)
             payload[:, : len(rows)] = local.index_select(1, rows_t)
@@ -282,6 +293,7 @@ def main():
             fused = torch.from_numpy(ctx.dev_to_host(fb, fb_bytes).reshape(F, H, W)).cuda()
             assert torch.equal(fused, frame0), "NCCL-gathered frames differ from the fused peer-store frames"
         del local, payload, gathered, frame0
+        ctx.set_option(rtb200.RT_OPT_SHARED_TARGET, 1)
 
     # ---- e2e: the reference-facing call with HOST buffers: per frame, camera down, kernel, 33 MB framebuffer up ------
     host = torch.empty((F, npix), dtype=torch.int32, pin_memory=True)

@@ -157,6 +157,14 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
 /* RT_OPT_PRIMARY_GATE (default 1): tiny-scene kernels skip the sphere loop of primary rays (RayTracer.cs:975-981) for pixels outside
  * a per-frame rectangle the host proves no sphere can be hit in (csrc/rt_gate.cuh); 0 = test every sphere for every pixel. Same pixels. */
 #define RT_OPT_PRIMARY_GATE 3
+/* RT_OPT_SHARED_TARGET (default 0), one process per GPU: a promise that the `dev_pixels` every rank of the partition passes to
+ * rt_render_device alias ONE framebuffer owned by rank 0 (rt_ipc_export / rt_ipc_open). Ranks other than 0 then do not store the
+ * spans the frame gates prove black, and rank 0 zero-fills those spans of all tiles locally: 35 % of the default scene's frame
+ * never crosses NVLink. 1 = used when the partition has more than 4 ranks (where rank 0's NVLink ingress is the bottleneck; with
+ * fewer ranks the fill pass costs rank 0 more than the link saves), 2 = always. Every rank must set the same value (and the same
+ * RT_OPT_PRIMARY_GATE). Leave 0 when ranks render into separate buffers. Multi-device contexts (one process) do this by
+ * themselves (above 4 devices; 2 forces it there too). */
+#define RT_OPT_SHARED_TARGET 4
 int rt_set_option(rt_context* ctx, int option, int value);
 
 /* ---- device-pointer / multi-process interface (torchrun: one process per GPU) --------------------------------- */
@@ -180,6 +188,7 @@ int rt_ipc_close(rt_context* ctx, void* dev_ptr);
 int rt_dev_alloc(rt_context* ctx, uint64_t bytes, void** out_dev_ptr);
 int rt_dev_free(rt_context* ctx, void* dev_ptr);
 int rt_dev_to_host(rt_context* ctx, void* host_dst, const void* dev_src, uint64_t bytes);
+int rt_dev_memset(rt_context* ctx, void* dev_dst, int byte_value, uint64_t bytes);   /* synchronous; tests poison framebuffers with it */
 int rt_sync(rt_context* ctx);
 
 /* Page-locks (cudaHostRegister) a host buffer the caller keeps alive — e.g. the pinned `Surface.pixels` array — so that

@@ -89,15 +89,42 @@ def test_multi_device_host_output_paths(rt, w, h, tile_rows):
     multi.close()
 
 
-def _ipc_worker(rank, world, w, h, tile_rows, q_handle, q_done, q_go):
+@need2
+def test_sparse_gather_leaves_no_stale_pixels(rt):
+    """Gather on device 0 (RT_OPT_HOST_VIA_GPU0): devices other than 0 do not send the spans the frame gates prove black, device 0
+    zero-fills them. Alternating a camera that sees only floor with one that sees mostly sky makes a missing fill visible as
+    stale floor pixels."""
+    g = min(N_GPUS, 4) if N_GPUS >= 4 else 2
+    sc = scenes.default_scene()
+    w, h = 1024, 600
+    down = scenes.make_camera(pos=(0.0, 3.0, 2.0), pitch=1.3, width=w, height=h)       # floor everywhere
+    up = scenes.make_camera(pos=(0.0, 0.5, 0.0), pitch=-0.6, width=w, height=h)        # mostly sky
+    level = scenes.make_camera(width=w, height=h)
+    one = rt.Context([0]); one.set_scene(sc)
+    refs = [one.render(c, w, h, 8)[0].copy() for c in (down, up, level)]
+    one.close()
+    assert (refs[0] != 0).mean() > 0.95 and (refs[1] == 0).mean() > 0.5
+    multi = rt.Context(list(range(g))); multi.set_scene(sc)
+    multi.set_option(rt.RT_OPT_HOST_VIA_GPU0, 1)
+    multi.set_option(rt.RT_OPT_SHARED_TARGET, 2)         # force the sparse gather (automatic only above 4 devices)
+    for rep in range(2):
+        for c, ref in zip((down, up, level), refs):
+            got, _ = multi.render(c, w, h, 8)
+            assert np.array_equal(got, ref), "%d pixels differ" % (got != ref).sum()
+    multi.close()
+
+
+def _ipc_worker(rank, world, w, h, tile_rows, q_handle, q_done, q_go, shared_target=0):
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, os.path.join(os.path.dirname(here), "uu-infogr-raytracer_b200"))
     import rtb200
     sc = scenes.default_scene()
     cam = scenes.make_camera(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15, width=w, height=h)
     ctx = rtb200.Context([rank]); ctx.set_scene(sc); ctx.set_partition(rank, world, tile_rows)
+    ctx.set_option(rtb200.RT_OPT_SHARED_TARGET, shared_target)
     if rank == 0:
         fb = ctx.dev_alloc(w * h * 4)
+        ctx.dev_memset(fb, 0x5A, w * h * 4)          # poison: a pixel nobody writes cannot pass for black
         handle = ctx.ipc_export(fb)
         for _ in range(world - 1):
             q_handle.put(handle)
@@ -125,13 +152,16 @@ def _ipc_worker(rank, world, w, h, tile_rows, q_handle, q_done, q_go):
 
 
 @need2
-def test_multi_process_ipc_peer_stores(built):
-    """One process per GPU (the torchrun shape): rank 1 stores its row tiles straight into rank 0's framebuffer (CUDA IPC)."""
+@pytest.mark.parametrize("shared_target,w,h,tile_rows", [(0, 1000, 563, 8), (2, 1000, 563, 8), (2, 1283, 97, 3)])
+def test_multi_process_ipc_peer_stores(built, shared_target, w, h, tile_rows):
+    """One process per GPU (the torchrun shape): rank 1 stores its row tiles straight into rank 0's framebuffer (CUDA IPC).
+    shared_target = 2 (forced; 1 = only above 4 ranks): sparse gather — rank 1 does not send the spans the frame gates prove black, rank 0 zero-fills them
+    (RT_OPT_SHARED_TARGET); the frame must still equal the single-GPU frame, also with ragged spans (odd width, 3-row tiles)."""
     import torch.multiprocessing as mp
     world = 2
     mctx = mp.get_context("spawn")
     qh, qd, qg = mctx.Queue(), mctx.Queue(), mctx.Queue()
-    procs = [mctx.Process(target=_ipc_worker, args=(r, world, 1000, 563, 8, qh, qd, qg)) for r in range(world)]
+    procs = [mctx.Process(target=_ipc_worker, args=(r, world, w, h, tile_rows, qh, qd, qg, shared_target)) for r in range(world)]
     for p in procs: p.start()
     for p in procs: p.join(timeout=180)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]

@@ -58,6 +58,7 @@ struct FrameParams {
     int tiles_mine;             // tiles of this rank rendered by this launch ...
     int k_begin;                // ... starting at the rank's k_begin-th tile (band pipelining, see render_frames)
     int chunks_per_tile;        // ceil(tile_rows * w / (BLOCK * pixels per thread))
+    int skip_black_store;       // sparse gather (launch_render): this rank does not store proven-black spans, rank 0 fills them locally
     float rcp_w, rcp_h;         // 1/w, 1/h correctly rounded (host): pixel-coordinate divisions of the single-sample kernels (rt_div_rcp)
     long long frame_stride;     // pixels between consecutive frames in `out`
     uint32_t* out;              // framebuffer(s): 0x00RRGGBB, row-major (Surface.pixels, surface.cs:9-20)
@@ -100,6 +101,7 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
             bool black = false;
             bits = gate_bits_span(gates, x, x + PPT - 1, y, sc.n_lights(), &black);
             if (black) {                                       // nothing can be hit anywhere in the span: 0x00000000 (:993) untraced
+                if (fp.skip_black_store) continue;             // ... and rank 0 writes those zeros itself (k_fill_black): nothing crosses NVLink
                 if (PPT == 4 && ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0)) *reinterpret_cast<uint4*>(out + p0) = make_uint4(0u, 0u, 0u, 0u);
                 else for (int q = 0; q < PPT; q++) out[p0 + q] = 0u;
                 continue;
@@ -127,6 +129,37 @@ template <int NS, int NL, int NP, bool SPP1>
 __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp) {
     render_loop<PPT_TINY, SPP1>(TinyScene<NS, NL, NP>(scd), fp);
 }
+// Sparse gather, rank 0's half: the proven-black spans of the tiles that belong to the OTHER ranks are zeroed here, in local HBM,
+// so that those ranks need not send zeros over NVLink (35 % of the bench frame). Same span geometry and the same gates as
+// render_loop<PPT_TINY, true> — both sides evaluate the identical predicate on identical data, so every span is written by exactly
+// one of them. fp is rank 0's own FrameParams (k_begin / tiles_mine = its band; it owns at least as many tiles as any other rank).
+__global__ void __launch_bounds__(BLOCK) k_fill_black(const __grid_constant__ FrameParams fp) {
+    constexpr int PPT = PPT_TINY, CHUNK = BLOCK * PPT;
+    const int npix = fp.w * fp.h;
+    const int tile_pix = fp.tile_rows * fp.w;
+    const int frame = blockIdx.z;
+    const FrameGates& gates = fp.gates[frame];
+    uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
+    for (int kk = blockIdx.y; kk < fp.tiles_mine; kk += gridDim.y) {
+        const int k = fp.k_begin + kk;
+        for (int r = 1; r < fp.world; r++) {
+            const int tile = k * fp.world + r;
+            if (tile >= fp.tiles_total) break;
+            const int base = tile * tile_pix;
+            int end = base + tile_pix; if (end > npix || end < base) end = npix;
+            const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
+            if (p0 >= end) continue;
+            const int y = p0 / fp.w, x = p0 - y * fp.w;
+            if (!(x + PPT <= fp.w && p0 + PPT <= end)) continue;
+            bool black = false;
+            gate_bits_span(gates, x, x + PPT - 1, y, 0, &black);
+            if (!black) continue;
+            if ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0) *reinterpret_cast<uint4*>(out + p0) = make_uint4(0u, 0u, 0u, 0u);
+            else for (int q = 0; q < PPT; q++) out[p0 + q] = 0u;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Opt-in variant (rt_set_option(RT_OPT_COMPACTION, 1)): warp-ballot ray compaction between bounces.
 // Pass 1 traces every pixel of the chunk up to its second hit. A chain that goes on (a mirror seen in a mirror) is not followed by
@@ -456,6 +489,7 @@ struct rt_context {
     bool compaction = false;        // RT_OPT_COMPACTION
     bool host_via_gpu0 = false;     // RT_OPT_HOST_VIA_GPU0
     bool primary_gate = true;       // RT_OPT_PRIMARY_GATE
+    int shared_target = 0;          // RT_OPT_SHARED_TARGET (0 / 1 = above 4 ranks / 2 = always)
     // last frame gates computed (a camera that does not move, batches of equal cameras): guarded, launches may come from workers
     std::mutex gate_mutex; bool gate_valid = false; CamRec gate_cam; int gate_w = 0, gate_h = 0; FrameGates gate_last;
     bool peer_ok = false;
@@ -617,8 +651,22 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
                 }
                 gp.gates[f] = ctx->gate_last;
             }
-            TinyKernel kern = (ctx->compaction && fp.spp == 1 && fastdiv_ok) ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np, fp.spp, fastdiv_ok);
+            const bool compact = ctx->compaction && fp.spp == 1 && fastdiv_ok;
+            TinyKernel kern = compact ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np, fp.spp, fastdiv_ok);
+            // Sparse gather: all ranks store into ONE framebuffer owned by rank 0 (fp.skip_black_store = the caller's promise).
+            // Only with the gated single-sample kernels, which are the ones that know black spans.
+            // It pays off only where rank 0's NVLink ingress is the bottleneck (measured: N = 8); with fewer ranks rank 0 itself is
+            // the critical path and its fill pass (55 us per 16 4K frames) costs more than the link saves -> automatic above 4 ranks,
+            // promise value 2 forces it (tests).
+            const bool sparse = fp.skip_black_store && (fp.world > 4 || fp.skip_black_store == 2) && fp.world > 1 && ctx->primary_gate &&
+                                fp.spp == 1 && fastdiv_ok && !compact;
+            gp.skip_black_store = sparse && fp.rank != 0;
             kern<<<grid, BLOCK, 0, stream>>>(t, gp);
+            if (sparse && fp.rank == 0 && fp.tiles_mine > 0) {
+                CU_TRY(ctx, cudaGetLastError());
+                k_fill_black<<<grid, BLOCK, 0, stream>>>(gp);
+                ctx->launches++;
+            }
             break;
         }
         case PATH_STAGED: k_render_staged<<<grid, BLOCK, smem, stream>>>(global_data(ctx, d), fp); break;
@@ -840,6 +888,7 @@ int rt_set_option(rt_context* ctx, int option, int value) {
         case RT_OPT_COMPACTION: ctx->compaction = value != 0; return RT_OK;
         case RT_OPT_HOST_VIA_GPU0: ctx->host_via_gpu0 = value != 0; return RT_OK;
         case RT_OPT_PRIMARY_GATE: ctx->primary_gate = value != 0; return RT_OK;
+        case RT_OPT_SHARED_TARGET: ctx->shared_target = value < 0 ? 0 : (value > 2 ? 2 : value); return RT_OK;
         default: return fail(ctx, RT_ERR_INVALID, "unknown option");
     }
 }
@@ -866,6 +915,7 @@ int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int w
         FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, ctx->rank, ctx->world,
                                      (uint32_t*)dev_pixels + (size_t)f0 * w * h, (long long)w * h);
         for (int i = 0; i < nf; i++) fp.cam_inline[i] = to_cam(cams[f0 + i]);
+        fp.skip_black_store = ctx->shared_target;
         rc = launch_render(ctx, d, fp, st);
         if (rc) return rc;
     }
@@ -929,6 +979,7 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         const int nf = pipelined ? 1 : (n_frames - frame < INLINE_CAMS ? n_frames - frame : INLINE_CAMS);
         const int rank = G > 1 ? g : ctx->rank;
         FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, rank, world, (direct ? d.fb : d0.fb) + (size_t)frame * npix, (long long)npix);
+        fp.skip_black_store = (G > 1 && !direct) ? (ctx->shared_target == 2 ? 2 : 1) : 0;   // every device stores into device 0's framebuffer
         if (pipelined) {
             fp.cam_inline[0] = to_cam(cams[frame]);
             const int k0 = band * (band_tiles / world), k1 = k0 + band_tiles / world;       // this rank's tiles of the band
@@ -1245,6 +1296,13 @@ int rt_dev_to_host(rt_context* ctx, void* host_dst, const void* dev_src, uint64_
     if (!ctx || !host_dst || !dev_src) return RT_ERR_INVALID;
     CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
     CU_TRY(ctx, cudaMemcpy(host_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+int rt_dev_memset(rt_context* ctx, void* dev_dst, int byte_value, uint64_t bytes) {
+    if (!ctx || !dev_dst) return RT_ERR_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    CU_TRY(ctx, cudaMemset(dev_dst, byte_value, (size_t)bytes));
+    CU_TRY(ctx, cudaDeviceSynchronize());
     return RT_OK;
 }
 int rt_sync(rt_context* ctx) {

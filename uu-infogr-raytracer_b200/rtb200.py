@@ -24,13 +24,14 @@ RT_ACCEL_AUTO, RT_ACCEL_BRUTE, RT_ACCEL_LBVH = 0, 1, 2
 RT_OPT_COMPACTION = 1
 RT_OPT_HOST_VIA_GPU0 = 2
 RT_OPT_PRIMARY_GATE = 3
+RT_OPT_SHARED_TARGET = 4
 COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_pos", "plane_tests",
                  "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"]
 
 # every symbol include/rtb200.h declares
 ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_update_spheres", "rt_render", "rt_render_batch", "rt_render_debug", "rt_query_spheres", "rt_ray_log", "rt_selftest",
                "rt_set_option", "rt_set_partition", "rt_render_device", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_dev_alloc",
-               "rt_dev_free", "rt_dev_to_host", "rt_sync", "rt_host_register", "rt_host_unregister", "rt_launch_count", "rt_destroy", "rt_last_error", "rt_abi_version"]
+               "rt_dev_free", "rt_dev_to_host", "rt_dev_memset", "rt_sync", "rt_host_register", "rt_host_unregister", "rt_launch_count", "rt_destroy", "rt_last_error", "rt_abi_version"]
 
 
 class RtCamera(C.Structure):
@@ -91,6 +92,7 @@ def load_library():
     lib.rt_dev_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     lib.rt_dev_free.argtypes = [vp, vp]
     lib.rt_dev_to_host.argtypes = [vp, vp, vp, C.c_uint64]
+    lib.rt_dev_memset.argtypes = [vp, vp, C.c_int, C.c_uint64]
     lib.rt_sync.argtypes = [vp]
     lib.rt_host_register.argtypes = [vp, vp, C.c_uint64]
     lib.rt_host_unregister.argtypes = [vp, vp]
@@ -271,6 +273,9 @@ class Context:
     def dev_to_host_into(self, arr: np.ndarray, ptr: int, nbytes: int):
         assert arr.nbytes >= nbytes and arr.flags.c_contiguous
         self._check(self.lib.rt_dev_to_host(self.h, arr.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), nbytes))
+
+    def dev_memset(self, ptr: int, byte_value: int, nbytes: int):
+        self._check(self.lib.rt_dev_memset(self.h, C.c_void_p(ptr), byte_value, nbytes))
 
     def host_register(self, arr: np.ndarray):
         self._check(self.lib.rt_host_register(self.h, arr.ctypes.data_as(C.c_void_p), arr.nbytes))

@@ -235,8 +235,10 @@ def main():
     torch.cuda.synchronize(); barrier()
     launches_timed = ctx.launch_count() - launches_before
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    launches_all = torch.tensor([float(launches_timed)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches_all, op=dist.ReduceOp.SUM)      # rank 0 also launches the sparse-gather fill kernel above 4 ranks
     total_ms = float(ms.item())
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0 and not clocks.get("samples"):
@@ -360,7 +362,7 @@ def main():
                     "d2h_bytes_per_step": fb_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "path": "rt_render per frame into a pinned host Surface.pixels" if world == 1 else
                             "rt_render_device on all ranks (peer stores), barrier, rank 0 D2H"},
-            "gpu_launches": int(launches_timed) * world,
+            "gpu_launches": int(launches_all.item()),
             "gather_compare": None if nccl_ms is None else {
                 "fused_peer_stores_ms_per_step": ms_per_step, "nccl_gather_ms_per_step": nccl_ms,
                 "note": "same step; NCCL path = render to a local framebuffer, pack rows, torch.distributed.gather, scatter on rank 0"},

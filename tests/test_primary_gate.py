@@ -233,3 +233,43 @@ def test_non_unit_normal_disables_only_the_mirror_gate(built):
     a = O.render(sc, cam, w, h, 5)
     b = E.render(sc, cam, w, h, 5, tiny=2)
     assert np.array_equal(a["pixels"], b["pixels"])
+
+
+def test_4k_gate_borders_against_the_oracle(built):
+    """At the bench resolution the margins are a few pixels wide: check every gated pixel within 5 pixels of a gate border (where
+    the skip bits change) plus a random sample, for the bench camera and a moved one, against the oracle's ray log."""
+    sc = scenes.default_scene()
+    w, h = 3840, 2160
+    ns = len(sc.spheres)
+    for camkw in (dict(), dict(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15)):
+        cam = scenes.make_camera(width=w, height=h, **camkw)
+        bits2 = E.gates(sc, cam, w, h)["bits"]
+        chg = np.zeros((h, w), bool)
+        chg[:, 1:] |= bits2[:, 1:] != bits2[:, :-1]
+        chg[1:, :] |= bits2[1:, :] != bits2[:-1, :]
+        ys, xs = np.nonzero(chg)
+        near = np.zeros((h, w), bool)
+        for dy in range(-5, 6):
+            for dx in range(-5, 6):
+                near[np.clip(ys + dy, 0, h - 1), np.clip(xs + dx, 0, w - 1)] = True
+        near &= bits2 != 0
+        b = bits2.reshape(-1)
+        rng = np.random.default_rng(3)
+        idx = np.flatnonzero(near.reshape(-1))
+        if len(idx) > 150000:
+            idx = rng.choice(idx, 150000, replace=False)
+        idx = np.unique(np.concatenate([idx, rng.choice(np.flatnonzero(b != 0), 50000, replace=False)])).astype(np.uint32)
+        log = O.ray_log(sc, cam, w, h, 3, idx)
+        prim = log[log["kind"] == 0]
+        assert np.array_equal(prim["pixel"], idx)
+        ph, pb = prim["hit"], b[idx]
+        assert (ph[(pb & E.GATE_BLACK) != 0] == -1).all()
+        assert not ((ph >= 0) & (ph < ns))[(pb & E.GATE_SPHERES) != 0].any()
+        on_plane = np.zeros(w * h, bool); on_plane[idx[ph >= ns]] = True
+        sec = log[(log["kind"] == 1) & (log["level"] == 1)]
+        s = sec[((b[sec["pixel"]] & E.GATE_MIRROR) != 0) & on_plane[sec["pixel"]]]
+        assert ((s["hit"] == -1) | ((s["hit"] >= ns) & (s["distance"] - np.float32(0.01) <= 0))).all()
+        sh = log[(log["kind"] == 2) & (log["level"] == 0)]
+        for l in range(len(sc.lights)):
+            q = sh[sh["light"] == l]
+            assert (q["hit"][((b[q["pixel"]] & (E.GATE_SHADOW0 << l)) != 0) & on_plane[q["pixel"]]] == -1).all()

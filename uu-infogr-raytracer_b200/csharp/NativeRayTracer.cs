@@ -43,6 +43,8 @@ internal sealed unsafe class NativeRayTracer : IDisposable {
 
     [DllImport(Lib)] private static extern int rt_ray_log(IntPtr ctx, ref RtCamera cam, int width, int height, int maxDepth, uint* pixels,
                                                           int nPixels, RtRayRecord* records, int maxRecords, out int nRecords);
+    [DllImport(Lib)] private static extern int rt_selftest(IntPtr ctx, int test, out ulong nChecked, out ulong nMismatch);
+    [DllImport(Lib)] private static extern int rt_set_option(IntPtr ctx, int option, int value);
     [DllImport(Lib)] private static extern int rt_host_register(IntPtr ctx, void* hostPtr, ulong bytes);
     [DllImport(Lib)] private static extern int rt_host_unregister(IntPtr ctx, void* hostPtr);
     [DllImport(Lib)] private static extern int rt_destroy(IntPtr ctx);
@@ -109,6 +111,16 @@ internal sealed unsafe class NativeRayTracer : IDisposable {
             return records;
         }
     }
+
+    /// <summary>Exhaustive on-device check of the library's hand-scheduled fp32 sequences (rt_selftest; 0 = 1/sqrt, 1 = pixel
+    /// division). Returns the number of mismatches, which must be 0. Worth running once on new hardware / drivers.</summary>
+    public ulong SelfTest(int test) {
+        Check(rt_selftest(_ctx, test, out _, out ulong bad));
+        return bad;
+    }
+
+    /// <summary>rt_set_option: 1 RT_OPT_COMPACTION, 2 RT_OPT_HOST_VIA_GPU0, 3 RT_OPT_PRIMARY_GATE (frame gates, default on).</summary>
+    public void SetOption(int option, int value) => Check(rt_set_option(_ctx, option, value));
 
     public void Dispose() {
         if (_ctx == IntPtr.Zero) return;

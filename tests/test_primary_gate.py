@@ -273,3 +273,25 @@ def test_4k_gate_borders_against_the_oracle(built):
         for l in range(len(sc.lights)):
             q = sh[sh["light"] == l]
             assert (q["hit"][((b[q["pixel"]] & (E.GATE_SHADOW0 << l)) != 0) & on_plane[q["pixel"]]] == -1).all()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_arbitrary_planes_lights_and_cameras(built, seed):
+    """Walls, ceilings, slopes (unit normals in any direction through a random point), random light vectors, cameras at any
+    distance and attitude, above or below the plane."""
+    rng = np.random.default_rng(9000 + seed)
+    for _ in range(10):
+        sc = scenes.default_scene() if rng.integers(0, 3) == 0 else scenes.small_random_scene(int(rng.integers(1, 9)), int(rng.integers(0, 10000)))
+        n = rng.normal(size=3)
+        n = (n / np.linalg.norm(n)).astype(np.float32)
+        sc.planes[0, 0:3] = (rng.normal(size=3) * 3).astype(np.float32)
+        sc.planes[0, 3:6] = n
+        if rng.integers(0, 2) and len(sc.lights):
+            sc.lights[:, 0:3] = rng.uniform(-40, 40, (len(sc.lights), 3)).astype(np.float32)
+        w, h = int(rng.integers(40, 140)), int(rng.integers(30, 100))
+        pos = tuple(rng.normal(size=3) * 10.0 ** rng.uniform(-0.5, 1.5))
+        cam = scenes.make_camera(pos=pos, yaw=float(rng.uniform(-3.2, 3.2)), pitch=float(rng.uniform(-1.55, 1.55)), width=w, height=h)
+        _check_bits_against_log(sc, cam, w, h)
+        a = O.render(sc, cam, w, h, 4)
+        b = E.render(sc, cam, w, h, 4, tiny=1)
+        assert np.array_equal(a["pixels"], b["pixels"])

@@ -507,6 +507,16 @@ int fail(rt_context* ctx, int code, const std::string& msg) {
     if (getenv("RT_LOG")) fprintf(stderr, "[rtb200] error %d: %s\n", code, msg.c_str());
     return code;
 }
+// Scratch device allocation of one ABI call: released on every return path (CU_TRY returns early).
+template <class T> struct DevMem {
+    T* p = nullptr;
+    DevMem() = default;
+    DevMem(const DevMem&) = delete;
+    DevMem& operator=(const DevMem&) = delete;
+    ~DevMem() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, count * sizeof(T)); }
+};
+
 #define CU_TRY(ctx, expr)                                                                          \
     do {                                                                                           \
         cudaError_t e__ = (expr);                                                                  \
@@ -1107,13 +1117,14 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int w, int h, int dep
     DeviceState& d = ctx->devs[0];
     CU_TRY(ctx, cudaSetDevice(d.dev));
     DebugOut dout; memset(&dout, 0, sizeof(dout));
-    unsigned long long* dcnt = nullptr;
-    CU_TRY(ctx, cudaMalloc(&dcnt, N_DEBUG_COUNTERS * sizeof(unsigned long long)));
+    DevMem<unsigned long long> m_cnt; DevMem<uint32_t> m_hash; DevMem<int32_t> m_id; DevMem<float> m_t;
+    CU_TRY(ctx, m_cnt.alloc(N_DEBUG_COUNTERS));
+    unsigned long long* dcnt = m_cnt.p;
     CU_TRY(ctx, cudaMemsetAsync(dcnt, 0, N_DEBUG_COUNTERS * sizeof(unsigned long long), d.stream));
     dout.counters = dcnt;
-    if (host_hash) CU_TRY(ctx, cudaMalloc(&dout.hash, npix * 4));
-    if (host_aov_id) CU_TRY(ctx, cudaMalloc(&dout.aov_id, npix * 4));
-    if (host_aov_t) CU_TRY(ctx, cudaMalloc(&dout.aov_t, npix * 4));
+    if (host_hash) { CU_TRY(ctx, m_hash.alloc(npix)); dout.hash = m_hash.p; }
+    if (host_aov_id) { CU_TRY(ctx, m_id.alloc(npix)); dout.aov_id = m_id.p; }
+    if (host_aov_t) { CU_TRY(ctx, m_t.alloc(npix)); dout.aov_t = m_t.p; }
     FrameParams fp = make_params(ctx, w, h, depth, spp, seed, 1, 0, 1, d.fb, (long long)npix);
     fp.cam_inline[0] = to_cam(*cam);
     long long grid = ((long long)npix + BLOCK - 1) / BLOCK;
@@ -1144,7 +1155,6 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int w, int h, int dep
     unsigned long long hc[N_DEBUG_COUNTERS];
     CU_TRY(ctx, cudaMemcpy(hc, dcnt, sizeof(hc), cudaMemcpyDeviceToHost));
     if (counters) for (int i = 0; i < N_DEBUG_COUNTERS; i++) counters[i] = hc[i];
-    cudaFree(dcnt); cudaFree(dout.hash); cudaFree(dout.aov_id); cudaFree(dout.aov_t);
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->primary = hc[0]; stats->shadow = hc[1]; stats->secondary = hc[2]; stats->kernel_ms = ms;
@@ -1161,10 +1171,11 @@ int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, 
     if (n_rays == 0) return RT_OK;
     DeviceState& d = ctx->devs[0];
     CU_TRY(ctx, cudaSetDevice(d.dev));
-    float* dr = nullptr; int32_t* di = nullptr; float* dt = nullptr;
-    CU_TRY(ctx, cudaMalloc(&dr, (size_t)n_rays * 24));
-    CU_TRY(ctx, cudaMalloc(&di, (size_t)n_rays * 4));
-    CU_TRY(ctx, cudaMalloc(&dt, (size_t)n_rays * 4));
+    DevMem<float> m_r, m_t; DevMem<int32_t> m_i;
+    CU_TRY(ctx, m_r.alloc((size_t)n_rays * 6));
+    CU_TRY(ctx, m_i.alloc((size_t)n_rays));
+    CU_TRY(ctx, m_t.alloc((size_t)n_rays));
+    float* dr = m_r.p; int32_t* di = m_i.p; float* dt = m_t.p;
     CU_TRY(ctx, cudaMemcpyAsync(dr, rays6, (size_t)n_rays * 24, cudaMemcpyHostToDevice, d.stream));   // stream-ordered before the kernel
     int grid = (n_rays + BLOCK - 1) / BLOCK; if (grid > d.sm_count * 32) grid = d.sm_count * 32;
     if (accel == RT_ACCEL_LBVH) k_query_lbvh<<<grid, BLOCK, 0, d.stream>>>(lbvh_data(ctx, d, false), dr, n_rays, kind, di, dt);
@@ -1174,7 +1185,6 @@ int rt_query_spheres(rt_context* ctx, const float* rays6, int n_rays, int kind, 
     CU_TRY(ctx, cudaStreamSynchronize(d.stream));
     CU_TRY(ctx, cudaMemcpy(out_id, di, (size_t)n_rays * 4, cudaMemcpyDeviceToHost));
     CU_TRY(ctx, cudaMemcpy(out_t, dt, (size_t)n_rays * 4, cudaMemcpyDeviceToHost));
-    cudaFree(dr); cudaFree(di); cudaFree(dt);
     return RT_OK;
 }
 
@@ -1183,8 +1193,9 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
     if (!n_checked || !n_mismatch) return fail(ctx, RT_ERR_INVALID, "bad selftest args");
     DeviceState& d = ctx->devs[0];
     CU_TRY(ctx, cudaSetDevice(d.dev));
-    unsigned long long* dbad = nullptr;
-    CU_TRY(ctx, cudaMalloc(&dbad, sizeof(unsigned long long)));
+    DevMem<unsigned long long> m_bad;
+    CU_TRY(ctx, m_bad.alloc(1));
+    unsigned long long* dbad = m_bad.p;
     CU_TRY(ctx, cudaMemsetAsync(dbad, 0, sizeof(unsigned long long), d.stream));
     uint64_t checked = 0;
     if (test == RT_SELFTEST_INV_LEN || test == RT_SELFTEST_INV_LEN_RSQ_SEED) {
@@ -1196,7 +1207,6 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
         k_selftest_pixel_div<<<d.sm_count * 8, 256, 0, d.stream>>>(RT_FASTDIV_MAX, dbad);
         checked = (uint64_t)RT_FASTDIV_MAX * (RT_FASTDIV_MAX + 1) / 2;
     } else {
-        cudaFree(dbad);
         return fail(ctx, RT_ERR_INVALID, "unknown selftest");
     }
     CU_TRY(ctx, cudaGetLastError());
@@ -1204,7 +1214,6 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
     CU_TRY(ctx, cudaStreamSynchronize(d.stream));
     unsigned long long bad = 0;
     CU_TRY(ctx, cudaMemcpy(&bad, dbad, sizeof(bad), cudaMemcpyDeviceToHost));
-    cudaFree(dbad);
     *n_checked = checked; *n_mismatch = bad;
     return RT_OK;
 }
@@ -1226,10 +1235,11 @@ int rt_ray_log(rt_context* ctx, const rt_camera* cam, int w, int h, int depth, c
         return fail(ctx, RT_ERR_UNSUPPORTED, "ray log too large: list fewer pixels per call");
     DeviceState& d = ctx->devs[0];
     CU_TRY(ctx, cudaSetDevice(d.dev));
-    uint32_t* dpix = nullptr; uint32_t* dcount = nullptr; RayRec* drecs = nullptr;
-    CU_TRY(ctx, cudaMalloc(&dpix, (size_t)n_pixels * 4));
-    CU_TRY(ctx, cudaMalloc(&dcount, (size_t)n_pixels * 4));
-    CU_TRY(ctx, cudaMalloc(&drecs, (size_t)n_pixels * slots * sizeof(RayRec)));
+    DevMem<uint32_t> m_pix, m_count; DevMem<RayRec> m_recs;
+    CU_TRY(ctx, m_pix.alloc((size_t)n_pixels));
+    CU_TRY(ctx, m_count.alloc((size_t)n_pixels));
+    CU_TRY(ctx, m_recs.alloc((size_t)n_pixels * slots));
+    uint32_t* dpix = m_pix.p; uint32_t* dcount = m_count.p; RayRec* drecs = m_recs.p;
     CU_TRY(ctx, cudaMemcpyAsync(dpix, pixels, (size_t)n_pixels * 4, cudaMemcpyHostToDevice, d.stream));
     FrameParams fp = make_params(ctx, w, h, depth, 1, 0u, 1, 0, 1, nullptr, (long long)npix);
     fp.cam_inline[0] = to_cam(*cam);
@@ -1243,14 +1253,13 @@ int rt_ray_log(rt_context* ctx, const rt_camera* cam, int w, int h, int depth, c
     long long total = 0, written = 0;
     for (int i = 0; i < n_pixels; i++) {
         const uint32_t c = hcount[(size_t)i];
-        if (c > (uint32_t)slots) { cudaFree(dpix); cudaFree(dcount); cudaFree(drecs); return fail(ctx, RT_ERR_CUDA, "ray log: slot bound violated"); }
+        if (c > (uint32_t)slots) return fail(ctx, RT_ERR_CUDA, "ray log: slot bound violated");
         const long long room = (long long)max_records - written;
         const long long take = (long long)c < room ? (long long)c : (room > 0 ? room : 0);
         if (take > 0)
             CU_TRY(ctx, cudaMemcpy(out + written, drecs + (size_t)i * slots, (size_t)take * sizeof(RayRec), cudaMemcpyDeviceToHost));
         written += take; total += c;
     }
-    cudaFree(dpix); cudaFree(dcount); cudaFree(drecs);
     if (total > 0x7fffffffLL) return fail(ctx, RT_ERR_UNSUPPORTED, "ray log: record count overflows int");
     *n_records = (int)total;
     return RT_OK;

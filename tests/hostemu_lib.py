@@ -6,14 +6,22 @@ import subprocess
 import numpy as np
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu")
-_lib = None
+_libs = {}
+VARIANT = ""          # "" = the shipped configuration; "_v2" = built with -DRT_GATES_V2 (set by tests through use_variant)
+
+
+def use_variant(name):
+    """Selects the library the module-level helpers call: "" (default build) or "_v2" (RT_GATES_V2)."""
+    global VARIANT
+    VARIANT = name
 
 
 def load():
-    global _lib
+    _lib = _libs.get(VARIANT)
     if _lib is None:
         subprocess.run(["make", "-C", HERE, "-s"], check=True)
-        _lib = C.CDLL(os.path.join(HERE, "libhostemu.so"))
+        _lib = C.CDLL(os.path.join(HERE, "libhostemu%s.so" % VARIANT))
+        _libs[VARIANT] = _lib
         fp = C.POINTER(C.c_float)
         _lib.emu_render.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                     C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), fp, C.POINTER(C.c_uint64)]

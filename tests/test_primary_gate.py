@@ -295,3 +295,49 @@ def test_arbitrary_planes_lights_and_cameras(built, seed):
         a = O.render(sc, cam, w, h, 4)
         b = E.render(sc, cam, w, h, 4, tiny=1)
         assert np.array_equal(a["pixels"], b["pixels"])
+
+
+# ---- RT_GATES_V2: tighter gate shapes (per-sphere mirror rectangles, shadow hull half-planes), compiled in only with
+# -DRT_GATES_V2 (not the shipped configuration: not yet measured on the GPU). Same soundness bar, on the CPU. --------------------
+
+@pytest.fixture()
+def v2(built):
+    E.use_variant("_v2")
+    yield
+    E.use_variant("")
+
+
+def test_v2_default_scene_is_sound_and_tighter(v2):
+    sc = scenes.default_scene()
+    w, h = 384, 216
+    cam = scenes.make_camera(width=w, height=h)
+    g, bits, on_plane, sec, sh = _check_bits_against_log(sc, cam, w, h)
+    E.use_variant("")
+    base = E.gates(sc, cam, w, h)["bits"].reshape(-1)
+    E.use_variant("_v2")
+    assert ((base & ~bits) == 0).all()                                    # never skips less than the shipped gates
+    assert ((bits & E.GATE_MIRROR) != 0).mean() > 1.4 * ((base & E.GATE_MIRROR) != 0).mean()
+    assert ((bits & (E.GATE_SHADOW0 << 1)) != 0).mean() > 1.8 * ((base & (E.GATE_SHADOW0 << 1)) != 0).mean()
+    a = O.render(sc, cam, w, h, 8)
+    b = E.render(sc, cam, w, h, 8, tiny=2)
+    assert np.array_equal(a["pixels"], b["pixels"])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_v2_random_scenes_planes_lights_cameras(v2, seed):
+    rng = np.random.default_rng(4000 + seed)
+    for _ in range(8):
+        sc = scenes.default_scene() if rng.integers(0, 3) == 0 else scenes.small_random_scene(int(rng.integers(1, 9)), int(rng.integers(0, 10000)))
+        if rng.integers(0, 2):
+            n = rng.normal(size=3)
+            sc.planes[0, 3:6] = (n / np.linalg.norm(n)).astype(np.float32)
+            sc.planes[0, 0:3] = (rng.normal(size=3) * 3).astype(np.float32)
+        if rng.integers(0, 2) and len(sc.lights):
+            sc.lights[:, 0:3] = rng.uniform(-40, 40, (len(sc.lights), 3)).astype(np.float32)
+        w, h = int(rng.integers(40, 160)), int(rng.integers(30, 110))
+        pos = tuple(rng.normal(size=3) * 10.0 ** rng.uniform(-0.5, 1.5) + np.array([0, 1.0, -2.0]))
+        cam = scenes.make_camera(pos=pos, yaw=float(rng.uniform(-3.2, 3.2)), pitch=float(rng.uniform(-1.55, 1.55)), width=w, height=h)
+        _check_bits_against_log(sc, cam, w, h)
+        a = O.render(sc, cam, w, h, 4)
+        b = E.render(sc, cam, w, h, 4, tiny=1)
+        assert np.array_equal(a["pixels"], b["pixels"])

@@ -46,12 +46,26 @@ constexpr int RT_GATE_LIGHTS = (int)RT_GATE_MAX_LIGHTS;   // shadow gates exist 
 
 struct GateRect { int x0, y0, x1, y1; };      // inclusive pixel ranges; empty = {w, h, w, h}
 struct GateAffine { float a, bx, by; };       // value(x, y) = fma(bx, x, fma(by, y, a)); "never" = {-1, 0, 0}, "always" = {+1, 0, 0}
+// RT_GATES_V2 (compile-time, default off — not yet measured on the GPU; the default build is unchanged): tighter SHAPES for the
+// two gates whose union rectangles leave the most on the table:
+//   mirror_s[i]   one rectangle per sphere (scenes of <= 4 spheres): the reflection is skipped if the span is outside ALL of them
+//   shadow_out[l] two half-planes per light, taken from the convex hull of the projected shadow polygons (the two hull edges that
+//                 cut the most off the rectangle): > 0 on the whole span => outside the hull => unoccluded. Fits the diagonal
+//                 streaks of low lights, which a rectangle cannot.
+#ifdef RT_GATES_V2
+constexpr int RT_GATE_MIRROR_RECTS = 4;
+#endif
 struct FrameGates {
     GateRect spheres;
     GateAffine sky;
     GateAffine deep;
     GateRect mirror;
     GateRect shadow[RT_GATE_LIGHTS];
+#ifdef RT_GATES_V2
+    int n_mirror_s;                                  // 0: only the union rectangle `mirror`
+    GateRect mirror_s[RT_GATE_MIRROR_RECTS];
+    GateAffine shadow_out[RT_GATE_LIGHTS][2];        // "never" = {-1, 0, 0}
+#endif
 };
 enum : uint32_t { GATE_SKIP_SPHERES = RT_GATE_SPHERES, GATE_SKIP_MIRROR = RT_GATE_MIRROR, GATE_SKIP_SHADOW0 = 1u << RT_GATE_SHADOW_SHIFT };   // bits of gate_bits() (rt_trace.cuh)
 
@@ -62,6 +76,11 @@ inline FrameGates gates_off(int w, int h) {
     g.spheres = gate_full(w, h); g.mirror = gate_full(w, h);
     for (int i = 0; i < RT_GATE_LIGHTS; i++) g.shadow[i] = gate_full(w, h);
     g.sky.a = -1.0f; g.sky.bx = 0.0f; g.sky.by = 0.0f; g.deep = g.sky;
+#ifdef RT_GATES_V2
+    g.n_mirror_s = 0;
+    for (int i = 0; i < RT_GATE_MIRROR_RECTS; i++) g.mirror_s[i] = gate_full(w, h);
+    for (int l = 0; l < RT_GATE_LIGHTS; l++) g.shadow_out[l][0] = g.shadow_out[l][1] = g.sky;
+#endif
     return g;
 }
 
@@ -168,6 +187,37 @@ inline GateAffine make_affine(double sgn, double a, double bx, double by, double
     return g;
 }
 
+#ifdef RT_GATES_V2
+struct P2 { double x, y; };
+// convex hull (Andrew's monotone chain), counter-clockwise, no repeated end point; n <= a few hundred
+inline int convex_hull(P2* pts, int n, P2* hull) {
+    for (int i = 1; i < n; i++) {                    // insertion sort by (x, y)
+        P2 v = pts[i]; int j = i - 1;
+        while (j >= 0 && (pts[j].x > v.x || (pts[j].x == v.x && pts[j].y > v.y))) { pts[j + 1] = pts[j]; j--; }
+        pts[j + 1] = v;
+    }
+    auto cross = [](const P2& o, const P2& a, const P2& b) { return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x); };
+    int k = 0;
+    for (int i = 0; i < n; i++) { while (k >= 2 && cross(hull[k - 2], hull[k - 1], pts[i]) <= 0) k--; hull[k++] = pts[i]; }
+    for (int i = n - 2, t = k + 1; i >= 0; i--) { while (k >= t && cross(hull[k - 2], hull[k - 1], pts[i]) <= 0) k--; hull[k++] = pts[i]; }
+    return k > 1 ? k - 1 : k;
+}
+// area of the part of rectangle r on the side nx x + ny y + c < 0 of a line (Sutherland-Hodgman against one half-plane)
+inline double rect_area_outside(const GateRect& r, double nx, double ny, double cc) {
+    const P2 q[4] = {{(double)r.x0, (double)r.y0}, {(double)r.x1 + 1, (double)r.y0}, {(double)r.x1 + 1, (double)r.y1 + 1}, {(double)r.x0, (double)r.y1 + 1}};
+    P2 out[8]; int m = 0;
+    for (int i = 0; i < 4; i++) {
+        const P2 a = q[i], b = q[(i + 1) & 3];
+        const double da = nx * a.x + ny * a.y + cc, db = nx * b.x + ny * b.y + cc;
+        if (da < 0) out[m++] = a;
+        if ((da < 0) != (db < 0)) { const double t = da / (da - db); out[m++] = {a.x + t * (b.x - a.x), a.y + t * (b.y - a.y)}; }
+    }
+    double area = 0;
+    for (int i = 0; i < m; i++) { const P2 a = out[i], b = out[(i + 1) % m]; area += a.x * b.y - a.y * b.x; }
+    return 0.5 * std::fabs(area);
+}
+#endif
+
 }  // namespace gate_detail
 
 // All gates of one frame. planes: PlaneRec as uploaded (n, cn); lights: LightRec (p).
@@ -273,8 +323,18 @@ inline FrameGates compute_frame_gates(const CamRec& camrec, int w, int h, const 
             const double ml = std::sqrt(dot3d(mc, mc));
             const double Rg = Rp + (eps + 2.0 * eps_r) * (ml + Rp) + 2.0 * delta_h;
             ok = add_ball_rect(m, ctr, Rg, 2.0, &acc);
+#ifdef RT_GATES_V2
+            if (ok && ns <= RT_GATE_MIRROR_RECTS) {
+                GateRect one = {w, h, -1, -1};
+                add_ball_rect(m, ctr, Rg, 2.0, &one);            // cannot fail: the union call above just succeeded
+                g.mirror_s[i] = finish_rect(one, w, h);
+            }
+#endif
         }
         g.mirror = ok ? finish_rect(acc, w, h) : gate_full(w, h);
+#ifdef RT_GATES_V2
+        g.n_mirror_s = (ok && ns <= RT_GATE_MIRROR_RECTS) ? ns : 0;
+#endif
     }
     // ---- shadow[l]: shadow ellipses on the plane, seen from the eye ---------------------------------------------------------
     for (int l = 0; l < nl && l < RT_GATE_LIGHTS; l++) {
@@ -304,8 +364,16 @@ inline FrameGates compute_frame_gates(const CamRec& camrec, int w, int h, const 
         const PolyTable& tab = poly_table();
         const double circ = tab.circ;                            // circumscribed polygon
         const double zc = 1e-4 * c.nearp;
+#ifdef RT_GATES_V2
+        constexpr int MAXP = 8 * 2 * GATE_POLY;                  // TINY_MAX_SPHERES polygons, clipping adds at most 2 points each
+        P2 pts[MAXP]; int npts = 0;
+#endif
         auto project = [&](double x, double y, double z) {
             const double px = (x / z * c.nearp / c.pw + 0.5) * w, py = (y / z * c.nearp / c.ph + 0.5) * h;
+#ifdef RT_GATES_V2
+            if (npts < MAXP) { pts[npts].x = px; pts[npts].y = py; }
+            npts++;
+#endif
             const double cx = std::fmax(-1e6, std::fmin(1e6, px)), cy = std::fmax(-1e6, std::fmin(1e6, py));   // before the int conversion
             const int x0 = (int)std::floor(cx - mpx), x1 = (int)std::ceil(cx + mpx), y0 = (int)std::floor(cy - mpx), y1 = (int)std::ceil(cy + mpx);
             if (x0 < acc.x0) acc.x0 = x0;
@@ -345,6 +413,33 @@ inline FrameGates compute_frame_gates(const CamRec& camrec, int w, int h, const 
         if (acc.x1 < acc.x0 || acc.y1 < acc.y0) { g.shadow[l] = gate_empty(w, h); continue; }
         GateRect r = {acc.x0 < 0 ? 0 : acc.x0, acc.y0 < 0 ? 0 : acc.y0, acc.x1 > w - 1 ? w - 1 : acc.x1, acc.y1 > h - 1 ? h - 1 : acc.y1};
         g.shadow[l] = (r.x1 < r.x0 || r.y1 < r.y0) ? gate_empty(w, h) : r;
+#ifdef RT_GATES_V2
+        if (!(r.x1 < r.x0 || r.y1 < r.y0) && npts >= 3 && npts <= MAXP) {
+            // Every possibly-shadowed pixel lies inside the convex hull of the projected (clipped) polygon vertices, grown by the
+            // pixel margin. Keep the two hull edges that cut the most area off the rectangle; coordinates are taken relative
+            // to the rectangle's centre so that the float coefficients stay small.
+            bool fin = true;
+            for (int i = 0; i < npts; i++) fin = fin && std::isfinite(pts[i].x) && std::isfinite(pts[i].y);
+            P2 hull[MAXP + 1];
+            const int nh_ = fin ? convex_hull(pts, npts, hull) : 0;
+            double best[2] = {0, 0}; double coef[2][3] = {{0, 0, 0}, {0, 0, 0}};
+            for (int i = 0; i < nh_ && nh_ >= 3; i++) {
+                const P2 a2 = hull[i], b2 = hull[(i + 1) % nh_];
+                const double ex = b2.x - a2.x, ey = b2.y - a2.y, el = std::sqrt(ex * ex + ey * ey);
+                if (!(el > 1e-9)) continue;
+                const double nx = -ey / el, ny = ex / el;         // inward normal of a counter-clockwise hull
+                const double cc = -(nx * a2.x + ny * a2.y) + mpx; // inside (grown by the margin): nx x + ny y + cc >= 0
+                if (!std::isfinite(cc) || std::fabs(nx * (0.5 * w) + ny * (0.5 * h) + cc) > 1e5) continue;    // a line far from the frame
+                const double area = rect_area_outside(r, nx, ny, cc);
+                int slot = area > best[0] ? 0 : (area > best[1] ? 1 : -1);
+                if (slot == 0) { best[1] = best[0]; for (int k = 0; k < 3; k++) coef[1][k] = coef[0][k]; }
+                if (slot >= 0) { best[slot] = area; coef[slot][0] = cc; coef[slot][1] = nx; coef[slot][2] = ny; }
+            }
+            for (int e = 0; e < 2; e++)
+                if (best[e] > 0.02 * (double)(r.x1 - r.x0 + 1) * (double)(r.y1 - r.y0 + 1))                    // worth two FMAs
+                    g.shadow_out[l][e] = make_affine(-1.0, coef[e][0], coef[e][1], coef[e][2], 0.0, w, h);      // > 0 => outside the hull
+        }
+#endif
     }
     return g;
 }
@@ -367,10 +462,24 @@ RT_HD uint32_t gate_bits_span(const FrameGates& g, int xa, int xb, int y, int nl
     uint32_t bits = span_outside(g.spheres, xa, xb, y) ? (uint32_t)GATE_SKIP_SPHERES : 0u;
     *black = bits != 0u && span_positive(g.sky, fxa, fxb, fy);
     if (!*black && span_positive(g.deep, fxa, fxb, fy)) {
+#ifdef RT_GATES_V2
+        bool no_mirror = span_outside(g.mirror, xa, xb, y);
+        if (!no_mirror && g.n_mirror_s > 0) {
+            no_mirror = true;
+#pragma unroll
+            for (int i = 0; i < RT_GATE_MIRROR_RECTS; i++) if (i < g.n_mirror_s && !span_outside(g.mirror_s[i], xa, xb, y)) no_mirror = false;
+        }
+        if (no_mirror) bits |= GATE_SKIP_MIRROR;
+#pragma unroll
+        for (int l = 0; l < RT_GATE_LIGHTS; l++)
+            if (l < nl && (span_outside(g.shadow[l], xa, xb, y) || span_positive(g.shadow_out[l][0], fxa, fxb, fy) ||
+                           span_positive(g.shadow_out[l][1], fxa, fxb, fy))) bits |= (uint32_t)GATE_SKIP_SHADOW0 << l;
+#else
         if (span_outside(g.mirror, xa, xb, y)) bits |= GATE_SKIP_MIRROR;
 #pragma unroll
         for (int l = 0; l < RT_GATE_LIGHTS; l++)
             if (l < nl && span_outside(g.shadow[l], xa, xb, y)) bits |= (uint32_t)GATE_SKIP_SHADOW0 << l;
+#endif
     }
     return bits;
 }

@@ -137,6 +137,78 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def moving_cameras(n: int):
+    """n distinct cameras around the default one: +-1-pixel yaw steps (one 4K pixel = view-plane width / 3840 / near clip radians),
+    so that every frame of a step needs its own host-side frame gates (csrc/rt_gate.cuh) — what a moving camera pays."""
+    px = float(scenes.view_params(W, H)[0]) / W / float(scenes.NEAR_CLIP)
+    return np.stack([scenes.make_camera(yaw=(k - n // 2) * px, width=W, height=H) for k in range(n)])
+
+
+def time_steps(torch, stream, fn, n):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(n):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def per_config_extras(rtb200, local_rank, peaks):
+    """BASELINE.json configs[0], [2], [3], [4] on ONE GPU, after the headline loop, in this process: single-frame launches through
+    rt_render (headless), kernel time from CUDA events inside the library (best of 5 after 2 warm-ups), ray / LBVH counters from the
+    instrumented kernel, and the returned frame compared with the instrumented render of the same frame."""
+    import zlib
+    out = {}
+    l2_gbs = None
+    specs = [
+        ("configs[0] default scene 1280x720 cap 32", scenes.default_scene, {}, 1280, 720, 32, 1, rtb200.RT_ACCEL_AUTO),
+        ("configs[2] 1024 spheres 4K cap 8, LBVH + shadow bins", scenes.config3_scene, scenes.SCALED_CAMERA, W, H, 8, 1, rtb200.RT_ACCEL_LBVH),
+        ("configs[2] 1024 spheres 4K cap 8, brute force staged in shared memory", scenes.config3_scene, scenes.SCALED_CAMERA, W, H, 8, 1, rtb200.RT_ACCEL_BRUTE),
+        ("configs[3] 100k spheres 4K cap 8, LBVH + shadow bins", scenes.config4_scene, scenes.SCALED_CAMERA, W, H, 8, 1, rtb200.RT_ACCEL_AUTO),
+        ("configs[4] default scene 7680x4320 x 16 spp cap 8", scenes.default_scene, {}, 7680, 4320, 8, 16, rtb200.RT_ACCEL_AUTO),
+    ]
+    for name, mk, camkw, w, h, depth, spp, accel in specs:
+        sc = mk()
+        cam = scenes.make_camera(width=w, height=h, **camkw)
+        ctx = rtb200.Context([local_rank])
+        t0 = time.perf_counter()
+        ctx.set_scene(sc, accel)
+        upload_s = time.perf_counter() - t0
+        dbg = ctx.render_debug(cam, w, h, depth, spp, 0, arrays=False)
+        cnt = dbg["counters"]
+        rays = cnt["primary"] + cnt["shadow"] + cnt["secondary"]
+        for _ in range(2):
+            ctx.render(cam, w, h, depth, spp, 0, headless=True)
+        ms = [ctx.render(cam, w, h, depth, spp, 0, headless=True)[1].kernel_ms for _ in range(5)]
+        px, _ = ctx.render(cam, w, h, depth, spp, 0)
+        rec = {"kernel_ms": min(ms), "kernel_ms_mean": float(np.mean(ms)), "mrays_per_s": rays / (min(ms) * 1e-3) / 1e6,
+               "rays": rays, "counters": cnt, "frame_crc32": zlib.crc32(px.tobytes()) & 0xFFFFFFFF,
+               "frame_equals_instrumented_render": bool(np.array_equal(px, dbg["pixels"])), "scene_upload_s": upload_s,
+               "path": ["tiny", "staged", "global", "lbvh"][ctx.get_info(rtb200.RT_INFO_SCENE_PATH)]}
+        if rec["path"] == "lbvh":
+            lb = dbg["lbvh"]
+            visits = lb["node_visits_primary"] + lb["node_visits_secondary"] + lb["node_visits_shadow"]
+            nbytes = visits * 64 + cnt["sphere_tests"] * 16
+            if l2_gbs is None:
+                l2_gbs = ctx.measure_l2_read(32 << 20)
+            ach = nbytes / (min(ms) * 1e-3) / 1e9
+            rec["lbvh"] = lb
+            rec["roofline"] = {"bound": "L2", "achieved": ach, "peak": l2_gbs, "unit": "GB/s", "frac": ach / l2_gbs,
+                               "bytes": nbytes, "note": "algorithmic bytes = node visits x 64 B + sphere tests x 16 B (SURVEY §8d); peak = L2->SM read "
+                                                        "bandwidth measured in this run by rt_measure_l2_read (every CTA of a full grid streams a 32 MB "
+                                                        "L2-resident set with 128-bit L1-bypassing loads, best of 3)"}
+        else:
+            fl = algorithmic_flops(cnt)
+            fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+            rec["roofline"] = {"bound": "fp32", "achieved": fl / (min(ms) * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                               "frac": fl / (min(ms) * 1e-3) / 1e12 / fp32_peak}
+        out[name] = rec
+        ctx.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -146,6 +218,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16, help="4K frames per step (ring of framebuffers > L2)")
     ap.add_argument("--tile-rows", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip per_config / single-frame / moving-camera / gates-off measurements")
     ap.add_argument("--compaction", type=int, default=0, help="1: opt-in warp-ballot compaction kernel variant (tuning)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -173,6 +246,7 @@ def main():
     sc = scenes.default_scene()
     cam = scenes.make_camera(width=W, height=H)
     cams = np.repeat(cam[None], F, 0)
+    cams_move = moving_cameras(F)
 
     ctx = rtb200.Context([local_rank])
     ctx.set_scene(sc)
@@ -185,6 +259,12 @@ def main():
     cnt = dbg["counters"]
     rays_per_frame = cnt["primary"] + cnt["shadow"] + cnt["secondary"]
     flops_per_frame = algorithmic_flops(cnt)
+    # ... and of the moving-camera frames (e2e, value_moving_camera); the last one is kept to check the frame that comes back
+    rays_move, dbg_move_last = 0, None
+    for f in range(F):
+        d = ctx.render_debug(cams_move[f], W, H, DEPTH, arrays=False)
+        rays_move += d["counters"]["primary"] + d["counters"]["shadow"] + d["counters"]["secondary"]
+        dbg_move_last = d["pixels"]
 
     # framebuffer ring on rank 0; other ranks map it through CUDA IPC (peer stores over NVLink)
     fb_bytes = F * npix * 4
@@ -217,7 +297,6 @@ def main():
     def step():
         ctx.render_device(cams, W, H, DEPTH, 1, 0, fb, sh)
 
-    launches0 = ctx.launch_count()
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize(); barrier()
@@ -254,6 +333,37 @@ def main():
     if world > 1:
         barrier()
 
+    # ---- N = 1 only: the same kernel seen three other ways (not the headline; each explains a part of it) ---------------------
+    extras = {}
+    if world == 1 and not args.no_extras:
+        k = max(3, min(args.steps, 20))
+        # (1) one frame per launch — what Tick() does (RayTracer.cs:886-901): launch latency and the tail of every frame included
+        def single():
+            for f in range(F):
+                ctx.render_device(cam[None], W, H, DEPTH, 1, 0, fb + f * npix * 4, sh)
+        single()
+        t = time_steps(torch, stream, single, k)
+        extras["value_single_frame"] = {"value": rays_per_frame * F * k / (t * 1e-3) / 1e6, "unit": UNIT, "ms_per_frame": t / (k * F),
+                                        "note": "one 4K frame per launch, back to back on one stream (what Tick() does)"}
+        # (2) a moving camera: 16 DISTINCT cameras per step, so every frame's gates are computed on the host inside the timed region
+        def moving():
+            ctx.render_device(cams_move, W, H, DEPTH, 1, 0, fb, sh)
+        moving()
+        g_ns0, g_n0 = ctx.get_info(rtb200.RT_INFO_GATE_HOST_NS), ctx.get_info(rtb200.RT_INFO_GATE_COMPUTES)
+        t = time_steps(torch, stream, moving, k)
+        g_ns1, g_n1 = ctx.get_info(rtb200.RT_INFO_GATE_HOST_NS), ctx.get_info(rtb200.RT_INFO_GATE_COMPUTES)
+        extras["value_moving_camera"] = {"value": rays_move * k / (t * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": t / k,
+                                         "gate_host_us": (g_ns1 - g_ns0) / max(1, g_n1 - g_n0) / 1e3, "gate_computes": g_n1 - g_n0,
+                                         "note": "16 distinct cameras per step (+-1-pixel yaw steps): frame gates recomputed for every frame"}
+        # (3) frame gates off: every pixel traces everything the reference traces (the rays actually traced)
+        ctx.set_option(rtb200.RT_OPT_PRIMARY_GATE, 0)
+        step()
+        t = time_steps(torch, stream, step, k)
+        ctx.set_option(rtb200.RT_OPT_PRIMARY_GATE, 1)
+        extras["value_gates_off"] = {"value": rays_per_frame * F * k / (t * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": t / k,
+                                     "note": "RT_OPT_PRIMARY_GATE = 0: no host-proven skips, all %d accounted rays are traced" % rays_per_frame}
+        step(); torch.cuda.synchronize()
+
     # ---- N > 1 only: the same step with a library collective instead of the fused peer stores (comparison, not the product):
     # every rank renders its tiles into a LOCAL framebuffer, packs its rows, NCCL-gathers them to rank 0, rank 0 scatters
     # them into the frame (partition.pack_rows / assemble — the code the gloo test covers on CPU).
@@ -279,54 +389,92 @@ def main():
                 for r in range(world):
                     frame0[:, all_rows[r]] = gathered[r][:, : len(all_rows[r])]
 
+        nccl_steps = max(3, min(args.steps, 20))
         for _ in range(3):
             nccl_step()
         torch.cuda.synchronize(); barrier()
         n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(nccl_steps):
             nccl_step()
         n1.record(stream)
         torch.cuda.synchronize(); barrier()
         t = torch.tensor([n0.elapsed_time(n1)], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        nccl_ms = float(t.item()) / args.steps
+        nccl_ms = float(t.item()) / nccl_steps
         if rank == 0:     # both gathers must produce the same frames
             fused = torch.from_numpy(ctx.dev_to_host(fb, fb_bytes).reshape(F, H, W)).cuda()
             assert torch.equal(fused, frame0), "NCCL-gathered frames differ from the fused peer-store frames"
+            del fused
         del local, payload, gathered, frame0
         ctx.set_option(rtb200.RT_OPT_SHARED_TARGET, 1)
 
-    # ---- e2e: the reference-facing call with HOST buffers: per frame, camera down, kernel, 33 MB framebuffer up ------
-    host = torch.empty((F, npix), dtype=torch.int32, pin_memory=True)
-    host_np = host.numpy()
+    # ---- e2e: the reference-facing call, rt_render, with HOST buffers: per frame the camera goes down, the kernel runs and the
+    # frame comes back into a page-locked Surface.pixels. 16 DISTINCT cameras per step (the host-side gate computation is inside
+    # the timing). N = 1: one context. N > 1: every rank's context is one rank of the row-tile partition and returns ITS OWN tiles
+    # over ITS OWN PCIe link into ONE frame in shared host memory (POSIX shm, page-locked by every rank) — no gather on GPU 0 at all.
     e2e_steps = max(2, min(args.steps, 5))
+    shm = None
+    if world == 1:
+        host = torch.empty((F, npix), dtype=torch.int32, pin_memory=True)
+        host_np = host.numpy()
+    else:
+        from multiprocessing import shared_memory
+        name = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=fb_bytes)
+            name[0] = shm.name
+        dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name[0])
+        host_np = np.ndarray((F, npix), dtype=np.int32, buffer=shm.buf)
+        if rank == 0:
+            host_np[...] = 0x5A5A5A5A
+        barrier()
+        ctx.host_register(host_np)
+    d2h_step = [0]
 
     def e2e_step():
-        if world == 1:
-            for f in range(F):
-                ctx.render(cam, W, H, DEPTH, out=host_np[f].reshape(H, W))
-        else:
-            ctx.render_device(cams, W, H, DEPTH, 1, 0, fb, sh)
-            torch.cuda.synchronize(); barrier()
-            if rank == 0:
-                ctx.dev_to_host_into(host_np, fb, fb_bytes)
-            barrier()
+        n = 0
+        for f in range(F):
+            ctx.render(cams_move[f], W, H, DEPTH, out=host_np[f].reshape(H, W))
+            n += ctx.get_info(rtb200.RT_INFO_LAST_D2H_BYTES)
+        d2h_step[0] = n
+        barrier()           # N > 1: the step is done when every rank's tiles of every frame have landed
 
     e2e_step()
     torch.cuda.synchronize(); barrier()
+    g_ns0, g_n0 = ctx.get_info(rtb200.RT_INFO_GATE_HOST_NS), ctx.get_info(rtb200.RT_INFO_GATE_COMPUTES)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize(); barrier()
     e2e_s = time.perf_counter() - t0
+    g_ns1, g_n1 = ctx.get_info(rtb200.RT_INFO_GATE_HOST_NS), ctx.get_info(rtb200.RT_INFO_GATE_COMPUTES)
     e2e_t = torch.tensor([e2e_s], device="cuda")
+    d2h_t = torch.tensor([float(d2h_step[0])], device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(d2h_t, op=dist.ReduceOp.SUM)
     e2e_s = float(e2e_t.item())
+    d2h_bytes_step = int(d2h_t.item())
     # sanity: the frame that came back is the frame the oracle-checked debug kernel produced
     if rank == 0:
-        assert np.array_equal(host_np[F - 1].reshape(H, W), dbg["pixels"]), "e2e frame differs from the instrumented render"
+        assert np.array_equal(host_np[F - 1].reshape(H, W), dbg_move_last), "e2e frame differs from the instrumented render"
+    # the dense return (RT_OPT_SPARSE_D2H = 0), for comparison: every byte of every frame crosses PCIe
+    ctx.set_option(rtb200.RT_OPT_SPARSE_D2H, 0)
+    e2e_step(); torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(); barrier()
+    dense_t = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(dense_t, op=dist.ReduceOp.MAX)
+    e2e_dense_s = float(dense_t.item())
+    ctx.set_option(rtb200.RT_OPT_SPARSE_D2H, 1)
+    if world > 1:
+        ctx.host_unregister(host_np)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -356,18 +504,28 @@ def main():
                          "note": "kernel is fp32-instruction bound, not HBM or tensor: peak = 148 SM x 128 lanes x 2 (FMA) x sm_max_mhz "
                                  "(%s); parity forbids FMA contraction, so the attainable ceiling is peak/2; achieved = SURVEY §8d "
                                  "algorithmic flops (%.3e per frame: every ray tests every sphere, as the reference does) / CUDA-event kernel time; the "
-                                 "kernel skips tests the host's frame gates prove fruitless (csrc/rt_gate.cuh), so it executes fewer" % (peaks["source"], flops_per_frame),
+                                 "kernel skips tests the host's frame gates prove fruitless (csrc/rt_gate.cuh), so it executes fewer — see "
+                                 "value_gates_off" % (peaks["source"], flops_per_frame),
                          "hbm_write": {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"]}},
-            "e2e": {"value": rays_step * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 60 * F,
-                    "d2h_bytes_per_step": fb_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "path": "rt_render per frame into a pinned host Surface.pixels" if world == 1 else
-                            "rt_render_device on all ranks (peer stores), barrier, rank 0 D2H"},
+            "e2e": {"value": rays_move * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 60 * F * world,
+                    "d2h_bytes_per_step": d2h_bytes_step, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "frame_bytes_per_step": fb_bytes,
+                    "gate_host_us": (g_ns1 - g_ns0) / max(1, g_n1 - g_n0) / 1e3,
+                    "dense_return": {"value": rays_move * e2e_steps / e2e_dense_s / 1e6, "d2h_bytes_per_step": fb_bytes,
+                                     "note": "RT_OPT_SPARSE_D2H = 0: every byte of every frame crosses PCIe"},
+                    "path": ("rt_render per frame into a page-locked host Surface.pixels, 16 distinct cameras per step; pixels the frame gates prove "
+                             "black are not copied but zero-filled by library threads (RT_OPT_SPARSE_D2H)") if world == 1 else
+                            ("rt_render per frame on every rank (each a rank of the row-tile partition): every GPU returns its own tiles over its own "
+                             "PCIe link into ONE frame in shared page-locked host memory; 16 distinct cameras per step; sparse return")},
             "gpu_launches": int(launches_all.item()),
             "gather_compare": None if nccl_ms is None else {
                 "fused_peer_stores_ms_per_step": ms_per_step, "nccl_gather_ms_per_step": nccl_ms,
                 "note": "same step; NCCL path = render to a local framebuffer, pack rows, torch.distributed.gather, scatter on rank 0"},
             "clocks": clocks,
         }
+        line.update(extras)
+        if world == 1 and not args.no_extras:
+            line["per_config"] = per_config_extras(rtb200, local_rank, peaks)
         if not args.no_cpu_baseline and world == 1:
             best, times, rays, cores = cpu_reference_run(frames=5, warm=1)
             line["cpu_baseline"] = {"value": rays / best / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
@@ -382,6 +540,12 @@ def main():
     if rank == 0:
         ctx.dev_free(fb)
     ctx.close()
+    if shm is not None:
+        del host_np
+        shm.close()
+        barrier()
+        if rank == 0:
+            shm.unlink()
     if world > 1:
         dist.destroy_process_group()
 

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RTB200_ABI_VERSION 1
+#define RTB200_ABI_VERSION 2
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -165,16 +165,43 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
  * RT_OPT_PRIMARY_GATE). Leave 0 when ranks render into separate buffers. Multi-device contexts (one process) do this by
  * themselves (above 4 devices; 2 forces it there too). */
 #define RT_OPT_SHARED_TARGET 4
+/* RT_OPT_DEBUG_SHIPPED (default 0): rt_render_debug of a tiny scene (<= 8 spheres) with spp == 1 runs the PRODUCTION kernel
+ * instantiation — exact-count unrolled loops, packed fp32 sphere pairs, fast pixel division, frame gates, 4-pixel spans — with an
+ * events-only debug policy, so that the per-pixel chain hash / primary AOV / ray counters certify the shipped code path itself.
+ * Work a gate skips is reported as the event the reference produces there (a reflection ray that hits nothing, an unoccluded
+ * shadow ray, a primary ray that hits nothing). The per-test counters (sphere_tests ... shaded_hits) stay 0 in this mode. */
+#define RT_OPT_DEBUG_SHIPPED 5
+/* RT_OPT_SPARSE_D2H (default 1): rt_render / rt_render_batch with a host buffer do not copy what the frame gates prove black
+ * (whole rows above the horizon outside the sphere rectangle, and the parts of sky rows beside it); those pixels of host_pixels are
+ * zero-filled by library threads (RTB200_FILL_THREADS, default 4) while the rest crosses PCIe. Same pixels; 35 % fewer PCIe bytes on
+ * the reference's default frame. rt_get_info(RT_INFO_LAST_D2H_BYTES) reports what was really copied. */
+#define RT_OPT_SPARSE_D2H 6
+/* RT_OPT_HOST_PRECLEARED (default 0): a promise that host_pixels is already all zero when rt_render is called — the reference's
+ * Tick() does `screen.Clear(0)` (RayTracer.cs:890) right before the pixel loop — so the library skips its own zero fill of the
+ * pixels it does not copy. */
+#define RT_OPT_HOST_PRECLEARED 7
+/* Options that change WHICH rank writes a pixel (RT_OPT_SHARED_TARGET, RT_OPT_PRIMARY_GATE) must be set identically on every rank
+ * of a partition. RT_OPT_COMPACTION may differ: a launch that takes part in a sparse gather always uses the default kernel. */
 int rt_set_option(rt_context* ctx, int option, int value);
+
+/* Counters / facts about the context. */
+#define RT_INFO_GATE_HOST_NS 1      /* host nanoseconds spent computing frame gates (csrc/rt_gate.cuh) so far */
+#define RT_INFO_GATE_COMPUTES 2     /* number of frame-gate evaluations so far (a camera that does not move is cached) */
+#define RT_INFO_LAST_D2H_BYTES 3    /* bytes the last rt_render / rt_render_batch with a host buffer copied device -> host */
+#define RT_INFO_SCENE_PATH 4        /* how the uploaded scene is traced: 0 tiny (constant bank), 1 staged (shared memory), 2 global, 3 LBVH */
+int rt_get_info(const rt_context* ctx, int what, uint64_t* value);
 
 /* ---- device-pointer / multi-process interface (torchrun: one process per GPU) --------------------------------- */
 
 /* Row-tile partition of this context inside a `world` of cooperating contexts (default rank 0 of 1). Tile t of
- * `tile_rows` rows belongs to rank t % world. */
+ * `tile_rows` rows belongs to rank t % world. rt_render / rt_render_batch of a partitioned context return ONLY this rank's tiles
+ * to host_pixels (the ranks of a job pass one shared page-locked frame and fill it together, each over its own PCIe link). */
 int rt_set_partition(rt_context* ctx, int rank, int world, int tile_rows);
 
 /* Renders this context's row tiles of one frame (or of n_frames frames, frame f at dev_pixels + f*w*h) into a
  * caller-provided DEVICE buffer, asynchronously on `cuda_stream` (a cudaStream_t, NULL = the legacy default stream).
+ * LBVH scenes keep one camera-inflated node copy per device: launches on different streams are ordered by the library (a refit
+ * waits for the previous LBVH launch), so they serialise on the device but never read a half-refitted tree.
  * dev_pixels may be a peer mapping of another GPU's framebuffer (CUDA IPC): the gather is then the kernel's own stores. */
 int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int width, int height, int max_depth, int spp,
                      uint32_t seed, void* dev_pixels, void* cuda_stream);
@@ -195,6 +222,33 @@ int rt_sync(rt_context* ctx);
  * the device->host copy of rt_render runs at full PCIe rate instead of through a staging buffer. Optional. */
 int rt_host_register(rt_context* ctx, void* host_ptr, uint64_t bytes);
 int rt_host_unregister(rt_context* ctx, void* host_ptr);
+
+/* ---- zero-copy display ---------------------------------------------------------------------------------
+ * Replaces the per-frame upload of Surface.pixels from HOST memory, template.cs:81 (`GL.TexImage2D(..., screen.pixels)`) and
+ * :188-193: the frame is rendered straight into a device buffer the display owns and never crosses PCIe.
+ *
+ * rt_render_mapped: `mapped_dev_pixels` is a DEVICE pointer to at least 4*width*height bytes on the context's first device — the
+ * pointer cudaGraphicsResourceGetMappedPointer returns for a mapped OpenGL pixel-unpack buffer (or any cudaMalloc'd buffer).
+ * Synchronous: when it returns the frame (0x00RRGGBB words, row-major, as Surface.pixels) is in the buffer and the host may unmap
+ * it and call glTexSubImage2D from the bound PBO. One device: the render kernel's 128-bit stores go straight into the buffer;
+ * several devices: the frame is gathered on device 0 (peer stores) and copied device-to-device. */
+int rt_render_mapped(rt_context* ctx, const rt_camera* cam, int width, int height, int max_depth, int spp, uint32_t seed,
+                     void* mapped_dev_pixels, uint64_t mapped_bytes, rt_stats* stats);
+/* Convenience wrappers so that the C# host needs no CUDA binding of its own. The calling thread must have the OpenGL context
+ * current (template.cs runs everything on the render thread). gl_buffer: a GL buffer object (PixelUnpackBuffer) of 4*w*h bytes.
+ *   rt_gl_register_buffer   cudaGraphicsGLRegisterBuffer(write-discard), once per buffer (re-register after a resize)
+ *   rt_render_gl            map -> rt_render_mapped -> unmap
+ *   rt_gl_unregister_buffer before the GL buffer is deleted (rt_destroy unregisters what is left)
+ * Without an OpenGL context rt_gl_register_buffer fails with RT_ERR_CUDA (nothing crashes). */
+int rt_gl_register_buffer(rt_context* ctx, unsigned int gl_buffer, void** out_resource);
+int rt_gl_unregister_buffer(rt_context* ctx, void* resource);
+int rt_render_gl(rt_context* ctx, const rt_camera* cam, int width, int height, int max_depth, int spp, uint32_t seed,
+                 void* resource, rt_stats* stats);
+
+/* Measured L2 -> SM read bandwidth in GB/s on the context's first device for a working set of `bytes` (1 MB .. 96 MB, L2-resident):
+ * every CTA of a full grid streams the set with 128-bit L1-bypassing loads; best of 3 launches. bench.py uses it as the peak of the
+ * LBVH kernels' roofline (their node / leaf fetches are L2 traffic). */
+int rt_measure_l2_read(rt_context* ctx, uint64_t bytes, double* gbs);
 
 /* Number of render-kernel launches issued by this context so far (bench.py reports it as gpu_launches). */
 uint64_t rt_launch_count(const rt_context* ctx);

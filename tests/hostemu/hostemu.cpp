@@ -64,7 +64,7 @@ static bool g_gate_on = false;
 static FrameGates g_gates;
 template <class SC, class DBG>
 static uint32_t px_of(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int d, int spp, uint32_t seed, HitRec* st, DBG& dbg) {
-    if constexpr (!DBG::enabled) {
+    if constexpr (!DBG::count_tests) {          // NoDbg (the shipped kernels) and ProdDbg (k_debug_tiny_prod): gated
         if (g_gate_on) {
             // as render_loop (rtb200.cu): gates per span of 4 consecutive pixels (linear index aligned to 4), only inside one row
             const int p = y * w + x, ps = p & ~3, ys = ps / w, xs = ps - ys * w;
@@ -72,7 +72,10 @@ static uint32_t px_of(const SC& sc, const CamRec& cam, int x, int y, int w, int 
             if (xs + 4 <= w && ps + 4 <= w * h) {
                 bool black = false;
                 bits = gate_bits_span(g_gates, xs, xs + 3, ys, sc.n_lights(), &black);
-                if (black) return 0u;
+                if (black) {                                  // render_loop's black-span branch: the reference's primary ray hits nothing
+                    if constexpr (DBG::enabled) dbg.ray(0u, 1u, 0xFFFFFFFFu, 0.0f);
+                    return 0u;
+                }
             }
             return trace_pixel<true>(sc, cam, x, y, w, h, d, 1, seed, st, dbg, 0.0f, 0.0f, bits);
         }
@@ -154,13 +157,15 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         shadow_grids_build(sg, lp, &g_sgh);
     }
     TinySceneData t; memset(&t, 0, sizeof(t));
-    if (use_tiny == 1 || use_tiny == 2 || use_tiny == 5) {
+    if (use_tiny == 1 || use_tiny == 2 || use_tiny == 5 || use_tiny == 11 || use_tiny == 12) {
         if (ns > TINY_MAX_SPHERES || np > TINY_MAX_PLANES || nl > TINY_MAX_LIGHTS) return -1;
         t.ns = ns; t.np = np; t.nl = nl; t.amb = g.amb;
         for (int i = 0; i < ns; i++) { t.sgeom[i] = sg[i]; t.smat[i] = sm[i]; }
         for (int i = 0; i < np; i++) t.planes[i] = pl[i];
         for (int i = 0; i < nl; i++) t.lights[i] = li[i];
     }
+    const bool prod_dbg = use_tiny >= 10;         // 11 / 12: TinyScene<-1> / <exact> with the events-only policy of k_debug_tiny_prod
+    if (prod_dbg) use_tiny -= 10;
     g_gate_on = (use_tiny == 1 || use_tiny == 2) && spp == 1;
     if (g_gate_on) g_gates = compute_frame_gates(cam, w, h, sg.data(), ns, pl.data(), np, li.data(), nl);
     uint64_t cnt[14] = {0};
@@ -173,7 +178,15 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++) {
                 size_t p = (size_t)y * w + x;
-                if (dbg_mode) {
+                if (dbg_mode && prod_dbg) {
+                    ProdDbg dbg;
+                    uint32_t c = dispatch(use_tiny, t, g, cam, x, y, w, h, max_depth, spp, seed, stack, dbg);
+                    pixels[p] = (int32_t)c;
+                    if (hash) hash[p] = dbg.hash;
+                    if (aov_id) aov_id[p] = dbg.aov_id;
+                    if (aov_t) aov_t[p] = dbg.aov_t;
+                    lc[0] += dbg.primary; lc[1] += dbg.n_shadow; lc[2] += dbg.secondary;
+                } else if (dbg_mode) {
                     FullDbg dbg;
                     uint32_t c = dispatch(use_tiny, t, g, cam, x, y, w, h, max_depth, spp, seed, stack, dbg);
                     pixels[p] = (int32_t)c;
@@ -220,6 +233,25 @@ extern "C" int emu_gates(const float* spheres, int ns, const float* planes, int 
             bits[(size_t)y * w + x] = (unsigned char)(b | (black ? 0x80u : 0u));
         }
     return 0;
+}
+
+// Row plan of the sparse device -> host return (plan_rows, rt_gate.cuh): kind[h] (0 copy, 1 rectangle columns only, 2 black), rx[2].
+extern "C" int emu_row_plan(const float* spheres, int ns, const float* planes, int np, const float* lights, int nl, const float* cam15,
+                            int w, int h, unsigned char* kind, int* rx) {
+    std::vector<f4> sg((size_t)ns); std::vector<PlaneRec> pl((size_t)np); std::vector<LightRec> li((size_t)nl);
+    for (int i = 0; i < ns; i++) { const float* f = spheres + 18 * (size_t)i; sg[i].x = f[0]; sg[i].y = f[1]; sg[i].z = f[2]; sg[i].w = f[17]; }
+    for (int i = 0; i < np; i++) pl[i] = make_plane(planes + 20 * (size_t)i);
+    for (int i = 0; i < nl; i++) li[i] = make_light(lights + 4 * (size_t)i);
+    CamRec cam;
+    cam.pos = mk3(cam15[0], cam15[1], cam15[2]); cam.right = mk3(cam15[3], cam15[4], cam15[5]);
+    cam.up = mk3(cam15[6], cam15[7], cam15[8]); cam.fwd = mk3(cam15[9], cam15[10], cam15[11]);
+    cam.view = mk3(cam15[12], cam15[13], cam15[14]);
+    const FrameGates g = compute_frame_gates(cam, w, h, sg.data(), ns, pl.data(), np, li.data(), nl);
+    RowPlan rp;
+    plan_rows(g, w, h, &rp);
+    for (int y = 0; y < h; y++) kind[y] = rp.kind[(size_t)y];
+    rx[0] = rp.rx0; rx[1] = rp.rx1;
+    return rp.sparse ? 1 : 0;
 }
 
 // The body of k_ray_log (rtb200.cu) on the host: LogDbg + the global-memory scene policy, one listed pixel after the other.

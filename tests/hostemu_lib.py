@@ -33,6 +33,8 @@ def load():
         _lib.emu_ray_log.restype = C.c_int
         _lib.emu_gates.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_int), fp, C.POINTER(C.c_ubyte)]
         _lib.emu_gates.restype = C.c_int
+        _lib.emu_row_plan.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_int)]
+        _lib.emu_row_plan.restype = C.c_int
     return _lib
 
 
@@ -116,3 +118,16 @@ def sky_mask(scene, cam, w, h):
     inner = np.float32(np.float64(by) * ys + np.float64(a))
     val = np.float32(np.float64(bx) * xs + np.float64(inner))
     return val > 0, g["sky"]
+
+
+ROW_COPY, ROW_RECT, ROW_BLACK = 0, 1, 2
+
+
+def row_plan(scene, cam, w, h):
+    """plan_rows (csrc/rt_gate.cuh) — what rt_render's sparse device->host return copies: (kind uint8[h], rx0, rx1, sparse)."""
+    lib = load()
+    cam = np.ascontiguousarray(cam, np.float32)
+    kind = np.zeros(h, np.uint8); rx = (C.c_int * 2)()
+    sparse = lib.emu_row_plan(_fp(scene.spheres), len(scene.spheres), _fp(scene.planes), len(scene.planes), _fp(scene.lights), len(scene.lights),
+                              _fp(cam), w, h, kind.ctypes.data_as(C.POINTER(C.c_ubyte)), rx)
+    return kind, int(rx[0]), int(rx[1]), bool(sparse)

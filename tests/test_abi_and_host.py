@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(built):
     assert sorted(declared) == sorted(rtb200.ABI_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rt_abi_version() == 1
+    assert lib.rt_abi_version() == 2
 
 
 @pytest.mark.skipif(HAS_GPU, reason="checks the no-device error path")

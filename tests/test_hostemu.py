@@ -92,3 +92,23 @@ def test_degenerate_scene(built, policy, camkw):
     assert np.array_equal(a["pixels"], O.render(sc, cam, w, h, 8, mode="faithful")["pixels"])
     b = E.render(sc, cam, w, h, 8, tiny=policy, debug=True)
     assert np.array_equal(a["pixels"], b["pixels"]) and np.array_equal(a["hash"], b["hash"])
+
+
+@pytest.mark.parametrize("tiny", [11, 12])
+@pytest.mark.parametrize("camkw,depth", [(dict(), 32), (dict(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15), 8),
+                                         (dict(pos=(0, 4.0, 6.0), pitch=1.2), 8), (dict(pos=(0.0, 0.5, 0.0), pitch=-0.6), 3)])
+def test_production_debug_policy(built, tiny, camkw, depth):
+    """ProdDbg (events only) on the GATED tiny-scene path — the logic of k_debug_tiny_prod: work a gate skips must be reported as the
+    event the reference produces there, so chain hashes, primary AOVs and ray counters still equal the oracle's."""
+    sc = scenes.default_scene()
+    w, h = 320, 180
+    cam = scenes.make_camera(width=w, height=h, **camkw)
+    a = O.render(sc, cam, w, h, depth, want_hash=True, want_aov=True)
+    b = E.render(sc, cam, w, h, depth, tiny=tiny, debug=True)
+    assert np.array_equal(a["pixels"], b["pixels"])
+    assert np.array_equal(a["hash"], b["hash"])
+    assert np.array_equal(a["aov_id"], b["aov_id"])
+    assert np.array_equal(a["aov_t"].view(np.uint32), b["aov_t"].view(np.uint32))
+    assert [a["counters"][k] for k in ("primary", "shadow", "secondary")] == b["counters"][:3]
+    g = E.gates(sc, cam, w, h)["bits"]
+    assert (g != 0).mean() > 0.2          # the gates really were active on this frame

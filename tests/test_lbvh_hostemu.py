@@ -151,3 +151,19 @@ def test_shadow_bins_in_the_fp_noise_regime(built):
         assert np.array_equal(a["hash"], b["hash"]), "%d hashes differ" % (a["hash"] != b["hash"]).sum()
         assert np.array_equal(a["pixels"], b["pixels"])
         assert a["counters"]["shadow"] > 10000
+
+
+@pytest.mark.parametrize("n", [56, 72, 200])
+def test_non_finite_spheres_do_not_break_the_shadow_bins(built, n):
+    """a NaN / Inf centre or radiusSquared used to index the per-light shadow bins out of bounds (floor(NaN) -> int).
+    Such spheres can never be hit (RayTracer.cs:622-635 sees a NaN or the wrong-signed infinity): they are left out of the bins and
+    the LBVH policy still equals the oracle."""
+    sc = scenes.small_random_scene(n, 5)
+    sph = sc.spheres.copy()
+    sph[3, 0] = np.nan; sph[7, 17] = np.inf; sph[11, 2] = -np.inf; sph[n - 1, 17] = np.nan; sph[20, 1] = np.inf
+    sc = scenes.Scene(sph, sc.planes, sc.lights, sc.ambient)
+    w, h = 120, 72
+    cam = scenes.make_camera(pos=(0, 1.5, -4.0), pitch=0.1, width=w, height=h)
+    a = O.render(sc, cam, w, h, 8, want_hash=True)
+    b = E.render(sc, cam, w, h, 8, tiny=3, debug=True)
+    assert np.array_equal(a["pixels"], b["pixels"]) and np.array_equal(a["hash"], b["hash"])

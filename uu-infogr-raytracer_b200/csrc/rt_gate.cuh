@@ -37,6 +37,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <vector>
 
 #include "rt_lbvh.cuh"
 
@@ -484,5 +485,37 @@ RT_HD uint32_t gate_bits_span(const FrameGates& g, int xa, int xb, int y, int nl
     return bits;
 }
 RT_HD uint32_t gate_bits(const FrameGates& g, int x, int y, bool* black) { return gate_bits_span(g, x, x, y, RT_GATE_LIGHTS, black); }
+
+// ---- sparse device -> host return (host side, used by render_frames in rtb200.cu) ------------------------------------------------
+// What the frame gates (rt_gate.cuh) prove black need not cross PCIe. Per frame the rows are classified on the host:
+//   ROW_COPY   the row is copied whole
+//   ROW_RECT   the whole row lies on the sky side of the plane's horizon and inside the sphere rectangle's row range: only columns
+//              rx0..rx1 (the rectangle, rounded out to 64-byte granules) can be non-black, the rest of the row is zero-filled
+//   ROW_BLACK  sky side and outside the rectangle's rows: every pixel is 0x00000000 (RayTracer.cs:993) — nothing is copied
+// and the zero fill of `Surface.pixels` is done by a small pool of library threads while the copies are in flight (FillPool).
+// Soundness: a pixel is skipped only if the gate predicate holds for that very pixel. The kernel evaluates the same predicate per
+// 4-pixel span; here it is evaluated per row at x = 0 and x = w-1 with the kernel's own two FMAs — fma(bx, x, base) is monotone in x
+// under rounding, so "positive at both ends" covers the row. 35 % of the bench frame never crosses PCIe.
+enum : uint8_t { ROW_COPY = 0, ROW_RECT = 1, ROW_BLACK = 2 };
+struct RowPlan {
+    std::vector<uint8_t> kind; int rx0 = 0, rx1 = -1; bool sparse = false;
+};
+inline void plan_rows(const FrameGates& g, int w, int h, RowPlan* rp) {
+    rp->kind.assign((size_t)h, (uint8_t)ROW_COPY); rp->sparse = false;
+    const bool rect_empty = g.spheres.x1 < g.spheres.x0 || g.spheres.y1 < g.spheres.y0 || g.spheres.x0 >= w || g.spheres.x1 < 0;
+    const int rx0 = rect_empty ? 0 : ((g.spheres.x0 < 0 ? 0 : g.spheres.x0) & ~15);
+    int rx1 = rect_empty ? -1 : (g.spheres.x1 | 15); if (rx1 > w - 1) rx1 = w - 1;
+    const bool rect_wide = !rect_empty && (long long)(rx1 - rx0 + 1) * 10 > (long long)w * 9;    // not worth a strided copy
+    rp->rx0 = rx0; rp->rx1 = rx1;
+    const float fx1 = (float)(w - 1);
+    for (int y = 0; y < h; y++) {
+        const float base = rt_fmaf(g.sky.by, (float)y, g.sky.a);                                  // span_positive(), rt_gate.cuh
+        if (!(rt_fmaf(g.sky.bx, 0.0f, base) > 0.0f && rt_fmaf(g.sky.bx, fx1, base) > 0.0f)) continue;
+        uint8_t k = ROW_BLACK;
+        if (!(rect_empty || y < g.spheres.y0 || y > g.spheres.y1)) k = rect_wide ? ROW_COPY : ROW_RECT;
+        rp->kind[(size_t)y] = k;
+        if (k != ROW_COPY) rp->sparse = true;
+    }
+}
 
 }  // namespace rtb

@@ -288,7 +288,7 @@ RT_HD bool bvh_shadow_any(const BvhView& bv, f3 hit, f3 lp, float a2, float a4, 
             float t;
             if (sphere_hit(sub3(hit, mk3(g.x, g.y, g.z)), lp, g.w, a2, a4, 0.001f, &t, dbg)) occluded = true;
         }
-        if (occluded && !DBG::enabled) return true;      // boolean OR: the first hit decides
+        if (occluded && !DBG::count_tests) return true;      // boolean OR: the first hit decides
         if (next >= 0) { node = next; continue; }
         if (sp == 0) break;
         node = stack[--sp];

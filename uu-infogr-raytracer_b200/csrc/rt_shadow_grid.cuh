@@ -75,7 +75,7 @@ RT_HD bool shadow_grid_any(const ShadowGridsView& sg, int li, f3 hit, f3 lp, flo
             float t;
             if (bs[h] < 0 && Ds[h] >= 0 && sphere_root(bs[h], Ds[h], a2, 0.001f, &t)) occluded = true;   // :622-635 (:578)
         }
-        if (occluded && !DBG::enabled) break;       // boolean OR
+        if (occluded && !DBG::count_tests) break;      // boolean OR
     }
     return occluded;
 }
@@ -89,12 +89,21 @@ inline void shadow_grids_build(const std::vector<f4>& sg, const std::vector<f3>&
     out->grids.clear(); out->cell_start.clear(); out->items.clear();
     const int n = (int)sg.size(), nl = (int)lights.size();
     if (n < 2 || nl == 0) return;
-    double lo[3] = {sg[0].x, sg[0].y, sg[0].z}, hi[3] = {sg[0].x, sg[0].y, sg[0].z}, r2max = 0.0;
-    for (const f4& g : sg) {
+    // A sphere with a non-finite centre or radiusSquared can never pass the reference's test (every comparison of :622-635 sees a NaN
+    // or the wrong-signed infinity), so it is simply left out of the bins; it must not reach the cell arithmetic below, where
+    // floor(NaN) -> int would index out of bounds.
+    std::vector<char> ok((size_t)n, 0);
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, r2max = 0.0; int n_ok = 0;
+    for (int i = 0; i < n; i++) {
+        const f4& g = sg[(size_t)i];
+        if (!(std::isfinite(g.x) && std::isfinite(g.y) && std::isfinite(g.z) && std::isfinite(g.w))) continue;
+        ok[(size_t)i] = 1;
         const double c[3] = {g.x, g.y, g.z};
-        for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], c[k]); hi[k] = std::fmax(hi[k], c[k]); }
+        for (int k = 0; k < 3; k++) { lo[k] = n_ok ? std::fmin(lo[k], c[k]) : c[k]; hi[k] = n_ok ? std::fmax(hi[k], c[k]) : c[k]; }
         if (g.w > r2max) r2max = g.w;
+        n_ok++;
     }
+    if (n_ok == 0) return;
     const double rmax = std::sqrt(r2max);
     double ext = 0.0; for (int k = 0; k < 3; k++) ext = std::fmax(ext, hi[k] - lo[k]);
     const double margin = 0.25 * ext + 4.0 * rmax + 1.0;
@@ -102,6 +111,8 @@ inline void shadow_grids_build(const std::vector<f4>& sg, const std::vector<f3>&
     out->lo = mk3((float)lo[0], (float)lo[1], (float)lo[2]); out->hi = mk3((float)hi[0], (float)hi[1], (float)hi[2]);
     // largest |oc| between a query point in the (float-rounded) box and a sphere centre inside it
     const double Dg = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2])) * 1.001;
+    if (!std::isfinite(Dg) || !std::isfinite(out->lo.x) || !std::isfinite(out->lo.y) || !std::isfinite(out->lo.z) ||
+        !std::isfinite(out->hi.x) || !std::isfinite(out->hi.y) || !std::isfinite(out->hi.z)) return;       // float overflow of the box: no grids
     const double K2 = (double)BVH_PAD_K * (double)BVH_PAD_K;
     out->grids.resize((size_t)nl);
     for (int li = 0; li < nl; li++) {
@@ -125,6 +136,7 @@ inline void shadow_grids_build(const std::vector<f4>& sg, const std::vector<f3>&
         std::vector<double> cs((size_t)n), ct((size_t)n), R((size_t)n);
         double smin = 1e300, smax = -1e300, tmin = 1e300, tmax = -1e300;
         for (int i = 0; i < n; i++) {
+            if (!ok[(size_t)i]) { cs[(size_t)i] = ct[(size_t)i] = R[(size_t)i] = 0.0; continue; }
             const double c[3] = {sg[(size_t)i].x, sg[(size_t)i].y, sg[(size_t)i].z};
             cs[(size_t)i] = c[0] * g.eu.x + c[1] * g.eu.y + c[2] * g.eu.z;
             ct[(size_t)i] = c[0] * g.ev.x + c[1] * g.ev.y + c[2] * g.ev.z;
@@ -138,6 +150,7 @@ inline void shadow_grids_build(const std::vector<f4>& sg, const std::vector<f3>&
         // scans (tests per query ~ density * (cell + 2R)^2) at the price of more (cell, sphere) entries
         double cells = getenv("RTB200_SG_CELLS_PER_SPHERE") ? atof(getenv("RTB200_SG_CELLS_PER_SPHERE")) : 4.0;
         int dim = (int)std::ceil(std::sqrt((double)n * cells)); if (dim < 1) dim = 1; if (dim > 2048) dim = 2048;
+        if (!(std::isfinite(smin) && std::isfinite(smax) && std::isfinite(tmin) && std::isfinite(tmax))) continue;   // no grid: LBVH traversal
         double cell = std::fmax(smax - smin, tmax - tmin) / dim; if (!(cell > 1e-9)) cell = 1e-9;
         cell *= 1.0001;
         const double slack = 2e-3 * cell;                    // fp32 rounding of (s - s0) * inv_cell near a cell border
@@ -151,9 +164,12 @@ inline void shadow_grids_build(const std::vector<f4>& sg, const std::vector<f3>&
         std::vector<int> count((size_t)ncell + 1, 0);
         auto range = [&](double c, double r, double o, int dimk, int* i0, int* i1) {
             double a0 = std::floor((c - r - slack - o) * ic), a1 = std::floor((c + r + slack - o) * ic);
-            *i0 = a0 < 0 ? 0 : (int)a0; *i1 = a1 >= dimk ? dimk - 1 : (int)a1;
+            if (!(a0 >= 0)) a0 = 0;                           // also catches NaN
+            if (!(a1 <= dimk - 1)) a1 = dimk - 1;
+            *i0 = (int)a0; *i1 = (int)a1;                     // an empty range (i0 > i1) inserts nothing
         };
         for (int i = 0; i < n; i++) {
+            if (!ok[(size_t)i]) continue;
             int x0, x1, y0, y1; range(cs[(size_t)i], R[(size_t)i], s0, g.dim_s, &x0, &x1); range(ct[(size_t)i], R[(size_t)i], t0, g.dim_t, &y0, &y1);
             for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) count[(size_t)(y * g.dim_s + x) + 1]++;
         }
@@ -165,6 +181,7 @@ inline void shadow_grids_build(const std::vector<f4>& sg, const std::vector<f3>&
         out->items.resize((size_t)item_base + (size_t)pstart[(size_t)ncell], never);
         std::vector<int> fill((size_t)ncell, 0);
         for (int i = 0; i < n; i++) {
+            if (!ok[(size_t)i]) continue;
             int x0, x1, y0, y1; range(cs[(size_t)i], R[(size_t)i], s0, g.dim_s, &x0, &x1); range(ct[(size_t)i], R[(size_t)i], t0, g.dim_t, &y0, &y1);
             for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) {
                 const int c = y * g.dim_s + x, slot = fill[(size_t)c]++;

@@ -54,6 +54,7 @@ struct HitRec { f3 o; f3 dir; float d; int prim; };   // prim >= 0: sphere index
 // ---------------------------------------------------------------------------------------------------------
 struct NoDbg {
     static constexpr bool enabled = false;
+    static constexpr bool count_tests = false;   // true: per-sphere test counters wanted -> the scalar (unpacked) sphere loops
     RT_HD void sphere_test(bool) {}
     RT_HD void plane_test() {}
     RT_HD void ray(uint32_t, uint32_t, uint32_t, float) {}
@@ -68,6 +69,7 @@ struct NoDbg {
 };
 struct FullDbg {
     static constexpr bool enabled = true;
+    static constexpr bool count_tests = true;
     uint32_t hash = 0;
     uint32_t primary = 0, n_shadow = 0, secondary = 0, sphere_tests = 0, sphere_disc_pos = 0, plane_tests = 0;
     uint32_t shade_diffuse = 0, shade_specular = 0, shade_mirror = 0, shaded_hits = 0;
@@ -87,6 +89,32 @@ struct FullDbg {
     RT_HD void primary_aov(int id, float t) { if (!aov_set) { aov_id = id; aov_t = t; aov_set = true; } }
     RT_HD void node_visit(int kind) { node_visits[kind]++; }
     RT_HD void fallback() { fallbacks++; }
+    template <class SC> RT_HD void ray_geom(const SC&, uint32_t, uint32_t, uint32_t, f3, f3, float) {}
+    template <class SC> RT_HD void shadow_geom(const SC&, uint32_t, uint32_t, f3, f3, float, float, bool) {}
+};
+
+// Events only (chain hash, ray counters, primary AOV) — no per-test counters, so the code it instruments is the PRODUCTION code:
+// packed-fp32 sphere pairs, exact-count unrolled loops, frame gates, fast pixel division. The shipped kernel instantiated with this
+// policy (k_debug_tiny_prod, rt_set_option(RT_OPT_DEBUG_SHIPPED)) certifies hit ids / t bits / shadow results of the gated path
+// against the oracle's chain hash; work a gate skips is reported as the event the reference would have produced (a reflection
+// ray that hits nothing, an unoccluded shadow ray, a primary ray that hits nothing).
+struct ProdDbg {
+    static constexpr bool enabled = true;
+    static constexpr bool count_tests = false;
+    uint32_t hash = 0, primary = 0, n_shadow = 0, secondary = 0;
+    int aov_id = -1; float aov_t = 0.0f; bool aov_set = false;
+    RT_HD void sphere_test(bool) {}
+    RT_HD void plane_test() {}
+    RT_HD void ray(uint32_t level, uint32_t kind, uint32_t code, float d) {
+        hash += event_hash(level, kind, code, f2bits(d));
+        if (kind == 1) primary++; else secondary++;
+    }
+    RT_HD void shadow(uint32_t level, uint32_t li, bool occluded) { hash += event_hash(level, 3, li, occluded ? 1u : 0u); n_shadow++; }
+    RT_HD void shaded(bool) {}
+    RT_HD void spec() {}
+    RT_HD void primary_aov(int id, float t) { if (!aov_set) { aov_id = id; aov_t = t; aov_set = true; } }
+    RT_HD void node_visit(int) {}
+    RT_HD void fallback() {}
     template <class SC> RT_HD void ray_geom(const SC&, uint32_t, uint32_t, uint32_t, f3, f3, float) {}
     template <class SC> RT_HD void shadow_geom(const SC&, uint32_t, uint32_t, f3, f3, float, float, bool) {}
 };
@@ -141,6 +169,7 @@ static_assert(sizeof(RayRec) == 64, "RayRec layout");
 
 struct LogDbg {
     static constexpr bool enabled = true;
+    static constexpr bool count_tests = true;
     RayRec* out = nullptr; uint32_t cap = 0, n = 0, pixel = 0;
     RT_HD void sphere_test(bool) {}
     RT_HD void plane_test() {}
@@ -213,7 +242,7 @@ RT_HD void brute_nearest(const SC& sc, f3 o, f3 dir, float a2, float a4, float o
         // fminf drops a NaN, b == 0 passes): it only decides whether the exact per-sphere tests below run at all.
         float bs[NS + 1], Ds[NS + 1]; float gate = -1.0f;
 #if defined(RT_HAVE_F32X2)
-        if constexpr (SC::has_pairs && NS >= 2 && !DBG::enabled) {
+        if constexpr (SC::has_pairs && NS >= 2 && !DBG::count_tests) {
             const float2 ox = make_float2(o.x, o.x), oy = make_float2(o.y, o.y), oz = make_float2(o.z, o.z);
             const float2 dx = make_float2(dir.x, dir.x), dy = make_float2(dir.y, dir.y), dz = make_float2(dir.z, dir.z);
             const float2 na4 = make_float2(-a4, -a4);
@@ -270,7 +299,7 @@ RT_HD bool brute_shadow_any(const SC& sc, f3 hit, f3 lp, float a2, float a4, DBG
     if constexpr (NS > 0) {
         float bs[NS + 1], Ds[NS + 1]; float gate = -1.0f;
 #if defined(RT_HAVE_F32X2)
-        if constexpr (SC::has_pairs && NS >= 2 && !DBG::enabled) {
+        if constexpr (SC::has_pairs && NS >= 2 && !DBG::count_tests) {
             const float2 ox = make_float2(hit.x, hit.x), oy = make_float2(hit.y, hit.y), oz = make_float2(hit.z, hit.z);
             const float2 dx = make_float2(lp.x, lp.x), dy = make_float2(lp.y, lp.y), dz = make_float2(lp.z, lp.z);
             const float2 na4 = make_float2(-a4, -a4);
@@ -432,6 +461,7 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
                        uint32_t gates = 0u) {
     f3 C = mk3(0, 0, 0);
     const int np = sc.n_planes();      // compile-time constant in the exact-count kernels
+    bool proven_no_sphere = false;     // debug policies only, see the mirror gate below
     for (;;) {
         if (top == defer_at) return false;
         float a = dot3(dir, dir);                                                          // :617
@@ -440,7 +470,7 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
         // gates (rt_gate.cuh, bits RT_GATE_*): what the host PROVED about this pixel. Bit 0: its primary ray cannot be reported
         // as hitting any sphere.
         int sel_s = -1; float d_s = RT_INF;
-        if (!((gates & RT_GATE_SPHERES) && bounce == 0))
+        if (!(((gates & RT_GATE_SPHERES) && bounce == 0) || (DBG::enabled && proven_no_sphere)))
             sc.nearest(o, dir, a2, a4, bounce == 0 ? 0.0f : 0.01f, &sel_s, &d_s, dbg);     // :975-981 / :792-808
         int sel_p = -1; float d_p = RT_INF;
 #pragma unroll
@@ -473,7 +503,14 @@ RT_HD bool trace_chain(const SC& sc, int cap, f3& o, f3& dir, int& bounce, int& 
         uint32_t flags = pick_s ? sc.sphere_flags(sel_s) : sc.plane_flags(sel_p);
         if (!(flags & MAT_MIRROR)) break;                                                  // :850 / :739
         // Bit 1: if the primary ray hit the (single) plane, its reflection ray hits nothing — the mirror term is (0,0,0), C as is.
-        if ((gates & RT_GATE_MIRROR) && bounce == 0 && !pick_s) break;
+        if ((gates & RT_GATE_MIRROR) && bounce == 0 && !pick_s) {
+            if (!DBG::enabled) break;
+            // Debug policies report the ray the reference traces here. The gate proves it meets no sphere and can hit its own plane
+            // only inside the 0.01 cut-off (:731) — which of the two decides the event, so the ray is followed against
+            // the planes alone; it ends the chain at the `none` / `d - 0.01f <= 0` exits above (anything else would be an unsound
+            // gate and shows up as a pixel that differs from the shipped kernel's).
+            proven_no_sphere = true;
+        }
         bounce++;                                                                          // :851 / :740
         f3 hit = add3(o, mulf3(dir, d));                                                   // :846 / :736
         f3 N;

@@ -11,8 +11,12 @@
 // them with one 128-bit store; the store address may be a peer (NVLink) mapping of rank 0's framebuffer — the gather is
 // fused into the render kernel.
 #include <cuda_runtime.h>
+// cuda_gl_interop.h needs <GL/gl.h>, which a headless build image does not have; the one entry point used is declared here
+// (GLuint is `unsigned int`; the symbol lives in the CUDA runtime).
+extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource** resource, unsigned int buffer, unsigned int flags);
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <thread>
@@ -75,11 +79,15 @@ struct DebugOut {
 // One CTA per work item: blockIdx = (chunk inside the tile, this rank's tile, frame) — no index divisions, and the hardware
 // block scheduler balances sky / floor / mirror chunks (measured 8 % faster than a one-wave persistent grid-stride loop,
 // profiles/r01/tuning.md). gridDim.y is folded when a launch has more than 65535 tiles.
-template <int PPT, bool SPP1 = false, class SC>
-__device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp) {
+// DBG = NoDbg: the shipped kernels. DBG = ProdDbg (k_debug_tiny_prod): the SAME loop, gates and trace instantiation, additionally
+// writing the per-pixel chain hash / primary AOV / ray counters of frame 0 to `dout` — the certificate that the gated, packed,
+// exact-count production path takes the reference's hits (tests/test_gpu_parity.py::test_shipped_kernel_chain_hashes).
+template <int PPT, bool SPP1 = false, class DBG = NoDbg, class SC>
+__device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp, const DebugOut* dout = nullptr) {
     constexpr int CHUNK = BLOCK * PPT;          // pixels per CTA work item
     HitRec stack[STACK_RECS];
-    NoDbg dbg;
+    NoDbg nodbg;
+    unsigned long long n_primary = 0, n_shadow = 0, n_secondary = 0;     // DBG::enabled only
     const int npix = fp.w * fp.h;
     const int tile_pix = fp.tile_rows * fp.w;
     const int frame = blockIdx.z;
@@ -101,6 +109,14 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
             bool black = false;
             bits = gate_bits_span(gates, x, x + PPT - 1, y, sc.n_lights(), &black);
             if (black) {                                       // nothing can be hit anywhere in the span: 0x00000000 (:993) untraced
+                if constexpr (DBG::enabled) {                  // what the reference's primary ray does there: one ray, no hit
+                    for (int q = 0; q < PPT; q++) {
+                        if (dout->hash) dout->hash[p0 + q] = event_hash(0u, 1u, 0xFFFFFFFFu, 0u);
+                        if (dout->aov_id) dout->aov_id[p0 + q] = -1;
+                        if (dout->aov_t) dout->aov_t[p0 + q] = 0.0f;
+                    }
+                    n_primary += PPT;
+                }
                 if (fp.skip_black_store) continue;             // ... and rank 0 writes those zeros itself (k_fill_black): nothing crosses NVLink
                 if (PPT == 4 && ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0)) *reinterpret_cast<uint4*>(out + p0) = make_uint4(0u, 0u, 0u, 0u);
                 else for (int q = 0; q < PPT; q++) out[p0 + q] = 0u;
@@ -110,8 +126,18 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
 #pragma unroll 1
         for (int q = 0; q < PPT; q++) {
             uint32_t c = 0u;
-            if (p0 + q < end)
-                c = trace_pixel<SPP1, SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg, fp.rcp_w, fp.rcp_h, bits);
+            if (p0 + q < end) {
+                if constexpr (DBG::enabled) {
+                    DBG dbg;
+                    c = trace_pixel<SPP1, SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg, fp.rcp_w, fp.rcp_h, bits);
+                    if (dout->hash) dout->hash[p0 + q] = dbg.hash;
+                    if (dout->aov_id) dout->aov_id[p0 + q] = dbg.aov_id;
+                    if (dout->aov_t) dout->aov_t[p0 + q] = dbg.aov_t;
+                    n_primary += dbg.primary; n_shadow += dbg.n_shadow; n_secondary += dbg.secondary;
+                } else {
+                    c = trace_pixel<SPP1, SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, nodbg, fp.rcp_w, fp.rcp_h, bits);
+                }
+            }
             if (++x == fp.w) { x = 0; ++y; }
 #pragma unroll
             for (int z = 0; z + 1 < PPT; z++) px[z] = px[z + 1];   // shift register: after PPT iterations px[] is in pixel order
@@ -121,6 +147,13 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp)
             *reinterpret_cast<uint4*>(out + p0) = make_uint4(px[0], px[PPT > 1 ? 1 : 0], px[PPT > 2 ? 2 : 0], px[PPT > 3 ? 3 : 0]);   // 128-bit coalesced store
         } else {
             for (int q = 0; q < PPT; q++) if (p0 + q < end) out[p0 + q] = px[q];
+        }
+    }
+    if constexpr (DBG::enabled) {
+        if (dout->counters) {
+            if (n_primary) atomicAdd(dout->counters + 0, n_primary);
+            if (n_shadow) atomicAdd(dout->counters + 1, n_shadow);
+            if (n_secondary) atomicAdd(dout->counters + 2, n_secondary);
         }
     }
 }
@@ -332,6 +365,24 @@ __device__ __forceinline__ void debug_loop(const SC& sc, const FrameParams& fp, 
 __global__ void __launch_bounds__(BLOCK) k_debug_tiny(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
     debug_loop(TinyScene<-1, -1, -1>(scd), fp, dout);
 }
+// The shipped tiny-scene kernel with the events-only debug policy: same template arguments, same gates, same grid as k_render_tiny.
+template <int NS, int NL, int NP>
+__global__ void __launch_bounds__(BLOCK) k_debug_tiny_prod(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
+    render_loop<PPT_TINY, true, ProdDbg>(TinyScene<NS, NL, NP>(scd), fp, &dout);
+}
+using TinyDebugKernel = void (*)(const TinySceneData, const FrameParams, DebugOut);
+// exact-count instantiations for a few scene shapes incl. the reference's (3 spheres, 2 lights, 1 plane); every other shape takes the
+// run-time-count instantiation (which is also what production uses for scenes outside its exact table)
+TinyDebugKernel tiny_debug_prod_kernel(int ns, int nl, int np) {
+    if (np == 1) {
+        if (ns == 3 && nl == 2) return k_debug_tiny_prod<3, 2, 1>;
+        if (ns == 0 && nl == 0) return k_debug_tiny_prod<0, 0, 1>;
+        if (ns == 1 && nl == 1) return k_debug_tiny_prod<1, 1, 1>;
+        if (ns == 2 && nl == 2) return k_debug_tiny_prod<2, 2, 1>;
+        if (ns == 4 && nl == 4) return k_debug_tiny_prod<4, 4, 1>;
+    }
+    return k_debug_tiny_prod<-1, -1, -1>;
+}
 __global__ void __launch_bounds__(BLOCK) k_debug_global(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
     debug_loop(GlobalScene(scd), fp, dout);
 }
@@ -395,6 +446,24 @@ __global__ void __launch_bounds__(256) k_selftest_pixel_div(int max_side, unsign
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// L2 read-bandwidth probe (rt_measure_l2_read): every CTA streams the whole working set (sized to stay L2-resident) with 128-bit
+// L1-bypassing loads, starting at a different offset so that the CTAs do not move in lock step; the xor keeps the loads alive.
+__global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ buf, size_t n_vec, int passes, unsigned int* sink) {
+    unsigned int acc = 0;
+    const size_t start = ((size_t)blockIdx.x * 7919u * 256u) % n_vec;
+    for (int p = 0; p < passes; p++) {
+        size_t i = start + threadIdx.x;
+#pragma unroll 4
+        for (size_t k = 0; k < n_vec / 256; k++) {
+            if (i >= n_vec) i -= n_vec;
+            const uint4 v = __ldcg(buf + i);
+            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+            i += 256;
+        }
+    }
+    if (acc == 0x12345u) *sink = acc;          // never true for the zero-filled buffer; defeats dead-code elimination
+}
+
 // Ray-log kernel (rt_ray_log): one thread per listed pixel, `slots` records reserved per pixel, count[i] = records produced.
 static_assert(sizeof(RayRec) == sizeof(rt_ray_record), "RayRec must mirror rt_ray_record");
 __global__ void __launch_bounds__(BLOCK) k_ray_log(const __grid_constant__ GlobalSceneData scd, const __grid_constant__ FrameParams fp,
@@ -424,6 +493,9 @@ struct DeviceState {
     ShadowGrid* sg_grids = nullptr; int* sg_cells = nullptr; GridPair* sg_items = nullptr;      // per-light shadow bins (rt_shadow_grid.cuh)
     float bvh_cam[3] = {0, 0, 0}; bool bvh_cam_valid = false;    // camera the nodes_cam copy is currently inflated for ...
     cudaStream_t bvh_cam_stream = nullptr;                        // ... by a refit issued on this stream
+    // nodes_cam / the refit arrival counters are ONE buffer per device: a refit issued on another stream than the last LBVH launch
+    // first waits for that launch (rt_render_device on several user streams, rt_update_spheres while user-stream frames are in flight)
+    cudaEvent_t bvh_done = nullptr; cudaStream_t bvh_last_stream = nullptr; bool bvh_done_valid = false;
     // framebuffer ring (device 0 of the context only, unless partitioned multi-process)
     uint32_t* fb = nullptr; size_t fb_pixels = 0;
     // band pipelining (render_frames): copy stream on device 0, per-segment "band rendered" events on every device
@@ -470,6 +542,57 @@ struct DeviceWorkers {
     }
 };
 
+// Host-side zero fill of the parts of `Surface.pixels` that are not copied (sparse D2H, render_frames): a few library threads
+// memset the segments while the copies of the rest are in flight. Threads are started on first use (RTB200_FILL_THREADS, default 4,
+// at most hardware_concurrency - 1; 0 = the calling thread does it all in wait()).
+struct FillPool {
+    struct Seg { char* p; size_t bytes; };
+    std::vector<std::thread> th;
+    std::mutex m; std::condition_variable cv, cv_done;
+    std::vector<Seg> segs; std::atomic<size_t> next{0};
+    uint64_t gen = 0; int active = 0; bool quit = false, started = false;
+    void drain() { for (;;) { const size_t i = next.fetch_add(1); if (i >= segs.size()) break; memset(segs[i].p, 0, segs[i].bytes); } }
+    void start() {
+        started = true;
+        int n = 4;
+        if (const char* e = getenv("RTB200_FILL_THREADS")) n = atoi(e);
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && n > hw - 1) n = hw - 1;
+        if (n < 0) n = 0;
+        for (int i = 0; i < n; i++)
+            th.emplace_back([this]() {
+                uint64_t seen = 0;
+                std::unique_lock<std::mutex> lk(m);
+                for (;;) {
+                    cv.wait(lk, [&] { return quit || gen != seen; });
+                    if (quit) return;
+                    seen = gen;
+                    lk.unlock();
+                    drain();
+                    lk.lock();
+                    if (--active == 0) cv_done.notify_all();
+                }
+            });
+    }
+    void run(std::vector<Seg>&& v) {             // asynchronous; pair with wait()
+        if (!started) start();
+        std::lock_guard<std::mutex> lk(m);
+        segs = std::move(v); next = 0; active = (int)th.size(); gen++;
+        cv.notify_all();
+    }
+    void wait() {                                // the caller helps, then waits for the workers' last segments
+        drain();
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return active == 0; });
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(m); quit = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+        th.clear();
+    }
+};
+
 struct rt_context {
     std::vector<DeviceState> devs;
     std::string err;
@@ -494,6 +617,13 @@ struct rt_context {
     std::mutex gate_mutex; bool gate_valid = false; CamRec gate_cam; int gate_w = 0, gate_h = 0; FrameGates gate_last;
     bool peer_ok = false;
     std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> gate_host_ns{0}, gate_computes{0};   // host time of compute_frame_gates, number of evaluations (rt_get_info)
+    bool debug_shipped = false;     // RT_OPT_DEBUG_SHIPPED
+    bool sparse_d2h = true;         // RT_OPT_SPARSE_D2H
+    bool host_precleared = false;   // RT_OPT_HOST_PRECLEARED
+    FillPool fill_pool;
+    uint64_t last_d2h_bytes = 0;    // bytes the last host-returning render really copied device -> host (rt_get_info)
+    std::vector<void*> gl_resources;   // cudaGraphicsResource* registered through rt_gl_register_buffer
 };
 
 namespace {
@@ -620,6 +750,25 @@ LbvhSceneData lbvh_data(const rt_context* ctx, const DeviceState& d, bool with_c
     return l;
 }
 
+// Per-frame gates of a tiny-scene launch (rt_gate.cuh): computed on the host for each distinct camera; a camera that does not move
+// (and batches of equal cameras) reuse the last result. Host time spent here is accumulated in ctx->gate_host_ns (rt_get_info).
+FrameGates gates_for(rt_context* ctx, const CamRec& cam, int w, int h) {
+    const TinySceneData& t = ctx->tiny_data;
+    std::lock_guard<std::mutex> lock(ctx->gate_mutex);
+    if (!(ctx->gate_valid && ctx->gate_w == w && ctx->gate_h == h && memcmp(&ctx->gate_cam, &cam, sizeof(CamRec)) == 0)) {
+        const auto t0 = std::chrono::steady_clock::now();
+        ctx->gate_last = compute_frame_gates(cam, w, h, t.sgeom, t.ns, t.planes, t.np, t.lights, t.nl);
+        ctx->gate_host_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        ctx->gate_computes++;
+        ctx->gate_cam = cam; ctx->gate_w = w; ctx->gate_h = h; ctx->gate_valid = true;
+    }
+    return ctx->gate_last;
+}
+void fill_gates(rt_context* ctx, FrameParams& gp) {
+    for (int f = 0; f < gp.n_frames; f++)
+        gp.gates[f] = (!ctx->primary_gate || gp.spp != 1) ? gates_off(gp.w, gp.h) : gates_for(ctx, gp.cam_inline[f], gp.w, gp.h);
+}
+
 // Launches the render kernel for one device's share. Asynchronous on `stream`.
 int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaStream_t stream) {
     if (ctx->path == PATH_LBVH && fp.n_frames > 1) {
@@ -639,6 +788,7 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
     if (ctx->path == PATH_LBVH) {
         const CamRec& c = fp.cam_inline[0];
         if (!(d.bvh_cam_valid && d.bvh_cam_stream == stream && d.bvh_cam[0] == c.pos.x && d.bvh_cam[1] == c.pos.y && d.bvh_cam[2] == c.pos.z)) {
+            if (d.bvh_done_valid && d.bvh_last_stream != stream) CU_TRY(ctx, cudaStreamWaitEvent(stream, d.bvh_done, 0));
             cudaError_t e = d.bvh.refit_for_camera(c.pos.x, c.pos.y, c.pos.z, stream);
             if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh refit: ") + cudaGetErrorString(e));
             d.bvh_cam[0] = c.pos.x; d.bvh_cam[1] = c.pos.y; d.bvh_cam[2] = c.pos.z; d.bvh_cam_valid = true; d.bvh_cam_stream = stream;
@@ -651,17 +801,11 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
         case PATH_TINY: {
             const TinySceneData& t = ctx->tiny_data;
             const bool fastdiv_ok = fp.w <= RT_FASTDIV_MAX && fp.h <= RT_FASTDIV_MAX;
-            FrameParams gp = fp;                      // + per-frame primary-ray sphere gate (a few hundred host flops per frame)
-            for (int f = 0; f < fp.n_frames; f++) {
-                if (!ctx->primary_gate || fp.spp != 1) { gp.gates[f] = gates_off(fp.w, fp.h); continue; }
-                std::lock_guard<std::mutex> lock(ctx->gate_mutex);
-                if (!(ctx->gate_valid && ctx->gate_w == fp.w && ctx->gate_h == fp.h && memcmp(&ctx->gate_cam, &fp.cam_inline[f], sizeof(CamRec)) == 0)) {
-                    ctx->gate_last = compute_frame_gates(fp.cam_inline[f], fp.w, fp.h, t.sgeom, t.ns, t.planes, t.np, t.lights, t.nl);
-                    ctx->gate_cam = fp.cam_inline[f]; ctx->gate_w = fp.w; ctx->gate_h = fp.h; ctx->gate_valid = true;
-                }
-                gp.gates[f] = ctx->gate_last;
-            }
-            const bool compact = ctx->compaction && fp.spp == 1 && fastdiv_ok;
+            FrameParams gp = fp;                      // + per-frame gates (a few microseconds of host work per distinct camera)
+            fill_gates(ctx, gp);
+            // the compacting variant knows no black spans: a launch that takes part in a sparse gather uses the default kernel on
+            // EVERY rank, so that a rank with RT_OPT_COMPACTION set differently cannot leave spans nobody writes
+            const bool compact = ctx->compaction && fp.spp == 1 && fastdiv_ok && !fp.skip_black_store;
             TinyKernel kern = compact ? tiny_kernel_compact(t.ns, t.nl, t.np) : tiny_kernel(t.ns, t.nl, t.np, fp.spp, fastdiv_ok);
             // Sparse gather: all ranks store into ONE framebuffer owned by rank 0 (fp.skip_black_store = the caller's promise).
             // Only with the gated single-sample kernels, which are the ones that know black spans.
@@ -685,6 +829,10 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
     }
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
+    if (ctx->path == PATH_LBVH) {
+        CU_TRY(ctx, cudaEventRecord(d.bvh_done, stream));
+        d.bvh_done_valid = true; d.bvh_last_stream = stream;
+    }
     return RT_OK;
 }
 
@@ -724,6 +872,7 @@ int rt_create(rt_context** out, const int* device_ids, int n_devices) {
             (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreate(&d.evc0)) != cudaSuccess || (e = cudaEventCreate(&d.evc1)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.bvh_done, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreate(&d.ev0)) != cudaSuccess || (e = cudaEventCreate(&d.ev1)) != cudaSuccess) {
             std::string m = std::string("device init: ") + cudaGetErrorString(e);
             delete ctx; return fail(nullptr, RT_ERR_CUDA, m);
@@ -750,6 +899,8 @@ int rt_create(rt_context** out, const int* device_ids, int n_devices) {
 int rt_destroy(rt_context* ctx) {
     if (!ctx) return RT_ERR_INVALID;
     ctx->workers.stop();
+    ctx->fill_pool.stop();
+    for (void* r : ctx->gl_resources) cudaGraphicsUnregisterResource((cudaGraphicsResource_t)r);
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.dev);
         cudaStreamSynchronize(d.stream);
@@ -759,6 +910,7 @@ int rt_destroy(rt_context* ctx) {
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.evc0) cudaEventDestroy(d.evc0);
         if (d.evc1) cudaEventDestroy(d.evc1);
+        if (d.bvh_done) cudaEventDestroy(d.bvh_done);
         for (cudaEvent_t ev : d.band_events) cudaEventDestroy(ev);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -859,7 +1011,7 @@ int rt_update_spheres(rt_context* ctx, const float* spheres, int first, int coun
     if (!ctx) return RT_ERR_INVALID;
     if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_set_scene has not been called");
     const int ns = ctx->gdata_host.ns;
-    if (count < 0 || first < 0 || first + count > ns || (count > 0 && !spheres)) return fail(ctx, RT_ERR_INVALID, "sphere range out of bounds");
+    if (count < 0 || first < 0 || first > ns || count > ns - first || (count > 0 && !spheres)) return fail(ctx, RT_ERR_INVALID, "sphere range out of bounds");
     if (count == 0) return RT_OK;
     std::vector<f4> sg((size_t)count); std::vector<MatRec> sm((size_t)count);
     float r2max = 0.0f;
@@ -876,6 +1028,7 @@ int rt_update_spheres(rt_context* ctx, const float* spheres, int first, int coun
     for (int i = 0; i < count; i++) ctx->host_sgeom[(size_t)(first + i)] = sg[(size_t)i];
     for (auto& d : ctx->devs) {
         CU_TRY(ctx, cudaSetDevice(d.dev));
+        if (d.bvh_done_valid && d.bvh_last_stream != d.stream) CU_TRY(ctx, cudaStreamWaitEvent(d.stream, d.bvh_done, 0));
         CU_TRY(ctx, cudaMemcpyAsync(d.sgeom + first, sg.data(), sizeof(f4) * (size_t)count, cudaMemcpyHostToDevice, d.stream));
         CU_TRY(ctx, cudaMemcpyAsync(d.smat + first, sm.data(), sizeof(MatRec) * (size_t)count, cudaMemcpyHostToDevice, d.stream));
         if (ctx->has_bvh) {
@@ -899,6 +1052,9 @@ int rt_set_option(rt_context* ctx, int option, int value) {
         case RT_OPT_HOST_VIA_GPU0: ctx->host_via_gpu0 = value != 0; return RT_OK;
         case RT_OPT_PRIMARY_GATE: ctx->primary_gate = value != 0; return RT_OK;
         case RT_OPT_SHARED_TARGET: ctx->shared_target = value < 0 ? 0 : (value > 2 ? 2 : value); return RT_OK;
+        case RT_OPT_DEBUG_SHIPPED: ctx->debug_shipped = value != 0; return RT_OK;
+        case RT_OPT_SPARSE_D2H: ctx->sparse_d2h = value != 0; return RT_OK;
+        case RT_OPT_HOST_PRECLEARED: ctx->host_precleared = value != 0; return RT_OK;
         default: return fail(ctx, RT_ERR_INVALID, "unknown option");
     }
 }
@@ -940,7 +1096,10 @@ int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int w
 //    Bands are multiples of `world` tiles so that every device owns the same share of each band.
 //    With several devices the frame is NOT gathered on device 0 first: each device renders into a local framebuffer and sends
 //    its own tiles to the host over ITS OWN PCIe link (one strided 2-D copy per band), so host bandwidth scales with the device
-//    count. rt_set_option(RT_OPT_HOST_VIA_GPU0, 1) restores gather-on-GPU-0-then-copy.
+//    count. rt_set_option(RT_OPT_HOST_VIA_GPU0, 1) restores gather-on-GPU-0-then-copy. A single-device context that is one rank of
+//    a partition (rt_set_partition, one process per GPU) returns ITS OWN tiles only — the ranks of a torchrun job all pass the same
+//    shared, page-locked host frame and fill it together, each over its own PCIe link.
+//    Pixels the frame gates prove black are not copied at all (RT_OPT_SPARSE_D2H, see plan_rows above).
 static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, int w, int h, int depth, int spp, uint32_t seed,
                          int32_t* host_pixels, rt_stats* stats) {
     int rc = check_frame_args(ctx, cams, w, h, depth, spp);
@@ -949,16 +1108,18 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
     const size_t npix = (size_t)w * h;
     const int G = (int)ctx->devs.size();
     const bool direct = host_pixels != nullptr && G > 1 && !ctx->host_via_gpu0;     // per-device D2H of own tiles
+    const bool tiles_mode = direct || (host_pixels != nullptr && G == 1 && ctx->world > 1);   // copies go tile by tile (strided)
     rc = ensure_fb(ctx, npix * (size_t)n_frames); if (rc) return rc;
     if (direct) for (int g = 1; g < G; g++) { rc = ensure_fb(ctx, npix * (size_t)n_frames, g); if (rc) return rc; }
     DeviceState& d0 = ctx->devs[0];
     const int world = G > 1 ? G : ctx->world;
-    const int tiles_total = (h + ctx->tile_rows - 1) / ctx->tile_rows;
+    const int tile_rows = ctx->tile_rows;
+    const int tiles_total = (h + tile_rows - 1) / tile_rows;
     // ---- band layout ----
     int n_bands = 1;
     if (host_pixels) {
         const char* be = getenv("RTB200_BANDS");
-        const size_t link_bytes = npix * 4 / (size_t)(direct ? G : 1);               // bytes one PCIe link carries per frame
+        const size_t link_bytes = npix * 4 / (size_t)(tiles_mode ? world : 1);        // bytes one PCIe link carries per frame
         n_bands = be ? atoi(be) : (int)((link_bytes + (4u << 20) - 1) / (4u << 20));  // ~4 MB per band and link
         if (n_bands > 16) n_bands = 16;
         if (n_bands < 1) n_bands = 1;
@@ -980,9 +1141,113 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             }
         }
     }
-    const long long tile_pix = (long long)ctx->tile_rows * w;
+    const long long tile_pix = (long long)tile_rows * w;
+    // ---- what need not be copied (per frame), and the host-side zero fill that replaces it ----
+    std::vector<RowPlan> plans;
+    std::atomic<uint64_t> d2h_bytes{0};
+    bool fill_started = false;
+    if (pipelined && ctx->sparse_d2h && ctx->path == PATH_TINY && ctx->primary_gate && spp == 1 &&
+        w <= RT_FASTDIV_MAX && h <= RT_FASTDIV_MAX && !ctx->compaction) {
+        plans.resize((size_t)n_frames);
+        bool any = false;
+        for (int f = 0; f < n_frames; f++) {
+            plan_rows(gates_for(ctx, to_cam(cams[f]), w, h), w, h, &plans[(size_t)f]);
+            any = any || plans[(size_t)f].sparse;
+        }
+        if (!any) plans.clear();
+    }
+    // tile kind in tiles mode: black only if every row of the tile is
+    auto tile_black = [&](const RowPlan& rp, long long tile) -> bool {
+        const long long ya = tile * tile_rows; long long yb = ya + tile_rows; if (yb > h) yb = h;
+        for (long long y = ya; y < yb; y++) if (rp.kind[(size_t)y] != ROW_BLACK) return false;
+        return true;
+    };
+    if (!plans.empty() && !ctx->host_precleared) {
+        std::vector<FillPool::Seg> segs;
+        auto add = [&](int32_t* p, size_t npx) {
+            const size_t piece = (size_t)1 << 18;                                       // 1 MB pieces: load balance across the pool
+            for (size_t o = 0; o < npx; o += piece) segs.push_back({(char*)(p + o), (npx - o < piece ? npx - o : piece) * 4});
+        };
+        for (int f = 0; f < n_frames; f++) {
+            const RowPlan& rp = plans[(size_t)f];
+            if (!rp.sparse) continue;
+            int32_t* dst = host_pixels + (size_t)f * npix;
+            if (tiles_mode) {
+                for (long long t = 0; t < tiles_total; t++) {
+                    if (G == 1 && (int)(t % world) != ctx->rank) continue;               // partitioned: own tiles only
+                    if (!tile_black(rp, t)) continue;
+                    const long long p0 = t * tile_pix; long long p1 = p0 + tile_pix; if (p1 > (long long)npix) p1 = (long long)npix;
+                    add(dst + p0, (size_t)(p1 - p0));
+                }
+            } else {
+                for (int y = 0; y < h;) {
+                    const uint8_t k = rp.kind[(size_t)y];
+                    int y2 = y + 1;
+                    while (y2 < h && rp.kind[(size_t)y2] == k) y2++;
+                    if (k == ROW_BLACK) add(dst + (size_t)y * w, (size_t)(y2 - y) * w);
+                    else if (k == ROW_RECT)
+                        for (int yy = y; yy < y2; yy++) {
+                            if (rp.rx0 > 0) segs.push_back({(char*)(dst + (size_t)yy * w), (size_t)rp.rx0 * 4});
+                            if (rp.rx1 < w - 1) segs.push_back({(char*)(dst + (size_t)yy * w + rp.rx1 + 1), (size_t)(w - 1 - rp.rx1) * 4});
+                        }
+                    y = y2;
+                }
+            }
+        }
+        if (!segs.empty()) { ctx->fill_pool.run(std::move(segs)); fill_started = true; }
+    }
+    struct FillGuard { FillPool* p; ~FillGuard() { if (p) p->wait(); } } fill_guard{fill_started ? &ctx->fill_pool : nullptr};   // every return path
     std::vector<char> first_copy_dev((size_t)G, 1);
-    // Everything device g has to enqueue for segment s (its launch, its band event, and in `direct` mode its own D2H copies).
+    // Device g's D2H copies for rows/tiles of one band of one frame, on its copy stream (which already waits for the band's event).
+    auto copy_tiles = [&](DeviceState& d, int rank, int frame, int k_begin, int k_count) -> int {
+        // tiles k*world + rank for k in [k_begin, k_begin + k_count): blocks of tile_pix pixels every world*tile_pix pixels -> one
+        // strided 2-D copy per run of tiles that need copying (+ a 1-D copy if the frame's last tile is short)
+        const RowPlan* rp = plans.empty() ? nullptr : &plans[(size_t)frame];
+        uint32_t* src = d.fb + (size_t)frame * npix; int32_t* dst = host_pixels + (size_t)frame * npix;
+        for (int k = k_begin; k < k_begin + k_count;) {
+            const long long t = (long long)k * world + rank;
+            if (rp && rp->sparse && tile_black(*rp, t)) { k++; continue; }
+            int k2 = k + 1;
+            while (k2 < k_begin + k_count && !(rp && rp->sparse && tile_black(*rp, (long long)k2 * world + rank))) k2++;
+            const long long first_px = t * tile_pix;
+            const long long last_tile = (long long)(k2 - 1) * world + rank;
+            const bool last_short = (last_tile + 1) * tile_pix > (long long)npix;
+            const int full = (k2 - k) - (last_short ? 1 : 0);
+            if (full > 0) {
+                CU_TRY(ctx, cudaMemcpy2DAsync(dst + first_px, (size_t)world * tile_pix * 4, src + first_px, (size_t)world * tile_pix * 4,
+                                              (size_t)tile_pix * 4, (size_t)full, cudaMemcpyDeviceToHost, d.copy_stream));
+                d2h_bytes += (uint64_t)full * (uint64_t)tile_pix * 4;
+            }
+            if (last_short) {
+                const long long p0 = last_tile * tile_pix;
+                CU_TRY(ctx, cudaMemcpyAsync(dst + p0, src + p0, (size_t)((long long)npix - p0) * 4, cudaMemcpyDeviceToHost, d.copy_stream));
+                d2h_bytes += (uint64_t)((long long)npix - p0) * 4;
+            }
+            k = k2;
+        }
+        return RT_OK;
+    };
+    auto copy_rows = [&](DeviceState& d, int frame, int ya, int yb) -> int {       // contiguous rows [ya, yb) of a complete frame on d
+        const RowPlan* rp = plans.empty() ? nullptr : &plans[(size_t)frame];
+        uint32_t* src = d.fb + (size_t)frame * npix; int32_t* dst = host_pixels + (size_t)frame * npix;
+        for (int y = ya; y < yb;) {
+            const uint8_t k = (rp && rp->sparse) ? rp->kind[(size_t)y] : (uint8_t)ROW_COPY;
+            int y2 = y + 1;
+            while (y2 < yb && ((rp && rp->sparse) ? rp->kind[(size_t)y2] : (uint8_t)ROW_COPY) == k) y2++;
+            if (k == ROW_COPY) {
+                CU_TRY(ctx, cudaMemcpyAsync(dst + (size_t)y * w, src + (size_t)y * w, (size_t)(y2 - y) * w * 4, cudaMemcpyDeviceToHost, d.copy_stream));
+                d2h_bytes += (uint64_t)(y2 - y) * (uint64_t)w * 4;
+            } else if (k == ROW_RECT) {
+                const size_t wb = (size_t)(rp->rx1 - rp->rx0 + 1) * 4;
+                CU_TRY(ctx, cudaMemcpy2DAsync(dst + (size_t)y * w + rp->rx0, (size_t)w * 4, src + (size_t)y * w + rp->rx0, (size_t)w * 4, wb,
+                                              (size_t)(y2 - y), cudaMemcpyDeviceToHost, d.copy_stream));
+                d2h_bytes += (uint64_t)(y2 - y) * wb;
+            }
+            y = y2;
+        }
+        return RT_OK;
+    };
+    // Everything device g has to enqueue for segment s (its launch, its band event, and in tiles mode its own D2H copies).
     auto enqueue = [&](int g, int s) -> int {
         DeviceState& d = ctx->devs[(size_t)g];
         const int frame = pipelined ? s / n_bands : s * INLINE_CAMS, band = pipelined ? s % n_bands : 0;
@@ -1001,23 +1266,10 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         }
         int rc2 = launch_render(ctx, d, fp, d.stream); if (rc2) return rc2;
         if (pipelined) CU_TRY(ctx, cudaEventRecord(d.band_events[(size_t)s], d.stream));
-        if (direct && fp.tiles_mine > 0) {
-            // this device's tiles of the band: tile k*world + g for k in [k_begin, k_begin + tiles_mine), i.e. blocks of
-            // tile_pix pixels every world*tile_pix pixels -> one strided 2-D copy (+ a 1-D copy if the frame's last tile is short)
+        if (tiles_mode && fp.tiles_mine > 0) {
             CU_TRY(ctx, cudaStreamWaitEvent(d.copy_stream, d.band_events[(size_t)s], 0));
             if (first_copy_dev[(size_t)g]) { CU_TRY(ctx, cudaEventRecord(d.evc0, d.copy_stream)); first_copy_dev[(size_t)g] = 0; }
-            const long long first_px = ((long long)fp.k_begin * world + g) * tile_pix;
-            const long long last_tile = ((long long)(fp.k_begin + fp.tiles_mine - 1)) * world + g;
-            const bool last_short = (last_tile + 1) * tile_pix > (long long)npix;
-            const int full = fp.tiles_mine - (last_short ? 1 : 0);
-            uint32_t* src = d.fb + (size_t)frame * npix; int32_t* dst = host_pixels + (size_t)frame * npix;
-            if (full > 0)
-                CU_TRY(ctx, cudaMemcpy2DAsync(dst + first_px, (size_t)world * tile_pix * 4, src + first_px, (size_t)world * tile_pix * 4,
-                                              (size_t)tile_pix * 4, (size_t)full, cudaMemcpyDeviceToHost, d.copy_stream));
-            if (last_short) {
-                const long long p0 = last_tile * tile_pix;
-                CU_TRY(ctx, cudaMemcpyAsync(dst + p0, src + p0, (size_t)((long long)npix - p0) * 4, cudaMemcpyDeviceToHost, d.copy_stream));
-            }
+            rc2 = copy_tiles(d, rank, frame, fp.k_begin, fp.tiles_mine); if (rc2) return rc2;
         }
         return RT_OK;
     };
@@ -1041,22 +1293,19 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             CU_TRY(ctx, cudaSetDevice(d.dev));
             CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
         }
-        bool first_copy = true;
         for (int s = 0; s < n_segments; s++) {
             const int frame = pipelined ? s / n_bands : s * INLINE_CAMS, band = pipelined ? s % n_bands : 0;
             for (int g = 0; g < G; g++) {
                 CU_TRY(ctx, cudaSetDevice(ctx->devs[(size_t)g].dev));
                 rc = enqueue(g, s); if (rc) return rc;
             }
-            if (pipelined && !direct) {       // gather-on-GPU-0 path: device 0's copy stream waits for every device's band
-                CU_TRY(ctx, cudaSetDevice(d0.dev));
+            if (pipelined && !tiles_mode) {   // the frame is complete on device 0 (one device, or gather-on-GPU-0): its copy stream
+                CU_TRY(ctx, cudaSetDevice(d0.dev));                                        // waits for every device's band
                 for (int g = 0; g < G; g++) CU_TRY(ctx, cudaStreamWaitEvent(d0.copy_stream, ctx->devs[(size_t)g].band_events[(size_t)s], 0));
-                if (first_copy) { CU_TRY(ctx, cudaEventRecord(d0.evc0, d0.copy_stream)); first_copy = false; }
-                long long p0 = (long long)band * band_tiles * tile_pix, p1 = p0 + (long long)band_tiles * tile_pix;
-                if (p1 > (long long)npix) p1 = (long long)npix;
-                if (p1 > p0)
-                    CU_TRY(ctx, cudaMemcpyAsync(host_pixels + (size_t)frame * npix + p0, d0.fb + (size_t)frame * npix + p0,
-                                                (size_t)(p1 - p0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, d0.copy_stream));
+                if (first_copy_dev[0]) { CU_TRY(ctx, cudaEventRecord(d0.evc0, d0.copy_stream)); first_copy_dev[0] = 0; }
+                const long long ya = (long long)band * band_tiles * tile_rows; long long yb = ya + (long long)band_tiles * tile_rows;
+                if (yb > h) yb = h;
+                if (yb > ya) { rc = copy_rows(d0, frame, (int)ya, (int)yb); if (rc) return rc; }
             }
         }
         for (int g = 0; g < G; g++) {
@@ -1074,16 +1323,10 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         CU_TRY(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
         if (ms > kernel_ms) kernel_ms = ms;
     }
-    if (pipelined && !direct) {
-        CU_TRY(ctx, cudaSetDevice(d0.dev));
-        CU_TRY(ctx, cudaEventRecord(d0.evc1, d0.copy_stream));
-        CU_TRY(ctx, cudaStreamSynchronize(d0.copy_stream));
-        CU_TRY(ctx, cudaEventElapsedTime(&d2h_ms, d0.evc0, d0.evc1));
-    }
-    if (direct) {
+    if (pipelined) {
         for (int g = 0; g < G; g++) {
             DeviceState& d = ctx->devs[(size_t)g];
-            if (first_copy_dev[(size_t)g]) continue;             // this device owned no tile
+            if (first_copy_dev[(size_t)g]) continue;             // this device issued no copy
             CU_TRY(ctx, cudaSetDevice(d.dev));
             CU_TRY(ctx, cudaEventRecord(d.evc1, d.copy_stream));
             CU_TRY(ctx, cudaStreamSynchronize(d.copy_stream));
@@ -1092,6 +1335,7 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             if (ms > d2h_ms) d2h_ms = ms;
         }
     }
+    if (pipelined) ctx->last_d2h_bytes = d2h_bytes.load();
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->kernel_ms = kernel_ms; stats->gather_ms = 0.0f; stats->d2h_ms = d2h_ms;   // d2h overlaps the kernel when banded
@@ -1132,10 +1376,25 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int w, int h, int dep
     if (grid > maxgrid) grid = maxgrid;
     CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
     switch (ctx->path) {
-        case PATH_TINY: k_debug_tiny<<<(unsigned)grid, BLOCK, 0, d.stream>>>(ctx->tiny_data, fp, dout); break;
+        case PATH_TINY: {
+            const bool fastdiv_ok = w <= RT_FASTDIV_MAX && h <= RT_FASTDIV_MAX;
+            if (ctx->debug_shipped && spp == 1 && fastdiv_ok) {
+                // the PRODUCTION instantiation (exact counts, packed fp32, fast division, frame gates) with the events-only policy,
+                // on the production grid
+                FrameParams gp = fp;
+                fill_gates(ctx, gp);
+                const TinySceneData& t = ctx->tiny_data;
+                const dim3 pgrid((unsigned)gp.chunks_per_tile, (unsigned)(gp.tiles_mine < 65535 ? gp.tiles_mine : 65535), 1u);
+                tiny_debug_prod_kernel(t.ns, t.nl, t.np)<<<pgrid, BLOCK, 0, d.stream>>>(t, gp, dout);
+            } else {
+                k_debug_tiny<<<(unsigned)grid, BLOCK, 0, d.stream>>>(ctx->tiny_data, fp, dout);
+            }
+            break;
+        }
         case PATH_STAGED: k_debug_staged<<<(unsigned)grid, BLOCK, sizeof(f4) * (size_t)ctx->gdata_host.ns, d.stream>>>(global_data(ctx, d), fp, dout); break;
         case PATH_GLOBAL: k_debug_global<<<(unsigned)grid, BLOCK, 0, d.stream>>>(global_data(ctx, d), fp, dout); break;
         default: {
+            if (d.bvh_done_valid && d.bvh_last_stream != d.stream) CU_TRY(ctx, cudaStreamWaitEvent(d.stream, d.bvh_done, 0));
             cudaError_t e = d.bvh.refit_for_camera(fp.cam_inline[0].pos.x, fp.cam_inline[0].pos.y, fp.cam_inline[0].pos.z, d.stream);
             if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh refit: ") + cudaGetErrorString(e));
             d.bvh_cam_valid = false;
@@ -1334,5 +1593,137 @@ int rt_host_unregister(rt_context* ctx, void* host_ptr) {
     return RT_OK;
 }
 uint64_t rt_launch_count(const rt_context* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+// Measured L2 -> SM read bandwidth (GB/s) for a working set of `bytes` (rounded down to 4 KB; 1 MB .. 96 MB): the denominator of the
+// LBVH kernels' roofline (node and leaf fetches are L2-resident: SURVEY §8(d)). Best of 3 timed launches after a warm-up pass.
+int rt_measure_l2_read(rt_context* ctx, uint64_t bytes, double* gbs) {
+    if (!ctx || !gbs) return RT_ERR_INVALID;
+    if (bytes < (1u << 20) || bytes > (96u << 20)) return fail(ctx, RT_ERR_INVALID, "working set must be 1 MB .. 96 MB");
+    DeviceState& d = ctx->devs[0];
+    CU_TRY(ctx, cudaSetDevice(d.dev));
+    const size_t n_vec = (size_t)(bytes / 4096) * 256;          // uint4 elements, a multiple of 256
+    DevMem<uint4> buf; DevMem<unsigned int> sink;
+    CU_TRY(ctx, buf.alloc(n_vec));
+    CU_TRY(ctx, sink.alloc(1));
+    CU_TRY(ctx, cudaMemsetAsync(buf.p, 0, n_vec * sizeof(uint4), d.stream));
+    const int grid = d.sm_count * 4, passes = 2;
+    k_l2_read<<<grid, 256, 0, d.stream>>>(buf.p, n_vec, 1, sink.p);                       // warm-up: pulls the set into L2
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
+        k_l2_read<<<grid, 256, 0, d.stream>>>(buf.p, n_vec, passes, sink.p);
+        CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
+        CU_TRY(ctx, cudaStreamSynchronize(d.stream));
+        CU_TRY(ctx, cudaGetLastError());
+        float ms = 0.0f; CU_TRY(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        if (ms < best) best = ms;
+        ctx->launches++;
+    }
+    *gbs = (double)grid * passes * (double)n_vec * 16.0 / ((double)best * 1e-3) / 1e9;
+    return RT_OK;
+}
+
+int rt_get_info(const rt_context* ctx, int what, uint64_t* value) {
+    if (!ctx || !value) return RT_ERR_INVALID;
+    switch (what) {
+        case RT_INFO_GATE_HOST_NS: *value = ctx->gate_host_ns.load(); return RT_OK;
+        case RT_INFO_GATE_COMPUTES: *value = ctx->gate_computes.load(); return RT_OK;
+        case RT_INFO_LAST_D2H_BYTES: *value = ctx->last_d2h_bytes; return RT_OK;
+        case RT_INFO_SCENE_PATH: *value = (uint64_t)ctx->path; return RT_OK;
+        default: return RT_ERR_INVALID;
+    }
+}
+
+// ---- zero-copy display ---------------------------------------------------------------------------------------
+// The frame is rendered straight into a device buffer the DISPLAY owns (a CUDA-mapped OpenGL pixel-unpack buffer) and never
+// crosses PCIe: replaces the upload of Surface.pixels from host memory (template.cs:81, :188-193).
+int rt_render_mapped(rt_context* ctx, const rt_camera* cam, int w, int h, int depth, int spp, uint32_t seed, void* mapped_dev_pixels,
+                     uint64_t mapped_bytes, rt_stats* stats) {
+    int rc = check_frame_args(ctx, cam, w, h, depth, spp);
+    if (rc) return rc;
+    if (!mapped_dev_pixels) return fail(ctx, RT_ERR_INVALID, "mapped_dev_pixels is NULL");
+    const uint64_t need = (uint64_t)w * (uint64_t)h * 4u;
+    if (mapped_bytes < need) return fail(ctx, RT_ERR_INVALID, "mapped buffer smaller than 4*width*height bytes");
+    if ((reinterpret_cast<uintptr_t>(mapped_dev_pixels) & 3u) != 0) return fail(ctx, RT_ERR_INVALID, "mapped buffer not 4-byte aligned");
+    DeviceState& d0 = ctx->devs[0];
+    CU_TRY(ctx, cudaSetDevice(d0.dev));
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, mapped_dev_pixels);
+    if (e != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return fail(ctx, RT_ERR_INVALID, "mapped_dev_pixels is not a device pointer");
+    }
+    if (attr.type == cudaMemoryTypeDevice && attr.device != d0.dev)
+        return fail(ctx, RT_ERR_INVALID, "the mapped buffer must live on the context's first device");
+    if (ctx->devs.size() == 1) {
+        // one device: the render kernel's 128-bit stores go straight into the mapped buffer
+        FrameParams fp = make_params(ctx, w, h, depth, spp, seed, 1, ctx->rank, ctx->world, (uint32_t*)mapped_dev_pixels, (long long)w * h);
+        fp.cam_inline[0] = to_cam(*cam);
+        CU_TRY(ctx, cudaEventRecord(d0.ev0, d0.stream));
+        rc = launch_render(ctx, d0, fp, d0.stream); if (rc) return rc;
+        CU_TRY(ctx, cudaEventRecord(d0.ev1, d0.stream));
+        CU_TRY(ctx, cudaStreamSynchronize(d0.stream));
+        float ms = 0.0f; CU_TRY(ctx, cudaEventElapsedTime(&ms, d0.ev0, d0.ev1));
+        if (stats) { memset(stats, 0, sizeof(*stats)); stats->kernel_ms = ms; }
+        return RT_OK;
+    }
+    // several devices: gather on device 0 as always (peer stores into the context's framebuffer; graphics-interop memory is not
+    // guaranteed to be peer-mappable), then one device-to-device copy into the mapped buffer
+    rt_stats st;
+    rc = render_frames(ctx, cam, 1, w, h, depth, spp, seed, nullptr, &st); if (rc) return rc;
+    CU_TRY(ctx, cudaSetDevice(d0.dev));
+    CU_TRY(ctx, cudaEventRecord(d0.ev0, d0.stream));
+    CU_TRY(ctx, cudaMemcpyAsync(mapped_dev_pixels, d0.fb, (size_t)need, cudaMemcpyDeviceToDevice, d0.stream));
+    CU_TRY(ctx, cudaEventRecord(d0.ev1, d0.stream));
+    CU_TRY(ctx, cudaStreamSynchronize(d0.stream));
+    float ms = 0.0f; CU_TRY(ctx, cudaEventElapsedTime(&ms, d0.ev0, d0.ev1));
+    if (stats) { *stats = st; stats->gather_ms += ms; }
+    return RT_OK;
+}
+
+int rt_gl_register_buffer(rt_context* ctx, unsigned int gl_buffer, void** out_resource) {
+    if (!ctx || !out_resource) return RT_ERR_INVALID;
+    *out_resource = nullptr;
+    CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    cudaGraphicsResource_t res = nullptr;
+    cudaError_t e = cudaGraphicsGLRegisterBuffer(&res, gl_buffer, cudaGraphicsRegisterFlagsWriteDiscard);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, RT_ERR_CUDA, std::string("cudaGraphicsGLRegisterBuffer: ") + cudaGetErrorString(e) +
+                                          " (needs a current OpenGL context on the calling thread)");
+    }
+    ctx->gl_resources.push_back((void*)res);
+    *out_resource = (void*)res;
+    return RT_OK;
+}
+int rt_gl_unregister_buffer(rt_context* ctx, void* resource) {
+    if (!ctx || !resource) return RT_ERR_INVALID;
+    for (size_t i = 0; i < ctx->gl_resources.size(); i++)
+        if (ctx->gl_resources[i] == resource) {
+            ctx->gl_resources.erase(ctx->gl_resources.begin() + (long)i);
+            CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+            CU_TRY(ctx, cudaGraphicsUnregisterResource((cudaGraphicsResource_t)resource));
+            return RT_OK;
+        }
+    return fail(ctx, RT_ERR_INVALID, "unknown graphics resource");
+}
+int rt_render_gl(rt_context* ctx, const rt_camera* cam, int w, int h, int depth, int spp, uint32_t seed, void* resource, rt_stats* stats) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!resource) return fail(ctx, RT_ERR_INVALID, "resource is NULL");
+    bool known = false;
+    for (void* r : ctx->gl_resources) known = known || r == resource;
+    if (!known) return fail(ctx, RT_ERR_INVALID, "unknown graphics resource");
+    DeviceState& d0 = ctx->devs[0];
+    CU_TRY(ctx, cudaSetDevice(d0.dev));
+    cudaGraphicsResource_t res = (cudaGraphicsResource_t)resource;
+    CU_TRY(ctx, cudaGraphicsMapResources(1, &res, d0.stream));
+    void* ptr = nullptr; size_t bytes = 0;
+    cudaError_t e = cudaGraphicsResourceGetMappedPointer(&ptr, &bytes, res);
+    int rc = e == cudaSuccess ? rt_render_mapped(ctx, cam, w, h, depth, spp, seed, ptr, (uint64_t)bytes, stats)
+                              : fail(ctx, RT_ERR_CUDA, std::string("cudaGraphicsResourceGetMappedPointer: ") + cudaGetErrorString(e));
+    cudaError_t e2 = cudaGraphicsUnmapResources(1, &res, d0.stream);      // always unmap: GL may not touch a mapped buffer
+    if (rc == RT_OK && e2 != cudaSuccess) rc = fail(ctx, RT_ERR_CUDA, std::string("cudaGraphicsUnmapResources: ") + cudaGetErrorString(e2));
+    return rc;
+}
 
 }  // extern "C"

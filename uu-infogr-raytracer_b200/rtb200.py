@@ -25,13 +25,18 @@ RT_OPT_COMPACTION = 1
 RT_OPT_HOST_VIA_GPU0 = 2
 RT_OPT_PRIMARY_GATE = 3
 RT_OPT_SHARED_TARGET = 4
+RT_OPT_DEBUG_SHIPPED = 5
+RT_OPT_SPARSE_D2H = 6
+RT_OPT_HOST_PRECLEARED = 7
+RT_INFO_GATE_HOST_NS, RT_INFO_GATE_COMPUTES, RT_INFO_LAST_D2H_BYTES, RT_INFO_SCENE_PATH = 1, 2, 3, 4
 COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_pos", "plane_tests",
                  "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"]
 
 # every symbol include/rtb200.h declares
 ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_update_spheres", "rt_render", "rt_render_batch", "rt_render_debug", "rt_query_spheres", "rt_ray_log", "rt_selftest",
                "rt_set_option", "rt_set_partition", "rt_render_device", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_dev_alloc",
-               "rt_dev_free", "rt_dev_to_host", "rt_dev_memset", "rt_sync", "rt_host_register", "rt_host_unregister", "rt_launch_count", "rt_destroy", "rt_last_error", "rt_abi_version"]
+               "rt_dev_free", "rt_dev_to_host", "rt_dev_memset", "rt_sync", "rt_host_register", "rt_host_unregister", "rt_launch_count", "rt_destroy", "rt_last_error", "rt_abi_version",
+               "rt_get_info", "rt_measure_l2_read", "rt_render_mapped", "rt_gl_register_buffer", "rt_gl_unregister_buffer", "rt_render_gl"]
 
 
 class RtCamera(C.Structure):
@@ -97,6 +102,12 @@ def load_library():
     lib.rt_host_register.argtypes = [vp, vp, C.c_uint64]
     lib.rt_host_unregister.argtypes = [vp, vp]
     lib.rt_launch_count.argtypes = [vp]
+    lib.rt_get_info.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
+    lib.rt_measure_l2_read.argtypes = [vp, C.c_uint64, C.POINTER(C.c_double)]
+    lib.rt_render_mapped.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, vp, C.c_uint64, statp]
+    lib.rt_gl_register_buffer.argtypes = [vp, C.c_uint, C.POINTER(vp)]
+    lib.rt_gl_unregister_buffer.argtypes = [vp, vp]
+    lib.rt_render_gl.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, vp, statp]
     lib.rt_launch_count.restype = C.c_uint64
     lib.rt_destroy.argtypes = [vp]
     lib.rt_last_error.argtypes = [vp]
@@ -190,16 +201,24 @@ class Context:
                                              None if headless else px.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)))
         return px, st
 
-    def render_debug(self, cam15, w, h, max_depth=32, spp=1, seed=0):
+    def render_debug(self, cam15, w, h, max_depth=32, spp=1, seed=0, arrays=True):
+        """Instrumented render. arrays=False: pixels and counters only (no per-pixel hash / AOV arrays)."""
         cam = to_rt_camera(cam15)
         st = RtStats()
         n = w * h
-        px = np.empty(n, np.int32); hsh = np.empty(n, np.uint32); aid = np.empty(n, np.int32); at = np.empty(n, np.float32)
+        px = np.empty(n, np.int32)
+        hsh = np.empty(n if arrays else 0, np.uint32); aid = np.empty(n if arrays else 0, np.int32); at = np.empty(n if arrays else 0, np.float32)
         cnt = np.zeros(16, np.uint64)
         self._check(self.lib.rt_render_debug(self.h, C.byref(cam), w, h, max_depth, spp, seed,
-                                             px.ctypes.data_as(C.POINTER(C.c_int32)), hsh.ctypes.data_as(C.POINTER(C.c_uint32)),
-                                             aid.ctypes.data_as(C.POINTER(C.c_int32)), _fp(at),
+                                             px.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             hsh.ctypes.data_as(C.POINTER(C.c_uint32)) if arrays else None,
+                                             aid.ctypes.data_as(C.POINTER(C.c_int32)) if arrays else None, _fp(at) if arrays else None,
                                              cnt.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(st)))
+        if not arrays:
+            return dict(pixels=px.reshape(h, w), hash=None, aov_id=None, aov_t=None,
+                        counters=dict(zip(COUNTER_NAMES, (int(v) for v in cnt[:10]))), stats=st,
+                        lbvh=dict(node_visits_primary=int(cnt[10]), node_visits_secondary=int(cnt[11]), node_visits_shadow=int(cnt[12]),
+                                  brute_fallbacks=int(cnt[13])))
         return dict(pixels=px.reshape(h, w), hash=hsh.reshape(h, w), aov_id=aid.reshape(h, w), aov_t=at.reshape(h, w),
                     counters=dict(zip(COUNTER_NAMES, (int(v) for v in cnt[:10]))), stats=st,
                     lbvh=dict(node_visits_primary=int(cnt[10]), node_visits_secondary=int(cnt[11]), node_visits_shadow=int(cnt[12]),
@@ -288,6 +307,39 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.rt_launch_count(self.h))
+
+    def get_info(self, what: int) -> int:
+        v = C.c_uint64(0)
+        self._check(self.lib.rt_get_info(self.h, what, C.byref(v)))
+        return int(v.value)
+
+    def measure_l2_read(self, nbytes: int = 32 << 20) -> float:
+        """Measured L2 -> SM read bandwidth in GB/s for an L2-resident working set (roofline peak of the LBVH kernels)."""
+        v = C.c_double(0.0)
+        self._check(self.lib.rt_measure_l2_read(self.h, nbytes, C.byref(v)))
+        return float(v.value)
+
+    # ---- zero-copy display (SURVEY §8(f).1) ----------------------------------------------------------------
+    def render_mapped(self, cam15, w, h, max_depth, dev_ptr: int, nbytes: int, spp=1, seed=0):
+        """One frame straight into a device buffer the display owns (a CUDA-mapped GL pixel-unpack buffer); synchronous."""
+        cam = to_rt_camera(cam15)
+        st = RtStats()
+        self._check(self.lib.rt_render_mapped(self.h, C.byref(cam), w, h, max_depth, spp, seed, C.c_void_p(dev_ptr), nbytes, C.byref(st)))
+        return st
+
+    def gl_register_buffer(self, gl_buffer: int) -> int:
+        out = C.c_void_p()
+        self._check(self.lib.rt_gl_register_buffer(self.h, gl_buffer, C.byref(out)))
+        return out.value
+
+    def gl_unregister_buffer(self, resource: int):
+        self._check(self.lib.rt_gl_unregister_buffer(self.h, C.c_void_p(resource)))
+
+    def render_gl(self, cam15, w, h, max_depth, resource: int, spp=1, seed=0):
+        cam = to_rt_camera(cam15)
+        st = RtStats()
+        self._check(self.lib.rt_render_gl(self.h, C.byref(cam), w, h, max_depth, spp, seed, C.c_void_p(resource), C.byref(st)))
+        return st
 
 
 # --------------------------------------------------------------------------------------------------------

@@ -434,12 +434,16 @@ def main():
         ctx.host_register(host_np)
     d2h_step = [0]
 
+    fill_wait_us = [0.0]
+
     def e2e_step():
-        n = 0
+        n, fw = 0, 0
         for f in range(F):
             ctx.render(cams_move[f], W, H, DEPTH, out=host_np[f].reshape(H, W))
             n += ctx.get_info(rtb200.RT_INFO_LAST_D2H_BYTES)
+            fw += ctx.get_info(rtb200.RT_INFO_LAST_FILL_WAIT_NS)
         d2h_step[0] = n
+        fill_wait_us[0] = fw / F / 1e3
         barrier()           # N > 1: the step is done when every rank's tiles of every frame have landed
 
     e2e_step()
@@ -461,6 +465,7 @@ def main():
     # sanity: the frame that came back is the frame the oracle-checked debug kernel produced
     if rank == 0:
         assert np.array_equal(host_np[F - 1].reshape(H, W), dbg_move_last), "e2e frame differs from the instrumented render"
+    fill_wait_sparse = fill_wait_us[0]
     # the dense return (RT_OPT_SPARSE_D2H = 0), for comparison: every byte of every frame crosses PCIe
     ctx.set_option(rtb200.RT_OPT_SPARSE_D2H, 0)
     e2e_step(); torch.cuda.synchronize(); barrier()
@@ -510,7 +515,7 @@ def main():
             "e2e": {"value": rays_move * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 60 * F * world,
                     "d2h_bytes_per_step": d2h_bytes_step, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "frame_bytes_per_step": fb_bytes,
-                    "gate_host_us": (g_ns1 - g_ns0) / max(1, g_n1 - g_n0) / 1e3,
+                    "gate_host_us": (g_ns1 - g_ns0) / max(1, g_n1 - g_n0) / 1e3, "host_fill_wait_us_per_frame": fill_wait_sparse,
                     "dense_return": {"value": rays_move * e2e_steps / e2e_dense_s / 1e6, "d2h_bytes_per_step": fb_bytes,
                                      "note": "RT_OPT_SPARSE_D2H = 0: every byte of every frame crosses PCIe"},
                     "path": ("rt_render per frame into a page-locked host Surface.pixels, 16 distinct cameras per step; pixels the frame gates prove "

@@ -173,7 +173,7 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
 #define RT_OPT_DEBUG_SHIPPED 5
 /* RT_OPT_SPARSE_D2H (default 1): rt_render / rt_render_batch with a host buffer do not copy what the frame gates prove black
  * (whole rows above the horizon outside the sphere rectangle, and the parts of sky rows beside it); those pixels of host_pixels are
- * zero-filled by library threads (RTB200_FILL_THREADS, default 4) while the rest crosses PCIe. Same pixels; 35 % fewer PCIe bytes on
+ * zero-filled by library threads (RTB200_FILL_THREADS, default 6) while the rest crosses PCIe. Same pixels; 35 % fewer PCIe bytes on
  * the reference's default frame. rt_get_info(RT_INFO_LAST_D2H_BYTES) reports what was really copied. */
 #define RT_OPT_SPARSE_D2H 6
 /* RT_OPT_HOST_PRECLEARED (default 0): a promise that host_pixels is already all zero when rt_render is called — the reference's
@@ -189,6 +189,8 @@ int rt_set_option(rt_context* ctx, int option, int value);
 #define RT_INFO_GATE_COMPUTES 2     /* number of frame-gate evaluations so far (a camera that does not move is cached) */
 #define RT_INFO_LAST_D2H_BYTES 3    /* bytes the last rt_render / rt_render_batch with a host buffer copied device -> host */
 #define RT_INFO_SCENE_PATH 4        /* how the uploaded scene is traced: 0 tiny (constant bank), 1 staged (shared memory), 2 global, 3 LBVH */
+#define RT_INFO_LAST_FILL_BYTES 5   /* bytes of host_pixels that render zero-filled on the host instead of copying them */
+#define RT_INFO_LAST_FILL_WAIT_NS 6 /* nanoseconds its calling thread spent in (helping with) that fill after enqueuing the GPU work */
 int rt_get_info(const rt_context* ctx, int what, uint64_t* value);
 
 /* ---- device-pointer / multi-process interface (torchrun: one process per GPU) --------------------------------- */

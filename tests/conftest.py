@@ -11,6 +11,7 @@ sys.path.insert(0, ROOT)
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "refpin: compares with frames rendered by the unmodified reference (tests/golden/ref); fails as UNPINNED when selected with -m refpin and the fixtures are absent")
 
 
 def _has_gpu():

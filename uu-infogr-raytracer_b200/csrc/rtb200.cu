@@ -11,6 +11,9 @@
 // them with one 128-bit store; the store address may be a peer (NVLink) mapping of rank 0's framebuffer — the gather is
 // fused into the render kernel.
 #include <cuda_runtime.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 // cuda_gl_interop.h needs <GL/gl.h>, which a headless build image does not have; the one entry point used is declared here
 // (GLuint is `unsigned int`; the symbol lives in the CUDA runtime).
 extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource** resource, unsigned int buffer, unsigned int flags);
@@ -543,7 +546,7 @@ struct DeviceWorkers {
 };
 
 // Host-side zero fill of the parts of `Surface.pixels` that are not copied (sparse D2H, render_frames): a few library threads
-// memset the segments while the copies of the rest are in flight. Threads are started on first use (RTB200_FILL_THREADS, default 4,
+// zero the segments while the copies of the rest are in flight. Threads are started on first use (RTB200_FILL_THREADS, default 6,
 // at most hardware_concurrency - 1; 0 = the calling thread does it all in wait()).
 struct FillPool {
     struct Seg { char* p; size_t bytes; };
@@ -551,10 +554,29 @@ struct FillPool {
     std::mutex m; std::condition_variable cv, cv_done;
     std::vector<Seg> segs; std::atomic<size_t> next{0};
     uint64_t gen = 0; int active = 0; bool quit = false, started = false;
-    void drain() { for (;;) { const size_t i = next.fetch_add(1); if (i >= segs.size()) break; memset(segs[i].p, 0, segs[i].bytes); } }
+    // Non-temporal zero fill: the lines are not read for ownership and do not evict the host's caches (the frame is consumed by
+    // the display path, not by this thread). SSE2 is x86-64 baseline.
+    static void zero_nt(char* p, size_t bytes) {
+#if defined(__SSE2__)
+        const size_t head = (size_t)(-(intptr_t)p & 15);
+        if (head >= bytes) { memset(p, 0, bytes); return; }
+        memset(p, 0, head); p += head; bytes -= head;
+        const __m128i z = _mm_setzero_si128();
+        size_t n = bytes / 64;
+        for (size_t i = 0; i < n; i++, p += 64) {
+            _mm_stream_si128((__m128i*)p, z); _mm_stream_si128((__m128i*)(p + 16), z);
+            _mm_stream_si128((__m128i*)(p + 32), z); _mm_stream_si128((__m128i*)(p + 48), z);
+        }
+        _mm_sfence();
+        memset(p, 0, bytes & 63);
+#else
+        memset(p, 0, bytes);
+#endif
+    }
+    void drain() { for (;;) { const size_t i = next.fetch_add(1); if (i >= segs.size()) break; zero_nt(segs[i].p, segs[i].bytes); } }
     void start() {
         started = true;
-        int n = 4;
+        int n = 6;
         if (const char* e = getenv("RTB200_FILL_THREADS")) n = atoi(e);
         const int hw = (int)std::thread::hardware_concurrency();
         if (hw > 0 && n > hw - 1) n = hw - 1;
@@ -623,6 +645,7 @@ struct rt_context {
     bool host_precleared = false;   // RT_OPT_HOST_PRECLEARED
     FillPool fill_pool;
     uint64_t last_d2h_bytes = 0;    // bytes the last host-returning render really copied device -> host (rt_get_info)
+    uint64_t last_fill_bytes = 0, last_fill_wait_ns = 0;   // host zero fill of that render: bytes, and time the caller waited for it
     std::vector<void*> gl_resources;   // cudaGraphicsResource* registered through rt_gl_register_buffer
 };
 
@@ -1194,8 +1217,13 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
                 }
             }
         }
+        uint64_t fb = 0; for (const auto& sg : segs) fb += sg.bytes;
+        ctx->last_fill_bytes = fb;
         if (!segs.empty()) { ctx->fill_pool.run(std::move(segs)); fill_started = true; }
+    } else {
+        ctx->last_fill_bytes = 0;
     }
+    ctx->last_fill_wait_ns = 0;
     struct FillGuard { FillPool* p; ~FillGuard() { if (p) p->wait(); } } fill_guard{fill_started ? &ctx->fill_pool : nullptr};   // every return path
     std::vector<char> first_copy_dev((size_t)G, 1);
     // Device g's D2H copies for rows/tiles of one band of one frame, on its copy stream (which already waits for the band's event).
@@ -1313,6 +1341,12 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             CU_TRY(ctx, cudaSetDevice(d.dev));
             CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
         }
+    }
+    if (fill_started) {      // everything is enqueued: help with the zero fill instead of idling in the stream synchronisation below
+        const auto t0 = std::chrono::steady_clock::now();
+        ctx->fill_pool.wait();
+        fill_guard.p = nullptr;
+        ctx->last_fill_wait_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     }
     float kernel_ms = 0.0f, d2h_ms = 0.0f;
     for (int g = 0; g < G; g++) {
@@ -1630,6 +1664,8 @@ int rt_get_info(const rt_context* ctx, int what, uint64_t* value) {
         case RT_INFO_GATE_COMPUTES: *value = ctx->gate_computes.load(); return RT_OK;
         case RT_INFO_LAST_D2H_BYTES: *value = ctx->last_d2h_bytes; return RT_OK;
         case RT_INFO_SCENE_PATH: *value = (uint64_t)ctx->path; return RT_OK;
+        case RT_INFO_LAST_FILL_BYTES: *value = ctx->last_fill_bytes; return RT_OK;
+        case RT_INFO_LAST_FILL_WAIT_NS: *value = ctx->last_fill_wait_ns; return RT_OK;
         default: return RT_ERR_INVALID;
     }
 }

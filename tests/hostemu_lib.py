@@ -7,11 +7,11 @@ import numpy as np
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu")
 _libs = {}
-VARIANT = ""          # "" = the shipped configuration; "_v2" = built with -DRT_GATES_V2 (set by tests through use_variant)
+VARIANT = ""          # "" = the shipped configuration; "_v1" = built with -DRT_GATES_V1, the first-generation gate shapes (use_variant)
 
 
 def use_variant(name):
-    """Selects the library the module-level helpers call: "" (default build) or "_v2" (RT_GATES_V2)."""
+    """Selects the library the module-level helpers call: "" (default build) or "_v1" (RT_GATES_V1)."""
     global VARIANT
     VARIANT = name
 

@@ -297,12 +297,12 @@ def test_arbitrary_planes_lights_and_cameras(built, seed):
         assert np.array_equal(a["pixels"], b["pixels"])
 
 
-# ---- RT_GATES_V2: tighter gate shapes (per-sphere mirror rectangles, shadow hull half-planes), compiled in only with
-# -DRT_GATES_V2 (not the shipped configuration: not yet measured on the GPU). Same soundness bar, on the CPU. --------------------
+# ---- second-generation gate shapes (per-sphere mirror rectangles, shadow hull half-planes; shipped since round 2): same soundness
+# bar, and never skipping less than the first-generation shapes (libhostemu_v1.so, -DRT_GATES_V1). ---------------------------------
 
 @pytest.fixture()
 def v2(built):
-    E.use_variant("_v2")
+    E.use_variant("")
     yield
     E.use_variant("")
 
@@ -312,9 +312,9 @@ def test_v2_default_scene_is_sound_and_tighter(v2):
     w, h = 384, 216
     cam = scenes.make_camera(width=w, height=h)
     g, bits, on_plane, sec, sh = _check_bits_against_log(sc, cam, w, h)
-    E.use_variant("")
+    E.use_variant("_v1")
     base = E.gates(sc, cam, w, h)["bits"].reshape(-1)
-    E.use_variant("_v2")
+    E.use_variant("")
     assert ((base & ~bits) == 0).all()                                    # never skips less than the shipped gates
     assert ((bits & E.GATE_MIRROR) != 0).mean() > 1.4 * ((base & E.GATE_MIRROR) != 0).mean()
     assert ((bits & (E.GATE_SHADOW0 << 1)) != 0).mean() > 1.8 * ((base & (E.GATE_SHADOW0 << 1)) != 0).mean()

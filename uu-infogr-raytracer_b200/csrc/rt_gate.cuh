@@ -47,12 +47,17 @@ constexpr int RT_GATE_LIGHTS = (int)RT_GATE_MAX_LIGHTS;   // shadow gates exist 
 
 struct GateRect { int x0, y0, x1, y1; };      // inclusive pixel ranges; empty = {w, h, w, h}
 struct GateAffine { float a, bx, by; };       // value(x, y) = fma(bx, x, fma(by, y, a)); "never" = {-1, 0, 0}, "always" = {+1, 0, 0}
-// RT_GATES_V2 (compile-time, default off — not yet measured on the GPU; the default build is unchanged): tighter SHAPES for the
-// two gates whose union rectangles leave the most on the table:
+// Gate SHAPES, second generation (shipped since round 2: the whole GPU parity suite, incl. the chain hashes of the production kernel,
+// passes with them; +3.2 % on the bench frame, profiles/r02/) — tighter shapes for the two gates whose union rectangles leave the
+// most on the table:
 //   mirror_s[i]   one rectangle per sphere (scenes of <= 4 spheres): the reflection is skipped if the span is outside ALL of them
 //   shadow_out[l] two half-planes per light, taken from the convex hull of the projected shadow polygons (the two hull edges that
 //                 cut the most off the rectangle): > 0 on the whole span => outside the hull => unoccluded. Fits the diagonal
 //                 streaks of low lights, which a rectangle cannot.
+// -DRT_GATES_V1 compiles the first-generation shapes (union rectangles only); the tests use it to show V2 never skips less.
+#ifndef RT_GATES_V1
+#define RT_GATES_V2 1
+#endif
 #ifdef RT_GATES_V2
 constexpr int RT_GATE_MIRROR_RECTS = 4;
 #endif

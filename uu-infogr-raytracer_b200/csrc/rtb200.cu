@@ -1138,32 +1138,7 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
     const int world = G > 1 ? G : ctx->world;
     const int tile_rows = ctx->tile_rows;
     const int tiles_total = (h + tile_rows - 1) / tile_rows;
-    // ---- band layout ----
-    int n_bands = 1;
-    if (host_pixels) {
-        const char* be = getenv("RTB200_BANDS");
-        const size_t link_bytes = npix * 4 / (size_t)(tiles_mode ? world : 1);        // bytes one PCIe link carries per frame
-        n_bands = be ? atoi(be) : (int)((link_bytes + (4u << 20) - 1) / (4u << 20));  // ~4 MB per band and link
-        if (n_bands > 16) n_bands = 16;
-        if (n_bands < 1) n_bands = 1;
-    }
-    int band_tiles = (tiles_total + n_bands - 1) / n_bands;
-    band_tiles = ((band_tiles + world - 1) / world) * world;
-    if (band_tiles < world) band_tiles = world;
-    n_bands = (tiles_total + band_tiles - 1) / band_tiles;
     const bool pipelined = host_pixels != nullptr;
-    const int n_groups = (n_frames + INLINE_CAMS - 1) / INLINE_CAMS;      // headless: one launch per <= INLINE_CAMS frames
-    const int n_segments = pipelined ? n_frames * n_bands : n_groups;
-    if (pipelined) {
-        for (int g = 0; g < G; g++) {
-            DeviceState& d = ctx->devs[(size_t)g];
-            CU_TRY(ctx, cudaSetDevice(d.dev));
-            while ((int)d.band_events.size() < n_segments) {
-                cudaEvent_t ev; CU_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                d.band_events.push_back(ev);
-            }
-        }
-    }
     const long long tile_pix = (long long)tile_rows * w;
     // ---- what need not be copied (per frame), and the host-side zero fill that replaces it ----
     std::vector<RowPlan> plans;
@@ -1185,6 +1160,49 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         for (long long y = ya; y < yb; y++) if (rp.kind[(size_t)y] != ROW_BLACK) return false;
         return true;
     };
+    // ---- band layout, per frame ----
+    // Bands are ranges of tile GROUPS (group q = tiles q*world .. q*world + world-1, one tile per rank), so that every device owns
+    // the same share of each band. Groups that are entirely proven black at either end of the frame are not rendered at all when
+    // the frame goes to the host (nobody reads those rows of the device framebuffer), and the number of bands follows the bytes that
+    // really cross PCIe (~4 MB per band and link).
+    constexpr int MAX_BANDS = 16;
+    struct Bands { int g_lo = 0, g_hi = 0, n = 0, groups = 1; };
+    const int groups_total = (tiles_total + world - 1) / world;
+    std::vector<Bands> bands((size_t)n_frames);
+    for (int f = 0; f < n_frames; f++) {
+        Bands& b = bands[(size_t)f];
+        b.g_lo = 0; b.g_hi = groups_total;
+        size_t copy_rows_n = (size_t)h;
+        if (!plans.empty() && plans[(size_t)f].sparse) {
+            const RowPlan& rp = plans[(size_t)f];
+            auto group_black = [&](int q) { for (int r = 0; r < world; r++) { const long long t = (long long)q * world + r; if (t < tiles_total && !tile_black(rp, t)) return false; } return true; };
+            while (b.g_lo < b.g_hi && group_black(b.g_lo)) b.g_lo++;
+            while (b.g_hi > b.g_lo && group_black(b.g_hi - 1)) b.g_hi--;
+            copy_rows_n = 0;
+            for (int y = 0; y < h; y++) if (rp.kind[(size_t)y] != ROW_BLACK) copy_rows_n++;
+        }
+        if (!pipelined) { b.n = 1; b.groups = groups_total > 0 ? groups_total : 1; continue; }
+        if (b.g_hi <= b.g_lo) { b.n = 0; continue; }
+        const char* be = getenv("RTB200_BANDS");
+        const size_t link_bytes = copy_rows_n * (size_t)w * 4 / (size_t)(tiles_mode ? world : 1);      // bytes one PCIe link carries
+        int nb = be ? atoi(be) : (int)((link_bytes + (4u << 20) - 1) / (4u << 20));                   // ~4 MB per band and link
+        if (nb > MAX_BANDS) nb = MAX_BANDS;
+        if (nb < 1) nb = 1;
+        b.groups = (b.g_hi - b.g_lo + nb - 1) / nb;
+        b.n = (b.g_hi - b.g_lo + b.groups - 1) / b.groups;
+    }
+    const int n_groups = (n_frames + INLINE_CAMS - 1) / INLINE_CAMS;      // headless: one launch per <= INLINE_CAMS frames
+    const int n_segments = pipelined ? n_frames * MAX_BANDS : n_groups;
+    if (pipelined) {
+        for (int g = 0; g < G; g++) {
+            DeviceState& d = ctx->devs[(size_t)g];
+            CU_TRY(ctx, cudaSetDevice(d.dev));
+            while ((int)d.band_events.size() < n_segments) {
+                cudaEvent_t ev; CU_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                d.band_events.push_back(ev);
+            }
+        }
+    }
     if (!plans.empty() && !ctx->host_precleared) {
         std::vector<FillPool::Seg> segs;
         auto add = [&](int32_t* p, size_t npx) {
@@ -1278,14 +1296,16 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
     // Everything device g has to enqueue for segment s (its launch, its band event, and in tiles mode its own D2H copies).
     auto enqueue = [&](int g, int s) -> int {
         DeviceState& d = ctx->devs[(size_t)g];
-        const int frame = pipelined ? s / n_bands : s * INLINE_CAMS, band = pipelined ? s % n_bands : 0;
+        const int frame = pipelined ? s / MAX_BANDS : s * INLINE_CAMS, band = pipelined ? s % MAX_BANDS : 0;
+        if (pipelined && band >= bands[(size_t)frame].n) return RT_OK;                       // this frame has fewer bands
         const int nf = pipelined ? 1 : (n_frames - frame < INLINE_CAMS ? n_frames - frame : INLINE_CAMS);
         const int rank = G > 1 ? g : ctx->rank;
         FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, rank, world, (direct ? d.fb : d0.fb) + (size_t)frame * npix, (long long)npix);
         fp.skip_black_store = (G > 1 && !direct) ? (ctx->shared_target == 2 ? 2 : 1) : 0;   // every device stores into device 0's framebuffer
         if (pipelined) {
             fp.cam_inline[0] = to_cam(cams[frame]);
-            const int k0 = band * (band_tiles / world), k1 = k0 + band_tiles / world;       // this rank's tiles of the band
+            const Bands& b = bands[(size_t)frame];
+            const int k0 = b.g_lo + band * b.groups; int k1 = k0 + b.groups; if (k1 > b.g_hi) k1 = b.g_hi;   // this rank's tiles of the band
             const int mine = fp.tiles_mine;
             fp.k_begin = k0 < mine ? k0 : mine;
             fp.tiles_mine = (k1 < mine ? k1 : mine) - fp.k_begin;
@@ -1322,7 +1342,8 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
         }
         for (int s = 0; s < n_segments; s++) {
-            const int frame = pipelined ? s / n_bands : s * INLINE_CAMS, band = pipelined ? s % n_bands : 0;
+            const int frame = pipelined ? s / MAX_BANDS : s * INLINE_CAMS, band = pipelined ? s % MAX_BANDS : 0;
+            if (pipelined && band >= bands[(size_t)frame].n) continue;
             for (int g = 0; g < G; g++) {
                 CU_TRY(ctx, cudaSetDevice(ctx->devs[(size_t)g].dev));
                 rc = enqueue(g, s); if (rc) return rc;
@@ -1331,7 +1352,9 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
                 CU_TRY(ctx, cudaSetDevice(d0.dev));                                        // waits for every device's band
                 for (int g = 0; g < G; g++) CU_TRY(ctx, cudaStreamWaitEvent(d0.copy_stream, ctx->devs[(size_t)g].band_events[(size_t)s], 0));
                 if (first_copy_dev[0]) { CU_TRY(ctx, cudaEventRecord(d0.evc0, d0.copy_stream)); first_copy_dev[0] = 0; }
-                const long long ya = (long long)band * band_tiles * tile_rows; long long yb = ya + (long long)band_tiles * tile_rows;
+                const Bands& b = bands[(size_t)frame];
+                const int q0 = b.g_lo + band * b.groups; int q1 = q0 + b.groups; if (q1 > b.g_hi) q1 = b.g_hi;
+                const long long ya = (long long)q0 * world * tile_rows; long long yb = (long long)q1 * world * tile_rows;
                 if (yb > h) yb = h;
                 if (yb > ya) { rc = copy_rows(d0, frame, (int)ya, (int)yb); if (rc) return rc; }
             }

@@ -126,6 +126,9 @@ def _fp(a):
 
 
 def to_rt_camera(cam15) -> RtCamera:
+    """15 floats -> rt_camera; an RtCamera is passed through (hosts that render many frames convert once)."""
+    if isinstance(cam15, RtCamera):
+        return cam15
     cam15 = np.asarray(cam15, dtype=np.float32).reshape(15)
     c = RtCamera()
     for k, name in enumerate(["pos", "right", "up", "forward", "view_params"]):

@@ -180,6 +180,13 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
  * Tick() does `screen.Clear(0)` (RayTracer.cs:890) right before the pixel loop — so the library skips its own zero fill of the
  * pixels it does not copy. */
 #define RT_OPT_HOST_PRECLEARED 7
+/* RT_OPT_HOST_ZERO_COPY (default 1): when host_pixels is page-locked memory the devices can address (rt_host_register, or memory from
+ * cudaHostAlloc), rt_render / rt_render_batch can let the render kernel store the frame straight into it over PCIe — no device
+ * framebuffer, no copy engine, one launch per device — and with RT_OPT_SPARSE_D2H what the frame gates prove black is neither stored
+ * nor copied but zero-filled by host threads. 0 = never (device framebuffer + band-pipelined copies), 1 = for frames up to 8 MB
+ * (the reference's 1280x720 window: 0.10 instead of 0.15 ms per frame on B200; at 4K the copy engine's higher PCIe rate wins),
+ * 2 = always. Pageable host memory always takes the copy path. */
+#define RT_OPT_HOST_ZERO_COPY 8
 /* Options that change WHICH rank writes a pixel (RT_OPT_SHARED_TARGET, RT_OPT_PRIMARY_GATE) must be set identically on every rank
  * of a partition. RT_OPT_COMPACTION may differ: a launch that takes part in a sparse gather always uses the default kernel. */
 int rt_set_option(rt_context* ctx, int option, int value);
@@ -191,6 +198,8 @@ int rt_set_option(rt_context* ctx, int option, int value);
 #define RT_INFO_SCENE_PATH 4        /* how the uploaded scene is traced: 0 tiny (constant bank), 1 staged (shared memory), 2 global, 3 LBVH */
 #define RT_INFO_LAST_FILL_BYTES 5   /* bytes of host_pixels that render zero-filled on the host instead of copying them */
 #define RT_INFO_LAST_FILL_WAIT_NS 6 /* nanoseconds its calling thread spent in (helping with) that fill after enqueuing the GPU work */
+#define RT_INFO_LAST_ENQUEUE_NS 7   /* host nanoseconds of the last rt_render / rt_render_batch from entry until all GPU work was enqueued */
+#define RT_INFO_LAST_TOTAL_NS 8     /* ... from entry to return */
 int rt_get_info(const rt_context* ctx, int what, uint64_t* value);
 
 /* ---- device-pointer / multi-process interface (torchrun: one process per GPU) --------------------------------- */
@@ -220,8 +229,9 @@ int rt_dev_to_host(rt_context* ctx, void* host_dst, const void* dev_src, uint64_
 int rt_dev_memset(rt_context* ctx, void* dev_dst, int byte_value, uint64_t bytes);   /* synchronous; tests poison framebuffers with it */
 int rt_sync(rt_context* ctx);
 
-/* Page-locks (cudaHostRegister) a host buffer the caller keeps alive — e.g. the pinned `Surface.pixels` array — so that
- * the device->host copy of rt_render runs at full PCIe rate instead of through a staging buffer. Optional. */
+/* Page-locks and maps (cudaHostRegister, portable + mapped) a host buffer the caller keeps alive — e.g. the pinned `Surface.pixels`
+ * array — so that rt_render can return the frame at full PCIe rate: by the render kernel's own stores (RT_OPT_HOST_ZERO_COPY) or by
+ * copy-engine transfers, instead of through a pageable staging copy. Optional. */
 int rt_host_register(rt_context* ctx, void* host_ptr, uint64_t bytes);
 int rt_host_unregister(rt_context* ctx, void* host_ptr);
 

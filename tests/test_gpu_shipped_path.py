@@ -192,14 +192,22 @@ def test_sparse_d2h_equals_dense(rt, w, h):
         ref, _ = ctx.render(cam, w, h, 8)
         assert ctx.get_info(rt.RT_INFO_LAST_D2H_BYTES) == w * h * 4
         ctx.set_option(rt.RT_OPT_SPARSE_D2H, 1)
-        for buf in (np.full((h, w), 0x5A5A5A5A, np.int32), pinned):
+        # pageable memory: copy engine; page-locked memory: the kernel's own stores over PCIe (zero copy), or the copy engine
+        for buf, zero_copy in ((np.full((h, w), 0x5A5A5A5A, np.int32), 1), (pinned, 1), (pinned, 0)):
+            ctx.set_option(rt.RT_OPT_HOST_ZERO_COPY, 2 * zero_copy)
             buf[...] = 0x5A5A5A5A
             ctx.render(cam, w, h, 8, out=buf)
-            assert np.array_equal(buf, ref), "%d pixels differ" % int((buf != ref).sum())
-        copied = ctx.get_info(rt.RT_INFO_LAST_D2H_BYTES)
-        assert copied <= w * h * 4
-        if camkw == {} and w >= 1000:
-            assert copied < 0.72 * w * h * 4, copied / (w * h * 4)          # a third of the default frame is proven black
+            assert np.array_equal(buf, ref), "%d pixels differ (zero_copy %d)" % (int((buf != ref).sum()), zero_copy)
+            copied = ctx.get_info(rt.RT_INFO_LAST_D2H_BYTES)
+            assert copied <= w * h * 4
+            if camkw == {} and w >= 1000:
+                assert copied < 0.72 * w * h * 4, copied / (w * h * 4)      # a third of the default frame is proven black
+        ctx.set_option(rt.RT_OPT_HOST_ZERO_COPY, 2)
+        ctx.set_option(rt.RT_OPT_SPARSE_D2H, 0)                             # zero copy without the sparse return: every pixel is stored
+        pinned[...] = 0x5A5A5A5A
+        ctx.render(cam, w, h, 8, out=pinned)
+        assert np.array_equal(pinned, ref) and ctx.get_info(rt.RT_INFO_LAST_D2H_BYTES) == w * h * 4
+        ctx.set_option(rt.RT_OPT_SPARSE_D2H, 1); ctx.set_option(rt.RT_OPT_HOST_ZERO_COPY, 1)
     # the caller's promise that the buffer is already zero (the reference's screen.Clear(0), RayTracer.cs:890): no fill by the library
     ctx.set_option(rt.RT_OPT_HOST_PRECLEARED, 1)
     cam = scenes.make_camera(width=w, height=h)
@@ -245,16 +253,21 @@ def test_partitioned_contexts_fill_one_host_frame(rt, world, tile_rows, w, h):
     for camkw in (dict(), dict(pos=(0.0, 0.5, 0.0), pitch=-0.6), dict(pos=(0.0, 3.0, 2.0), pitch=1.3)):
         cam = scenes.make_camera(width=w, height=h, **camkw)
         ref, _ = base.render(cam, w, h, 8)
-        for sparse in (1, 0):
+        for sparse, pin in ((1, 0), (0, 0), (1, 1), (0, 1)):
             frame = np.full((h, w), 0x5A5A5A5A, np.int32)
+            if pin:
+                base.host_register(frame)         # page-locked: every rank's kernel stores its tiles straight into the frame
             total = 0
             for r in range(world):
                 c = rt.Context([0]); c.set_scene(sc); c.set_partition(r, world, tile_rows)
                 c.set_option(rt.RT_OPT_SPARSE_D2H, sparse)
+                c.set_option(rt.RT_OPT_HOST_ZERO_COPY, 2 if pin else 0)
                 c.render(cam, w, h, 8, out=frame)
                 total += c.get_info(rt.RT_INFO_LAST_D2H_BYTES)
                 c.close()
-            assert np.array_equal(frame, ref), "%d pixels differ" % int((frame != ref).sum())
+            if pin:
+                base.host_unregister(frame)
+            assert np.array_equal(frame, ref), "%d pixels differ (sparse %d, pinned %d)" % (int((frame != ref).sum()), sparse, pin)
             assert total <= w * h * 4
             if not sparse:
                 assert total == w * h * 4

@@ -37,6 +37,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include "rt_lbvh.cuh"
@@ -510,7 +511,10 @@ inline void plan_rows(const FrameGates& g, int w, int h, RowPlan* rp) {
     const bool rect_empty = g.spheres.x1 < g.spheres.x0 || g.spheres.y1 < g.spheres.y0 || g.spheres.x0 >= w || g.spheres.x1 < 0;
     const int rx0 = rect_empty ? 0 : ((g.spheres.x0 < 0 ? 0 : g.spheres.x0) & ~15);
     int rx1 = rect_empty ? -1 : (g.spheres.x1 | 15); if (rx1 > w - 1) rx1 = w - 1;
-    const bool rect_wide = !rect_empty && (long long)(rx1 - rx0 + 1) * 10 > (long long)w * 9;    // not worth a strided copy
+    // a strided (2-D) copy must save enough bytes to beat the whole-row copy: rows whose rectangle covers more than `max_frac`
+    // of the width are copied whole (RTB200_RECT_MAX_FRAC, percent; measured on B200: profiles/r02/)
+    static const int max_frac = [] { const char* e = getenv("RTB200_RECT_MAX_FRAC"); return e ? atoi(e) : 90; }();
+    const bool rect_wide = !rect_empty && (long long)(rx1 - rx0 + 1) * 100 > (long long)w * max_frac;
     rp->rx0 = rx0; rp->rx1 = rx1;
     const float fx1 = (float)(w - 1);
     for (int y = 0; y < h; y++) {

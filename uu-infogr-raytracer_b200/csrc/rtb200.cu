@@ -56,6 +56,15 @@ constexpr int N_DEBUG_COUNTERS = 16;
 #define RT_MIN_BLOCKS 8      // resident CTAs per SM the register allocator must allow (tuned on B200, profiles/)
 #endif
 
+// Zero-copy host return: the render kernel stores straight into the caller's page-locked Surface.pixels over PCIe, and the pixels
+// the frame gates prove black are zero-filled by host threads instead of being stored. The host's fill set (plan_rows, rt_gate.cuh)
+// is passed down in this form: rows [yb0, yb1) and [yc0, yc1) are filled whole, rows [yr0, yr1) outside the columns rx0..rx1 (the largest
+// runs of the plan; whatever does not fit this shape is simply stored by the kernel). Empty ranges = nothing.
+struct HostSkip { int yb0, yb1, yc0, yc1, yr0, yr1, rx0, rx1; };     // two whole-row ranges, one rectangle-rows range
+__host__ __device__ __forceinline__ bool host_fills_span(const HostSkip& k, int xa, int xb, int y) {
+    return (y >= k.yb0 && y < k.yb1) || (y >= k.yc0 && y < k.yc1) || (y >= k.yr0 && y < k.yr1 && (xb < k.rx0 || xa > k.rx1));
+}
+
 struct FrameParams {
     int w, h, cap, spp;
     uint32_t seed;
@@ -69,6 +78,7 @@ struct FrameParams {
     float rcp_w, rcp_h;         // 1/w, 1/h correctly rounded (host): pixel-coordinate divisions of the single-sample kernels (rt_div_rcp)
     long long frame_stride;     // pixels between consecutive frames in `out`
     uint32_t* out;              // framebuffer(s): 0x00RRGGBB, row-major (Surface.pixels, surface.cs:9-20)
+    HostSkip hskip[INLINE_CAMS];      // per frame: pixels the HOST zero-fills itself (zero-copy return, render_frames): not stored
     FrameGates gates[INLINE_CAMS];    // per frame: what the host proved pixel regions cannot hit (rt_gate.cuh; tiny single-sample kernels)
     CamRec cam_inline[INLINE_CAMS];   // the launch's cameras travel in the parameter block (constant bank): no upload, no host
                                       // sync; batches of more than INLINE_CAMS frames are split into several launches
@@ -121,6 +131,7 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp,
                     n_primary += PPT;
                 }
                 if (fp.skip_black_store) continue;             // ... and rank 0 writes those zeros itself (k_fill_black): nothing crosses NVLink
+                if (host_fills_span(fp.hskip[frame], x, x + PPT - 1, y)) continue;   // ... or the host does (zero-copy return): nothing crosses PCIe
                 if (PPT == 4 && ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0)) *reinterpret_cast<uint4*>(out + p0) = make_uint4(0u, 0u, 0u, 0u);
                 else for (int q = 0; q < PPT; q++) out[p0 + q] = 0u;
                 continue;
@@ -643,8 +654,10 @@ struct rt_context {
     bool debug_shipped = false;     // RT_OPT_DEBUG_SHIPPED
     bool sparse_d2h = true;         // RT_OPT_SPARSE_D2H
     bool host_precleared = false;   // RT_OPT_HOST_PRECLEARED
+    int zero_copy = 1;              // RT_OPT_HOST_ZERO_COPY: 0 never, 1 frames up to 8 MB, 2 always
     FillPool fill_pool;
     uint64_t last_d2h_bytes = 0;    // bytes the last host-returning render really copied device -> host (rt_get_info)
+    uint64_t last_enqueue_ns = 0, last_total_ns = 0;       // host time of the last render_frames: entry -> everything enqueued, entry -> return
     uint64_t last_fill_bytes = 0, last_fill_wait_ns = 0;   // host zero fill of that render: bytes, and time the caller waited for it
     std::vector<void*> gl_resources;   // cudaGraphicsResource* registered through rt_gl_register_buffer
 };
@@ -1078,6 +1091,7 @@ int rt_set_option(rt_context* ctx, int option, int value) {
         case RT_OPT_DEBUG_SHIPPED: ctx->debug_shipped = value != 0; return RT_OK;
         case RT_OPT_SPARSE_D2H: ctx->sparse_d2h = value != 0; return RT_OK;
         case RT_OPT_HOST_PRECLEARED: ctx->host_precleared = value != 0; return RT_OK;
+        case RT_OPT_HOST_ZERO_COPY: ctx->zero_copy = value < 0 ? 0 : (value > 2 ? 2 : value); return RT_OK;
         default: return fail(ctx, RT_ERR_INVALID, "unknown option");
     }
 }
@@ -1111,6 +1125,139 @@ int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int w
     return RT_OK;
 }
 
+// HostSkip of a row plan: its two longest runs of ROW_BLACK rows and its longest run of ROW_RECT rows.
+static HostSkip host_skip_of(const RowPlan& rp, int h) {
+    HostSkip k; memset(&k, 0, sizeof(k));
+    if (!rp.sparse) return k;
+    int best_b[2][2] = {{0, 0}, {0, 0}}, best_r[2] = {0, 0};
+    for (int y = 0; y < h;) {
+        const uint8_t kind = rp.kind[(size_t)y];
+        int y2 = y + 1;
+        while (y2 < h && rp.kind[(size_t)y2] == kind) y2++;
+        if (kind == ROW_BLACK) {
+            if (y2 - y > best_b[0][1] - best_b[0][0]) { best_b[1][0] = best_b[0][0]; best_b[1][1] = best_b[0][1]; best_b[0][0] = y; best_b[0][1] = y2; }
+            else if (y2 - y > best_b[1][1] - best_b[1][0]) { best_b[1][0] = y; best_b[1][1] = y2; }
+        } else if (kind == ROW_RECT && y2 - y > best_r[1] - best_r[0]) { best_r[0] = y; best_r[1] = y2; }
+        y = y2;
+    }
+    k.yb0 = best_b[0][0]; k.yb1 = best_b[0][1]; k.yc0 = best_b[1][0]; k.yc1 = best_b[1][1];
+    k.yr0 = best_r[0]; k.yr1 = best_r[1]; k.rx0 = rp.rx0; k.rx1 = rp.rx1;
+    return k;
+}
+
+// Zero-copy host return (RT_OPT_HOST_ZERO_COPY, default on): when host_pixels is page-locked memory the devices can address
+// (rt_host_register, cudaHostAlloc), the render kernel's 128-bit stores go straight into it over PCIe — no device framebuffer, no copy
+// engine, no bands, one launch per device and <= 16 frames — and what the frame gates prove black is neither stored nor copied: host
+// threads zero-fill those rows / row parts while the kernel runs (HostSkip). Every device (or rank of a partition) writes its own row
+// tiles over its own PCIe link. `dev_out` is the device-side address of host_pixels.
+static int render_frames_zero_copy(rt_context* ctx, const rt_camera* cams, int n_frames, int w, int h, int depth, int spp, uint32_t seed,
+                                   int32_t* host_pixels, uint32_t* dev_out, rt_stats* stats) {
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto since_enter_ns = [&]() { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_enter).count(); };
+    const size_t npix = (size_t)w * h;
+    const int G = (int)ctx->devs.size();
+    const int world = G > 1 ? G : ctx->world;
+    const int tile_rows = ctx->tile_rows;
+    std::vector<HostSkip> hs((size_t)n_frames);
+    memset(hs.data(), 0, sizeof(HostSkip) * (size_t)n_frames);
+    const bool gated = ctx->sparse_d2h && ctx->path == PATH_TINY && ctx->primary_gate && spp == 1 && w <= RT_FASTDIV_MAX && h <= RT_FASTDIV_MAX &&
+                       !ctx->compaction;
+    if (gated) {
+        RowPlan rp;
+        for (int f = 0; f < n_frames; f++) {
+            plan_rows(gates_for(ctx, to_cam(cams[f]), w, h), w, h, &rp);
+            hs[(size_t)f] = host_skip_of(rp, h);
+        }
+    }
+    bool fill_started = false;
+    struct FillGuard { FillPool* p; const bool* started; ~FillGuard() { if (p && *started) p->wait(); } } fill_guard{&ctx->fill_pool, &fill_started};
+    ctx->last_fill_bytes = 0; ctx->last_fill_wait_ns = 0;
+    auto start_fill = [&]() {
+        if (!gated || ctx->host_precleared) return;
+        std::vector<FillPool::Seg> segs;
+        uint64_t total = 0;
+        const bool own_only = G == 1 && world > 1;                      // one rank of a partition fills the skipped rows of ITS tiles
+        auto add_rows = [&](int32_t* dst, int ya, int yb, int xa, int xb) {     // columns [xa, xb) of rows [ya, yb)
+            if (xb <= xa) return;
+            for (int y = ya; y < yb;) {
+                if (own_only && (y / tile_rows) % world != ctx->rank) { y = (y / tile_rows + 1) * tile_rows; continue; }
+                int y2 = yb;
+                if (own_only) { const int te = (y / tile_rows + 1) * tile_rows; if (te < y2) y2 = te; }
+                if (xa == 0 && xb == w) {
+                    const size_t piece_rows = ((size_t)1 << 18) / (size_t)w + 1;            // ~1 MB pieces: load balance across the pool
+                    for (int yy = y; yy < y2; yy += (int)piece_rows) {
+                        const int ye = yy + (int)piece_rows < y2 ? yy + (int)piece_rows : y2;
+                        segs.push_back({(char*)(dst + (size_t)yy * w), (size_t)(ye - yy) * w * 4}); total += (uint64_t)(ye - yy) * w * 4;
+                    }
+                } else {
+                    for (int yy = y; yy < y2; yy++) { segs.push_back({(char*)(dst + (size_t)yy * w + xa), (size_t)(xb - xa) * 4}); total += (uint64_t)(xb - xa) * 4; }
+                }
+                y = y2;
+            }
+        };
+        for (int f = 0; f < n_frames; f++) {
+            const HostSkip& k = hs[(size_t)f];
+            int32_t* dst = host_pixels + (size_t)f * npix;
+            add_rows(dst, k.yb0, k.yb1, 0, w); add_rows(dst, k.yc0, k.yc1, 0, w);
+            add_rows(dst, k.yr0, k.yr1, 0, k.rx0); add_rows(dst, k.yr0, k.yr1, k.rx1 + 1, w);
+        }
+        ctx->last_fill_bytes = total;
+        if (!segs.empty()) { ctx->fill_pool.run(std::move(segs)); fill_started = true; }
+    };
+    auto device_job = [&](int g) -> int {
+        DeviceState& d = ctx->devs[(size_t)g];
+        CU_TRY(ctx, cudaSetDevice(d.dev));
+        CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
+        for (int f0 = 0; f0 < n_frames; f0 += INLINE_CAMS) {
+            const int nf = n_frames - f0 < INLINE_CAMS ? n_frames - f0 : INLINE_CAMS;
+            FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, G > 1 ? g : ctx->rank, world, dev_out + (size_t)f0 * npix, (long long)npix);
+            for (int i = 0; i < nf; i++) { fp.cam_inline[i] = to_cam(cams[f0 + i]); fp.hskip[i] = hs[(size_t)(f0 + i)]; }
+            int rc2 = launch_render(ctx, d, fp, d.stream); if (rc2) return rc2;
+            if (g == 0 && f0 == 0) start_fill();                        // after the first launch: the GPU and the link start first
+        }
+        CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
+        return RT_OK;
+    };
+    int rc = RT_OK;
+    for (int g = 1; g < G; g++) ctx->workers.post(g - 1, [&device_job, g]() { return device_job(g); });
+    rc = device_job(0);
+    for (int g = 1; g < G; g++) { int rc2 = ctx->workers.wait(g - 1); if (!rc) rc = rc2; }
+    if (rc) return rc;
+    ctx->last_enqueue_ns = since_enter_ns();
+    if (fill_started) {
+        const auto t0 = std::chrono::steady_clock::now();
+        ctx->fill_pool.wait();
+        fill_started = false;
+        ctx->last_fill_wait_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    }
+    float kernel_ms = 0.0f;
+    for (int g = 0; g < G; g++) {
+        DeviceState& d = ctx->devs[(size_t)g];
+        CU_TRY(ctx, cudaSetDevice(d.dev));
+        CU_TRY(ctx, cudaStreamSynchronize(d.stream));
+        float ms = 0.0f;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        if (ms > kernel_ms) kernel_ms = ms;
+    }
+    // bytes that crossed PCIe: every pixel of this context's tiles that the host did not fill
+    uint64_t sent = 0;
+    for (int f = 0; f < n_frames; f++) {
+        const HostSkip& k = hs[(size_t)f];
+        for (int y = 0; y < h; y++) {
+            if (G == 1 && world > 1 && (y / tile_rows) % world != ctx->rank) continue;
+            if ((y >= k.yb0 && y < k.yb1) || (y >= k.yc0 && y < k.yc1)) continue;
+            sent += (uint64_t)((y >= k.yr0 && y < k.yr1) ? (k.rx1 - k.rx0 + 1) : w) * 4;
+        }
+    }
+    ctx->last_d2h_bytes = sent;
+    ctx->last_total_ns = since_enter_ns();
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->kernel_ms = kernel_ms; stats->d2h_ms = kernel_ms;        // the return IS the kernel's stores
+    }
+    return RT_OK;
+}
+
 // Renders n_frames frames and, if host_pixels != NULL, returns them to the host.
 //  * headless: ONE launch per device covers (up to 16) frames; with several devices every device stores its row tiles straight
 //    into device 0's framebuffer ring (peer stores over NVLink: the gather is fused into the kernel).
@@ -1125,11 +1272,25 @@ int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int w
 //    Pixels the frame gates prove black are not copied at all (RT_OPT_SPARSE_D2H, see plan_rows above).
 static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, int w, int h, int depth, int spp, uint32_t seed,
                          int32_t* host_pixels, rt_stats* stats) {
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto since_enter_ns = [&]() { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_enter).count(); };
     int rc = check_frame_args(ctx, cams, w, h, depth, spp);
     if (rc) return rc;
     if (n_frames < 1) return fail(ctx, RT_ERR_INVALID, "n_frames");
     const size_t npix = (size_t)w * h;
     const int G = (int)ctx->devs.size();
+    // zero copy: 2 = always, 1 = frames up to 8 MB (measured on B200, profiles/r02/e2e_probe3.jsonl: the kernel's own PCIe stores reach
+    // 37-46 GB/s against the copy engine's 56, but need no copy hand-off: 0.098 vs 0.148 ms at 1280x720, 0.62 vs 0.52 ms at 4K)
+    if (host_pixels && !ctx->host_via_gpu0 && (ctx->zero_copy == 2 || (ctx->zero_copy == 1 && npix * 4 <= ((size_t)8 << 20)))) {
+        // page-locked, device-addressable host memory? (first and last byte in one registered / cudaHostAlloc'd range)
+        cudaPointerAttributes a0, a1;
+        const char* last = (const char*)host_pixels + npix * (size_t)n_frames * 4 - 1;
+        if (cudaPointerGetAttributes(&a0, host_pixels) == cudaSuccess && cudaPointerGetAttributes(&a1, last) == cudaSuccess &&
+            a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost && a0.devicePointer && a1.devicePointer &&
+            (const char*)a1.devicePointer - (const char*)a0.devicePointer == last - (const char*)host_pixels)
+            return render_frames_zero_copy(ctx, cams, n_frames, w, h, depth, spp, seed, host_pixels, (uint32_t*)a0.devicePointer, stats);
+        cudaGetLastError();       // pageable memory: cudaPointerGetAttributes may leave an error behind on older drivers
+    }
     const bool direct = host_pixels != nullptr && G > 1 && !ctx->host_via_gpu0;     // per-device D2H of own tiles
     const bool tiles_mode = direct || (host_pixels != nullptr && G == 1 && ctx->world > 1);   // copies go tile by tile (strided)
     rc = ensure_fb(ctx, npix * (size_t)n_frames); if (rc) return rc;
@@ -1166,7 +1327,7 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
     // the frame goes to the host (nobody reads those rows of the device framebuffer), and the number of bands follows the bytes that
     // really cross PCIe (~4 MB per band and link).
     constexpr int MAX_BANDS = 16;
-    struct Bands { int g_lo = 0, g_hi = 0, n = 0, groups = 1; };
+    struct Bands { int g_lo = 0, g_hi = 0, n = 0; int bound[MAX_BANDS + 1] = {0}; };      // band i = groups [bound[i], bound[i + 1])
     const int groups_total = (tiles_total + world - 1) / world;
     std::vector<Bands> bands((size_t)n_frames);
     for (int f = 0; f < n_frames; f++) {
@@ -1181,15 +1342,22 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             copy_rows_n = 0;
             for (int y = 0; y < h; y++) if (rp.kind[(size_t)y] != ROW_BLACK) copy_rows_n++;
         }
-        if (!pipelined) { b.n = 1; b.groups = groups_total > 0 ? groups_total : 1; continue; }
+        if (!pipelined) { b.n = 1; b.bound[0] = 0; b.bound[1] = groups_total; continue; }
         if (b.g_hi <= b.g_lo) { b.n = 0; continue; }
         const char* be = getenv("RTB200_BANDS");
         const size_t link_bytes = copy_rows_n * (size_t)w * 4 / (size_t)(tiles_mode ? world : 1);      // bytes one PCIe link carries
         int nb = be ? atoi(be) : (int)((link_bytes + (4u << 20) - 1) / (4u << 20));                   // ~4 MB per band and link
-        if (nb > MAX_BANDS) nb = MAX_BANDS;
+        if (nb > MAX_BANDS - 1) nb = MAX_BANDS - 1;
         if (nb < 1) nb = 1;
-        b.groups = (b.g_hi - b.g_lo + nb - 1) / nb;
-        b.n = (b.g_hi - b.g_lo + b.groups - 1) / b.groups;
+        const int range = b.g_hi - b.g_lo;
+        const int per = (range + nb - 1) / nb;
+        // a short head band (a quarter of the others): its kernel is done within microseconds, so the first copy starts almost at
+        // once and the link — the bottleneck of the whole call — is busy from then on (measured: profiles/r02/e2e_probe*.jsonl)
+        int head = (nb > 1 && !getenv("RTB200_NO_HEAD_BAND")) ? per / 4 : 0;
+        b.n = 0; b.bound[0] = b.g_lo;
+        if (head > 0) b.bound[++b.n] = b.g_lo + head;
+        const int rest = range - head, per2 = (rest + nb - 1) / nb;
+        for (int q = b.g_lo + head; q < b.g_hi; q += per2) { const int e = q + per2 < b.g_hi ? q + per2 : b.g_hi; b.bound[++b.n] = e; }
     }
     const int n_groups = (n_frames + INLINE_CAMS - 1) / INLINE_CAMS;      // headless: one launch per <= INLINE_CAMS frames
     const int n_segments = pipelined ? n_frames * MAX_BANDS : n_groups;
@@ -1203,7 +1371,10 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             }
         }
     }
-    if (!plans.empty() && !ctx->host_precleared) {
+    // The host-side zero fill is prepared and handed to the pool AFTER the first band is enqueued (the GPU and the link start first).
+    auto start_fill = [&]() {
+        ctx->last_fill_bytes = 0;
+        if (plans.empty() || ctx->host_precleared) return;
         std::vector<FillPool::Seg> segs;
         auto add = [&](int32_t* p, size_t npx) {
             const size_t piece = (size_t)1 << 18;                                       // 1 MB pieces: load balance across the pool
@@ -1238,11 +1409,9 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         uint64_t fb = 0; for (const auto& sg : segs) fb += sg.bytes;
         ctx->last_fill_bytes = fb;
         if (!segs.empty()) { ctx->fill_pool.run(std::move(segs)); fill_started = true; }
-    } else {
-        ctx->last_fill_bytes = 0;
-    }
+    };
     ctx->last_fill_wait_ns = 0;
-    struct FillGuard { FillPool* p; ~FillGuard() { if (p) p->wait(); } } fill_guard{fill_started ? &ctx->fill_pool : nullptr};   // every return path
+    struct FillGuard { FillPool* p; const bool* started; ~FillGuard() { if (p && *started) p->wait(); } } fill_guard{&ctx->fill_pool, &fill_started};   // every return path
     std::vector<char> first_copy_dev((size_t)G, 1);
     // Device g's D2H copies for rows/tiles of one band of one frame, on its copy stream (which already waits for the band's event).
     auto copy_tiles = [&](DeviceState& d, int rank, int frame, int k_begin, int k_count) -> int {
@@ -1305,7 +1474,7 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         if (pipelined) {
             fp.cam_inline[0] = to_cam(cams[frame]);
             const Bands& b = bands[(size_t)frame];
-            const int k0 = b.g_lo + band * b.groups; int k1 = k0 + b.groups; if (k1 > b.g_hi) k1 = b.g_hi;   // this rank's tiles of the band
+            const int k0 = b.bound[band], k1 = b.bound[band + 1];                             // this rank's tiles of the band
             const int mine = fp.tiles_mine;
             fp.k_begin = k0 < mine ? k0 : mine;
             fp.tiles_mine = (k1 < mine ? k1 : mine) - fp.k_begin;
@@ -1327,7 +1496,12 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             DeviceState& d = ctx->devs[(size_t)g];
             CU_TRY(ctx, cudaSetDevice(d.dev));
             CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
-            for (int s = 0; s < n_segments; s++) { int rc2 = enqueue(g, s); if (rc2) return rc2; }
+            bool fill_pending = g == 0;
+            for (int s = 0; s < n_segments; s++) {
+                int rc2 = enqueue(g, s); if (rc2) return rc2;
+                if (fill_pending && (!pipelined || s % MAX_BANDS < bands[(size_t)(s / MAX_BANDS)].n)) { start_fill(); fill_pending = false; }
+            }
+            if (fill_pending) start_fill();
             CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
             return RT_OK;
         };
@@ -1341,34 +1515,60 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
             CU_TRY(ctx, cudaSetDevice(d.dev));
             CU_TRY(ctx, cudaEventRecord(d.ev0, d.stream));
         }
-        for (int s = 0; s < n_segments; s++) {
-            const int frame = pipelined ? s / MAX_BANDS : s * INLINE_CAMS, band = pipelined ? s % MAX_BANDS : 0;
-            if (pipelined && band >= bands[(size_t)frame].n) continue;
+        bool fill_pending_serial = true;
+        // Frame complete on device 0 (one device, or gather-on-GPU-0): per frame, the first band's launch and copy are enqueued first
+        // (the link starts as early as possible), then the launches of ALL other bands (the kernels run ahead at full speed, no band
+        // waits for the host), then their copies — each on the copy stream behind its band's event.
+        auto copy_band = [&](int s) -> int {
+            const int frame = s / MAX_BANDS, band = s % MAX_BANDS;
+            CU_TRY(ctx, cudaSetDevice(d0.dev));
+            for (int g = 0; g < G; g++) CU_TRY(ctx, cudaStreamWaitEvent(d0.copy_stream, ctx->devs[(size_t)g].band_events[(size_t)s], 0));
+            if (first_copy_dev[0]) { CU_TRY(ctx, cudaEventRecord(d0.evc0, d0.copy_stream)); first_copy_dev[0] = 0; }
+            const Bands& b = bands[(size_t)frame];
+            const int q0 = b.bound[band], q1 = b.bound[band + 1];
+            const long long ya = (long long)q0 * world * tile_rows; long long yb = (long long)q1 * world * tile_rows;
+            if (yb > h) yb = h;
+            if (yb > ya) return copy_rows(d0, frame, (int)ya, (int)yb);
+            return RT_OK;
+        };
+        auto launch_band = [&](int s) -> int {
             for (int g = 0; g < G; g++) {
                 CU_TRY(ctx, cudaSetDevice(ctx->devs[(size_t)g].dev));
-                rc = enqueue(g, s); if (rc) return rc;
+                int rc2 = enqueue(g, s); if (rc2) return rc2;
             }
-            if (pipelined && !tiles_mode) {   // the frame is complete on device 0 (one device, or gather-on-GPU-0): its copy stream
-                CU_TRY(ctx, cudaSetDevice(d0.dev));                                        // waits for every device's band
-                for (int g = 0; g < G; g++) CU_TRY(ctx, cudaStreamWaitEvent(d0.copy_stream, ctx->devs[(size_t)g].band_events[(size_t)s], 0));
-                if (first_copy_dev[0]) { CU_TRY(ctx, cudaEventRecord(d0.evc0, d0.copy_stream)); first_copy_dev[0] = 0; }
-                const Bands& b = bands[(size_t)frame];
-                const int q0 = b.g_lo + band * b.groups; int q1 = q0 + b.groups; if (q1 > b.g_hi) q1 = b.g_hi;
-                const long long ya = (long long)q0 * world * tile_rows; long long yb = (long long)q1 * world * tile_rows;
-                if (yb > h) yb = h;
-                if (yb > ya) { rc = copy_rows(d0, frame, (int)ya, (int)yb); if (rc) return rc; }
+            return RT_OK;
+        };
+        if (pipelined && !tiles_mode) {
+            for (int f = 0; f < n_frames; f++) {
+                const int nb = bands[(size_t)f].n;
+                if (nb <= 0) continue;
+                const int s0 = f * MAX_BANDS;
+                rc = launch_band(s0); if (rc) return rc;
+                rc = copy_band(s0); if (rc) return rc;
+                if (fill_pending_serial) { start_fill(); fill_pending_serial = false; }
+                for (int band = 1; band < nb; band++) { rc = launch_band(s0 + band); if (rc) return rc; }
+                for (int band = 1; band < nb; band++) { rc = copy_band(s0 + band); if (rc) return rc; }
+            }
+        } else {
+            for (int s = 0; s < n_segments; s++) {
+                const int frame = pipelined ? s / MAX_BANDS : s * INLINE_CAMS, band = pipelined ? s % MAX_BANDS : 0;
+                if (pipelined && band >= bands[(size_t)frame].n) continue;
+                rc = launch_band(s); if (rc) return rc;
+                if (fill_pending_serial) { start_fill(); fill_pending_serial = false; }
             }
         }
+        if (fill_pending_serial) start_fill();
         for (int g = 0; g < G; g++) {
             DeviceState& d = ctx->devs[(size_t)g];
             CU_TRY(ctx, cudaSetDevice(d.dev));
             CU_TRY(ctx, cudaEventRecord(d.ev1, d.stream));
         }
     }
+    ctx->last_enqueue_ns = since_enter_ns();
     if (fill_started) {      // everything is enqueued: help with the zero fill instead of idling in the stream synchronisation below
         const auto t0 = std::chrono::steady_clock::now();
         ctx->fill_pool.wait();
-        fill_guard.p = nullptr;
+        fill_started = false;
         ctx->last_fill_wait_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     }
     float kernel_ms = 0.0f, d2h_ms = 0.0f;
@@ -1393,6 +1593,7 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         }
     }
     if (pipelined) ctx->last_d2h_bytes = d2h_bytes.load();
+    ctx->last_total_ns = since_enter_ns();
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->kernel_ms = kernel_ms; stats->gather_ms = 0.0f; stats->d2h_ms = d2h_ms;   // d2h overlaps the kernel when banded
@@ -1641,7 +1842,7 @@ int rt_sync(rt_context* ctx) {
 int rt_host_register(rt_context* ctx, void* host_ptr, uint64_t bytes) {
     if (!ctx || !host_ptr || bytes == 0) return RT_ERR_INVALID;
     CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
-    CU_TRY(ctx, cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable));
+    CU_TRY(ctx, cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
     return RT_OK;
 }
 int rt_host_unregister(rt_context* ctx, void* host_ptr) {
@@ -1689,6 +1890,8 @@ int rt_get_info(const rt_context* ctx, int what, uint64_t* value) {
         case RT_INFO_SCENE_PATH: *value = (uint64_t)ctx->path; return RT_OK;
         case RT_INFO_LAST_FILL_BYTES: *value = ctx->last_fill_bytes; return RT_OK;
         case RT_INFO_LAST_FILL_WAIT_NS: *value = ctx->last_fill_wait_ns; return RT_OK;
+        case RT_INFO_LAST_ENQUEUE_NS: *value = ctx->last_enqueue_ns; return RT_OK;
+        case RT_INFO_LAST_TOTAL_NS: *value = ctx->last_total_ns; return RT_OK;
         default: return RT_ERR_INVALID;
     }
 }

@@ -28,8 +28,9 @@ RT_OPT_SHARED_TARGET = 4
 RT_OPT_DEBUG_SHIPPED = 5
 RT_OPT_SPARSE_D2H = 6
 RT_OPT_HOST_PRECLEARED = 7
+RT_OPT_HOST_ZERO_COPY = 8
 RT_INFO_GATE_HOST_NS, RT_INFO_GATE_COMPUTES, RT_INFO_LAST_D2H_BYTES, RT_INFO_SCENE_PATH = 1, 2, 3, 4
-RT_INFO_LAST_FILL_BYTES, RT_INFO_LAST_FILL_WAIT_NS = 5, 6
+RT_INFO_LAST_FILL_BYTES, RT_INFO_LAST_FILL_WAIT_NS, RT_INFO_LAST_ENQUEUE_NS, RT_INFO_LAST_TOTAL_NS = 5, 6, 7, 8
 COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_pos", "plane_tests",
                  "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"]
 

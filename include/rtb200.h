@@ -183,9 +183,9 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
 /* RT_OPT_HOST_ZERO_COPY (default 1): when host_pixels is page-locked memory the devices can address (rt_host_register, or memory from
  * cudaHostAlloc), rt_render / rt_render_batch can let the render kernel store the frame straight into it over PCIe — no device
  * framebuffer, no copy engine, one launch per device — and with RT_OPT_SPARSE_D2H what the frame gates prove black is neither stored
- * nor copied but zero-filled by host threads. 0 = never (device framebuffer + band-pipelined copies), 1 = for frames up to 8 MB
- * (the reference's 1280x720 window: 0.10 instead of 0.15 ms per frame on B200; at 4K the copy engine's higher PCIe rate wins),
- * 2 = always. Pageable host memory always takes the copy path. */
+ * nor copied but zero-filled by host threads. 0 = never (device framebuffer + band-pipelined copies), 1 = for frames up to 40 MB
+ * (the reference's 1280x720 window: 0.105 instead of 0.149 ms per frame on B200, 4K: 0.508 vs 0.517; beyond, the copy engine's higher
+ * PCIe rate catches up), 2 = always. Pageable host memory always takes the copy path. */
 #define RT_OPT_HOST_ZERO_COPY 8
 /* Options that change WHICH rank writes a pixel (RT_OPT_SHARED_TARGET, RT_OPT_PRIMARY_GATE) must be set identically on every rank
  * of a partition. RT_OPT_COMPACTION may differ: a launch that takes part in a sparse gather always uses the default kernel. */

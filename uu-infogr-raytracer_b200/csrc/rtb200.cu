@@ -654,7 +654,7 @@ struct rt_context {
     bool debug_shipped = false;     // RT_OPT_DEBUG_SHIPPED
     bool sparse_d2h = true;         // RT_OPT_SPARSE_D2H
     bool host_precleared = false;   // RT_OPT_HOST_PRECLEARED
-    int zero_copy = 1;              // RT_OPT_HOST_ZERO_COPY: 0 never, 1 frames up to 8 MB, 2 always
+    int zero_copy = 1;              // RT_OPT_HOST_ZERO_COPY: 0 never, 1 frames up to 40 MB, 2 always
     FillPool fill_pool;
     uint64_t last_d2h_bytes = 0;    // bytes the last host-returning render really copied device -> host (rt_get_info)
     uint64_t last_enqueue_ns = 0, last_total_ns = 0;       // host time of the last render_frames: entry -> everything enqueued, entry -> return
@@ -1279,9 +1279,11 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
     if (n_frames < 1) return fail(ctx, RT_ERR_INVALID, "n_frames");
     const size_t npix = (size_t)w * h;
     const int G = (int)ctx->devs.size();
-    // zero copy: 2 = always, 1 = frames up to 8 MB (measured on B200, profiles/r02/e2e_probe3.jsonl: the kernel's own PCIe stores reach
-    // 37-46 GB/s against the copy engine's 56, but need no copy hand-off: 0.098 vs 0.148 ms at 1280x720, 0.62 vs 0.52 ms at 4K)
-    if (host_pixels && !ctx->host_via_gpu0 && (ctx->zero_copy == 2 || (ctx->zero_copy == 1 && npix * 4 <= ((size_t)8 << 20)))) {
+    // zero copy: 2 = always, 1 = frames up to 40 MB. Measured on B200 (profiles/r02/e2e_ab.json, in-process A/B, ms per frame, copy engine
+    // vs the kernel's own PCIe stores): 1280x720 0.149 / 0.105, 1920x1080 0.21 / 0.165, 2560x1440 0.30 / 0.25, 3840x2160 0.517 / 0.508,
+    // 7680x4320 1.88 / 1.89 — the stores reach ~47 GB/s against the copy engine's 56, but need no copy hand-off and a tenth of the
+    // API calls; beyond 4K the higher DMA rate catches up.
+    if (host_pixels && !ctx->host_via_gpu0 && (ctx->zero_copy == 2 || (ctx->zero_copy == 1 && npix * 4 <= ((size_t)40 << 20)))) {
         // page-locked, device-addressable host memory? (first and last byte in one registered / cudaHostAlloc'd range)
         cudaPointerAttributes a0, a1;
         const char* last = (const char*)host_pixels + npix * (size_t)n_frames * 4 - 1;

@@ -187,6 +187,19 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
  * (the reference's 1280x720 window: 0.105 instead of 0.149 ms per frame on B200, 4K: 0.508 vs 0.517; beyond, the copy engine's higher
  * PCIe rate catches up), 2 = always. Pageable host memory always takes the copy path. */
 #define RT_OPT_HOST_ZERO_COPY 8
+/* Packed multi-GPU gather (csrc/rt_gather.cuh): when every rank stores into rank 0's framebuffer (RT_OPT_SHARED_TARGET, or a multi-device
+ * context) and a gather area is attached (rt_gather_attach; multi-device contexts own one), ranks != 0 send their tiles in a
+ * compressed wire format — nothing for quads the frame gates prove black, 1 byte per pixel for grey quads, 3 bytes per pixel
+ * otherwise — into planes in rank 0's memory, and rank 0 expands them into the 0x00RRGGBB framebuffer; the kernels synchronise among
+ * themselves through flags in rank 0's memory. Rank 0 gets a smaller share of the tiles (it also runs the expand pass).
+ *   RT_OPT_GATHER_MODE  -1 automatic (2 from 4 ranks on, else 0), 0 off (plain 4 B / pixel stores), 1 RGB24 only, 2 RGB24 + grey quads
+ *   RT_OPT_SINK_TILES / RT_OPT_PEER_TILES  tiles per period for rank 0 / for every other rank (0 = automatic: 1/1 for 2 ranks,
+ *                        4/5 for 4, 1/2 for 8); period = sink + peer * (world - 1) <= 64
+ * Applies to single-sample frames of tiny scenes whose width is a multiple of 128; everything else takes the plain gather. All three
+ * options must be identical on every rank. Frames are byte-identical either way (tests/test_gpu_shipped_path.py). */
+#define RT_OPT_GATHER_MODE 9
+#define RT_OPT_SINK_TILES 10
+#define RT_OPT_PEER_TILES 11
 /* Options that change WHICH rank writes a pixel (RT_OPT_SHARED_TARGET, RT_OPT_PRIMARY_GATE) must be set identically on every rank
  * of a partition. RT_OPT_COMPACTION may differ: a launch that takes part in a sparse gather always uses the default kernel. */
 int rt_set_option(rt_context* ctx, int option, int value);
@@ -198,6 +211,8 @@ int rt_set_option(rt_context* ctx, int option, int value);
 #define RT_INFO_SCENE_PATH 4        /* how the uploaded scene is traced: 0 tiny (constant bank), 1 staged (shared memory), 2 global, 3 LBVH */
 #define RT_INFO_LAST_FILL_BYTES 5   /* bytes of host_pixels that render zero-filled on the host instead of copying them */
 #define RT_INFO_LAST_FILL_WAIT_NS 6 /* nanoseconds its calling thread spent in (helping with) that fill after enqueuing the GPU work */
+#define RT_INFO_GATHER_TIMEOUTS 9   /* packed gather: spin waits that gave up after 2 s (must be 0; a non-zero value means ranks were out of step) */
+#define RT_INFO_GATHER_ACTIVE 10    /* 1 if the last rt_render_device launch group used the packed gather */
 #define RT_INFO_LAST_ENQUEUE_NS 7   /* host nanoseconds of the last rt_render / rt_render_batch from entry until all GPU work was enqueued */
 #define RT_INFO_LAST_TOTAL_NS 8     /* ... from entry to return */
 int rt_get_info(const rt_context* ctx, int what, uint64_t* value);
@@ -216,6 +231,13 @@ int rt_set_partition(rt_context* ctx, int rank, int world, int tile_rows);
  * dev_pixels may be a peer mapping of another GPU's framebuffer (CUDA IPC): the gather is then the kernel's own stores. */
 int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int width, int height, int max_depth, int spp,
                      uint32_t seed, void* dev_pixels, void* cuda_stream);
+
+/* Gather area of the packed multi-GPU gather (see RT_OPT_GATHER_MODE). One process per GPU: rank 0 allocates rt_gather_bytes(w, h)
+ * bytes (rt_dev_alloc), ZEROES them (rt_dev_memset) and exports them (rt_ipc_export); every rank — rank 0 with its own pointer, the
+ * others with the pointer rt_ipc_open returned — then calls rt_gather_attach, which also restarts the epoch counter: all ranks must
+ * attach before any of them renders, and must issue the same sequence of rt_render_device calls afterwards. NULL detaches. */
+uint64_t rt_gather_bytes(int width, int height);
+int rt_gather_attach(rt_context* ctx, void* area_dev_ptr, uint64_t bytes);
 
 /* CUDA IPC plumbing so that ranks 1..N-1 can store straight into rank 0's framebuffer. handle64 = 64 bytes. */
 int rt_ipc_export(rt_context* ctx, void* dev_ptr, void* handle64);

@@ -361,3 +361,94 @@ def test_lbvh_launches_on_two_streams_are_ordered(rt):
         if rep == 1:          # a scene update between frames that were launched on user streams
             c.update_spheres(sph, 0)
     c.close()
+
+
+# ---- packed multi-GPU gather (csrc/rt_gather.cuh) with the ranks emulated on ONE device ------------------------------------------
+def _packed_ranks(rt, sc, world, tile_rows, w, h, mode, sink, peer, shared_target=1):
+    base = rt.Context([0]); base.set_scene(sc)
+    nbytes = base.gather_bytes(w, h)
+    area = base.dev_alloc(nbytes)
+    base.dev_memset(area, 0, nbytes)
+    ranks = []
+    for r in range(world):
+        c = rt.Context([0]); c.set_scene(sc); c.set_partition(r, world, tile_rows)
+        c.set_option(rt.RT_OPT_SHARED_TARGET, shared_target)
+        c.set_option(rt.RT_OPT_GATHER_MODE, mode); c.set_option(rt.RT_OPT_SINK_TILES, sink); c.set_option(rt.RT_OPT_PEER_TILES, peer)
+        c.gather_attach(area, nbytes)
+        ranks.append(c)
+    return base, area, ranks
+
+
+@pytest.mark.parametrize("world,tile_rows,w,h,mode,sink,peer", [
+    (2, 8, 1024, 600, 2, 1, 1), (4, 8, 1280, 720, 2, 0, 0), (8, 8, 1280, 720, 2, 0, 0), (8, 8, 1280, 720, 1, 0, 0), (8, 3, 640, 97, 2, 1, 2),
+    (4, 16, 1152, 333, 1, 2, 3), (8, 1, 256, 131, 2, 3, 5), (3, 8, 1280, 720, 2, 0, 4), (8, 8, 3840, 2160, 2, 0, 0), (4, 8, 3840, 2160, 2, 0, 0)])
+def test_packed_gather_emulated_ranks(rt, world, tile_rows, w, h, mode, sink, peer):
+    """Ranks != 0 write the wire format (nothing / grey bytes / RGB24 + flag bytes) into the planes of the gather area, rank 0 renders
+    its (smaller, weighted) share and expands the rest; flags and epochs as between real GPUs. Four alternating cameras, two rounds
+    (eight epochs) into one poisoned framebuffer must reproduce the single-context frames byte for byte, with no spin time-outs.
+    sink = 0 with peer > 0: rank 0 renders nothing and only expands."""
+    sc = scenes.default_scene()
+    cams = [scenes.make_camera(pos=(0.0, 3.0, 2.0), pitch=1.3, width=w, height=h),
+            scenes.make_camera(pos=(0.0, 0.5, 0.0), pitch=-0.6, width=w, height=h),
+            scenes.make_camera(width=w, height=h), scenes.make_camera(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15, width=w, height=h)]
+    base, area, ranks = _packed_ranks(rt, sc, world, tile_rows, w, h, mode, sink, peer)
+    refs = [base.render(c, w, h, 8)[0].copy() for c in cams]
+    fb = base.dev_alloc(w * h * 4)
+    base.dev_memset(fb, 0x5A, w * h * 4)
+    for rep in range(2):
+        for cam, ref in zip(cams, refs):
+            for r in list(range(1, world)) + [0]:             # the peers first: on ONE device rank 0's expand pass would spin on them
+                ranks[r].render_device(cam[None], w, h, 8, 1, 0, fb)
+                ranks[r].sync()
+            assert all(c.get_info(rt.RT_INFO_GATHER_ACTIVE) == 1 for c in ranks)
+            got = base.dev_to_host(fb, w * h * 4).reshape(h, w)
+            assert np.array_equal(got, ref), "%d pixels differ (world %d, mode %d)" % (int((got != ref).sum()), world, mode)
+    assert ranks[0].get_info(rt.RT_INFO_GATHER_TIMEOUTS) == 0
+    for c in ranks:
+        c.close()
+    base.dev_free(fb); base.dev_free(area); base.close()
+
+
+def test_packed_gather_batches_colours_and_fallbacks(rt):
+    """16 distinct cameras per launch (the bench shape) through world 8; a scene with coloured planes and every material class
+    (run-time-count kernels, gates that never skip); and frames the packed gather does not apply to (width not a multiple of 128,
+    supersampling) must fall back to the plain gather on every rank and stay correct."""
+    w, h, world, F = 640, 360, 8, 16
+    sc = scenes.default_scene()
+    cams = np.stack([scenes.make_camera(pos=(0.02 * i, 0.01 * i, -0.03 * i), yaw=0.004 * i, pitch=0.002 * i - 0.01, width=w, height=h) for i in range(F)])
+    base, area, ranks = _packed_ranks(rt, sc, world, 8, w, h, 2, 0, 0)
+    fb = base.dev_alloc(F * w * h * 4)
+    base.dev_memset(fb, 0x5A, F * w * h * 4)
+    for rep in range(3):
+        for r in list(range(1, world)) + [0]:
+            ranks[r].render_device(cams, w, h, 8, 1, 0, fb); ranks[r].sync()
+        got = base.dev_to_host(fb, F * w * h * 4).reshape(F, h, w)
+        for i in range(F):
+            assert np.array_equal(got[i], base.render(cams[i], w, h, 8)[0]), (rep, i)
+    # not applicable: odd width / supersampled -> plain gather, still exact
+    for (w2, h2, spp) in ((1000, 563, 1), (640, 360, 4)):
+        cam = scenes.make_camera(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15, width=w2, height=h2)
+        base.dev_memset(fb, 0x5A, w2 * h2 * 4)
+        for r in list(range(1, world)) + [0]:
+            ranks[r].render_device(cam[None], w2, h2, 8, spp, 3, fb); ranks[r].sync()
+            assert ranks[r].get_info(rt.RT_INFO_GATHER_ACTIVE) == 0
+        assert np.array_equal(base.dev_to_host(fb, w2 * h2 * 4).reshape(h2, w2), base.render(cam, w2, h2, 8, spp=spp, seed=3)[0])
+    assert ranks[0].get_info(rt.RT_INFO_GATHER_TIMEOUTS) == 0
+    for c in ranks:
+        c.close()
+    base.dev_free(fb); base.dev_free(area); base.close()
+    # coloured planes, 5 spheres of every material class
+    sc2 = scenes.small_random_scene(5, 3)
+    w, h = 768, 432
+    cam = scenes.make_camera(pos=(0, 1.5, -4.0), pitch=0.1, width=w, height=h)
+    base, area, ranks = _packed_ranks(rt, sc2, 4, 8, w, h, 2, 0, 0)
+    fb = base.dev_alloc(w * h * 4)
+    base.dev_memset(fb, 0x5A, w * h * 4)
+    for rep in range(2):
+        for r in (1, 2, 3, 0):
+            ranks[r].render_device(cam[None], w, h, 8, 1, 0, fb); ranks[r].sync()
+        assert np.array_equal(base.dev_to_host(fb, w * h * 4).reshape(h, w), O.render(sc2, cam, w, h, 8)["pixels"])
+    assert ranks[0].get_info(rt.RT_INFO_GATHER_TIMEOUTS) == 0
+    for c in ranks:
+        c.close()
+    base.dev_free(fb); base.dev_free(area); base.close()

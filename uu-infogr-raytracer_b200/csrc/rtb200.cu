@@ -34,6 +34,7 @@ extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource*
 #include "rt_scene.cuh"
 #include "rt_lbvh_build.cuh"
 #include "rt_gate.cuh"
+#include "rt_gather.cuh"
 
 using namespace rtb;
 
@@ -65,11 +66,19 @@ __host__ __device__ __forceinline__ bool host_fills_span(const HostSkip& k, int 
     return (y >= k.yb0 && y < k.yb1) || (y >= k.yc0 && y < k.yc1) || (y >= k.yr0 && y < k.yr1 && (xb < k.rx0 || xa > k.rx1));
 }
 
+constexpr int PART_MAX_PERIOD = 64, PART_MAX_CNT = 16;
 struct FrameParams {
     int w, h, cap, spp;
     uint32_t seed;
     int n_frames;
     int rank, world, tile_rows;
+    // Row-tile partition: tiles are dealt out in PERIODS of part_period tiles; slot j of a period belongs to rank part_owner[j]; this
+    // rank owns part_cnt slots per period, part_pos[0..part_cnt). Equal shares: period = world, owner[j] = j (tile t -> rank t % world).
+    // Weighted (packed gather): GPU 0, the sink that also runs the expand pass, gets fewer slots than the others (PartTable).
+    int part_period, part_cnt;
+    unsigned char part_pos[PART_MAX_CNT];
+    unsigned char part_owner[PART_MAX_PERIOD];
+    GatherParams gather;        // packed multi-GPU gather (rt_gather.cuh); area == nullptr: plain stores into `out`
     int tiles_total;            // ceil(h / tile_rows)
     int tiles_mine;             // tiles of this rank rendered by this launch ...
     int k_begin;                // ... starting at the rank's k_begin-th tile (band pipelining, see render_frames)
@@ -87,6 +96,14 @@ struct FrameParams {
 struct DebugOut {
     uint32_t* hash; int32_t* aov_id; float* aov_t; unsigned long long* counters;
 };
+
+// this rank's k-th tile
+__device__ __forceinline__ int tile_of(const FrameParams& fp, int k) {
+    if (fp.gather.area == nullptr) return k * fp.world + fp.rank;            // equal shares (any world size)
+    if (fp.part_cnt == 1) return k * fp.part_period + fp.part_pos[0];
+    const int q = k / fp.part_cnt;
+    return q * fp.part_period + fp.part_pos[k - q * fp.part_cnt];
+}
 
 
 // One CTA per work item: blockIdx = (chunk inside the tile, this rank's tile, frame) — no index divisions, and the hardware
@@ -106,7 +123,7 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp,
     const int frame = blockIdx.z;
     for (int kk = blockIdx.y; kk < fp.tiles_mine; kk += gridDim.y) {
         const int k = fp.k_begin + kk;                         // my k-th tile
-        const int tile = k * fp.world + fp.rank;
+        const int tile = tile_of(fp, k);
         const int base = tile * tile_pix;
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
         const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
@@ -207,6 +224,153 @@ __global__ void __launch_bounds__(BLOCK) k_fill_black(const __grid_constant__ Fr
     }
 }
 
+using TinyKernel = void (*)(const TinySceneData, const FrameParams);
+// ---------------------------------------------------------------------------------------------------------------------
+// Packed multi-GPU gather (rt_gather.cuh): the render kernel of ranks 1..N-1 and the expand pass of rank 0.
+// Requirements checked on the host (gather_applicable): single-sample gated tiny-scene launch, width a multiple of 128 (a warp's
+// 128 pixels then never straddle a row, a tile or the end of the frame, so validity and quad membership are warp-uniform).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NS, int NL, int NP>
+__global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_pack(const __grid_constant__ TinySceneData scd, const __grid_constant__ FrameParams fp) {
+    constexpr int PPT = PPT_TINY, CHUNK = BLOCK * PPT;
+    TinyScene<NS, NL, NP> sc(scd);
+    HitRec stack[STACK_RECS];
+    NoDbg nodbg;
+    const GatherParams& ga = fp.gather;
+    GatherCtl* ctl = reinterpret_cast<GatherCtl*>(ga.area);
+    const int frame = blockIdx.z, lane = threadIdx.x & 31;
+    // write-after-read: rank 0 must have consumed this slot's planes of the previous epoch before anything is stored into them
+    if (threadIdx.x == 0 && ga.epoch > 1) {
+        volatile unsigned long long* seen = &ga.local->seen_freed[frame];
+        if (*seen < ga.epoch - 1) {
+            gather_wait_ge(&ctl->freed[frame], ga.epoch - 1, ctl);           // over NVLink; rare: rank 0 trails by less than a frame
+            *seen = ga.epoch - 1;
+        }
+    }
+    __syncthreads();
+    unsigned char* plane_c = ga.area + ga.off_c + (unsigned long long)frame * ga.stride_c;
+    unsigned char* plane_g = ga.area + ga.off_g + (unsigned long long)frame * ga.stride_g;
+    unsigned char* plane_f = ga.area + ga.off_f + (unsigned long long)frame * ga.stride_f;
+    const int npix = fp.w * fp.h;
+    const int tile_pix = fp.tile_rows * fp.w;
+    const CamRec& cam = fp.cam_inline[frame];
+    const FrameGates& gates = fp.gates[frame];
+    const unsigned qmask = 0xFu << (lane & 28);
+    const int q = lane >> 2, ql = lane & 3;
+    for (int kk = blockIdx.y; kk < fp.tiles_mine; kk += gridDim.y) {
+        const int tile = tile_of(fp, fp.k_begin + kk);
+        const int base = tile * tile_pix;
+        int end = base + tile_pix; if (end > npix || end < base) end = npix;
+        const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
+        if (p0 >= end) continue;                                   // warp-uniform (see above)
+        int y = p0 / fp.w, x = p0 - y * fp.w;
+        bool black = false;
+        const uint32_t bits = gate_bits_span(gates, x, x + PPT - 1, y, sc.n_lights(), &black);
+        uint32_t px[PPT] = {0u, 0u, 0u, 0u};
+        if (!black) {
+#pragma unroll 1
+            for (int i = 0; i < PPT; i++) {
+                const uint32_t c = trace_pixel<true, true>(sc, cam, x + i, y, fp.w, fp.h, fp.cap, 1, fp.seed, stack, nodbg, fp.rcp_w, fp.rcp_h, bits);
+#pragma unroll
+                for (int z = 0; z + 1 < PPT; z++) px[z] = px[z + 1];
+                px[PPT - 1] = c;
+            }
+        }
+        __syncwarp();
+        const uint32_t qblack = gather_quad_all(black);
+        const bool grey4 = gather_is_grey(px[0]) && gather_is_grey(px[1]) && gather_is_grey(px[2]) && gather_is_grey(px[3]);
+        const uint32_t qgrey = ga.grey ? gather_quad_all(grey4) : 0u;
+        if (!((qblack >> q) & 1u)) {                               // quad-uniform from here on
+            if ((qgrey >> q) & 1u) {
+                *reinterpret_cast<uint32_t*>(plane_g + p0) = (px[0] & 0xFFu) | ((px[1] & 0xFFu) << 8) | ((px[2] & 0xFFu) << 16) | ((px[3] & 0xFFu) << 24);
+            } else {
+                // 4 lanes x 12 bytes -> 3 lanes x 16 bytes: quad word m = 3 * lane + slot goes to output lane m / 4, word m % 4
+                uint32_t wd[3];
+                gather_pack_rgb(px, wd);
+                const int l0 = lane & 28;
+                const uint32_t a = ql == 0 ? wd[0] : (ql == 1 ? wd[1] : wd[2]);
+                const uint32_t b = ql == 0 ? wd[1] : (ql == 1 ? wd[2] : wd[0]);
+                const uint32_t c = ql == 0 ? wd[2] : (ql == 2 ? wd[0] : wd[1]);
+                const uint32_t d = ql == 1 ? wd[0] : (ql == 2 ? wd[1] : wd[2]);
+                const uint32_t o0 = __shfl_sync(qmask, a, l0 + (ql < 3 ? ql : 0));
+                const uint32_t o1 = __shfl_sync(qmask, b, l0 + (ql == 0 ? 0 : (ql == 1 ? 1 : 3)));
+                const uint32_t o2 = __shfl_sync(qmask, c, l0 + (ql == 0 ? 0 : (ql == 1 ? 2 : 3)));
+                const uint32_t o3 = __shfl_sync(qmask, d, l0 + (ql < 3 ? ql + 1 : 3));
+                if (ql < 3)
+                    *reinterpret_cast<uint4*>(plane_c + 3ull * (unsigned long long)(p0 - ql * PPT) + 16u * (unsigned)ql) = make_uint4(o0, o1, o2, o3);
+            }
+        }
+        if (ga.grey && lane == 0 && qblack != 0xFFu) plane_f[p0 >> 7] = (unsigned char)qgrey;
+    }
+    // this rank's planes of the slot have landed once its LAST CTA is through
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int prev = atomicAdd(&ga.local->cta_count[frame], 1u);
+        if (prev == gridDim.x * gridDim.y - 1u) {
+            ga.local->cta_count[frame] = 0u;
+            __threadfence_system();
+            gather_st_release(&ctl->done[fp.rank][frame], ga.epoch);
+        }
+    }
+}
+TinyKernel tiny_kernel_pack(int ns, int nl, int np) {
+    return (ns == 3 && nl == 2 && np == 1) ? k_render_tiny_pack<3, 2, 1> : k_render_tiny_pack<-1, -1, -1>;
+}
+
+// Rank 0: expands the other ranks' tiles from the planes into the framebuffer (local HBM), zero-fills their proven-black quads,
+// and hands the slot back. One CTA per (chunk, tile, frame) over ALL tiles; CTAs of rank 0's own tiles have nothing to do.
+__global__ void __launch_bounds__(BLOCK) k_gather_expand(const __grid_constant__ FrameParams fp) {
+    constexpr int PPT = PPT_TINY, CHUNK = BLOCK * PPT;
+    const GatherParams& ga = fp.gather;
+    GatherCtl* ctl = reinterpret_cast<GatherCtl*>(ga.area);
+    const int frame = blockIdx.z, lane = threadIdx.x & 31, q = lane >> 2;
+    const unsigned char* plane_c = ga.area + ga.off_c + (unsigned long long)frame * ga.stride_c;
+    const unsigned char* plane_g = ga.area + ga.off_g + (unsigned long long)frame * ga.stride_g;
+    const unsigned char* plane_f = ga.area + ga.off_f + (unsigned long long)frame * ga.stride_f;
+    const int npix = fp.w * fp.h;
+    const int tile_pix = fp.tile_rows * fp.w;
+    const FrameGates& gates = fp.gates[frame];
+    uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
+    for (int t = blockIdx.y; t < fp.tiles_total; t += gridDim.y) {           // CTA-uniform
+        const int owner = fp.part_owner[t % fp.part_period];
+        if (owner == 0) continue;
+        if (threadIdx.x == 0) gather_wait_ge(&ctl->done[owner][frame], ga.epoch, ctl);
+        __syncthreads();
+        const int base = t * tile_pix;
+        int end = base + tile_pix; if (end > npix || end < base) end = npix;
+        const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
+        if (p0 >= end) continue;                                             // warp-uniform; the barrier above was CTA-wide
+        const int y = p0 / fp.w, x = p0 - y * fp.w;
+        bool black = false;
+        gate_bits_span(gates, x, x + PPT - 1, y, 0, &black);
+        const uint32_t qblack = gather_quad_all(black);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (!((qblack >> q) & 1u)) {
+            // the planes were written by another GPU: read them from L2 (the coherence point), never through L1 — a line of the F
+            // plane can hold flags of two tiles, i.e. of two ranks that finish at different times
+            const uint32_t qgrey = ga.grey ? (uint32_t)__ldcg(plane_f + (p0 >> 7)) : 0u;
+            if ((qgrey >> q) & 1u) {
+                v = gather_unpack_grey(__ldcg(reinterpret_cast<const uint32_t*>(plane_g + p0)));
+            } else {
+                const uint32_t* c = reinterpret_cast<const uint32_t*>(plane_c + 3ull * (unsigned long long)p0);
+                v = gather_unpack_rgb(__ldcg(c), __ldcg(c + 1), __ldcg(c + 2));
+            }
+        }
+        *reinterpret_cast<uint4*>(out + p0) = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(&ctl->expand_count[frame], 1u);
+        if (prev == gridDim.x * gridDim.y - 1u) {
+            ctl->expand_count[frame] = 0u;
+            __threadfence_system();
+            gather_st_release(&ctl->freed[frame], ga.epoch);                 // the other ranks poll this over NVLink
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Opt-in variant (rt_set_option(RT_OPT_COMPACTION, 1)): warp-ballot ray compaction between bounces.
 // Pass 1 traces every pixel of the chunk up to its second hit. A chain that goes on (a mirror seen in a mirror) is not followed by
@@ -242,7 +406,7 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_compact(co
     const float fw = (float)fp.w, fh = (float)fp.h;
     for (int kk = blockIdx.y; kk < fp.tiles_mine; kk += gridDim.y) {       // uniform per CTA
         const int k = fp.k_begin + kk;
-        const int tile = k * fp.world + fp.rank;
+        const int tile = tile_of(fp, k);
         const int base = tile * tile_pix;
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
         const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
@@ -310,7 +474,6 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_compact(co
     }
 }
 
-using TinyKernel = void (*)(const TinySceneData, const FrameParams);
 // Exact-count instantiations (sphere and light loops unrolled, records addressed statically) for scenes of the
 // reference's size; everything else up to the TINY_MAX_* limits takes the run-time-count instantiation.
 constexpr int EXACT_MAX = 4;
@@ -654,6 +817,13 @@ struct rt_context {
     bool debug_shipped = false;     // RT_OPT_DEBUG_SHIPPED
     bool sparse_d2h = true;         // RT_OPT_SPARSE_D2H
     bool host_precleared = false;   // RT_OPT_HOST_PRECLEARED
+    // packed multi-GPU gather (rt_gather.cuh)
+    int gather_mode = -1;           // RT_OPT_GATHER_MODE: -1 auto (2 from 4 ranks on), 0 off, 1 RGB24, 2 RGB24 + grey quads
+    int sink_tiles = 0, peer_tiles = 0;   // RT_OPT_SINK_TILES / RT_OPT_PEER_TILES: 0 = automatic per world size
+    unsigned char* gather_area = nullptr; uint64_t gather_bytes = 0; bool gather_owned = false;    // as this context addresses it
+    std::vector<GatherLocal*> gather_local;     // per device, in its own memory
+    uint64_t gather_epoch = 0;
+    bool gather_active = false;     // the last launch group used the packed gather (rt_get_info)
     int zero_copy = 1;              // RT_OPT_HOST_ZERO_COPY: 0 never, 1 frames up to 40 MB, 2 always
     FillPool fill_pool;
     uint64_t last_d2h_bytes = 0;    // bytes the last host-returning render really copied device -> host (rt_get_info)
@@ -729,14 +899,47 @@ int check_frame_args(rt_context* ctx, const void* cam, int w, int h, int depth, 
     return RT_OK;
 }
 
+// Partition table of a launch: sink_tiles slots per period for rank 0, peer_tiles for every other rank (1, 1 = equal shares,
+// period = world, tile t -> rank t % world). Rank 0's slots are spread evenly over the period (Bresenham), the others' dealt round robin.
+struct PartTable { int period; int cnt[GATHER_MAX_RANKS]; unsigned char owner[PART_MAX_PERIOD]; };
+PartTable make_part_table(int world, int sink_tiles, int peer_tiles) {
+    PartTable t; memset(&t, 0, sizeof(t));
+    if (world > GATHER_MAX_RANKS || sink_tiles < 0 || peer_tiles < 1 || sink_tiles > PART_MAX_CNT || peer_tiles > PART_MAX_CNT ||
+        sink_tiles + peer_tiles * (world - 1) > PART_MAX_PERIOD || world < 2) { sink_tiles = 1; peer_tiles = 1; }
+    if (world > PART_MAX_PERIOD) { t.period = 0; return t; }         // not representable: the caller falls back to t % world
+    t.period = world < 2 ? 1 : sink_tiles + peer_tiles * (world - 1);
+    int next_peer = 1;
+    for (int j = 0; j < t.period; j++) {
+        const bool sink = world < 2 || ((long long)(j + 1) * sink_tiles) / t.period > ((long long)j * sink_tiles) / t.period;
+        int r = 0;
+        if (!sink) { r = next_peer; next_peer = next_peer + 1 < world ? next_peer + 1 : 1; }
+        t.owner[j] = (unsigned char)r;
+        if (r < GATHER_MAX_RANKS) t.cnt[r]++;
+    }
+    return t;
+}
+
 FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp, uint32_t seed, int n_frames,
-                        int rank, int world, uint32_t* out, long long frame_stride) {
+                        int rank, int world, uint32_t* out, long long frame_stride, const PartTable* pt = nullptr) {
     FrameParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.w = w; fp.h = h; fp.cap = depth; fp.spp = spp; fp.seed = seed; fp.n_frames = n_frames;
     fp.rank = rank; fp.world = world; fp.tile_rows = ctx->tile_rows;
     fp.tiles_total = (h + fp.tile_rows - 1) / fp.tile_rows;
-    fp.tiles_mine = fp.tiles_total > rank ? (fp.tiles_total - rank + world - 1) / world : 0;
+    if (pt && pt->period > 0 && rank < GATHER_MAX_RANKS) {
+        fp.part_period = pt->period; fp.part_cnt = 0;
+        for (int j = 0; j < pt->period; j++) {
+            fp.part_owner[j] = pt->owner[j];
+            if (pt->owner[j] == rank && fp.part_cnt < PART_MAX_CNT) fp.part_pos[fp.part_cnt++] = (unsigned char)j;
+        }
+        const int full = fp.tiles_total / pt->period, rem = fp.tiles_total % pt->period;
+        fp.tiles_mine = full * fp.part_cnt;
+        for (int i = 0; i < fp.part_cnt; i++) if (fp.part_pos[i] < rem) fp.tiles_mine++;
+        if (fp.part_cnt == 0) { fp.part_cnt = 1; fp.part_pos[0] = 0; fp.tiles_mine = 0; }     // a rank without slots renders nothing
+    } else {                                                         // equal shares: tile t -> rank t % world
+        fp.part_period = world; fp.part_cnt = 1; fp.part_pos[0] = (unsigned char)rank;       // (part_owner is not needed: no expand pass)
+        fp.tiles_mine = fp.tiles_total > rank ? (fp.tiles_total - rank + world - 1) / world : 0;
+    }
     const int chunk = BLOCK * (ctx->path == PATH_TINY ? PPT_TINY : PPT_HEAVY);
     fp.chunks_per_tile = (int)(((long long)fp.tile_rows * w + chunk - 1) / chunk);
     fp.rcp_w = 1.0f / (float)w; fp.rcp_h = 1.0f / (float)h;      // host fp32 division: IEEE
@@ -805,6 +1008,54 @@ void fill_gates(rt_context* ctx, FrameParams& gp) {
         gp.gates[f] = (!ctx->primary_gate || gp.spp != 1) ? gates_off(gp.w, gp.h) : gates_for(ctx, gp.cam_inline[f], gp.w, gp.h);
 }
 
+// Does a launch that stores into rank 0's framebuffer (shared target) use the packed gather? If so: the partition table to render
+// with and the GatherParams of this device for `epoch`. Every rank evaluates this on identical inputs and must agree.
+struct GatherPlan { bool on = false; PartTable pt; GatherParams gp; };
+GatherPlan plan_gather(rt_context* ctx, int dev_index, int w, int h, int spp, int world, int shared_target, uint64_t epoch) {
+    GatherPlan g;
+    memset(&g.gp, 0, sizeof(g.gp)); memset(&g.pt, 0, sizeof(g.pt));
+    int mode = ctx->gather_mode;
+    if (mode < 0) mode = world >= 4 ? 2 : 0;                     // measured: profiles/r02/ (the expand pass costs rank 0 more than 2 ranks save)
+    if (getenv("RTB200_GATHER_MODE")) mode = atoi(getenv("RTB200_GATHER_MODE"));
+    if (mode <= 0 || !shared_target || world < 2 || world > GATHER_MAX_RANKS || ctx->path != PATH_TINY || !ctx->primary_gate || spp != 1 ||
+        w > RT_FASTDIV_MAX || h > RT_FASTDIV_MAX || (w % 128) != 0 || !ctx->gather_area ||
+        ctx->gather_bytes < gather_area_bytes(w, h) || (size_t)dev_index >= ctx->gather_local.size() || !ctx->gather_local[(size_t)dev_index])
+        return g;
+    int st = ctx->sink_tiles, ptl = ctx->peer_tiles;
+    if (getenv("RTB200_SINK_TILES")) st = atoi(getenv("RTB200_SINK_TILES"));
+    if (getenv("RTB200_PEER_TILES")) ptl = atoi(getenv("RTB200_PEER_TILES"));
+    if (ptl <= 0) {                                               // automatic: rank 0's share shrinks as its expand work grows
+        if (world >= 8) { st = 1; ptl = 2; }                      // 1 / 15 of the tiles
+        else if (world >= 4) { st = 4; ptl = 5; }                 // 4 / 19
+        else { st = 1; ptl = 1; }
+    }
+    g.pt = make_part_table(world, st, ptl);
+    if (g.pt.period <= 0) return g;
+    const unsigned long long npix = (unsigned long long)w * (unsigned long long)h;
+    g.gp.area = ctx->gather_area; g.gp.local = ctx->gather_local[(size_t)dev_index]; g.gp.epoch = epoch;
+    g.gp.stride_c = 3 * npix; g.gp.stride_g = npix; g.gp.stride_f = (npix + 127) / 128 + 64;
+    g.gp.off_c = GATHER_CTL_BYTES; g.gp.off_g = g.gp.off_c + GATHER_SLOTS * g.gp.stride_c; g.gp.off_f = g.gp.off_g + GATHER_SLOTS * g.gp.stride_g;
+    g.gp.grey = mode >= 2 ? 1 : 0;
+    g.on = true;
+    return g;
+}
+void free_gather_local(rt_context* ctx) {
+    for (size_t i = 0; i < ctx->gather_local.size(); i++)
+        if (ctx->gather_local[i]) { cudaSetDevice(ctx->devs[i].dev); cudaFree(ctx->gather_local[i]); }
+    ctx->gather_local.clear();
+}
+// Per-device GatherLocal blocks (zeroed) for the context's devices.
+int ensure_gather_local(rt_context* ctx) {
+    if (ctx->gather_local.size() == ctx->devs.size()) return RT_OK;
+    ctx->gather_local.assign(ctx->devs.size(), nullptr);
+    for (size_t i = 0; i < ctx->devs.size(); i++) {
+        CU_TRY(ctx, cudaSetDevice(ctx->devs[i].dev));
+        CU_TRY(ctx, cudaMalloc(&ctx->gather_local[i], sizeof(GatherLocal)));
+        CU_TRY(ctx, cudaMemset(ctx->gather_local[i], 0, sizeof(GatherLocal)));
+    }
+    return RT_OK;
+}
+
 // Launches the render kernel for one device's share. Asynchronous on `stream`.
 int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaStream_t stream) {
     if (ctx->path == PATH_LBVH && fp.n_frames > 1) {
@@ -819,7 +1070,8 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
         }
         return RT_OK;
     }
-    if (fp.tiles_mine <= 0 || fp.chunks_per_tile <= 0 || fp.n_frames <= 0) return RT_OK;
+    const bool gather_sink = fp.gather.area != nullptr && fp.rank == 0;      // rank 0 of a packed gather runs the expand pass even without own tiles
+    if ((fp.tiles_mine <= 0 && !gather_sink) || fp.chunks_per_tile <= 0 || fp.n_frames <= 0) return RT_OK;
     if (fp.n_frames > 65535) return fail(ctx, RT_ERR_UNSUPPORTED, "more than 65535 frames in one launch");
     if (ctx->path == PATH_LBVH) {
         const CamRec& c = fp.cam_inline[0];
@@ -848,6 +1100,23 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
             // It pays off only where rank 0's NVLink ingress is the bottleneck (measured: N = 8); with fewer ranks rank 0 itself is
             // the critical path and its fill pass (55 us per 16 4K frames) costs more than the link saves -> automatic above 4 ranks,
             // promise value 2 forces it (tests).
+            if (fp.gather.area) {
+                // Packed gather (rt_gather.cuh; plan_gather has checked that it applies): ranks != 0 render into the planes in GPU 0's
+                // memory; rank 0 renders its own (smaller) share straight into the framebuffer, then expands the others' tiles.
+                if (fp.rank != 0) {
+                    tiny_kernel_pack(t.ns, t.nl, t.np)<<<grid, BLOCK, 0, stream>>>(t, gp);
+                } else {
+                    gp.skip_black_store = 0;
+                    if (fp.tiles_mine > 0) {
+                        kern<<<grid, BLOCK, 0, stream>>>(t, gp);
+                        CU_TRY(ctx, cudaGetLastError());
+                        ctx->launches++;
+                    }
+                    const dim3 egrid((unsigned)fp.chunks_per_tile, (unsigned)(fp.tiles_total < 65535 ? fp.tiles_total : 65535), (unsigned)fp.n_frames);
+                    k_gather_expand<<<egrid, BLOCK, 0, stream>>>(gp);
+                }
+                break;
+            }
             const bool sparse = fp.skip_black_store && (fp.world > 4 || fp.skip_black_store == 2) && fp.world > 1 && ctx->primary_gate &&
                                 fp.spp == 1 && fastdiv_ok && !compact;
             gp.skip_black_store = sparse && fp.rank != 0;
@@ -936,6 +1205,9 @@ int rt_destroy(rt_context* ctx) {
     if (!ctx) return RT_ERR_INVALID;
     ctx->workers.stop();
     ctx->fill_pool.stop();
+    for (auto& d : ctx->devs) { cudaSetDevice(d.dev); cudaDeviceSynchronize(); }
+    free_gather_local(ctx);
+    if (ctx->gather_owned && ctx->gather_area) { cudaSetDevice(ctx->devs[0].dev); cudaFree(ctx->gather_area); }
     for (void* r : ctx->gl_resources) cudaGraphicsUnregisterResource((cudaGraphicsResource_t)r);
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.dev);
@@ -1091,6 +1363,9 @@ int rt_set_option(rt_context* ctx, int option, int value) {
         case RT_OPT_DEBUG_SHIPPED: ctx->debug_shipped = value != 0; return RT_OK;
         case RT_OPT_SPARSE_D2H: ctx->sparse_d2h = value != 0; return RT_OK;
         case RT_OPT_HOST_PRECLEARED: ctx->host_precleared = value != 0; return RT_OK;
+        case RT_OPT_GATHER_MODE: ctx->gather_mode = value < -1 ? -1 : (value > 2 ? 2 : value); return RT_OK;
+        case RT_OPT_SINK_TILES: ctx->sink_tiles = value < 0 ? 0 : value; return RT_OK;
+        case RT_OPT_PEER_TILES: ctx->peer_tiles = value < 0 ? 0 : value; return RT_OK;
         case RT_OPT_HOST_ZERO_COPY: ctx->zero_copy = value < 0 ? 0 : (value > 2 ? 2 : value); return RT_OK;
         default: return fail(ctx, RT_ERR_INVALID, "unknown option");
     }
@@ -1115,8 +1390,12 @@ int rt_render_device(rt_context* ctx, const rt_camera* cams, int n_frames, int w
     cudaStream_t st = (cudaStream_t)cuda_stream;
     for (int f0 = 0; f0 < n_frames; f0 += INLINE_CAMS) {          // <= INLINE_CAMS frames per launch (cameras in the parameter block)
         const int nf = n_frames - f0 < INLINE_CAMS ? n_frames - f0 : INLINE_CAMS;
+        const GatherPlan gp = plan_gather(ctx, 0, w, h, spp, ctx->world, ctx->shared_target, ctx->gather_epoch + 1);
+        if (gp.on) ctx->gather_epoch++;
+        ctx->gather_active = gp.on;
         FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, ctx->rank, ctx->world,
-                                     (uint32_t*)dev_pixels + (size_t)f0 * w * h, (long long)w * h);
+                                     (uint32_t*)dev_pixels + (size_t)f0 * w * h, (long long)w * h, gp.on ? &gp.pt : nullptr);
+        if (gp.on) fp.gather = gp.gp;
         for (int i = 0; i < nf; i++) fp.cam_inline[i] = to_cam(cams[f0 + i]);
         fp.skip_black_store = ctx->shared_target;
         rc = launch_render(ctx, d, fp, st);
@@ -1464,6 +1743,25 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         }
         return RT_OK;
     };
+    uint64_t gather_epoch0 = ctx->gather_epoch;
+    if (G > 1 && !pipelined) {
+        // the context's own gather area on device 0 (the other devices reach it through peer access, like the framebuffer)
+        const uint64_t need = gather_area_bytes(w, h);
+        if (ctx->gather_owned && ctx->gather_bytes < need) {
+            CU_TRY(ctx, cudaSetDevice(d0.dev)); CU_TRY(ctx, cudaFree(ctx->gather_area));
+            ctx->gather_area = nullptr; ctx->gather_bytes = 0; ctx->gather_owned = false;
+        }
+        if (!ctx->gather_area && (w % 128) == 0 && ctx->path == PATH_TINY) {
+            CU_TRY(ctx, cudaSetDevice(d0.dev));
+            if (cudaMalloc(&ctx->gather_area, (size_t)need) == cudaSuccess) {
+                CU_TRY(ctx, cudaMemset(ctx->gather_area, 0, GATHER_CTL_BYTES));
+                ctx->gather_bytes = need; ctx->gather_owned = true; ctx->gather_epoch = 0; gather_epoch0 = 0;
+                free_gather_local(ctx);                               // epochs restart with the area: fresh (zeroed) per-device blocks
+            } else { cudaGetLastError(); ctx->gather_area = nullptr; }
+        }
+        rc = ensure_gather_local(ctx); if (rc) return rc;
+        if (plan_gather(ctx, 0, w, h, spp, world, 1, 1).on) ctx->gather_epoch += (uint64_t)n_groups;
+    }
     // Everything device g has to enqueue for segment s (its launch, its band event, and in tiles mode its own D2H copies).
     auto enqueue = [&](int g, int s) -> int {
         DeviceState& d = ctx->devs[(size_t)g];
@@ -1471,7 +1769,13 @@ static int render_frames(rt_context* ctx, const rt_camera* cams, int n_frames, i
         if (pipelined && band >= bands[(size_t)frame].n) return RT_OK;                       // this frame has fewer bands
         const int nf = pipelined ? 1 : (n_frames - frame < INLINE_CAMS ? n_frames - frame : INLINE_CAMS);
         const int rank = G > 1 ? g : ctx->rank;
-        FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, rank, world, (direct ? d.fb : d0.fb) + (size_t)frame * npix, (long long)npix);
+        // several devices, headless: every device stores into device 0's framebuffer — through the packed gather when it applies
+        // (one epoch per launch group, the same on every device)
+        GatherPlan gpl;
+        if (G > 1 && !pipelined) gpl = plan_gather(ctx, g, w, h, spp, world, 1, gather_epoch0 + (uint64_t)s + 1);
+        FrameParams fp = make_params(ctx, w, h, depth, spp, seed, nf, rank, world, (direct ? d.fb : d0.fb) + (size_t)frame * npix, (long long)npix,
+                                     gpl.on ? &gpl.pt : nullptr);
+        if (gpl.on) fp.gather = gpl.gp;
         fp.skip_black_store = (G > 1 && !direct) ? (ctx->shared_target == 2 ? 2 : 1) : 0;   // every device stores into device 0's framebuffer
         if (pipelined) {
             fp.cam_inline[0] = to_cam(cams[frame]);
@@ -1883,9 +2187,40 @@ int rt_measure_l2_read(rt_context* ctx, uint64_t bytes, double* gbs) {
     return RT_OK;
 }
 
+uint64_t rt_gather_bytes(int width, int height) {
+    if (width <= 0 || height <= 0) return 0;
+    return gather_area_bytes(width, height);
+}
+int rt_gather_attach(rt_context* ctx, void* area_dev_ptr, uint64_t bytes) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (ctx->devs.size() != 1) return fail(ctx, RT_ERR_INVALID, "rt_gather_attach needs a single-device context (multi-device contexts own their gather area)");
+    if (area_dev_ptr && bytes < GATHER_CTL_BYTES) return fail(ctx, RT_ERR_INVALID, "gather area too small");
+    CU_TRY(ctx, cudaSetDevice(ctx->devs[0].dev));
+    CU_TRY(ctx, cudaDeviceSynchronize());
+    if (ctx->gather_owned && ctx->gather_area) cudaFree(ctx->gather_area);
+    ctx->gather_owned = false;
+    free_gather_local(ctx);
+    ctx->gather_area = (unsigned char*)area_dev_ptr; ctx->gather_bytes = area_dev_ptr ? bytes : 0;
+    ctx->gather_epoch = 0; ctx->gather_active = false;
+    if (area_dev_ptr) return ensure_gather_local(ctx);
+    return RT_OK;
+}
+
 int rt_get_info(const rt_context* ctx, int what, uint64_t* value) {
     if (!ctx || !value) return RT_ERR_INVALID;
     switch (what) {
+        case RT_INFO_GATHER_ACTIVE: *value = ctx->gather_active ? 1u : 0u; return RT_OK;
+        case RT_INFO_GATHER_TIMEOUTS: {
+            *value = 0;
+            if (!ctx->gather_area) return RT_OK;
+            GatherCtl c;
+            if (cudaSetDevice(ctx->devs[0].dev) != cudaSuccess || cudaMemcpy(&c, ctx->gather_area, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) {
+                cudaGetLastError();
+                return RT_ERR_CUDA;
+            }
+            *value = c.timeouts;
+            return RT_OK;
+        }
         case RT_INFO_GATE_HOST_NS: *value = ctx->gate_host_ns.load(); return RT_OK;
         case RT_INFO_GATE_COMPUTES: *value = ctx->gate_computes.load(); return RT_OK;
         case RT_INFO_LAST_D2H_BYTES: *value = ctx->last_d2h_bytes; return RT_OK;

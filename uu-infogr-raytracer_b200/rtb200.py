@@ -29,6 +29,8 @@ RT_OPT_DEBUG_SHIPPED = 5
 RT_OPT_SPARSE_D2H = 6
 RT_OPT_HOST_PRECLEARED = 7
 RT_OPT_HOST_ZERO_COPY = 8
+RT_OPT_GATHER_MODE, RT_OPT_SINK_TILES, RT_OPT_PEER_TILES = 9, 10, 11
+RT_INFO_GATHER_TIMEOUTS, RT_INFO_GATHER_ACTIVE = 9, 10
 RT_INFO_GATE_HOST_NS, RT_INFO_GATE_COMPUTES, RT_INFO_LAST_D2H_BYTES, RT_INFO_SCENE_PATH = 1, 2, 3, 4
 RT_INFO_LAST_FILL_BYTES, RT_INFO_LAST_FILL_WAIT_NS, RT_INFO_LAST_ENQUEUE_NS, RT_INFO_LAST_TOTAL_NS = 5, 6, 7, 8
 COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_pos", "plane_tests",
@@ -38,7 +40,7 @@ COUNTER_NAMES = ["primary", "shadow", "secondary", "sphere_tests", "sphere_disc_
 ABI_SYMBOLS = ["rt_create", "rt_set_scene", "rt_update_spheres", "rt_render", "rt_render_batch", "rt_render_debug", "rt_query_spheres", "rt_ray_log", "rt_selftest",
                "rt_set_option", "rt_set_partition", "rt_render_device", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_dev_alloc",
                "rt_dev_free", "rt_dev_to_host", "rt_dev_memset", "rt_sync", "rt_host_register", "rt_host_unregister", "rt_launch_count", "rt_destroy", "rt_last_error", "rt_abi_version",
-               "rt_get_info", "rt_measure_l2_read", "rt_render_mapped", "rt_gl_register_buffer", "rt_gl_unregister_buffer", "rt_render_gl"]
+               "rt_get_info", "rt_gather_bytes", "rt_gather_attach", "rt_measure_l2_read", "rt_render_mapped", "rt_gl_register_buffer", "rt_gl_unregister_buffer", "rt_render_gl"]
 
 
 class RtCamera(C.Structure):
@@ -105,6 +107,9 @@ def load_library():
     lib.rt_host_unregister.argtypes = [vp, vp]
     lib.rt_launch_count.argtypes = [vp]
     lib.rt_get_info.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
+    lib.rt_gather_bytes.argtypes = [C.c_int, C.c_int]
+    lib.rt_gather_bytes.restype = C.c_uint64
+    lib.rt_gather_attach.argtypes = [vp, vp, C.c_uint64]
     lib.rt_measure_l2_read.argtypes = [vp, C.c_uint64, C.POINTER(C.c_double)]
     lib.rt_render_mapped.argtypes = [vp, camp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, vp, C.c_uint64, statp]
     lib.rt_gl_register_buffer.argtypes = [vp, C.c_uint, C.POINTER(vp)]
@@ -116,7 +121,7 @@ def load_library():
     lib.rt_last_error.restype = C.c_char_p
     lib.rt_abi_version.restype = C.c_int
     for name in ABI_SYMBOLS:
-        if name not in ("rt_launch_count", "rt_last_error"):
+        if name not in ("rt_launch_count", "rt_last_error", "rt_gather_bytes"):
             getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
@@ -309,6 +314,13 @@ class Context:
 
     def sync(self):
         self._check(self.lib.rt_sync(self.h))
+
+    def gather_bytes(self, w: int, h: int) -> int:
+        return int(self.lib.rt_gather_bytes(w, h))
+
+    def gather_attach(self, dev_ptr, nbytes: int = 0):
+        """Attaches (or with None detaches) the gather area of the packed multi-GPU gather; see rt_gather_attach."""
+        self._check(self.lib.rt_gather_attach(self.h, C.c_void_p(dev_ptr) if dev_ptr else None, nbytes))
 
     def launch_count(self) -> int:
         return int(self.lib.rt_launch_count(self.h))

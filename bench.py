@@ -278,6 +278,22 @@ def main():
         if rank != 0:
             fb = ctx.ipc_open(handle[0])
 
+    # gather area of the packed multi-GPU gather (csrc/rt_gather.cuh), in rank 0's memory like the framebuffer ring
+    ga = None
+    if world > 1:
+        ga_bytes = ctx.gather_bytes(W, H)
+        if rank == 0:
+            ga = ctx.dev_alloc(ga_bytes)
+            ctx.dev_memset(ga, 0, ga_bytes)
+            h2 = [ctx.ipc_export(ga)]
+        else:
+            h2 = [None]
+        dist.broadcast_object_list(h2, src=0)
+        if rank != 0:
+            ga = ctx.ipc_open(h2[0])
+        ctx.gather_attach(ga, ga_bytes)
+        dist.barrier()
+
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
 
@@ -313,6 +329,9 @@ def main():
     ev1.record(stream)
     torch.cuda.synchronize(); barrier()
     launches_timed = ctx.launch_count() - launches_before
+    gather_active = ctx.get_info(rtb200.RT_INFO_GATHER_ACTIVE) if world > 1 else 0
+    gather_timeouts = ctx.get_info(rtb200.RT_INFO_GATHER_TIMEOUTS) if world > 1 else 0
+    assert gather_timeouts == 0, "packed gather: %d spin waits timed out (ranks out of step)" % gather_timeouts
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     launches_all = torch.tensor([float(launches_timed)], device="cuda")
     if world > 1:
@@ -504,8 +523,11 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": F, "rays_per_frame": rays_per_frame,
                        "l2": "ring of %d framebuffers (%.0f MB) larger than the 126 MB L2; the path reads no input from HBM" % (F, fb_bytes / 1e6),
-                       "partition": "interleaved row tiles of %d rows, tile t -> rank t %% N, peer stores into rank 0 (CUDA IPC)" % args.tile_rows
-                       if world > 1 else "single GPU"},
+                       "partition": ("interleaved row tiles of %d rows into rank 0's framebuffer over NVLink (CUDA IPC): " % args.tile_rows +
+                                     ("packed gather — ranks != 0 send nothing / 1 B / 3 B per pixel for black / grey / coloured quads into planes on GPU 0, "
+                                      "rank 0 renders a smaller share and expands them; device-side flags, no collective" if gather_active else
+                                      "tile t -> rank t % N, plain 128-bit peer stores"))
+                       if world > 1 else "single GPU", "packed_gather": bool(gather_active)},
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_peak, "traffic": traffic,
                          "note": "kernel is fp32-instruction bound, not HBM or tensor: peak = 148 SM x 128 lanes x 2 (FMA) x sm_max_mhz "
@@ -541,11 +563,16 @@ def main():
         print(json.dumps(line), flush=True)
 
     barrier()
+    if world > 1:
+        ctx.gather_attach(None)
     if rank != 0 and world > 1:
         ctx.ipc_close(fb)
+        ctx.ipc_close(ga)
     barrier()
     if rank == 0:
         ctx.dev_free(fb)
+        if ga is not None:
+            ctx.dev_free(ga)
     ctx.close()
     if shm is not None:
         host_frames.clear()

@@ -169,3 +169,83 @@ def test_multi_process_ipc_peer_stores(built, shared_target, w, h, tile_rows):
     while not qd.empty():
         res.append(qd.get())
     assert "ok" in res, res
+
+
+def _packed_worker(rank, world, w, h, mode, steps, q_handle, q_done, q_go):
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(os.path.dirname(here), "uu-infogr-raytracer_b200"))
+    import rtb200
+    sc = scenes.default_scene()
+    F = 4
+    cam_sets = [np.stack([scenes.make_camera(pos=(0.05 * i + 0.1 * s, 0.3 * (s % 2), -0.2 * i), yaw=0.02 * i - 0.1 * s, pitch=0.05 * s - 0.1,
+                                             width=w, height=h) for i in range(F)]) for s in range(3)]
+    ctx = rtb200.Context([rank]); ctx.set_scene(sc); ctx.set_partition(rank, world, 8)
+    ctx.set_option(rtb200.RT_OPT_SHARED_TARGET, 1)
+    ctx.set_option(rtb200.RT_OPT_GATHER_MODE, mode)
+    nbytes = ctx.gather_bytes(w, h)
+    if rank == 0:
+        fb = ctx.dev_alloc(F * w * h * 4)
+        ctx.dev_memset(fb, 0x5A, F * w * h * 4)
+        ga = ctx.dev_alloc(nbytes)
+        ctx.dev_memset(ga, 0, nbytes)
+        hs = (ctx.ipc_export(fb), ctx.ipc_export(ga))
+        for _ in range(world - 1):
+            q_handle.put(hs)
+    else:
+        hs = q_handle.get(timeout=60)
+        fb, ga = ctx.ipc_open(hs[0]), ctx.ipc_open(hs[1])
+    ctx.gather_attach(ga, nbytes)
+    q_done.put(("attached", rank))
+    q_go.get(timeout=60)                      # everybody attached: go
+    # `steps` launch groups back to back, NO host synchronisation in between: the kernels' own flags order producers and consumer
+    for s in range(steps):
+        ctx.render_device(cam_sets[s % 3], w, h, 8, 1, 0, fb)
+    ctx.sync()
+    active = ctx.get_info(rtb200.RT_INFO_GATHER_ACTIVE)
+    timeouts = ctx.get_info(rtb200.RT_INFO_GATHER_TIMEOUTS)
+    q_done.put(("rendered", rank, active, timeouts))
+    ok = q_go.get(timeout=120)
+    if rank == 0:
+        got = ctx.dev_to_host(fb, F * w * h * 4).reshape(F, h, w)
+        one = rtb200.Context([0]); one.set_scene(sc)
+        last = cam_sets[(steps - 1) % 3]
+        same = all(np.array_equal(got[i], one.render(last[i], w, h, 8)[0]) for i in range(F))
+        one.close()
+        q_done.put(("checked", bool(same)))
+        q_go.get(timeout=60)
+        ctx.gather_attach(None)
+        ctx.dev_free(fb); ctx.dev_free(ga)
+    else:
+        ctx.gather_attach(None)
+        ctx.ipc_close(fb); ctx.ipc_close(ga)
+    ctx.close()
+
+
+@need2
+@pytest.mark.parametrize("mode,w,h", [(2, 1280, 720), (1, 1024, 600), (2, 3840, 2160)])
+def test_multi_process_packed_gather(built, mode, w, h):
+    """One process per GPU, the packed gather over real NVLink: every rank issues 7 launch groups of 4 frames back to back without
+    any host synchronisation; producers (ranks != 0) and the consumer (rank 0's expand pass) are ordered only by the flags the kernels
+    write into rank 0's memory. The last group's frames on rank 0 must equal single-GPU frames; no spin may time out."""
+    import torch.multiprocessing as mp
+    world = min(N_GPUS, 4)
+    mctx = mp.get_context("spawn")
+    qh, qd, qg = mctx.Queue(), mctx.Queue(), mctx.Queue()
+    procs = [mctx.Process(target=_packed_worker, args=(r, world, w, h, mode, 7, qh, qd, qg)) for r in range(world)]
+    for p in procs: p.start()
+    try:
+        for _ in range(world): assert qd.get(timeout=180)[0] == "attached"
+        for _ in range(world): qg.put(True)
+        rendered = [qd.get(timeout=300) for _ in range(world)]
+        assert all(r[0] == "rendered" for r in rendered), rendered
+        assert all(r[2] == 1 for r in rendered), "packed gather not active: %r" % (rendered,)
+        assert all(r[3] == 0 for r in rendered), "spin time-outs: %r" % (rendered,)
+        for _ in range(world): qg.put(True)
+        checked = qd.get(timeout=300)
+        assert checked == ("checked", True), checked
+        qg.put(True)
+    finally:
+        for p in procs: p.join(timeout=120)
+        for p in procs:
+            if p.is_alive(): p.kill()
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]

@@ -490,6 +490,11 @@ RT_HD uint32_t gate_bits_span(const FrameGates& g, int xa, int xb, int y, int nl
     }
     return bits;
 }
+// Only the `black` verdict of gate_bits_span (same two predicates, same arithmetic): what the fill / expand passes of the multi-GPU
+// gathers need — they never look at the mirror and shadow gates.
+RT_HD bool gate_black_span(const FrameGates& g, int xa, int xb, int y) {
+    return span_outside(g.spheres, xa, xb, y) && span_positive(g.sky, (float)xa, (float)xb, (float)y);
+}
 RT_HD uint32_t gate_bits(const FrameGates& g, int x, int y, bool* black) { return gate_bits_span(g, x, x, y, RT_GATE_LIGHTS, black); }
 
 // ---- sparse device -> host return (host side, used by render_frames in rtb200.cu) ------------------------------------------------

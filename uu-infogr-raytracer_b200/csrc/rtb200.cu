@@ -83,6 +83,7 @@ struct FrameParams {
     int tiles_mine;             // tiles of this rank rendered by this launch ...
     int k_begin;                // ... starting at the rank's k_begin-th tile (band pipelining, see render_frames)
     int chunks_per_tile;        // ceil(tile_rows * w / (BLOCK * pixels per thread))
+    int tile_rot;               // this rank's tiles are visited starting at its tile_rot-th one, wrapping around (launch_render: tail of the launch)
     int skip_black_store;       // sparse gather (launch_render): this rank does not store proven-black spans, rank 0 fills them locally
     float rcp_w, rcp_h;         // 1/w, 1/h correctly rounded (host): pixel-coordinate divisions of the single-sample kernels (rt_div_rcp)
     long long frame_stride;     // pixels between consecutive frames in `out`
@@ -122,7 +123,8 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp,
     const int tile_pix = fp.tile_rows * fp.w;
     const int frame = blockIdx.z;
     for (int kk = blockIdx.y; kk < fp.tiles_mine; kk += gridDim.y) {
-        const int k = fp.k_begin + kk;                         // my k-th tile
+        int kr = kk + fp.tile_rot; if (kr >= fp.tiles_mine) kr -= fp.tiles_mine;
+        const int k = fp.k_begin + kr;                         // my k-th tile
         const int tile = tile_of(fp, k);
         const int base = tile * tile_pix;
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
@@ -215,9 +217,7 @@ __global__ void __launch_bounds__(BLOCK) k_fill_black(const __grid_constant__ Fr
             if (p0 >= end) continue;
             const int y = p0 / fp.w, x = p0 - y * fp.w;
             if (!(x + PPT <= fp.w && p0 + PPT <= end)) continue;
-            bool black = false;
-            gate_bits_span(gates, x, x + PPT - 1, y, 0, &black);
-            if (!black) continue;
+            if (!gate_black_span(gates, x, x + PPT - 1, y)) continue;
             if ((reinterpret_cast<uintptr_t>(out + p0) & 15) == 0) *reinterpret_cast<uint4*>(out + p0) = make_uint4(0u, 0u, 0u, 0u);
             else for (int q = 0; q < PPT; q++) out[p0 + q] = 0u;
         }
@@ -257,11 +257,17 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_pack(const
     const FrameGates& gates = fp.gates[frame];
     const unsigned qmask = 0xFu << (lane & 28);
     const int q = lane >> 2, ql = lane & 3;
-    for (int kk = blockIdx.y; kk < fp.tiles_mine; kk += gridDim.y) {
-        const int tile = tile_of(fp, fp.k_begin + kk);
+    // gridDim.x CTAs per frame, each striding over the (tile, chunk) items of this rank: a few hundred fat CTAs instead of one per
+    // chunk, because every CTA ends with a system-scope fence that waits for its NVLink stores to be acknowledged (measured at N = 2:
+    // 16 200 fences per frame cost 0.4 ms per step, profiles/r02/)
+    const int n_items = fp.tiles_mine * fp.chunks_per_tile;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int kk = item / fp.chunks_per_tile, chunk = item - kk * fp.chunks_per_tile;
+        int kr = kk + fp.tile_rot; if (kr >= fp.tiles_mine) kr -= fp.tiles_mine;
+        const int tile = tile_of(fp, fp.k_begin + kr);
         const int base = tile * tile_pix;
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
-        const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
+        const int p0 = base + chunk * CHUNK + (int)threadIdx.x * PPT;
         if (p0 >= end) continue;                                   // warp-uniform (see above)
         int y = p0 / fp.w, x = p0 - y * fp.w;
         bool black = false;
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_pack(const
     if (threadIdx.x == 0) {
         __threadfence_system();
         const unsigned int prev = atomicAdd(&ga.local->cta_count[frame], 1u);
-        if (prev == gridDim.x * gridDim.y - 1u) {
+        if (prev == gridDim.x - 1u) {
             ga.local->cta_count[frame] = 0u;
             __threadfence_system();
             gather_st_release(&ctl->done[fp.rank][frame], ga.epoch);
@@ -332,29 +338,42 @@ __global__ void __launch_bounds__(BLOCK) k_gather_expand(const __grid_constant__
     const int tile_pix = fp.tile_rows * fp.w;
     const FrameGates& gates = fp.gates[frame];
     uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
-    for (int t = blockIdx.y; t < fp.tiles_total; t += gridDim.y) {           // CTA-uniform
+    // gridDim.x CTAs per frame striding over the (tile, chunk) items of the frame; a rank's `done` flag is awaited once per CTA
+    unsigned ready = 1u;                                                     // bit r: rank r's planes of this slot have landed (CTA-uniform)
+    const int n_items = fp.tiles_total * fp.chunks_per_tile;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {         // CTA-uniform
+        const int t = item / fp.chunks_per_tile, chunk = item - t * fp.chunks_per_tile;
         const int owner = fp.part_owner[t % fp.part_period];
         if (owner == 0) continue;
-        if (threadIdx.x == 0) gather_wait_ge(&ctl->done[owner][frame], ga.epoch, ctl);
-        __syncthreads();
+        if (!((ready >> owner) & 1u)) {
+            if (threadIdx.x == 0) gather_wait_ge(&ctl->done[owner][frame], ga.epoch, ctl);
+            __syncthreads();
+            ready |= 1u << owner;
+        }
         const int base = t * tile_pix;
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
-        const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
+        const int p0 = base + chunk * CHUNK + (int)threadIdx.x * PPT;
         if (p0 >= end) continue;                                             // warp-uniform; the barrier above was CTA-wide
-        const int y = p0 / fp.w, x = p0 - y * fp.w;
-        bool black = false;
-        gate_bits_span(gates, x, x + PPT - 1, y, 0, &black);
+        // row of the span without an integer division: p0 < 2^24 is exact in fp32, 1/w is correctly rounded -> off by one at most
+        int y = (int)((float)p0 * fp.rcp_w);
+        if (y * fp.w > p0) y--; else if ((y + 1) * fp.w <= p0) y++;
+        const int x = p0 - y * fp.w;
+        const bool black = gate_black_span(gates, x, x + PPT - 1, y);
         const uint32_t qblack = gather_quad_all(black);
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (!((qblack >> q) & 1u)) {
-            // the planes were written by another GPU: read them from L2 (the coherence point), never through L1 — a line of the F
-            // plane can hold flags of two tiles, i.e. of two ranks that finish at different times
+        if (qblack != 0xFFu) {                                               // warp-uniform
+            // The planes were written by another GPU: read them from L2 (the coherence point), never through L1 — a line of the F
+            // plane can hold flags of two tiles, i.e. of two ranks that finish at different times. The flag byte and the G-plane
+            // word are fetched together (one round trip for grey quads); only coloured quads pay a second one for the C plane.
             const uint32_t qgrey = ga.grey ? (uint32_t)__ldcg(plane_f + (p0 >> 7)) : 0u;
-            if ((qgrey >> q) & 1u) {
-                v = gather_unpack_grey(__ldcg(reinterpret_cast<const uint32_t*>(plane_g + p0)));
-            } else {
-                const uint32_t* c = reinterpret_cast<const uint32_t*>(plane_c + 3ull * (unsigned long long)p0);
-                v = gather_unpack_rgb(__ldcg(c), __ldcg(c + 1), __ldcg(c + 2));
+            const uint32_t gword = ga.grey ? __ldcg(reinterpret_cast<const uint32_t*>(plane_g + p0)) : 0u;
+            if (!((qblack >> q) & 1u)) {
+                if ((qgrey >> q) & 1u) {
+                    v = gather_unpack_grey(gword);
+                } else {
+                    const uint32_t* c = reinterpret_cast<const uint32_t*>(plane_c + 3ull * (unsigned long long)p0);
+                    v = gather_unpack_rgb(__ldcg(c), __ldcg(c + 1), __ldcg(c + 2));
+                }
             }
         }
         *reinterpret_cast<uint4*>(out + p0) = v;
@@ -363,7 +382,7 @@ __global__ void __launch_bounds__(BLOCK) k_gather_expand(const __grid_constant__
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned int prev = atomicAdd(&ctl->expand_count[frame], 1u);
-        if (prev == gridDim.x * gridDim.y - 1u) {
+        if (prev == gridDim.x - 1u) {
             ctl->expand_count[frame] = 0u;
             __threadfence_system();
             gather_st_release(&ctl->freed[frame], ga.epoch);                 // the other ranks poll this over NVLink
@@ -1091,6 +1110,21 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
             const bool fastdiv_ok = fp.w <= RT_FASTDIV_MAX && fp.h <= RT_FASTDIV_MAX;
             FrameParams gp = fp;                      // + per-frame gates (a few microseconds of host work per distinct camera)
             fill_gates(ctx, gp);
+            // Tail of the launch: CTAs are dispatched in grid order and a chunk on the mirror sphere costs ~10x an average one, so a
+            // launch that ends with expensive chunks leaves most SMs idle while the last ones finish — a fixed ~45 us per launch,
+            // 15 % of a 1/8 share of the 16-frame step (profiles/r02/gather_probe_launches.csv). Tiles are therefore visited starting
+            // at the top of the sphere rectangle of the launch's LAST frame and wrapping around: spheres first, then the floor below
+            // them (plentiful, uniform), the sky above last.
+            if (ctx->primary_gate && fp.spp == 1 && fp.tiles_mine > 1 && fp.tiles_total > 0 && !getenv("RTB200_NO_TILE_ORDER")) {
+                const GateRect& r = gp.gates[fp.n_frames - 1].spheres;
+                if (r.y0 > 0 && r.y0 < fp.h && r.y1 >= r.y0) {
+                    const long long t0 = r.y0 / fp.tile_rows;
+                    long long rot = t0 * (fp.k_begin + fp.tiles_mine) / fp.tiles_total - fp.k_begin;      // ~ this rank's first tile at / below t0
+                    if (rot < 0) rot = 0;
+                    if (rot >= fp.tiles_mine) rot = 0;
+                    gp.tile_rot = (int)rot;
+                }
+            }
             // the compacting variant knows no black spans: a launch that takes part in a sparse gather uses the default kernel on
             // EVERY rank, so that a rank with RT_OPT_COMPACTION set differently cannot leave spans nobody writes
             const bool compact = ctx->compaction && fp.spp == 1 && fastdiv_ok && !fp.skip_black_store;
@@ -1103,8 +1137,14 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
             if (fp.gather.area) {
                 // Packed gather (rt_gather.cuh; plan_gather has checked that it applies): ranks != 0 render into the planes in GPU 0's
                 // memory; rank 0 renders its own (smaller) share straight into the framebuffer, then expands the others' tiles.
+                // a few hundred CTAs per frame (each ends with a system-scope fence): ~6 items per CTA, between 1 and 4 per SM
+                auto fat_grid = [&](long long items) {
+                    long long c = items / 6; const long long lo = d.sm_count, hi = 4LL * d.sm_count;
+                    if (c < lo) c = lo; if (c > hi) c = hi; if (c > items) c = items; if (c < 1) c = 1;
+                    return dim3((unsigned)c, 1u, (unsigned)fp.n_frames);
+                };
                 if (fp.rank != 0) {
-                    tiny_kernel_pack(t.ns, t.nl, t.np)<<<grid, BLOCK, 0, stream>>>(t, gp);
+                    tiny_kernel_pack(t.ns, t.nl, t.np)<<<fat_grid((long long)fp.tiles_mine * fp.chunks_per_tile), BLOCK, 0, stream>>>(t, gp);
                 } else {
                     gp.skip_black_store = 0;
                     if (fp.tiles_mine > 0) {
@@ -1112,8 +1152,7 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
                         CU_TRY(ctx, cudaGetLastError());
                         ctx->launches++;
                     }
-                    const dim3 egrid((unsigned)fp.chunks_per_tile, (unsigned)(fp.tiles_total < 65535 ? fp.tiles_total : 65535), (unsigned)fp.n_frames);
-                    k_gather_expand<<<egrid, BLOCK, 0, stream>>>(gp);
+                    k_gather_expand<<<fat_grid((long long)fp.tiles_total * fp.chunks_per_tile), BLOCK, 0, stream>>>(gp);
                 }
                 break;
             }

@@ -321,3 +321,37 @@ extern "C" int emu_query(const float* spheres, int ns, const float* rays6, int n
     }
     return 0;
 }
+
+// Shadow-bin soundness (rt_shadow_grid.cuh): for every query point and every light, the answer of the binned query must equal the
+// reference's loop over ALL spheres (RayTracer.cs:573-582). out[0] = queries decided by the bins, out[1] = mismatches among them,
+// out[2] = queries left to the traversal (outside the validity box / no grid), out[3] = occluded answers, out[4] = sphere tests run.
+extern "C" int emu_shadow_bins_check(const float* spheres, int ns, const float* lights, int nl, const float* points3, int n_points, uint64_t* out) {
+    std::vector<f4> sg((size_t)ns); std::vector<LightRec> li((size_t)nl); std::vector<f3> lp((size_t)nl);
+    for (int i = 0; i < ns; i++) { const float* f = spheres + 18 * (size_t)i; sg[i].x = f[0]; sg[i].y = f[1]; sg[i].z = f[2]; sg[i].w = f[17]; }
+    for (int i = 0; i < nl; i++) { li[i] = make_light(lights + 4 * (size_t)i); lp[i] = li[i].p; }
+    ShadowGridsHost h;
+    shadow_grids_build(sg, lp, &h);
+    ShadowGridsView v; memset(&v, 0, sizeof(v));
+    if (!h.empty() && !h.cell_start.empty()) { v.grids = h.grids.data(); v.cell_start = h.cell_start.data(); v.items = h.items.data(); v.lo = h.lo; v.hi = h.hi; }
+    uint64_t decided_n = 0, bad = 0, undecided = 0, occ_n = 0, tests = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : decided_n, bad, undecided, occ_n, tests)
+    for (int p = 0; p < n_points; p++) {
+        const f3 P = mk3(points3[3 * p], points3[3 * p + 1], points3[3 * p + 2]);
+        for (int l = 0; l < nl; l++) {
+            FullDbg dbg;
+            bool decided = false;
+            const bool got = shadow_grid_any(v, l, P, li[l].p, li[l].a2, li[l].a4, &decided, dbg);
+            if (!decided) { undecided++; continue; }
+            decided_n++; tests += dbg.sphere_tests;
+            bool want = false; NoDbg nd;
+            for (int i = 0; i < ns; i++) {
+                float t;
+                if (sphere_hit(sub3(P, mk3(sg[i].x, sg[i].y, sg[i].z)), li[l].p, sg[i].w, li[l].a2, li[l].a4, 0.001f, &t, nd)) want = true;
+            }
+            if (want != got) bad++;
+            if (got) occ_n++;
+        }
+    }
+    out[0] = decided_n; out[1] = bad; out[2] = undecided; out[3] = occ_n; out[4] = tests;
+    return 0;
+}

@@ -35,6 +35,8 @@ def load():
         _lib.emu_gates.restype = C.c_int
         _lib.emu_row_plan.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_int)]
         _lib.emu_row_plan.restype = C.c_int
+        _lib.emu_shadow_bins_check.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, C.POINTER(C.c_uint64)]
+        _lib.emu_shadow_bins_check.restype = C.c_int
     return _lib
 
 
@@ -131,3 +133,15 @@ def row_plan(scene, cam, w, h):
     sparse = lib.emu_row_plan(_fp(scene.spheres), len(scene.spheres), _fp(scene.planes), len(scene.planes), _fp(scene.lights), len(scene.lights),
                               _fp(cam), w, h, kind.ctypes.data_as(C.POINTER(C.c_ubyte)), rx)
     return kind, int(rx[0]), int(rx[1]), bool(sparse)
+
+
+def shadow_bins_check(spheres, lights, points):
+    """Binned shadow query (rt_shadow_grid.cuh) against the reference's loop over all spheres for every (point, light):
+    dict(decided, mismatches, undecided, occluded, sphere_tests)."""
+    lib = load()
+    spheres = np.ascontiguousarray(spheres, np.float32); lights = np.ascontiguousarray(lights, np.float32)
+    points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    out = np.zeros(5, np.uint64)
+    rc = lib.emu_shadow_bins_check(_fp(spheres), len(spheres), _fp(lights), len(lights), _fp(points), len(points), out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    assert rc == 0
+    return dict(zip(("decided", "mismatches", "undecided", "occluded", "sphere_tests"), (int(v) for v in out)))

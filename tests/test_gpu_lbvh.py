@@ -169,3 +169,67 @@ def test_update_spheres_refit_stays_exact(rt, n, accel_name):
     with pytest.raises(rt.RtError):
         ctx.update_spheres(moved[:2], first=n - 1)          # out of range
     ctx.close()
+
+
+@pytest.mark.parametrize("which", ["config3", "noise", "non_finite"])
+def test_device_shadow_bins_equal_host_bins(rt, which):
+    """The per-light shadow bins are built on the GPU (csrc/rt_shadow_grid_build.cuh) with the geometry code of the host build
+    (rt_shadow_grid.cuh, checked against the reference's loop over all spheres in tests/test_shadow_bins.py): same frame, same chain
+    hashes, and the same NUMBER of sphere tests — every shadow query scans a cell with the same population under both builds."""
+    if which == "config3":
+        sc = scenes.config3_scene(); cam_kw = scenes.SCALED_CAMERA
+    elif which == "noise":
+        rng = np.random.default_rng(21)
+        sph = np.stack([scenes.sphere((rng.uniform(-400, 400), rng.uniform(-0.8, 6), rng.uniform(20, 700)), rng.uniform(0.05, 0.35),
+                                      scenes.mat_diffuse((0.9, 0.6, 0.3))) for _ in range(1500)])
+        lights = np.stack([scenes.light((-300, 40, 100), 1.0), scenes.light((0, 500, 0), 1.0), scenes.light((250, 3, 650), 1.0), scenes.light((0, 0, 0), 1.0)])
+        sc = scenes.Scene(sph, scenes.reference_plane()[None], lights, scenes.REF_AMBIENT); cam_kw = dict(pos=(0, 8, -5), pitch=0.12)
+    else:
+        sc = scenes.small_random_scene(200, 5)
+        sph = sc.spheres.copy()
+        sph[3, 0] = np.nan; sph[7, 17] = np.inf; sph[11, 2] = -np.inf; sph[199, 17] = np.nan; sph[20, 1] = np.inf
+        sc = scenes.Scene(sph, sc.planes, sc.lights, sc.ambient); cam_kw = dict(pos=(0, 1.5, -4.0), pitch=0.1)
+    w, h = 640, 360
+    cam = scenes.make_camera(width=w, height=h, **cam_kw)
+    res = []
+    for host in (1, 0):
+        ctx = rt.Context([0])
+        ctx.set_option(rt.RT_OPT_HOST_SHADOW_BINS, host)
+        ctx.set_scene(sc, rt.RT_ACCEL_LBVH)
+        px, _ = ctx.render(cam, w, h, 8)
+        dbg = ctx.render_debug(cam, w, h, 8)
+        res.append((px, dbg, ctx.get_info(rt.RT_INFO_SHADOW_BIN_PAIRS)))
+        ctx.close()
+    (pa, da, na), (pb, db, nb) = res
+    assert na > 0 and na == nb                                   # same number of (cell, sphere) pairs
+    assert np.array_equal(pa, pb) and np.array_equal(da["hash"], db["hash"])
+    assert da["counters"] == db["counters"] and da["lbvh"] == db["lbvh"]
+    assert np.array_equal(da["pixels"], pa)
+    if which == "config3":
+        assert da["lbvh"]["node_visits_shadow"] < da["counters"]["shadow"]       # the bins, not the traversal, answered most shadow rays
+
+
+def test_update_spheres_rebuilds_the_bins_on_the_gpu(rt):
+    """rt_update_spheres at 100 k spheres (BASELINE configs[3]): refit + shadow-bin rebuild on the GPU stay exact (same frame as a
+    freshly built context) and take milliseconds, not the 0.2-0.6 s of the former host build."""
+    import time
+    sc = scenes.config4_scene()
+    w, h = 480, 270
+    cam = scenes.make_camera(width=w, height=h, **scenes.SCALED_CAMERA)
+    ctx = rt.Context([0]); ctx.set_scene(sc, rt.RT_ACCEL_LBVH)
+    moved = sc.spheres.copy()
+    rng = np.random.default_rng(3)
+    moved[:, 0] += rng.normal(size=len(moved)).astype(np.float32) * np.float32(0.3)
+    moved[:, 1] += np.abs(rng.normal(size=len(moved))).astype(np.float32) * np.float32(0.2)
+    ctx.update_spheres(moved, first=0)                          # warm-up (buffers grow once)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); ctx.update_spheres(moved, first=0); ts.append(time.perf_counter() - t0)
+    bins_ms = ctx.get_info(rt.RT_INFO_SHADOW_BINS_NS) / 1e6
+    got, _ = ctx.render(cam, w, h, 8)
+    fresh = rt.Context([0]); fresh.set_scene(scenes.Scene(moved, sc.planes, sc.lights, sc.ambient), rt.RT_ACCEL_LBVH)
+    ref, _ = fresh.render(cam, w, h, 8)
+    fresh.close(); ctx.close()
+    assert np.array_equal(got, ref)
+    print("rt_update_spheres(100k): %.2f ms total, shadow bins %.2f ms" % (min(ts) * 1e3, bins_ms))
+    assert bins_ms < 20.0

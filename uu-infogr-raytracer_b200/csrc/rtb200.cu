@@ -33,6 +33,7 @@ extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource*
 #include "../../include/rtb200.h"
 #include "rt_scene.cuh"
 #include "rt_lbvh_build.cuh"
+#include "rt_shadow_grid_build.cuh"
 #include "rt_gate.cuh"
 #include "rt_gather.cuh"
 
@@ -686,7 +687,7 @@ struct DeviceState {
     // scene
     f4* sgeom = nullptr; MatRec* smat = nullptr; PlaneRec* planes = nullptr; LightRec* lights = nullptr;
     LbvhDevice bvh;
-    ShadowGrid* sg_grids = nullptr; int* sg_cells = nullptr; GridPair* sg_items = nullptr;      // per-light shadow bins (rt_shadow_grid.cuh)
+    ShadowGridsDevice sg;                                         // per-light shadow bins (rt_shadow_grid.cuh), built on this device
     float bvh_cam[3] = {0, 0, 0}; bool bvh_cam_valid = false;    // camera the nodes_cam copy is currently inflated for ...
     cudaStream_t bvh_cam_stream = nullptr;                        // ... by a refit issued on this stream
     // nodes_cam / the refit arrival counters are ONE buffer per device: a refit issued on another stream than the last LBVH launch
@@ -818,6 +819,8 @@ struct rt_context {
     int path = PATH_TINY;           // how rt_render traces spheres
     bool has_bvh = false;
     bool has_shadow_grids = false;
+    bool host_shadow_bins = false;       // RT_OPT_HOST_SHADOW_BINS: build the bins on the host (tests: device build == host build)
+    uint64_t sg_build_ns = 0;            // wall time of the last shadow-bin (re)build (rt_get_info)
     std::vector<f4> host_sgeom; std::vector<f3> host_lights;     // kept for rt_update_spheres (shadow bins are rebuilt on the host)
     f3 sg_lo, sg_hi;
     TinySceneData tiny_data;
@@ -882,8 +885,7 @@ template <class T> struct DevMem {
 void free_scene(DeviceState& d) {
     cudaSetDevice(d.dev);
     d.bvh.release(); d.bvh_cam_valid = false;
-    cudaFree(d.sg_grids); cudaFree(d.sg_cells); cudaFree(d.sg_items);
-    d.sg_grids = nullptr; d.sg_cells = nullptr; d.sg_items = nullptr;
+    d.sg.release();
     cudaFree(d.sgeom); cudaFree(d.smat); cudaFree(d.planes); cudaFree(d.lights);
     d.sgeom = nullptr; d.smat = nullptr; d.planes = nullptr; d.lights = nullptr;
 }
@@ -967,27 +969,37 @@ FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp,
     return fp;
 }
 
-// (Re)builds the per-light shadow bins on the host from ctx->host_sgeom / host_lights and uploads them to every device.
+// (Re)builds the per-light shadow bins from ctx->host_sgeom / host_lights on every device. The host only sizes the grids (sg_setup:
+// bounds of the centres); binning runs on the GPU from the sphere records already there (rt_shadow_grid_build.cuh) — 100 k spheres
+// x 4 lights in well under a millisecond, so rt_update_spheres can run per frame. RTB200_SG_HOST=1 (or RT_OPT_HOST_SHADOW_BINS)
+// selects the host build (same geometry code, same bins) and uploads it.
 int upload_shadow_grids(rt_context* ctx) {
     ctx->has_shadow_grids = false;
     if (!ctx->has_bvh || getenv("RTB200_NO_SHADOW_GRID")) return RT_OK;
-    ShadowGridsHost h;
-    shadow_grids_build(ctx->host_sgeom, ctx->host_lights, &h);
-    if (h.empty() || h.cell_start.empty()) return RT_OK;
-    for (auto& d : ctx->devs) {
-        CU_TRY(ctx, cudaSetDevice(d.dev));
-        cudaFree(d.sg_grids); cudaFree(d.sg_cells); cudaFree(d.sg_items);
-        d.sg_grids = nullptr; d.sg_cells = nullptr; d.sg_items = nullptr;
-        CU_TRY(ctx, cudaMalloc(&d.sg_grids, sizeof(ShadowGrid) * h.grids.size()));
-        CU_TRY(ctx, cudaMalloc(&d.sg_cells, sizeof(int) * h.cell_start.size()));
-        CU_TRY(ctx, cudaMalloc(&d.sg_items, sizeof(GridPair) * (h.items.empty() ? 1 : h.items.size())));
-        CU_TRY(ctx, cudaMemcpyAsync(d.sg_grids, h.grids.data(), sizeof(ShadowGrid) * h.grids.size(), cudaMemcpyHostToDevice, d.stream));
-        CU_TRY(ctx, cudaMemcpyAsync(d.sg_cells, h.cell_start.data(), sizeof(int) * h.cell_start.size(), cudaMemcpyHostToDevice, d.stream));
-        if (!h.items.empty())
-            CU_TRY(ctx, cudaMemcpyAsync(d.sg_items, h.items.data(), sizeof(GridPair) * h.items.size(), cudaMemcpyHostToDevice, d.stream));
-        CU_TRY(ctx, cudaStreamSynchronize(d.stream));
+    const auto t0 = std::chrono::steady_clock::now();
+    if (ctx->host_shadow_bins || getenv("RTB200_SG_HOST")) {
+        ShadowGridsHost h;
+        shadow_grids_build(ctx->host_sgeom, ctx->host_lights, &h);
+        if (h.empty() || h.cell_start.empty()) return RT_OK;
+        for (auto& d : ctx->devs) {
+            CU_TRY(ctx, cudaSetDevice(d.dev));
+            CU_TRY(ctx, d.sg.upload(h, d.stream));
+        }
+        ctx->sg_lo = h.lo; ctx->sg_hi = h.hi;
+    } else {
+        SgSetup su;
+        sg_setup(ctx->host_sgeom.data(), (int)ctx->host_sgeom.size(), ctx->host_lights, &su);
+        if (!su.ok || su.total_cells <= 0) return RT_OK;
+        for (auto& d : ctx->devs) {
+            CU_TRY(ctx, cudaSetDevice(d.dev));
+            uint64_t nl = 0;
+            cudaError_t e = d.sg.build(d.sgeom, (int)ctx->host_sgeom.size(), su, d.stream, &nl);
+            if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("shadow bins: ") + cudaGetErrorString(e));
+            ctx->launches += nl;
+        }
+        ctx->sg_lo = su.lo; ctx->sg_hi = su.hi;
     }
-    ctx->sg_lo = h.lo; ctx->sg_hi = h.hi;
+    ctx->sg_build_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     ctx->has_shadow_grids = true;
     return RT_OK;
 }
@@ -1003,7 +1015,7 @@ LbvhSceneData lbvh_data(const rt_context* ctx, const DeviceState& d, bool with_c
     l.g = global_data(ctx, d);
     l.bv.nodes = d.bvh.nodes; l.bv.nodes_cam = with_cam_boxes ? d.bvh.nodes_cam : nullptr; l.bv.sgeom_sorted = d.bvh.sorted; l.bv.orig = d.bvh.orig; l.bv.n = d.bvh.n; l.bv.r2max = d.bvh.r2max;
     const bool grids = ctx->has_shadow_grids && with_cam_boxes;      // free single-ray queries always traverse
-    l.sg.grids = grids ? d.sg_grids : nullptr; l.sg.cell_start = d.sg_cells; l.sg.items = d.sg_items;
+    l.sg.grids = grids ? d.sg.grids : nullptr; l.sg.cell_start = d.sg.cells; l.sg.items = d.sg.items;
     l.sg.lo = ctx->sg_lo; l.sg.hi = ctx->sg_hi;
     return l;
 }
@@ -1405,6 +1417,7 @@ int rt_set_option(rt_context* ctx, int option, int value) {
         case RT_OPT_GATHER_MODE: ctx->gather_mode = value < -1 ? -1 : (value > 2 ? 2 : value); return RT_OK;
         case RT_OPT_SINK_TILES: ctx->sink_tiles = value < 0 ? 0 : value; return RT_OK;
         case RT_OPT_PEER_TILES: ctx->peer_tiles = value < 0 ? 0 : value; return RT_OK;
+        case RT_OPT_HOST_SHADOW_BINS: ctx->host_shadow_bins = value != 0; return RT_OK;
         case RT_OPT_HOST_ZERO_COPY: ctx->zero_copy = value < 0 ? 0 : (value > 2 ? 2 : value); return RT_OK;
         default: return fail(ctx, RT_ERR_INVALID, "unknown option");
     }
@@ -2268,6 +2281,8 @@ int rt_get_info(const rt_context* ctx, int what, uint64_t* value) {
         case RT_INFO_LAST_FILL_WAIT_NS: *value = ctx->last_fill_wait_ns; return RT_OK;
         case RT_INFO_LAST_ENQUEUE_NS: *value = ctx->last_enqueue_ns; return RT_OK;
         case RT_INFO_LAST_TOTAL_NS: *value = ctx->last_total_ns; return RT_OK;
+        case RT_INFO_SHADOW_BINS_NS: *value = ctx->sg_build_ns; return RT_OK;
+        case RT_INFO_SHADOW_BIN_PAIRS: *value = (ctx->has_shadow_grids && !ctx->devs.empty()) ? (uint64_t)ctx->devs[0].sg.n_pairs : 0u; return RT_OK;
         default: return RT_ERR_INVALID;
     }
 }

@@ -142,10 +142,11 @@ int rt_ray_log(rt_context* ctx, const rt_camera* cam, int width, int height, int
  *                          :687, :706, :854, :971): every float in [2^-65, 2^65)
  *   RT_SELFTEST_PIXEL_DIV  x / w (:964) for every integer 0 <= x < w <= 16384
  *   RT_SELFTEST_INV_LEN_RSQ_SEED  a rejected cheaper variant, kept to document WHY it is rejected (it has mismatches)
- * n_mismatch must come back 0 for the first two. */
+ * n_mismatch must come back 0 for all but the rejected variant. */
 #define RT_SELFTEST_INV_LEN 0
 #define RT_SELFTEST_PIXEL_DIV 1
 #define RT_SELFTEST_INV_LEN_RSQ_SEED 2
+#define RT_SELFTEST_INV_LEN_PAIR 3   /* the packed two-at-a-time version used by the two-light Phong pass: every float of the range in either half */
 int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mismatch);
 
 /* Tuning options. RT_OPT_COMPACTION (default 0): tiny-scene kernel variant that parks rays needing a third or later bounce in a

@@ -102,19 +102,40 @@ def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu(built, tmp_path):
     assert not (tmp_path / "x.ppm").exists()
 
 
-def test_sass_has_packed_fp32_but_no_packed_fma(built):
-    """The exact-count kernels use Blackwell's packed fp32 instructions (FADD2 / FMUL2) for two spheres at a time, but a
-    packed FMA must never appear: ptxas contracts packed mul+add into FFMA2 even under --fmad=false, which would round dot
-    products and discriminants once instead of twice (csrc/rt_trace.cuh). Scalar FFMA only comes from IEEE div / sqrt sequences."""
+def test_sass_has_packed_fp32_but_no_contracted_packed_fma(built, tmp_path):
+    """The exact-count kernels use Blackwell's packed fp32 instructions (FADD2 / FMUL2) for two spheres / two lights at a time,
+    but a packed FMA must never appear in REFERENCE arithmetic: ptxas contracts packed mul+add into FFMA2 even under --fmad=false,
+    which would round dot products and discriminants once instead of twice (csrc/rt_trace.cuh). The only FFMA2 allowed are the
+    ones written on purpose — rt_fma2 in the correctly rounded sqrt / reciprocal cores of rt_inv_len2 (csrc/rt_math.cuh): every
+    FFMA2 of the library must carry the source line of that asm statement. Scalar FFMA only comes from IEEE div / sqrt sequences."""
+    import re
     import shutil
     import subprocess
-    if not shutil.which("cuobjdump"):
-        pytest.skip("cuobjdump not available")
+    if not (shutil.which("cuobjdump") and shutil.which("nvdisasm")):
+        pytest.skip("cuobjdump / nvdisasm not available")
     lib = os.path.join(ROOT, "uu-infogr-raytracer_b200", "librtb200.so")
     sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    assert sass.count("FFMA2") == 0
     assert sass.count("FADD2") > 0 and sass.count("FMUL2") > 0
     assert "STG.E.128" in sass                      # 128-bit framebuffer stores
     for mnem in ("HMMA", "UTCHMMA", "UTCQMMA"):      # no tensor cores on this path (north_star)
         assert mnem not in sass
+    # where does each FFMA2 come from?
+    math_src = open(os.path.join(ROOT, "uu-infogr-raytracer_b200", "csrc", "rt_math.cuh")).read().splitlines()
+    fma_lines = {i + 1 + k for i, l in enumerate(math_src) if "fma.rn.f32x2" in l for k in (0, 1)}    # the asm statement spans two lines
+    assert len(fma_lines) == 2
+    subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp_path, capture_output=True, check=True)
+    cubins = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert cubins
+    n_ffma2 = 0
+    for cb in cubins:
+        dis = subprocess.run(["nvdisasm", "-g", "-c", str(tmp_path / cb)], capture_output=True, text=True).stdout
+        cur = None
+        for l in dis.splitlines():
+            m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+            if m:
+                cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            elif "FFMA2" in l:
+                n_ffma2 += 1
+                assert cur is not None and cur[0] == "rt_math.cuh" and cur[1] in fma_lines, (cur, l)
+    assert n_ffma2 == sass.count("FFMA2") and n_ffma2 % 4 == 0      # four per rt_inv_len2 instance

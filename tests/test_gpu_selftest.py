@@ -20,6 +20,13 @@ def test_inverse_length_is_two_correctly_rounded_operations(ctx):
     assert n == 0x41000000 and bad == 0          # every float in [2^-65, 2^65)
 
 
+def test_packed_inverse_length_pair_equals_the_scalar_one(ctx):
+    """rt_inv_len2 (two normalisations per pass of packed FMUL2 / FFMA2, the two-light Phong pass of shade_light_pair)."""
+    import rtb200
+    n, bad = ctx.selftest(rtb200.RT_SELFTEST_INV_LEN_PAIR)
+    assert n == 2 * 0x41000000 and bad == 0      # every float in [2^-65, 2^65), in either half of the pair
+
+
 def test_pixel_division_equals_ieee_division(ctx):
     import rtb200
     n, bad = ctx.selftest(rtb200.RT_SELFTEST_PIXEL_DIV)

@@ -23,6 +23,7 @@ struct TinySceneData {
     MatRec smat[TINY_MAX_SPHERES];
     PlaneRec planes[TINY_MAX_PLANES];
     LightRec lights[TINY_MAX_LIGHTS];
+    LightPair lpairs[TINY_MAX_LIGHTS / 2];
 };
 
 // NS >= 0: the sphere count is a compile-time constant — the sphere loops unroll and every record is addressed
@@ -39,6 +40,8 @@ struct TinyScene {
     RT_HD f4 sphere_geom(int i) const { return s.sgeom[i]; }
     RT_HD const SpherePair& sphere_pair(int k) const { return s.pairs[k]; }
     static constexpr bool has_pairs = true;
+    static constexpr int static_lights = NL;      // >= 0: compile-time light count (an even count takes the packed two-light pass)
+    RT_HD const LightPair& light_pair(int k) const { return s.lpairs[k]; }
     RT_HD MatRec sphere_mat(int i) const { return s.smat[i]; }
     RT_HD uint32_t sphere_flags(int i) const { return s.smat[i].flags; }
     RT_HD f4 plane_n(int i) const { f4 r; r.x = s.planes[i].n.x; r.y = s.planes[i].n.y; r.z = s.planes[i].n.z; r.w = s.planes[i].cn; return r; }
@@ -92,6 +95,7 @@ struct GlobalScene {
     RT_HD int n_spheres() const { return s.ns; }
     RT_HD int n_planes() const { return s.np; }
     RT_HD int n_lights() const { return s.nl; }
+    static constexpr int static_lights = -1;
     RT_HD f3 ambient() const { return s.amb; }
     RT_HD f4 sphere_geom(int i) const { return load_f4(s.sgeom + i); }
     RT_HD MatRec sphere_mat(int i) const { return load_mat(s.smat + i); }
@@ -151,6 +155,13 @@ inline void tiny_fill_pairs(TinySceneData& t) {
             SpherePair& p = t.pairs[k];
             if (i < t.ns) { p.ncx[h] = -t.sgeom[i].x; p.ncy[h] = -t.sgeom[i].y; p.ncz[h] = -t.sgeom[i].z; p.nr2[h] = -t.sgeom[i].w; }
             else { p.ncx[h] = 0.0f; p.ncy[h] = 0.0f; p.ncz[h] = 0.0f; p.nr2[h] = 1e30f; }
+        }
+    for (int k = 0; k < TINY_MAX_LIGHTS / 2; k++)
+        for (int h = 0; h < 2; h++) {
+            const int i = 2 * k + h;
+            LightPair& p = t.lpairs[k];
+            if (i < t.nl) { p.px[h] = t.lights[i].p.x; p.py[h] = t.lights[i].p.y; p.pz[h] = t.lights[i].p.z; p.intensity[h] = t.lights[i].intensity; }
+            else { p.px[h] = 0.0f; p.py[h] = 0.0f; p.pz[h] = 0.0f; p.intensity[h] = 0.0f; }
         }
 }
 

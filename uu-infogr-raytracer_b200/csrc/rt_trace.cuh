@@ -41,6 +41,9 @@ struct LightRec {          // Light RayTracer.cs:236-255 + invariants of the sha
     f3 p; float intensity;
     float a, a2, a4, pad;  // Dot(p,p), 2*a, 4*a  (:617, :624, :621)
 };
+// Position and intensity of lights 2k and 2k+1 side by side: 64-bit constant-bank operands of the packed two-light Phong pass
+// (shade_light_pair).
+struct LightPair { float px[2], py[2], pz[2], intensity[2]; };
 struct CamRec { f3 pos, right, up, fwd, view; };
 
 struct HitRec { f3 o; f3 dir; float d; int prim; };   // prim >= 0: sphere index; prim < 0: ~plane index
@@ -365,6 +368,55 @@ RT_HD float spec_pow(float base, float n) {
 #endif
 }
 
+#if defined(RT_HAVE_F32X2)
+// ShapePhongShading :665-695 and the light term :866-869 / :754-775 for lights 2k and 2k+1 in ONE pass of packed fp32: half .x
+// of every pair is light 2k, half .y light 2k+1; hit point, normal, view vector and material are scalar operands broadcast to
+// both halves. Per half the operations and their order are exactly the scalar loop's (shade_hit below). As in sphere_pair_bd,
+// only instructions that cannot be contracted are packed: differences of inputs, products, the two normalisations (rt_inv_len2);
+// every sum that consumes a product — the dot products, L - N*(2 L.N), ph + ks*pow — stays a scalar FADD on the register halves,
+// because ptxas fuses a packed multiply into a following packed add even under -fmad=false. ~130 instead of ~190 instructions
+// per shaded hit with two lights. I0 / I1: the lights' intensities after the shadow test (:581).
+template <class DBG>
+__device__ __forceinline__ void shade_light_pair(const LightPair& lp, const MatRec& m, f3 hit, f3 N, f3 V, float att, float tile,
+                                                 bool is_plane, float I0, float I1, f3* tA, f3* tB, DBG& dbg) {
+    float2 Lx = rt_sub2(make_float2(lp.px[0], lp.px[1]), rt_splat2(hit.x));                   // :667  light.position - hit
+    float2 Ly = rt_sub2(make_float2(lp.py[0], lp.py[1]), rt_splat2(hit.y));
+    float2 Lz = rt_sub2(make_float2(lp.pz[0], lp.pz[1]), rt_splat2(hit.z));
+    {
+        const float2 xx = rt_mul2(Lx, Lx), yy = rt_mul2(Ly, Ly), zz = rt_mul2(Lz, Lz);
+        const float2 sc = rt_inv_len2(make_float2((xx.x + yy.x) + zz.x, (xx.y + yy.y) + zz.y));   // Normalize: 1f / Length
+        Lx = rt_mul2(Lx, sc); Ly = rt_mul2(Ly, sc); Lz = rt_mul2(Lz, sc);
+    }
+    const float2 nlx = rt_mul2(rt_splat2(N.x), Lx), nly = rt_mul2(rt_splat2(N.y), Ly), nlz = rt_mul2(rt_splat2(N.z), Lz);
+    const float2 ndl = make_float2((nlx.x + nly.x) + nlz.x, (nlx.y + nly.y) + nlz.y);         // Dot(N, L) == Dot(L, N) bit for bit
+    const float2 diff = make_float2(cs_max0(ndl.x), cs_max0(ndl.y));                          // :678
+    float2 phx = rt_mul2(rt_splat2(m.kd.x), diff), phy = rt_mul2(rt_splat2(m.kd.y), diff), phz = rt_mul2(rt_splat2(m.kd.z), diff);   // :672-678
+    if (m.flags & MAT_SPEC) {                                                                 // :682
+        const float2 two = rt_mul2(rt_splat2(2.0f), ndl);                                     // :684  2 * Dot(L, N)
+        const float2 qx = rt_mul2(rt_splat2(N.x), two), qy = rt_mul2(rt_splat2(N.y), two), qz = rt_mul2(rt_splat2(N.z), two);
+        float2 rx = make_float2(Lx.x - qx.x, Lx.y - qx.y), ry = make_float2(Ly.x - qy.x, Ly.y - qy.y), rz = make_float2(Lz.x - qz.x, Lz.y - qz.y);   // :683
+        {
+            const float2 xx = rt_mul2(rx, rx), yy = rt_mul2(ry, ry), zz = rt_mul2(rz, rz);
+            const float2 sc = rt_inv_len2(make_float2((xx.x + yy.x) + zz.x, (xx.y + yy.y) + zz.y));   // :687 Normalize
+            rx = rt_mul2(rx, sc); ry = rt_mul2(ry, sc); rz = rt_mul2(rz, sc);
+        }
+        const float2 vx = rt_mul2(rt_splat2(V.x), rx), vy = rt_mul2(rt_splat2(V.y), ry), vz = rt_mul2(rt_splat2(V.z), rz);   // :685-688 Dot(V, Rv)
+        const float2 pw = make_float2(spec_pow(cs_max0((vx.x + vy.x) + vz.x), m.n), spec_pow(cs_max0((vx.y + vy.y) + vz.y), m.n));   // :691
+        const float2 kx = rt_mul2(rt_splat2(m.ks.x), pw), ky = rt_mul2(rt_splat2(m.ks.y), pw), kz = rt_mul2(rt_splat2(m.ks.z), pw);
+        phx = make_float2(phx.x + kx.x, phx.y + kx.y); phy = make_float2(phy.x + ky.x, phy.y + ky.y); phz = make_float2(phz.x + kz.x, phz.y + kz.y);   // :690-694
+        dbg.spec(); dbg.spec();
+    }
+    const float2 ia = rt_mul2(make_float2(I0, I1), rt_splat2(att));                           // (I,I,I) * att
+    const float2 tl = rt_splat2(tile);
+    const float2 tx = rt_mul2(rt_mul2(ia, phx), tl), ty = rt_mul2(rt_mul2(ia, phy), tl), tz = rt_mul2(rt_mul2(ia, phz), tl);   // :868-869 / :774
+    if (is_plane) {                                                                           // :775 (.Max(0))
+        *tA = mk3(cs_max0(tx.x), cs_max0(ty.x), cs_max0(tz.x)); *tB = mk3(cs_max0(tx.y), cs_max0(ty.y), cs_max0(tz.y));
+    } else {
+        *tA = mk3(tx.x, ty.x, tz.x); *tB = mk3(tx.y, ty.y, tz.y);
+    }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 // Colour of one recorded hit given the colour Cin seen by its reflection ray:
 // TraceSphere :846-875 / TracePlane :736-779 with ShapePhongShading :665-695 inlined into ONE light loop.
@@ -400,6 +452,28 @@ RT_HD f3 shade_hit(const SC& sc, const HitRec& h, f3 Cin, uint32_t level, DBG& d
     if (m.flags & MAT_DIFFUSE) {                                  // :862 / :750
         const f3 V = normalize3(h.dir);                           // :668
         const int nl = sc.n_lights();
+#if defined(RT_HAVE_F32X2)
+        // Exact even light counts (the reference scene has two): lights are shaded two at a time (shade_light_pair). The shadow
+        // tests stay scalar and come first; the two terms are added to the colour in light order, as the loop below does.
+        if constexpr (SC::static_lights >= 2 && (SC::static_lights & 1) == 0 && !DBG::count_tests) {
+#pragma unroll
+            for (int li = 0; li < SC::static_lights; li += 2) {
+                float I[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const LightRec l = sc.light(li + k);
+                    const bool proven_clear = li + k < (int)RT_GATE_MAX_LIGHTS && ((gates >> (RT_GATE_SHADOW_SHIFT + li + k)) & 1u) && level == 0 && is_plane;
+                    const bool occ = proven_clear ? false : sc.shadow_any(li + k, hit, l.p, l.a2, l.a4, dbg);   // :864 / :752
+                    dbg.shadow(level, (uint32_t)(li + k), occ);
+                    dbg.shadow_geom(sc, level, (uint32_t)(li + k), hit, l.p, l.a2, l.a4, occ);
+                    I[k] = occ ? 0.0f : l.intensity;              // :581
+                }
+                f3 tA, tB;
+                shade_light_pair(sc.light_pair(li >> 1), m, hit, N, V, att, tile, is_plane, I[0], I[1], &tA, &tB, dbg);
+                col = add3(add3(col, tA), tB);
+            }
+        } else
+#endif
 #pragma unroll
         for (int li = 0; li < nl; li++) {                         // :863 / :751
             const LightRec l = sc.light(li);

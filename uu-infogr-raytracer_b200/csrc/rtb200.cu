@@ -135,7 +135,16 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp,
         const FrameGates& gates = fp.gates[frame];
         uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
         uint32_t px[PPT];
-        int y = p0 / fp.w, x = p0 - y * fp.w;                  // one division per thread; then step along the row
+        // row of the span: frames below 2^24 pixels without an integer division (p0 is exact in fp32 and 1/w is correctly rounded,
+        // so the estimate is off by one at most; as in k_gather_expand); then step along the row
+        int y;
+        if (npix < (1 << 24)) {
+            y = (int)((float)p0 * fp.rcp_w);
+            if (y * fp.w > p0) y--; else if ((y + 1) * fp.w <= p0) y++;
+        } else {
+            y = p0 / fp.w;
+        }
+        int x = p0 - y * fp.w;
         // What the host proved about this thread's span of pixels (rt_gate.cuh): evaluated once, for spans inside one row.
         uint32_t bits = 0u;
         if (SPP1 && x + PPT <= fp.w && p0 + PPT <= end) {
@@ -630,6 +639,20 @@ __global__ void __launch_bounds__(256) k_selftest_inv_len(uint32_t first_bits, u
         if (__float_as_uint(got) != __float_as_uint(rt_inv_len_ieee(s))) bad++;
     }
     if (bad) atomicAdd(mismatches, bad);
+}
+// The packed pair version (rt_inv_len2): every float of the range in half .x, and — through a bijection of the range — in half .y.
+__global__ void __launch_bounds__(256) k_selftest_inv_len_pair(uint32_t first_bits, uint32_t count, unsigned long long* mismatches) {
+#if defined(RT_HAVE_F32X2)
+    unsigned long long bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(((unsigned long long)i * 2654435761ull) % count);       // 2654435761 is prime: a permutation
+        const float s0 = __uint_as_float(first_bits + i), s1 = __uint_as_float(first_bits + j);
+        const float2 got = rt_inv_len2(make_float2(s0, s1));
+        if (__float_as_uint(got.x) != __float_as_uint(rt_inv_len_ieee(s0))) bad++;
+        if (__float_as_uint(got.y) != __float_as_uint(rt_inv_len_ieee(s1))) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+#endif
 }
 __global__ void __launch_bounds__(256) k_selftest_pixel_div(int max_side, unsigned long long* mismatches) {
     unsigned long long bad = 0;
@@ -2078,6 +2101,10 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
         const uint32_t first = 0x1F000000u, count = 0x41000000u;
         k_selftest_inv_len<<<d.sm_count * 16, 256, 0, d.stream>>>(first, count, test == RT_SELFTEST_INV_LEN ? 0 : 1, dbad);
         checked = count;
+    } else if (test == RT_SELFTEST_INV_LEN_PAIR) {
+        const uint32_t first = 0x1F000000u, count = 0x41000000u;
+        k_selftest_inv_len_pair<<<d.sm_count * 16, 256, 0, d.stream>>>(first, count, dbad);
+        checked = 2ull * count;
     } else if (test == RT_SELFTEST_PIXEL_DIV) {
         k_selftest_pixel_div<<<d.sm_count * 8, 256, 0, d.stream>>>(RT_FASTDIV_MAX, dbad);
         checked = (uint64_t)RT_FASTDIV_MAX * (RT_FASTDIV_MAX + 1) / 2;

@@ -55,7 +55,7 @@ RAY_RECORD = np.dtype([("origin", np.float32, 3), ("direction", np.float32, 3), 
                        ("hit", np.int32), ("kind", np.uint32), ("pixel", np.uint32), ("level", np.uint32), ("light", np.uint32),
                        ("reserved", np.uint32)])
 assert RAY_RECORD.itemsize == 64
-RT_SELFTEST_INV_LEN, RT_SELFTEST_PIXEL_DIV, RT_SELFTEST_INV_LEN_RSQ_SEED = 0, 1, 2
+RT_SELFTEST_INV_LEN, RT_SELFTEST_PIXEL_DIV, RT_SELFTEST_INV_LEN_RSQ_SEED, RT_SELFTEST_INV_LEN_PAIR = 0, 1, 2, 3
 RAY_PRIMARY, RAY_SECONDARY, RAY_SHADOW = 0, 1, 2      # RayKind RayTracer.cs:343-362
 
 

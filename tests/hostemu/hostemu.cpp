@@ -26,14 +26,14 @@ static BvhBox host_refit_cam(HostBvh& b, f3 cam, int child) {
         return sphere_box(g, inflated_radius(g.w, dx * dx + dy * dy + dz * dz));
     }
     BvhNode& nd = b.nodes_cam[child];
-    BvhBox b0 = host_refit_cam(b, cam, nd.c0), b1 = host_refit_cam(b, cam, nd.c1);
+    BvhBox b0 = host_refit_cam(b, cam, nd.c[0]), b1 = host_refit_cam(b, cam, nd.c[1]);
     node_set_child_box(nd, 0, b0); node_set_child_box(nd, 1, b1);
     return box_union(b0, b1);
 }
 static BvhBox host_refit(HostBvh& b, const std::vector<float>& reff, int child) {
     if (child < 0) return sphere_box(b.sorted[~child], reff[b.orig[~child]]);
     BvhNode& nd = b.nodes[child];
-    BvhBox b0 = host_refit(b, reff, nd.c0), b1 = host_refit(b, reff, nd.c1);
+    BvhBox b0 = host_refit(b, reff, nd.c[0]), b1 = host_refit(b, reff, nd.c[1]);
     node_set_child_box(nd, 0, b0); node_set_child_box(nd, 1, b1);
     return box_union(b0, b1);
 }
@@ -55,7 +55,7 @@ static void host_build(const std::vector<f4>& sg, HostBvh& b) {
     std::sort(keys.begin(), keys.end());
     b.sorted.resize(n); b.orig.resize(n); b.nodes.resize(n - 1);
     for (int j = 0; j < n; j++) { int idx = (int)(keys[j] & 0xFFFFFFFFull); b.sorted[j] = sg[idx]; b.orig[j] = idx; }
-    for (int i = 0; i < n - 1; i++) { int l, r; karras_node(keys.data(), n, i, &l, &r); memset(&b.nodes[i], 0, sizeof(BvhNode)); b.nodes[i].c0 = l; b.nodes[i].c1 = r; }
+    for (int i = 0; i < n - 1; i++) { int l, r; karras_node(keys.data(), n, i, &l, &r); memset(&b.nodes[i], 0, sizeof(BvhNode)); b.nodes[i].c[0] = l; b.nodes[i].c[1] = r; }
     host_refit(b, reff, 0);
 }
 

@@ -106,8 +106,9 @@ def test_sass_has_packed_fp32_but_no_contracted_packed_fma(built, tmp_path):
     """The exact-count kernels use Blackwell's packed fp32 instructions (FADD2 / FMUL2) for two spheres / two lights at a time,
     but a packed FMA must never appear in REFERENCE arithmetic: ptxas contracts packed mul+add into FFMA2 even under --fmad=false,
     which would round dot products and discriminants once instead of twice (csrc/rt_trace.cuh). The only FFMA2 allowed are the
-    ones written on purpose — rt_fma2 in the correctly rounded sqrt / reciprocal cores of rt_inv_len2 (csrc/rt_math.cuh): every
-    FFMA2 of the library must carry the source line of that asm statement. Scalar FFMA only comes from IEEE div / sqrt sequences."""
+    ones written on purpose with rt_fma2 (csrc/rt_math.cuh) — the correctly rounded sqrt / reciprocal cores of rt_inv_len2 and the
+    LBVH slab tests (box_entry2, not reference arithmetic): every FFMA2 of the library must carry the source line of that asm
+    statement; a contracted one would carry the line of rt_mul2 / rt_add2. Scalar FFMA only comes from IEEE div / sqrt sequences."""
     import re
     import shutil
     import subprocess
@@ -138,4 +139,4 @@ def test_sass_has_packed_fp32_but_no_contracted_packed_fma(built, tmp_path):
             elif "FFMA2" in l:
                 n_ffma2 += 1
                 assert cur is not None and cur[0] == "rt_math.cuh" and cur[1] in fma_lines, (cur, l)
-    assert n_ffma2 == sass.count("FFMA2") and n_ffma2 % 4 == 0      # four per rt_inv_len2 instance
+    assert n_ffma2 == sass.count("FFMA2") and n_ffma2 > 0

@@ -20,11 +20,15 @@
 
 namespace rtb {
 
-struct alignas(16) BvhNode {            // 64 B: both children's boxes live in the parent (one fetch = two box tests)
-    float lo0x, lo0y, lo0z; int c0;     // child >= 0: internal node index; child < 0: ~leaf (sorted sphere position)
-    float hi0x, hi0y, hi0z; int c1;
-    float lo1x, lo1y, lo1z; int pad0;
-    float hi1x, hi1y, hi1z; int pad1;
+// 64 B: both children's boxes live in the parent (one fetch = two box tests), interleaved per coordinate — [child 0, child 1] —
+// so that each pair sits in an aligned 64-bit register pair and the two slab tests of a visit run as ONE pass of packed fp32
+// (box_entry2: FADD2 / FFMA2; the box test is not reference arithmetic, only its conservativeness matters).
+struct alignas(16) BvhNode {
+    float lox[2], loy[2];
+    float loz[2], hix[2];
+    float hiy[2], hiz[2];
+    int c[2];                           // child >= 0: internal node index; child < 0: ~leaf (sorted sphere position)
+    int pad[2];
 };
 struct BvhBox { float lox, loy, loz, hix, hiy, hiz; };
 
@@ -94,8 +98,7 @@ RT_HD BvhBox box_union(const BvhBox& a, const BvhBox& b) {
     return r;
 }
 RT_HD void node_set_child_box(BvhNode& nd, int which, const BvhBox& b) {
-    if (which == 0) { nd.lo0x = b.lox; nd.lo0y = b.loy; nd.lo0z = b.loz; nd.hi0x = b.hix; nd.hi0y = b.hiy; nd.hi0z = b.hiz; }
-    else { nd.lo1x = b.lox; nd.lo1y = b.loy; nd.lo1z = b.loz; nd.hi1x = b.hix; nd.hi1y = b.hiy; nd.hi1z = b.hiz; }
+    nd.lox[which] = b.lox; nd.loy[which] = b.loy; nd.loz[which] = b.loz; nd.hix[which] = b.hix; nd.hiy[which] = b.hiy; nd.hiz[which] = b.hiz;
 }
 
 // ---- traversal ---------------------------------------------------------------------------------------------------------
@@ -163,6 +166,40 @@ RT_HD float box_entry(f3 o, f3 inv, f3 noi, float lox, float loy, float loz, flo
     return (tn <= tf * BVH_T_SLACK) ? tn : RT_INF;
 }
 
+// Both children of a node at once. Device: one pass of packed fp32 — per half exactly the operations of box_entry (an IEEE fma
+// per half is the scalar fma), so e0 / e1 carry the same bits as two scalar calls; only the min / max trees stay scalar.
+template <bool PAD>
+RT_HD void box_entry2(const BvhNode& nd, f3 o, f3 inv, f3 noi, float r2max, float tmax, float* e0, float* e1) {
+#if defined(RT_HAVE_F32X2)
+    float2 lox = make_float2(nd.lox[0], nd.lox[1]), loy = make_float2(nd.loy[0], nd.loy[1]), loz = make_float2(nd.loz[0], nd.loz[1]);
+    float2 hix = make_float2(nd.hix[0], nd.hix[1]), hiy = make_float2(nd.hiy[0], nd.hiy[1]), hiz = make_float2(nd.hiz[0], nd.hiz[1]);
+    if (PAD) {
+        const float2 ax = rt_sub2(lox, rt_splat2(o.x)), bx = rt_sub2(hix, rt_splat2(o.x));
+        const float2 ay = rt_sub2(loy, rt_splat2(o.y)), by = rt_sub2(hiy, rt_splat2(o.y));
+        const float2 az = rt_sub2(loz, rt_splat2(o.z)), bz = rt_sub2(hiz, rt_splat2(o.z));
+        const float2 dx = make_float2(fmaxf(fabsf(ax.x), fabsf(bx.x)), fmaxf(fabsf(ax.y), fabsf(bx.y)));
+        const float2 dy = make_float2(fmaxf(fabsf(ay.x), fabsf(by.x)), fmaxf(fabsf(ay.y), fabsf(by.y)));
+        const float2 dz = make_float2(fmaxf(fabsf(az.x), fabsf(bz.x)), fmaxf(fabsf(az.y), fabsf(bz.y)));
+        const float2 q = rt_fma2(dx, dx, rt_fma2(dy, dy, rt_fma2(dz, dz, rt_splat2(r2max))));
+        const float2 pad = make_float2(BVH_PAD_K * approx_sqrt(q.x), BVH_PAD_K * approx_sqrt(q.y));
+        lox = rt_sub2(lox, pad); loy = rt_sub2(loy, pad); loz = rt_sub2(loz, pad);
+        hix = rt_add2(hix, pad); hiy = rt_add2(hiy, pad); hiz = rt_add2(hiz, pad);
+    }
+    const float2 t0x = rt_fma2(lox, rt_splat2(inv.x), rt_splat2(noi.x)), t1x = rt_fma2(hix, rt_splat2(inv.x), rt_splat2(noi.x));
+    const float2 t0y = rt_fma2(loy, rt_splat2(inv.y), rt_splat2(noi.y)), t1y = rt_fma2(hiy, rt_splat2(inv.y), rt_splat2(noi.y));
+    const float2 t0z = rt_fma2(loz, rt_splat2(inv.z), rt_splat2(noi.z)), t1z = rt_fma2(hiz, rt_splat2(inv.z), rt_splat2(noi.z));
+    const float tn0 = fmaxf(fmaxf(fminf(t0x.x, t1x.x), fminf(t0y.x, t1y.x)), fmaxf(fminf(t0z.x, t1z.x), 0.0f));
+    const float tf0 = fminf(fminf(fmaxf(t0x.x, t1x.x), fmaxf(t0y.x, t1y.x)), fminf(fmaxf(t0z.x, t1z.x), tmax));
+    const float tn1 = fmaxf(fmaxf(fminf(t0x.y, t1x.y), fminf(t0y.y, t1y.y)), fmaxf(fminf(t0z.y, t1z.y), 0.0f));
+    const float tf1 = fminf(fminf(fmaxf(t0x.y, t1x.y), fmaxf(t0y.y, t1y.y)), fminf(fmaxf(t0z.y, t1z.y), tmax));
+    *e0 = (tn0 <= tf0 * BVH_T_SLACK) ? tn0 : RT_INF;
+    *e1 = (tn1 <= tf1 * BVH_T_SLACK) ? tn1 : RT_INF;
+#else
+    *e0 = box_entry<PAD>(o, inv, noi, nd.lox[0], nd.loy[0], nd.loz[0], nd.hix[0], nd.hiy[0], nd.hiz[0], r2max, tmax);
+    *e1 = box_entry<PAD>(o, inv, noi, nd.lox[1], nd.loy[1], nd.loz[1], nd.hix[1], nd.hiy[1], nd.hiz[1], r2max, tmax);
+#endif
+}
+
 // Reciprocal direction for the slab test, kept FINITE: a component below 1e-12 of the largest one (incl. exact zeros:
 // axis-parallel rays, e.g. a light with a zero coordinate used as shadow direction, RayTracer.cs:574) is treated as that
 // threshold. With an infinite reciprocal the FMA form fma(bound, inv, -o*inv) yields inf - inf = NaN on one face and +inf on
@@ -203,14 +240,9 @@ RT_HD void bvh_nearest(const BvhView& bv, f3 o, f3 dir, float a2, float a4, floa
         dbg.node_visit(secondary ? 1 : 0);
         const float bound = (best_t + window) * BVH_T_SLACK;
         float e0, e1;
-        if (cam_boxes) {
-            e0 = box_entry<false>(o, inv, noi, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, bound);
-            e1 = box_entry<false>(o, inv, noi, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, bound);
-        } else {
-            e0 = box_entry<true>(o, inv, noi, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, bound);
-            e1 = box_entry<true>(o, inv, noi, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, bound);
-        }
-        int c0 = nd.c0, c1 = nd.c1;
+        if (cam_boxes) box_entry2<false>(nd, o, inv, noi, bv.r2max, bound, &e0, &e1);
+        else box_entry2<true>(nd, o, inv, noi, bv.r2max, bound, &e0, &e1);
+        int c0 = nd.c[0], c1 = nd.c[1];
         if (e1 < e0) { float te = e0; e0 = e1; e1 = te; int tc = c0; c0 = c1; c1 = tc; }   // near child first
         int next = -1;
 #pragma unroll
@@ -275,12 +307,12 @@ RT_HD bool bvh_shadow_any(const BvhView& bv, f3 hit, f3 lp, float a2, float a4, 
     for (;;) {
         const BvhNode nd = bv.nodes[node];
         dbg.node_visit(2);
-        float e0 = box_entry<true>(hit, inv, noi, nd.lo0x, nd.lo0y, nd.lo0z, nd.hi0x, nd.hi0y, nd.hi0z, bv.r2max, RT_INF);
-        float e1 = box_entry<true>(hit, inv, noi, nd.lo1x, nd.lo1y, nd.lo1z, nd.hi1x, nd.hi1y, nd.hi1z, bv.r2max, RT_INF);
+        float e0, e1;
+        box_entry2<true>(nd, hit, inv, noi, bv.r2max, RT_INF, &e0, &e1);
         int next = -1;
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const int c = k == 0 ? nd.c0 : nd.c1;
+            const int c = nd.c[k];
             const float e = k == 0 ? e0 : e1;
             if (!(e < RT_INF)) continue;
             if (c >= 0) { if (next < 0) next = c; else stack[sp++] = c; continue; }

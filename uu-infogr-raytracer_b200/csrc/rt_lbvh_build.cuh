@@ -34,21 +34,22 @@ __global__ void k_lbvh_karras(const uint64_t* keys, int n, BvhNode* nodes, int* 
     if (i >= n - 1) return;
     int l, r;
     karras_node(keys, n, i, &l, &r);
-    nodes[i].c0 = l; nodes[i].c1 = r; nodes[i].pad0 = 0; nodes[i].pad1 = 0;
+    nodes[i].c[0] = l; nodes[i].c[1] = r; nodes[i].pad[0] = 0; nodes[i].pad[1] = 0;
     if (l >= 0) parent_node[l] = (i << 1) | 0; else parent_leaf[~l] = (i << 1) | 0;
     if (r >= 0) parent_node[r] = (i << 1) | 1; else parent_leaf[~r] = (i << 1) | 1;
     if (i == 0) parent_node[0] = -1;
 }
 
+// node words: lox[2] loy[2] loz[2] hix[2] hiy[2] hiz[2] (child `which` = the odd / even word of each pair)
 __device__ __forceinline__ BvhBox load_child_box_volatile(const BvhNode* nd, int which) {
-    const volatile float* p = reinterpret_cast<const volatile float*>(nd) + (which ? 8 : 0);
+    const volatile float* p = reinterpret_cast<const volatile float*>(nd) + which;
     BvhBox b;
-    b.lox = p[0]; b.loy = p[1]; b.loz = p[2]; b.hix = p[4]; b.hiy = p[5]; b.hiz = p[6];
+    b.lox = p[0]; b.loy = p[2]; b.loz = p[4]; b.hix = p[6]; b.hiy = p[8]; b.hiz = p[10];
     return b;
 }
 __device__ __forceinline__ void store_child_box_volatile(BvhNode* nd, int which, const BvhBox& b) {
-    volatile float* p = reinterpret_cast<volatile float*>(nd) + (which ? 8 : 0);
-    p[0] = b.lox; p[1] = b.loy; p[2] = b.loz; p[4] = b.hix; p[5] = b.hiy; p[6] = b.hiz;
+    volatile float* p = reinterpret_cast<volatile float*>(nd) + which;
+    p[0] = b.lox; p[2] = b.loy; p[4] = b.loz; p[6] = b.hix; p[8] = b.hiy; p[10] = b.hiz;
 }
 
 // Effective radius of a leaf box: the reference's test only ever sees radiusSquared (:619), so sqrt(r^2) rounded up.

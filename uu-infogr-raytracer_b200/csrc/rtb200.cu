@@ -83,7 +83,9 @@ struct FrameParams {
     int tiles_total;            // ceil(h / tile_rows)
     int tiles_mine;             // tiles of this rank rendered by this launch ...
     int k_begin;                // ... starting at the rank's k_begin-th tile (band pipelining, see render_frames)
-    int chunks_per_tile;        // ceil(tile_rows * w / (BLOCK * pixels per thread))
+    int chunks_per_tile;        // ceil(tile_rows * w / (BLOCK * pixels per thread)); tile2d: (tile_rows / 8) * ceil(w / 16)
+    int tile2d;                 // heavy paths (one pixel per thread), tile_rows a multiple of 8: a CTA is 16 x 8 pixels, a warp 8 x 4
+                                // (coherent rays for the LBVH traversal) instead of 128 / 32 consecutive pixels of a row
     int tile_rot;               // this rank's tiles are visited starting at its tile_rot-th one, wrapping around (launch_render: tail of the launch)
     int skip_black_store;       // sparse gather (launch_render): this rank does not store proven-black spans, rank 0 fills them locally
     float rcp_w, rcp_h;         // 1/w, 1/h correctly rounded (host): pixel-coordinate divisions of the single-sample kernels (rt_div_rcp)
@@ -129,22 +131,33 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp,
         const int tile = tile_of(fp, k);
         const int base = tile * tile_pix;
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
-        const int p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
-        if (p0 >= end) continue;
+        int p0, x, y;
+        if (PPT == 1 && fp.tile2d) {
+            // 2-D pixel blocks: blockIdx.x = (row group of 8 rows inside the tile, block of 16 columns); warp = 8 x 4 pixels
+            const int cols = (fp.w + 15) >> 4;
+            const int rg = (int)blockIdx.x / cols, cb = (int)blockIdx.x - rg * cols;          // CTA-uniform
+            const int lane = (int)threadIdx.x & 31, wp = (int)threadIdx.x >> 5;
+            x = cb * 16 + (wp & 1) * 8 + (lane & 7);
+            y = tile * fp.tile_rows + rg * 8 + (wp >> 1) * 4 + (lane >> 3);
+            if (x >= fp.w || y >= fp.h) continue;
+            p0 = y * fp.w + x;
+        } else {
+            p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
+            if (p0 >= end) continue;
+            // row of the span: frames below 2^24 pixels without an integer division (p0 is exact in fp32 and 1/w is correctly
+            // rounded, so the estimate is off by one at most; as in k_gather_expand); then step along the row
+            if (npix < (1 << 24)) {
+                y = (int)((float)p0 * fp.rcp_w);
+                if (y * fp.w > p0) y--; else if ((y + 1) * fp.w <= p0) y++;
+            } else {
+                y = p0 / fp.w;
+            }
+            x = p0 - y * fp.w;
+        }
         const CamRec& cam = fp.cam_inline[frame];               // constant bank (LDC); batches > INLINE_CAMS are split on the host
         const FrameGates& gates = fp.gates[frame];
         uint32_t* out = fp.out + (long long)frame * fp.frame_stride;
         uint32_t px[PPT];
-        // row of the span: frames below 2^24 pixels without an integer division (p0 is exact in fp32 and 1/w is correctly rounded,
-        // so the estimate is off by one at most; as in k_gather_expand); then step along the row
-        int y;
-        if (npix < (1 << 24)) {
-            y = (int)((float)p0 * fp.rcp_w);
-            if (y * fp.w > p0) y--; else if ((y + 1) * fp.w <= p0) y++;
-        } else {
-            y = p0 / fp.w;
-        }
-        int x = p0 - y * fp.w;
         // What the host proved about this thread's span of pixels (rt_gate.cuh): evaluated once, for spans inside one row.
         uint32_t bits = 0u;
         if (SPP1 && x + PPT <= fp.w && p0 + PPT <= end) {
@@ -541,7 +554,11 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_staged(const __
     render_loop<PPT_HEAVY>(StagedScene(scd, stage_spheres(scd)), fp);
 }
 struct LbvhSceneData { GlobalSceneData g; BvhView bv; ShadowGridsView sg; };
-__global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_lbvh(const __grid_constant__ LbvhSceneData scd, const __grid_constant__ FrameParams fp) {
+#ifndef RT_LBVH_MIN_BLOCKS
+#define RT_LBVH_MIN_BLOCKS 10    // 48 registers: the traversal hides its node fetches with resident warps — measured on B200 (profiles/r02/tuning.md):
+                                 // 8 CTAs / SM 1.399 ms, 9 1.332, 10 1.292, 11 1.316, 12 1.303 on configs[3]; fewer than 8 is slower still
+#endif
+__global__ void __launch_bounds__(BLOCK, RT_LBVH_MIN_BLOCKS) k_render_lbvh(const __grid_constant__ LbvhSceneData scd, const __grid_constant__ FrameParams fp) {
     render_loop<PPT_HEAVY>(LbvhScene(scd.g, scd.bv, scd.sg), fp);
 }
 
@@ -986,6 +1003,10 @@ FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp,
     }
     const int chunk = BLOCK * (ctx->path == PATH_TINY ? PPT_TINY : PPT_HEAVY);
     fp.chunks_per_tile = (int)(((long long)fp.tile_rows * w + chunk - 1) / chunk);
+    if (ctx->path != PATH_TINY && BLOCK == 128 && PPT_HEAVY == 1 && fp.tile_rows % 8 == 0 && !getenv("RTB200_NO_TILE2D")) {
+        fp.tile2d = 1;
+        fp.chunks_per_tile = (fp.tile_rows / 8) * ((w + 15) / 16);
+    }
     fp.rcp_w = 1.0f / (float)w; fp.rcp_h = 1.0f / (float)h;      // host fp32 division: IEEE
     fp.frame_stride = frame_stride;
     fp.out = out;

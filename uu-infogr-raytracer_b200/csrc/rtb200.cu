@@ -132,15 +132,17 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp,
         const int base = tile * tile_pix;
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
         int p0, x, y;
-        if (PPT == 1 && fp.tile2d) {
-            // 2-D pixel blocks: blockIdx.x = (row group of 8 rows inside the tile, block of 16 columns); warp = 8 x 4 pixels
-            const int cols = (fp.w + 15) >> 4;
+        if ((PPT == 1 || PPT == 4) && fp.tile2d) {
+            // 2-D pixel blocks: blockIdx.x = (row group of 8 rows inside the tile, block of 16 * PPT columns); a warp covers
+            // 8 * PPT x 4 pixels (8 threads side by side, 4 rows), the CTA's four warps 2 x 2 of those
+            const int cols = (fp.w + 16 * PPT - 1) / (16 * PPT);
             const int rg = (int)blockIdx.x / cols, cb = (int)blockIdx.x - rg * cols;          // CTA-uniform
             const int lane = (int)threadIdx.x & 31, wp = (int)threadIdx.x >> 5;
-            x = cb * 16 + (wp & 1) * 8 + (lane & 7);
+            x = (cb * 16 + (wp & 1) * 8 + (lane & 7)) * PPT;
             y = tile * fp.tile_rows + rg * 8 + (wp >> 1) * 4 + (lane >> 3);
             if (x >= fp.w || y >= fp.h) continue;
             p0 = y * fp.w + x;
+            end = p0 + (fp.w - x < PPT ? fp.w - x : PPT);      // the thread's span ends with its row
         } else {
             p0 = base + (int)blockIdx.x * CHUNK + (int)threadIdx.x * PPT;
             if (p0 >= end) continue;
@@ -1003,9 +1005,13 @@ FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp,
     }
     const int chunk = BLOCK * (ctx->path == PATH_TINY ? PPT_TINY : PPT_HEAVY);
     fp.chunks_per_tile = (int)(((long long)fp.tile_rows * w + chunk - 1) / chunk);
-    if (ctx->path != PATH_TINY && BLOCK == 128 && PPT_HEAVY == 1 && fp.tile_rows % 8 == 0 && !getenv("RTB200_NO_TILE2D")) {
+    // 2-D pixel blocks (render_loop): heavy paths always; the tiny path when a row is a whole number of 4-pixel spans (the spans —
+    // and with them every black-span / host-fill decision, k_fill_black, the packed gather — are then the same as in linear order)
+    static const bool no_tile2d = getenv("RTB200_NO_TILE2D") != nullptr;
+    const int ppt = ctx->path == PATH_TINY ? PPT_TINY : PPT_HEAVY;
+    if (BLOCK == 128 && fp.tile_rows % 8 == 0 && w % ppt == 0 && (ppt == 1 || ppt == 4) && !no_tile2d) {
         fp.tile2d = 1;
-        fp.chunks_per_tile = (fp.tile_rows / 8) * ((w + 15) / 16);
+        fp.chunks_per_tile = (fp.tile_rows / 8) * ((w + 16 * ppt - 1) / (16 * ppt));
     }
     fp.rcp_w = 1.0f / (float)w; fp.rcp_h = 1.0f / (float)h;      // host fp32 division: IEEE
     fp.frame_stride = frame_stride;

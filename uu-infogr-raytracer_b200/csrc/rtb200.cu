@@ -292,11 +292,25 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_pack(const
         const int tile = tile_of(fp, fp.k_begin + kr);
         const int base = tile * tile_pix;
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
-        const int p0 = base + chunk * CHUNK + (int)threadIdx.x * PPT;
-        if (p0 >= end) continue;                                   // warp-uniform (see above)
-        int y = p0 / fp.w, x = p0 - y * fp.w;
+        int p0, x, y;
         bool black = false;
-        const uint32_t bits = gate_bits_span(gates, x, x + PPT - 1, y, sc.n_lights(), &black);
+        if (fp.tile2d && !ga.grey) {
+            // RGB24-only wire format (no per-warp flag byte): the same 2-D pixel blocks as render_loop — a warp is 32 x 4 pixels, a
+            // quad still 16 consecutive pixels of one row. Rows below the frame (last tile) count as black: nothing traced or stored.
+            const int cols = fp.w >> 6;                            // w % 128 == 0
+            const int rg = chunk / cols, cb = chunk - rg * cols;
+            const int wp = (int)threadIdx.x >> 5;
+            x = (cb * 16 + (wp & 1) * 8 + (lane & 7)) * PPT;
+            y = tile * fp.tile_rows + rg * 8 + (wp >> 1) * 4 + (lane >> 3);
+            p0 = y * fp.w + x;
+            black = y >= fp.h;
+        } else {
+            p0 = base + chunk * CHUNK + (int)threadIdx.x * PPT;
+            if (p0 >= end) continue;                               // warp-uniform (see above)
+            y = p0 / fp.w; x = p0 - y * fp.w;
+        }
+        uint32_t bits = 0u;
+        if (!black) bits = gate_bits_span(gates, x, x + PPT - 1, y, sc.n_lights(), &black);
         uint32_t px[PPT] = {0u, 0u, 0u, 0u};
         if (!black) {
 #pragma unroll 1
@@ -882,7 +896,7 @@ struct rt_context {
     bool sparse_d2h = true;         // RT_OPT_SPARSE_D2H
     bool host_precleared = false;   // RT_OPT_HOST_PRECLEARED
     // packed multi-GPU gather (rt_gather.cuh)
-    int gather_mode = -1;           // RT_OPT_GATHER_MODE: -1 auto (2 from 4 ranks on), 0 off, 1 RGB24, 2 RGB24 + grey quads
+    int gather_mode = -1;           // RT_OPT_GATHER_MODE: -1 auto (1 for 4-7 ranks, 2 from 8 on), 0 off, 1 RGB24, 2 RGB24 + grey quads
     int sink_tiles = 0, peer_tiles = 0;   // RT_OPT_SINK_TILES / RT_OPT_PEER_TILES: 0 = automatic per world size
     unsigned char* gather_area = nullptr; uint64_t gather_bytes = 0; bool gather_owned = false;    // as this context addresses it
     std::vector<GatherLocal*> gather_local;     // per device, in its own memory
@@ -1096,7 +1110,10 @@ GatherPlan plan_gather(rt_context* ctx, int dev_index, int w, int h, int spp, in
     GatherPlan g;
     memset(&g.gp, 0, sizeof(g.gp)); memset(&g.pt, 0, sizeof(g.pt));
     int mode = ctx->gather_mode;
-    if (mode < 0) mode = world >= 4 ? 2 : 0;                     // measured: profiles/r02/ (the expand pass costs rank 0 more than 2 ranks save)
+    // automatic (measured: profiles/r02/): 2 ranks: off (the expand pass costs rank 0 more than the link saves); 4-7 ranks: RGB24 —
+    // the ranks are compute-bound, and without the per-warp grey flags the render kernel keeps its 2-D pixel blocks (+10 %);
+    // 8 ranks: RGB24 + grey quads — GPU 0's NVLink ingress is the limit
+    if (mode < 0) mode = world >= 8 ? 2 : (world >= 4 ? 1 : 0);
     if (getenv("RTB200_GATHER_MODE")) mode = atoi(getenv("RTB200_GATHER_MODE"));
     if (mode <= 0 || !shared_target || world < 2 || world > GATHER_MAX_RANKS || ctx->path != PATH_TINY || !ctx->primary_gate || spp != 1 ||
         w > RT_FASTDIV_MAX || h > RT_FASTDIV_MAX || (w % 128) != 0 || !ctx->gather_area ||

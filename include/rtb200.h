@@ -193,7 +193,7 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
  * compressed wire format — nothing for quads the frame gates prove black, 1 byte per pixel for grey quads, 3 bytes per pixel
  * otherwise — into planes in rank 0's memory, and rank 0 expands them into the 0x00RRGGBB framebuffer; the kernels synchronise among
  * themselves through flags in rank 0's memory. Rank 0 gets a smaller share of the tiles (it also runs the expand pass).
- *   RT_OPT_GATHER_MODE  -1 automatic (1 for 4-7 ranks, 2 from 8 ranks on, else 0), 0 off (plain 4 B / pixel stores), 1 RGB24 only, 2 RGB24 + grey quads
+ *   RT_OPT_GATHER_MODE  -1 automatic (2 from 8 ranks on, else 0), 0 off (plain 4 B / pixel stores), 1 RGB24 only, 2 RGB24 + grey quads
  *   RT_OPT_SINK_TILES / RT_OPT_PEER_TILES  tiles per period for rank 0 / for every other rank (0 = automatic: 1/1 for 2 ranks,
  *                        4/5 for 4, 1/2 for 8); period = sink + peer * (world - 1) <= 64
  * Applies to single-sample frames of tiny scenes whose width is a multiple of 128; everything else takes the plain gather. All three

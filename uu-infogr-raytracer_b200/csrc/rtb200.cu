@@ -896,7 +896,7 @@ struct rt_context {
     bool sparse_d2h = true;         // RT_OPT_SPARSE_D2H
     bool host_precleared = false;   // RT_OPT_HOST_PRECLEARED
     // packed multi-GPU gather (rt_gather.cuh)
-    int gather_mode = -1;           // RT_OPT_GATHER_MODE: -1 auto (1 for 4-7 ranks, 2 from 8 on), 0 off, 1 RGB24, 2 RGB24 + grey quads
+    int gather_mode = -1;           // RT_OPT_GATHER_MODE: -1 auto (2 from 8 ranks on), 0 off, 1 RGB24, 2 RGB24 + grey quads
     int sink_tiles = 0, peer_tiles = 0;   // RT_OPT_SINK_TILES / RT_OPT_PEER_TILES: 0 = automatic per world size
     unsigned char* gather_area = nullptr; uint64_t gather_bytes = 0; bool gather_owned = false;    // as this context addresses it
     std::vector<GatherLocal*> gather_local;     // per device, in its own memory
@@ -1110,10 +1110,11 @@ GatherPlan plan_gather(rt_context* ctx, int dev_index, int w, int h, int spp, in
     GatherPlan g;
     memset(&g.gp, 0, sizeof(g.gp)); memset(&g.pt, 0, sizeof(g.pt));
     int mode = ctx->gather_mode;
-    // automatic (measured: profiles/r02/): 2 ranks: off (the expand pass costs rank 0 more than the link saves); 4-7 ranks: RGB24 —
-    // the ranks are compute-bound, and without the per-warp grey flags the render kernel keeps its 2-D pixel blocks (+10 %);
-    // 8 ranks: RGB24 + grey quads — GPU 0's NVLink ingress is the limit
-    if (mode < 0) mode = world >= 8 ? 2 : (world >= 4 ? 1 : 0);
+    // automatic (measured: profiles/r02/multi4/, push_gather/): below 8 ranks off — at N = 4 the plain stores (659 Grays/s) beat
+    // RGB24 (607; its render kernel keeps the 2-D pixel blocks) and RGB24 + grey (575; 128-pixel strips for the per-warp flag
+    // byte): the expand pass and the per-CTA fences cost more than the link saves; 8 ranks: RGB24 + grey quads — GPU 0's NVLink
+    // ingress is the limit there
+    if (mode < 0) mode = world >= 8 ? 2 : 0;
     if (getenv("RTB200_GATHER_MODE")) mode = atoi(getenv("RTB200_GATHER_MODE"));
     if (mode <= 0 || !shared_target || world < 2 || world > GATHER_MAX_RANKS || ctx->path != PATH_TINY || !ctx->primary_gate || spp != 1 ||
         w > RT_FASTDIV_MAX || h > RT_FASTDIV_MAX || (w % 128) != 0 || !ctx->gather_area ||
@@ -1235,7 +1236,8 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
                 }
                 break;
             }
-            const bool sparse = fp.skip_black_store && (fp.world > 4 || fp.skip_black_store == 2) && fp.world > 1 && ctx->primary_gate &&
+            static const int sparse_min_world = getenv("RTB200_SPARSE_MIN_WORLD") ? atoi(getenv("RTB200_SPARSE_MIN_WORLD")) : 5;
+            const bool sparse = fp.skip_black_store && (fp.world >= sparse_min_world || fp.skip_black_store == 2) && fp.world > 1 && ctx->primary_gate &&
                                 fp.spp == 1 && fastdiv_ok && !compact;
             gp.skip_black_store = sparse && fp.rank != 0;
             kern<<<grid, BLOCK, 0, stream>>>(t, gp);

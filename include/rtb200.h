@@ -202,7 +202,7 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
 #define RT_OPT_SINK_TILES 10
 #define RT_OPT_PEER_TILES 11
 /* RT_OPT_HOST_SHADOW_BINS (default 0): build the per-light shadow bins of LBVH scenes on the host instead of on the GPU (same
- * geometry code, same bins; 0.1-0.3 s at 100 k spheres instead of < 1 ms). Takes effect at the next rt_set_scene / rt_update_spheres.
+ * geometry code, same bins; 0.1-0.3 s at 100 k spheres instead of ~2 ms). Takes effect at the next rt_set_scene / rt_update_spheres.
  * Exists for the test that shows both builds agree. */
 #define RT_OPT_HOST_SHADOW_BINS 12
 /* Options that change WHICH rank writes a pixel (RT_OPT_SHARED_TARGET, RT_OPT_PRIMARY_GATE) must be set identically on every rank

@@ -45,6 +45,14 @@ internal sealed unsafe class NativeRayTracer : IDisposable {
                                                           int nPixels, RtRayRecord* records, int maxRecords, out int nRecords);
     [DllImport(Lib)] private static extern int rt_selftest(IntPtr ctx, int test, out ulong nChecked, out ulong nMismatch);
     [DllImport(Lib)] private static extern int rt_set_option(IntPtr ctx, int option, int value);
+    [DllImport(Lib)] private static extern int rt_get_info(IntPtr ctx, int what, out ulong value);
+    [DllImport(Lib)] private static extern int rt_update_spheres(IntPtr ctx, float* spheres, int first, int count);
+    [DllImport(Lib)] private static extern int rt_render_mapped(IntPtr ctx, ref RtCamera cam, int width, int height, int maxDepth, int spp,
+                                                                uint seed, void* mappedDevPixels, ulong mappedBytes, out RtStats stats);
+    [DllImport(Lib)] private static extern int rt_gl_register_buffer(IntPtr ctx, uint glBuffer, out IntPtr resource);
+    [DllImport(Lib)] private static extern int rt_gl_unregister_buffer(IntPtr ctx, IntPtr resource);
+    [DllImport(Lib)] private static extern int rt_render_gl(IntPtr ctx, ref RtCamera cam, int width, int height, int maxDepth, int spp,
+                                                            uint seed, IntPtr resource, out RtStats stats);
     [DllImport(Lib)] private static extern int rt_host_register(IntPtr ctx, void* hostPtr, ulong bytes);
     [DllImport(Lib)] private static extern int rt_host_unregister(IntPtr ctx, void* hostPtr);
     [DllImport(Lib)] private static extern int rt_destroy(IntPtr ctx);
@@ -119,8 +127,37 @@ internal sealed unsafe class NativeRayTracer : IDisposable {
         return bad;
     }
 
-    /// <summary>rt_set_option: 1 RT_OPT_COMPACTION, 2 RT_OPT_HOST_VIA_GPU0, 3 RT_OPT_PRIMARY_GATE (frame gates, default on).</summary>
+    /// <summary>rt_set_option (RT_OPT_* of include/rtb200.h), e.g. 7 RT_OPT_HOST_PRECLEARED = 1 when Tick() keeps its screen.Clear(0)
+    /// (RayTracer.cs:890): the library then skips its own zero fill of the pixels the sparse return does not copy.</summary>
     public void SetOption(int option, int value) => Check(rt_set_option(_ctx, option, value));
+
+    /// <summary>rt_get_info (RT_INFO_* of include/rtb200.h), e.g. 3 = bytes the last Render copied device -> host.</summary>
+    public ulong GetInfo(int what) { Check(rt_get_info(_ctx, what, out ulong v)); return v; }
+
+    /// <summary>Scene mutation (SURVEY §8(f)): re-uploads spheres[first .. first + count), refits the LBVH and rebuilds the shadow bins
+    /// on the GPU. The reference's arrays are readonly (RayTracer.cs:441-465); a host that animates them calls this per frame.</summary>
+    public void UpdateSpheres(Sphere[] spheres, int first, int count) {
+        fixed (Sphere* s = spheres) Check(rt_update_spheres(_ctx, (float*)(s + first), first, count));
+    }
+
+    // ---- zero-copy display (INTEGRATION.md §6): the frame goes straight into a GL pixel-unpack buffer, never through Surface.pixels ----
+    /// <summary>Registers a GL PixelUnpackBuffer of 4*w*h bytes (render thread, GL context current). Re-register after a resize.</summary>
+    public IntPtr GlRegisterBuffer(int glBuffer) { Check(rt_gl_register_buffer(_ctx, (uint)glBuffer, out IntPtr res)); return res; }
+    public void GlUnregisterBuffer(IntPtr resource) => Check(rt_gl_unregister_buffer(_ctx, resource));
+    /// <summary>map -> render -> unmap; afterwards GL.TexSubImage2D(..., IntPtr.Zero) from the bound buffer replaces template.cs:188-193.</summary>
+    public RtStats RenderGl(Vector3 position, Vector3 right, Vector3 up, Vector3 forward, Vector3 viewParams,
+                            int width, int height, int maxDepth, IntPtr resource) {
+        RtCamera cam = new() { pos = position, right = right, up = up, forward = forward, viewParams = viewParams };
+        Check(rt_render_gl(_ctx, ref cam, width, height, maxDepth, 1, 0u, resource, out RtStats stats));
+        return stats;
+    }
+    /// <summary>For hosts that map the buffer themselves: devPixels = cudaGraphicsResourceGetMappedPointer of the mapped PBO.</summary>
+    public RtStats RenderMapped(Vector3 position, Vector3 right, Vector3 up, Vector3 forward, Vector3 viewParams,
+                                int width, int height, int maxDepth, IntPtr devPixels) {
+        RtCamera cam = new() { pos = position, right = right, up = up, forward = forward, viewParams = viewParams };
+        Check(rt_render_mapped(_ctx, ref cam, width, height, maxDepth, 1, 0u, (void*)devPixels, 4ul * (ulong)width * (ulong)height, out RtStats stats));
+        return stats;
+    }
 
     public void Dispose() {
         if (_ctx == IntPtr.Zero) return;

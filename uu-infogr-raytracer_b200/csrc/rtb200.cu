@@ -753,6 +753,8 @@ struct DeviceState {
     uint32_t* fb = nullptr; size_t fb_pixels = 0;
     // band pipelining (render_frames): copy stream on device 0, per-segment "band rendered" events on every device
     cudaStream_t copy_stream = nullptr;
+    // sparse gather, rank 0: k_fill_black runs on its own stream beside the render kernel (it only touches the OTHER ranks' tiles)
+    cudaStream_t fill_stream = nullptr; cudaEvent_t fill_go = nullptr, fill_done = nullptr;
     cudaEvent_t evc0 = nullptr, evc1 = nullptr;
     std::vector<cudaEvent_t> band_events;
 };
@@ -1240,11 +1242,20 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
             const bool sparse = fp.skip_black_store && (fp.world >= sparse_min_world || fp.skip_black_store == 2) && fp.world > 1 && ctx->primary_gate &&
                                 fp.spp == 1 && fastdiv_ok && !compact;
             gp.skip_black_store = sparse && fp.rank != 0;
-            kern<<<grid, BLOCK, 0, stream>>>(t, gp);
             if (sparse && fp.rank == 0 && fp.tiles_mine > 0) {
+                // The fill touches only the other ranks' tiles, the render kernel only rank 0's: they run side by side (one is bound
+                // by HBM writes, the other by issue slots). Stream order is kept on both sides: the fill starts after everything
+                // already queued on `stream` (the previous consumer of the framebuffer), and `stream` continues after it.
+                CU_TRY(ctx, cudaEventRecord(d.fill_go, stream));
+                CU_TRY(ctx, cudaStreamWaitEvent(d.fill_stream, d.fill_go, 0));
+                k_fill_black<<<grid, BLOCK, 0, d.fill_stream>>>(gp);
                 CU_TRY(ctx, cudaGetLastError());
-                k_fill_black<<<grid, BLOCK, 0, stream>>>(gp);
+                CU_TRY(ctx, cudaEventRecord(d.fill_done, d.fill_stream));
                 ctx->launches++;
+                kern<<<grid, BLOCK, 0, stream>>>(t, gp);
+                CU_TRY(ctx, cudaStreamWaitEvent(stream, d.fill_done, 0));
+            } else {
+                kern<<<grid, BLOCK, 0, stream>>>(t, gp);
             }
             break;
         }
@@ -1296,6 +1307,9 @@ int rt_create(rt_context** out, const int* device_ids, int n_devices) {
         if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&d.fill_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.fill_go, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.fill_done, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreate(&d.evc0)) != cudaSuccess || (e = cudaEventCreate(&d.evc1)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&d.bvh_done, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreate(&d.ev0)) != cudaSuccess || (e = cudaEventCreate(&d.ev1)) != cudaSuccess) {
@@ -1340,6 +1354,9 @@ int rt_destroy(rt_context* ctx) {
         if (d.evc1) cudaEventDestroy(d.evc1);
         if (d.bvh_done) cudaEventDestroy(d.bvh_done);
         for (cudaEvent_t ev : d.band_events) cudaEventDestroy(ev);
+        if (d.fill_go) cudaEventDestroy(d.fill_go);
+        if (d.fill_done) cudaEventDestroy(d.fill_done);
+        if (d.fill_stream) cudaStreamDestroy(d.fill_stream);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.stream) cudaStreamDestroy(d.stream);
     }

@@ -382,7 +382,8 @@ def _packed_ranks(rt, sc, world, tile_rows, w, h, mode, sink, peer, shared_targe
 @pytest.mark.parametrize("world,tile_rows,w,h,mode,sink,peer", [
     (2, 8, 1024, 600, 2, 1, 1), (4, 8, 1280, 720, 2, 0, 0), (8, 8, 1280, 720, 2, 0, 0), (8, 8, 1280, 720, 1, 0, 0), (8, 3, 640, 97, 2, 1, 2),
     (4, 16, 1152, 333, 1, 2, 3), (8, 1, 256, 131, 2, 3, 5), (3, 8, 1280, 720, 2, 0, 4), (8, 8, 3840, 2160, 2, 0, 0), (4, 8, 3840, 2160, 2, 0, 0),
-    (4, 8, 3840, 2160, 1, 0, 0), (4, 8, 1280, 724, 1, 0, 0), (5, 24, 896, 500, 1, 1, 2)])   # RGB24 only: the render kernel keeps its 2-D pixel blocks
+    (4, 8, 3840, 2160, 1, 0, 0), (4, 8, 1280, 724, 1, 0, 0), (5, 24, 896, 500, 1, 1, 2),
+    (4, 8, 1280, 724, 2, 0, 0), (8, 16, 1152, 333, 2, 1, 2)])   # tile_rows % 8 == 0: 2-D pixel blocks (flag bytes assembled per CTA); else row strips
 def test_packed_gather_emulated_ranks(rt, world, tile_rows, w, h, mode, sink, peer):
     """Ranks != 0 write the wire format (nothing / grey bytes / RGB24 + flag bytes) into the planes of the gather area, rank 0 renders
     its (smaller, weighted) share and expands the rest; flags and epochs as between real GPUs. Four alternating cameras, two rounds

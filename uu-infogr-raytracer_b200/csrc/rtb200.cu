@@ -282,6 +282,10 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_pack(const
     const FrameGates& gates = fp.gates[frame];
     const unsigned qmask = 0xFu << (lane & 28);
     const int q = lane >> 2, ql = lane & 3;
+    __shared__ unsigned int flag_bits[2][4];                       // 2-D blocks: the flag bytes of the item's four rows (double-buffered)
+    int flag_par = 0;
+    if (threadIdx.x < 8) flag_bits[threadIdx.x >> 2][threadIdx.x & 3] = 0u;
+    __syncthreads();
     // gridDim.x CTAs per frame, each striding over the (tile, chunk) items of this rank: a few hundred fat CTAs instead of one per
     // chunk, because every CTA ends with a system-scope fence that waits for its NVLink stores to be acknowledged (measured at N = 2:
     // 16 200 fences per frame cost 0.4 ms per step, profiles/r02/)
@@ -294,14 +298,19 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_pack(const
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
         int p0, x, y;
         bool black = false;
-        if (fp.tile2d && !ga.grey) {
-            // RGB24-only wire format (no per-warp flag byte): the same 2-D pixel blocks as render_loop — a warp is 32 x 4 pixels, a
-            // quad still 16 consecutive pixels of one row. Rows below the frame (last tile) count as black: nothing traced or stored.
-            const int cols = fp.w >> 6;                            // w % 128 == 0
-            const int rg = chunk / cols, cb = chunk - rg * cols;
-            const int wp = (int)threadIdx.x >> 5;
-            x = (cb * 16 + (wp & 1) * 8 + (lane & 7)) * PPT;
-            y = tile * fp.tile_rows + rg * 8 + (wp >> 1) * 4 + (lane >> 3);
+        const int wp = (int)threadIdx.x >> 5;
+        int cb = 0, y_first = 0;
+        if (fp.tile2d) {
+            // 2-D pixel blocks as in render_loop: a warp is 32 x 4 pixels (a quad still 16 consecutive pixels of one row); here the
+            // CTA's four warps lie side by side — 128 x 4 pixels — so that the CTA owns whole flag bytes (one per row and 128-pixel
+            // group, assembled from the warps' quad bits in shared memory below). Rows below the frame (last tile) count as black:
+            // nothing traced or stored. No warp leaves the item early: the item loop and its barriers are CTA-uniform.
+            const int cols = fp.w >> 7;                            // w % 128 == 0
+            const int rg = chunk / cols;
+            cb = chunk - rg * cols;
+            x = cb * 128 + wp * 32 + (lane & 7) * PPT;
+            y_first = tile * fp.tile_rows + rg * 4;
+            y = y_first + (lane >> 3);
             p0 = y * fp.w + x;
             black = y >= fp.h;
         } else {
@@ -345,7 +354,23 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_pack(const
                     *reinterpret_cast<uint4*>(plane_c + 3ull * (unsigned long long)(p0 - ql * PPT) + 16u * (unsigned)ql) = make_uint4(o0, o1, o2, o3);
             }
         }
-        if (ga.grey && lane == 0 && qblack != 0xFFu) plane_f[p0 >> 7] = (unsigned char)qgrey;
+        if (ga.grey) {
+            if (fp.tile2d) {
+                // quad 2 r + h of the warp = row r, half h of the warp's 32 pixels -> bits 2 wp + h of the flag byte of (row r, group cb)
+                unsigned int* fl = flag_bits[flag_par];
+                if (lane == 0)
+                    for (int r = 0; r < 4; r++) atomicOr(&fl[r], ((qgrey >> (2 * r)) & 3u) << (2 * wp));
+                __syncthreads();
+                if (threadIdx.x < 4) {
+                    const int yr = y_first + (int)threadIdx.x;
+                    if (yr < fp.h) plane_f[((long long)yr * fp.w >> 7) + cb] = (unsigned char)fl[threadIdx.x];
+                    fl[threadIdx.x] = 0u;                          // this buffer is used again two items on, behind the next item's barrier
+                }
+                flag_par ^= 1;
+            } else if (lane == 0 && qblack != 0xFFu) {
+                plane_f[p0 >> 7] = (unsigned char)qgrey;
+            }
+        }
     }
     // this rank's planes of the slot have landed once its LAST CTA is through
     __syncthreads();

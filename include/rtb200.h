@@ -64,7 +64,9 @@ typedef struct rt_stats {
 
 /* Creates a context on `n_devices` CUDA devices (1, 2, 4 or 8; device_ids NULL => 0..n-1).  With n > 1 every frame is
  * partitioned by interleaved row tiles and gathered on device_ids[0] over NVLink by peer stores fused into the
- * render kernel.  Replaces `new RayTracer(screen)` (RayTracer.cs:535, template.cs:80). */
+ * render kernel.  Replaces `new RayTracer(screen)` (RayTracer.cs:535, template.cs:80).
+ * A device id may repeat: the context then runs several of its partitions on one physical GPU, each with its own streams, scene
+ * copy and launch thread (how a single-GPU machine exercises the multi-device code; no performance meaning). */
 int rt_create(rt_context** out, const int* device_ids, int n_devices);
 
 /* Uploads (copies) the scene: the arrays RayTracer.cs:441-465 and `_ambientLightColor` :469, in C# field order.

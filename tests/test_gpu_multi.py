@@ -1,5 +1,10 @@
-"""Multi-GPU tests (need >= 2 CUDA devices; skipped otherwise): interleaved row tiles across GPUs with the gather fused into
-the render kernel as peer stores over NVLink. G-GPU output must be byte-identical to 1-GPU output."""
+"""Multi-GPU tests: interleaved row tiles across GPUs with the gather fused into the render kernel as peer stores over NVLink.
+G-GPU output must be byte-identical to 1-GPU output.
+
+With fewer physical GPUs than a test wants, its partitions are mapped onto the GPUs that exist (device r % N_GPUS; rt_create accepts
+repeated device ids, CUDA IPC works between processes on one device): the same partition / launch-thread / gather / per-device return
+code runs, only the wire is local memory instead of NVLink. The one thing that needs real concurrency between ranks — the packed
+gather's kernel-to-kernel flags in the multi-process test — still needs >= 2 GPUs."""
 import os
 import sys
 
@@ -25,7 +30,13 @@ def _n_gpus():
 
 
 N_GPUS = _n_gpus()
-need2 = pytest.mark.skipif(N_GPUS < 2, reason="needs >= 2 GPUs")
+need1 = pytest.mark.skipif(N_GPUS < 1, reason="needs a GPU")
+need2 = pytest.mark.skipif(N_GPUS < 2, reason="needs >= 2 GPUs (kernels of different ranks must run concurrently)")
+
+
+def _devices(g):
+    """g partitions on the GPUs that exist"""
+    return [i % N_GPUS for i in range(g)]
 
 
 @pytest.fixture(scope="module")
@@ -34,11 +45,9 @@ def rt(built):
     return rtb200
 
 
-@need2
+@need1
 @pytest.mark.parametrize("g", [2, 4, 8])
 def test_in_library_multi_device_equals_single(rt, g):
-    if g > N_GPUS:
-        pytest.skip("only %d GPUs" % N_GPUS)
     w, h = 1280, 720
     for sc, camkw, accel in ((scenes.default_scene(), dict(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15), rt.RT_ACCEL_AUTO),
                              (scenes.config3_scene(), scenes.SCALED_CAMERA, rt.RT_ACCEL_LBVH)):
@@ -46,7 +55,11 @@ def test_in_library_multi_device_equals_single(rt, g):
         one = rt.Context([0]); one.set_scene(sc, accel)
         ref, _ = one.render(cam, w, h, 8)
         one.close()
-        multi = rt.Context(list(range(g))); multi.set_scene(sc, accel)
+        multi = rt.Context(_devices(g)); multi.set_scene(sc, accel)
+        if g > N_GPUS:
+            # partitions sharing a GPU: the packed gather (automatic from 8 devices on) makes rank 0's expand kernel wait for flags the
+            # other partitions' kernels write — on one GPU those may not be resident at the same time. Plain / sparse gather there.
+            multi.set_option(rt.RT_OPT_GATHER_MODE, 0)
         got, st = multi.render(cam, w, h, 8)
         assert np.array_equal(got, ref)
         cams = np.stack([scenes.make_camera(pos=(0.1 * i, 0.4, -1.0), yaw=0.05 * i, width=w, height=h) for i in range(3)])
@@ -58,19 +71,19 @@ def test_in_library_multi_device_equals_single(rt, g):
         one.close()
 
 
-@need2
+@need1
 @pytest.mark.parametrize("w,h,tile_rows", [(1280, 723, 8), (640, 97, 16), (96, 5, 8)])
 def test_multi_device_host_output_paths(rt, w, h, tile_rows):
     """Host output from a multi-device context: (a) default — every device sends its own row tiles over its own PCIe link
     (strided 2-D copies, incl. a short last tile), (b) RT_OPT_HOST_VIA_GPU0 — gather on device 0, then copy. Both must equal the
     single-device frame, into pageable and into page-locked host memory."""
-    g = min(N_GPUS, 4) if N_GPUS >= 4 else 2
+    g = 4 if N_GPUS != 2 else 2
     sc = scenes.default_scene()
     cam = scenes.make_camera(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15, width=w, height=h)
     one = rt.Context([0]); one.set_scene(sc)
     ref, _ = one.render(cam, w, h, 8)
     one.close()
-    multi = rt.Context(list(range(g))); multi.set_scene(sc); multi.set_partition(0, 1, tile_rows)
+    multi = rt.Context(_devices(g)); multi.set_scene(sc); multi.set_partition(0, 1, tile_rows)
     for via0 in (0, 1):
         multi.set_option(rt.RT_OPT_HOST_VIA_GPU0, via0)
         got, st = multi.render(cam, w, h, 8)
@@ -89,12 +102,12 @@ def test_multi_device_host_output_paths(rt, w, h, tile_rows):
     multi.close()
 
 
-@need2
+@need1
 def test_sparse_gather_leaves_no_stale_pixels(rt):
     """Gather on device 0 (RT_OPT_HOST_VIA_GPU0): devices other than 0 do not send the spans the frame gates prove black, device 0
     zero-fills them. Alternating a camera that sees only floor with one that sees mostly sky makes a missing fill visible as
     stale floor pixels."""
-    g = min(N_GPUS, 4) if N_GPUS >= 4 else 2
+    g = 4 if N_GPUS != 2 else 2
     sc = scenes.default_scene()
     w, h = 1024, 600
     down = scenes.make_camera(pos=(0.0, 3.0, 2.0), pitch=1.3, width=w, height=h)       # floor everywhere
@@ -104,7 +117,7 @@ def test_sparse_gather_leaves_no_stale_pixels(rt):
     refs = [one.render(c, w, h, 8)[0].copy() for c in (down, up, level)]
     one.close()
     assert (refs[0] != 0).mean() > 0.95 and (refs[1] == 0).mean() > 0.5
-    multi = rt.Context(list(range(g))); multi.set_scene(sc)
+    multi = rt.Context(_devices(g)); multi.set_scene(sc)
     multi.set_option(rt.RT_OPT_HOST_VIA_GPU0, 1)
     multi.set_option(rt.RT_OPT_SHARED_TARGET, 2)         # force the sparse gather (automatic only above 4 devices)
     for rep in range(2):
@@ -120,7 +133,7 @@ def _ipc_worker(rank, world, w, h, tile_rows, q_handle, q_done, q_go, shared_tar
     import rtb200
     sc = scenes.default_scene()
     cam = scenes.make_camera(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15, width=w, height=h)
-    ctx = rtb200.Context([rank]); ctx.set_scene(sc); ctx.set_partition(rank, world, tile_rows)
+    ctx = rtb200.Context([rank % max(N_GPUS, 1)]); ctx.set_scene(sc); ctx.set_partition(rank, world, tile_rows)
     ctx.set_option(rtb200.RT_OPT_SHARED_TARGET, shared_target)
     if rank == 0:
         fb = ctx.dev_alloc(w * h * 4)
@@ -151,7 +164,7 @@ def _ipc_worker(rank, world, w, h, tile_rows, q_handle, q_done, q_go, shared_tar
     ctx.close()
 
 
-@need2
+@need1
 @pytest.mark.parametrize("shared_target,w,h,tile_rows", [(0, 1000, 563, 8), (2, 1000, 563, 8), (2, 1283, 97, 3)])
 def test_multi_process_ipc_peer_stores(built, shared_target, w, h, tile_rows):
     """One process per GPU (the torchrun shape): rank 1 stores its row tiles straight into rank 0's framebuffer (CUDA IPC).

@@ -1346,6 +1346,9 @@ int rt_create(rt_context** out, const int* device_ids, int n_devices) {
     // Peer access so that devices 1..n-1 can store straight into device 0's framebuffer (fused gather over NVLink).
     ctx->peer_ok = true;
     for (int i = 1; i < n_devices; i++) {
+        // a device id may repeat: several partitions of one context on ONE physical GPU (each with its own streams, scene copy and
+        // launch thread) — how the single-GPU test run exercises the multi-device code; memory of the same device needs no peer mapping
+        if (ctx->devs[(size_t)i].dev == ctx->devs[0].dev) continue;
         int can = 0;
         cudaDeviceCanAccessPeer(&can, ctx->devs[(size_t)i].dev, ctx->devs[0].dev);
         if (!can) { ctx->peer_ok = false; break; }

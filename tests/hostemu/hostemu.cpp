@@ -6,6 +6,7 @@
 #include <vector>
 #include "../../uu-infogr-raytracer_b200/csrc/rt_scene.cuh"
 #include "../../uu-infogr-raytracer_b200/csrc/rt_gate.cuh"
+#include "../../uu-infogr-raytracer_b200/csrc/rt_tiles.cuh"
 
 using namespace rtb;
 
@@ -354,4 +355,28 @@ extern "C" int emu_shadow_bins_check(const float* spheres, int ns, const float* 
     }
     out[0] = decided_n; out[1] = bad; out[2] = undecided; out[3] = occ_n; out[4] = tests;
     return 0;
+}
+
+// 2-D pixel blocks (rt_tiles.cuh): runs every (tile, item, thread) of a frame through the kernels' own mapping and counts how often
+// each pixel is owned. kind 0: render_loop (ppt 1 or 4), kind 1: k_render_tiny_pack (ppt 4, w % 128 == 0). cover: w*h bytes.
+// Returns the number of spans that leave the frame or their tile (must be 0).
+extern "C" int emu_tile_cover(int kind, int ppt, int w, int h, int tile_rows, unsigned char* cover) {
+    int bad = 0;
+    const int tiles = (h + tile_rows - 1) / tile_rows;
+    const int items = kind == 0 ? tile2d_items_per_tile(ppt, w, tile_rows) : (tile_rows / 4) * (w / 128);
+    if (kind == 1 && items != tile2d_items_per_tile(4, w, tile_rows)) return -1;      // the launch sizes both from chunks_per_tile
+    for (int t = 0; t < tiles; t++)
+        for (int b = 0; b < items; b++)
+            for (int tid = 0; tid < 128; tid++) {
+                int x, y, cb = 0, yf = 0;
+                const bool ok = kind == 0 ? tile2d_span(ppt, w, h, t, tile_rows, b, tid, &x, &y) : pack2d_span(w, h, t, tile_rows, b, tid, &x, &y, &cb, &yf);
+                if (!ok) continue;
+                if (y < t * tile_rows || y >= (t + 1) * tile_rows || y >= h || x < 0) { bad++; continue; }
+                if (kind == 1 && (cb != x / 128 || yf > y || y - yf > 3 || (yf - t * tile_rows) % 4 != 0)) bad++;
+                for (int q = 0; q < ppt; q++) {
+                    if (x + q >= w) { if (kind == 1 || ppt == 4) bad++; continue; }   // ragged spans only exist on the 1-pixel paths' right edge (none there)
+                    cover[(size_t)y * w + x + q]++;
+                }
+            }
+    return bad;
 }

@@ -37,6 +37,8 @@ def load():
         _lib.emu_row_plan.restype = C.c_int
         _lib.emu_shadow_bins_check.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, C.POINTER(C.c_uint64)]
         _lib.emu_shadow_bins_check.restype = C.c_int
+        _lib.emu_tile_cover.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
+        _lib.emu_tile_cover.restype = C.c_int
     return _lib
 
 
@@ -145,3 +147,11 @@ def shadow_bins_check(spheres, lights, points):
     rc = lib.emu_shadow_bins_check(_fp(spheres), len(spheres), _fp(lights), len(lights), _fp(points), len(points), out.ctypes.data_as(C.POINTER(C.c_uint64)))
     assert rc == 0
     return dict(zip(("decided", "mismatches", "undecided", "occluded", "sphere_tests"), (int(v) for v in out)))
+
+
+def tile_cover(kind, ppt, w, h, tile_rows):
+    """How often each pixel is owned under the kernels' 2-D block mapping (csrc/rt_tiles.cuh): (cover uint8[h, w], bad spans)."""
+    lib = load()
+    cover = np.zeros(w * h, np.uint8)
+    bad = lib.emu_tile_cover(kind, ppt, w, h, tile_rows, cover.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return cover.reshape(h, w), bad

@@ -112,3 +112,16 @@ def test_production_debug_policy(built, tiny, camkw, depth):
     assert [a["counters"][k] for k in ("primary", "shadow", "secondary")] == b["counters"][:3]
     g = E.gates(sc, cam, w, h)["bits"]
     assert (g != 0).mean() > 0.2          # the gates really were active on this frame
+
+
+@pytest.mark.parametrize("kind,ppt,w,h,tile_rows", [
+    (0, 4, 3840, 2160, 8), (0, 4, 1280, 720, 8), (0, 4, 1000, 563, 8), (0, 4, 1284, 397, 16), (0, 4, 4, 1, 8), (0, 4, 68, 19, 24),
+    (0, 1, 3840, 2160, 8), (0, 1, 1283, 397, 16), (0, 1, 250, 131, 8), (0, 1, 37, 23, 8), (0, 1, 1, 1, 8), (0, 1, 17, 9, 32),
+    (1, 4, 3840, 2160, 8), (1, 4, 1280, 724, 8), (1, 4, 1152, 333, 16), (1, 4, 128, 3, 8), (1, 4, 896, 500, 24)])
+def test_2d_pixel_blocks_cover_every_pixel_once(kind, ppt, w, h, tile_rows):
+    """csrc/rt_tiles.cuh — the thread -> pixel mapping of the render kernels (render_loop: 16 ppt x 8-pixel CTAs; the packed gather's
+    render kernel: 128 x 4): over all tiles, items and threads every pixel of the frame is owned exactly once, no span leaves its
+    tile, its row or the frame — for ragged widths / heights and several tile heights."""
+    cover, bad = E.tile_cover(kind, ppt, w, h, tile_rows)
+    assert bad == 0
+    assert cover.min() == 1 and cover.max() == 1, (int(cover.min()), int(cover.max()))

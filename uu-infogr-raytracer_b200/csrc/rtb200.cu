@@ -36,6 +36,7 @@ extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource*
 #include "rt_shadow_grid_build.cuh"
 #include "rt_gate.cuh"
 #include "rt_gather.cuh"
+#include "rt_tiles.cuh"
 
 using namespace rtb;
 
@@ -133,14 +134,9 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp,
         int end = base + tile_pix; if (end > npix || end < base) end = npix;
         int p0, x, y;
         if ((PPT == 1 || PPT == 4) && fp.tile2d) {
-            // 2-D pixel blocks: blockIdx.x = (row group of 8 rows inside the tile, block of 16 * PPT columns); a warp covers
-            // 8 * PPT x 4 pixels (8 threads side by side, 4 rows), the CTA's four warps 2 x 2 of those
-            const int cols = (fp.w + 16 * PPT - 1) / (16 * PPT);
-            const int rg = (int)blockIdx.x / cols, cb = (int)blockIdx.x - rg * cols;          // CTA-uniform
-            const int lane = (int)threadIdx.x & 31, wp = (int)threadIdx.x >> 5;
-            x = (cb * 16 + (wp & 1) * 8 + (lane & 7)) * PPT;
-            y = tile * fp.tile_rows + rg * 8 + (wp >> 1) * 4 + (lane >> 3);
-            if (x >= fp.w || y >= fp.h) continue;
+            // 2-D pixel blocks (rt_tiles.cuh): blockIdx.x = (row group of 8 rows inside the tile, block of 16 * PPT columns); a warp
+            // covers 8 * PPT x 4 pixels (8 threads side by side, 4 rows), the CTA's four warps 2 x 2 of those
+            if (!tile2d_span(PPT, fp.w, fp.h, tile, fp.tile_rows, (int)blockIdx.x, (int)threadIdx.x, &x, &y)) continue;
             p0 = y * fp.w + x;
             end = p0 + (fp.w - x < PPT ? fp.w - x : PPT);      // the thread's span ends with its row
         } else {
@@ -305,14 +301,8 @@ __global__ void __launch_bounds__(BLOCK, RT_MIN_BLOCKS) k_render_tiny_pack(const
             // CTA's four warps lie side by side — 128 x 4 pixels — so that the CTA owns whole flag bytes (one per row and 128-pixel
             // group, assembled from the warps' quad bits in shared memory below). Rows below the frame (last tile) count as black:
             // nothing traced or stored. No warp leaves the item early: the item loop and its barriers are CTA-uniform.
-            const int cols = fp.w >> 7;                            // w % 128 == 0
-            const int rg = chunk / cols;
-            cb = chunk - rg * cols;
-            x = cb * 128 + wp * 32 + (lane & 7) * PPT;
-            y_first = tile * fp.tile_rows + rg * 4;
-            y = y_first + (lane >> 3);
+            black = !pack2d_span(fp.w, fp.h, tile, fp.tile_rows, chunk, (int)threadIdx.x, &x, &y, &cb, &y_first);     // rt_tiles.cuh; w % 128 == 0
             p0 = y * fp.w + x;
-            black = y >= fp.h;
         } else {
             p0 = base + chunk * CHUNK + (int)threadIdx.x * PPT;
             if (p0 >= end) continue;                               // warp-uniform (see above)
@@ -1052,7 +1042,7 @@ FrameParams make_params(const rt_context* ctx, int w, int h, int depth, int spp,
     const int ppt = ctx->path == PATH_TINY ? PPT_TINY : PPT_HEAVY;
     if (BLOCK == 128 && fp.tile_rows % 8 == 0 && w % ppt == 0 && (ppt == 1 || ppt == 4) && !no_tile2d) {
         fp.tile2d = 1;
-        fp.chunks_per_tile = (fp.tile_rows / 8) * ((w + 16 * ppt - 1) / (16 * ppt));
+        fp.chunks_per_tile = tile2d_items_per_tile(ppt, w, fp.tile_rows);      // == (tile_rows / 4) * (w / 128) for the packed gather's items
     }
     fp.rcp_w = 1.0f / (float)w; fp.rcp_h = 1.0f / (float)h;      // host fp32 division: IEEE
     fp.frame_stride = frame_stride;

@@ -6,10 +6,12 @@
 // ShiftColor/SetPixel :1037-1052).  Strict fp32 (see rt_math.cuh); no tensor cores (no dense contraction on this path).
 //
 // Work decomposition: a frame is cut into ROW TILES of `tile_rows` rows (contiguous pixel ranges in the row-major
-// framebuffer); tile t belongs to rank t % world (multi-GPU row interleave).  A rank's tiles are cut into chunks of
-// CHUNK = 256 threads x PPT pixels, one CTA per (chunk, tile, frame).  Each thread owns PPT=4 adjacent pixels and writes
-// them with one 128-bit store; the store address may be a peer (NVLink) mapping of rank 0's framebuffer — the gather is
-// fused into the render kernel.
+// framebuffer); tile t belongs to rank t % world (multi-GPU row interleave).  A rank's tiles are cut into work items of
+// 128 threads x PPT pixels, one CTA per (item, tile, frame).  Each thread owns a span of PPT=4 adjacent pixels and writes
+// it with one 128-bit store; the store address may be a peer (NVLink) mapping of rank 0's framebuffer — the gather is
+// fused into the render kernel — or the caller's page-locked Surface.pixels.  Items are 2-D pixel blocks (rt_tiles.cuh: a warp
+// covers 32 x 4 pixels, 8 x 4 on the one-pixel-per-thread paths) whenever tile_rows % 8 == 0 and a row is whole spans; linear
+// runs of the pixel index otherwise.
 #include <cuda_runtime.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>

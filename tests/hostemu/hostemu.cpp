@@ -113,6 +113,14 @@ static uint32_t dispatch(int use_tiny, const TinySceneData& t, const GlobalScene
         }
         return pack_color(C);
     }
+    if (use_tiny == 2 && t.np == 1 && (t.nl == 2 || t.nl == 4)) {
+        // the device's exact (spheres, lights, 1 plane) instantiations with an even light count: the packed two-light pass
+        // (shade_light_pair) is compiled in when the library is built with -DRT_EMULATE_F32X2
+#define EMU_EXACT(NS, NL) if (t.ns == NS && t.nl == NL) return px_of(TinyScene<NS, NL, 1>(t), cam, x, y, w, h, d, spp, seed, st, dbg)
+        EMU_EXACT(0, 2); EMU_EXACT(1, 2); EMU_EXACT(2, 2); EMU_EXACT(3, 2); EMU_EXACT(4, 2);
+        EMU_EXACT(0, 4); EMU_EXACT(1, 4); EMU_EXACT(2, 4); EMU_EXACT(3, 4); EMU_EXACT(4, 4);
+#undef EMU_EXACT
+    }
     if (use_tiny == 2) {
         switch (t.ns) {
             case 0: return px_of(TinyScene<0>(t), cam, x, y, w, h, d, spp, seed, st, dbg);
@@ -164,6 +172,7 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         for (int i = 0; i < ns; i++) { t.sgeom[i] = sg[i]; t.smat[i] = sm[i]; }
         for (int i = 0; i < np; i++) t.planes[i] = pl[i];
         for (int i = 0; i < nl; i++) t.lights[i] = li[i];
+        tiny_fill_pairs(t);                       // sphere / light pairs of the packed-fp32 paths (used with -DRT_EMULATE_F32X2)
     }
     const bool prod_dbg = use_tiny >= 10;         // 11 / 12: TinyScene<-1> / <exact> with the events-only policy of k_debug_tiny_prod
     if (prod_dbg) use_tiny -= 10;

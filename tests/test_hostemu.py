@@ -125,3 +125,60 @@ def test_2d_pixel_blocks_cover_every_pixel_once(kind, ppt, w, h, tile_rows):
     cover, bad = E.tile_cover(kind, ppt, w, h, tile_rows)
     assert bad == 0
     assert cover.min() == 1 and cover.max() == 1, (int(cover.min()), int(cover.max()))
+
+
+@pytest.fixture
+def packed():
+    """libhostemu_packed.so: the device headers with -DRT_EMULATE_F32X2 — the PACKED fp32 code paths (two spheres, two lights, two bin
+    entries, two child boxes per pass), each packed operation emulated as two scalar IEEE operations."""
+    E.use_variant("_packed")
+    try:
+        yield
+    finally:
+        E.use_variant("")
+
+
+def _scene_with_lights(n_spheres, n_lights, seed):
+    sc = scenes.small_random_scene(n_spheres, seed)
+    rng = np.random.default_rng(seed)
+    lights = np.stack([scenes.light((rng.uniform(-6, 6), rng.uniform(2, 8), rng.uniform(-4, 10)), float(rng.uniform(0.4, 1.2))) for _ in range(n_lights)])
+    return scenes.Scene(sc.spheres, sc.planes[:1], lights, sc.ambient)      # one plane: the exact-count instantiations
+
+
+@pytest.mark.parametrize("ns,nl,seed", [(3, 2, 1), (2, 2, 2), (4, 4, 3), (4, 2, 4), (1, 4, 5), (3, 3, 6), (0, 2, 7)])
+def test_packed_sphere_and_light_pairs_equal_the_oracle(built, packed, ns, nl, seed):
+    """The production code path of the exact-count kernels — sphere_pair_bd, shade_light_pair (even light counts), xy-packed vector
+    products, frame gates — as the shipped policy (no per-test counters: tiny = 2) and as the events-only policy of k_debug_tiny_prod
+    (tiny = 12): pixels and chain hashes must equal the oracle's. Odd light counts take the scalar loop inside the same build."""
+    sc = _scene_with_lights(ns, nl, seed)
+    for camkw in (dict(pos=(0, 1.5, -4.0), pitch=0.1), dict(pos=(2.0, 3.0, 1.0), yaw=-0.5, pitch=0.6)):
+        cam = scenes.make_camera(width=200, height=120, **camkw)
+        a = O.render(sc, cam, 200, 120, 8, want_hash=True)
+        c = E.render(sc, cam, 200, 120, 8, tiny=2, debug=False)
+        assert np.array_equal(a["pixels"], c["pixels"]), "%d pixels differ" % (a["pixels"] != c["pixels"]).sum()
+        p = E.render(sc, cam, 200, 120, 8, tiny=12, debug=True)
+        assert np.array_equal(a["pixels"], p["pixels"]) and np.array_equal(a["hash"], p["hash"])
+
+
+@pytest.mark.parametrize("camkw,depth", [(dict(), 32), (dict(pos=(0.3, 0.5, -1.0), yaw=0.2, pitch=0.15), 8), (dict(pos=(0, 4.0, 6.0), pitch=1.2), 32)])
+def test_packed_default_scene(built, packed, camkw, depth):
+    sc = scenes.default_scene()
+    cam = scenes.make_camera(width=320, height=180, **camkw)
+    a = O.render(sc, cam, 320, 180, depth, want_hash=True)
+    assert np.array_equal(a["pixels"], E.render(sc, cam, 320, 180, depth, tiny=2)["pixels"])
+    p = E.render(sc, cam, 320, 180, depth, tiny=12, debug=True)
+    assert np.array_equal(a["pixels"], p["pixels"]) and np.array_equal(a["hash"], p["hash"])
+    d = scenes.degenerate_scene()                 # NaN / zero / negative records through the run-time-count packed-free path
+    assert np.array_equal(O.render(d, cam, 320, 180, 8)["pixels"], E.render(d, cam, 320, 180, 8, tiny=1)["pixels"])
+
+
+def test_packed_lbvh_paths(built, packed):
+    """LBVH policy in the packed build: two-child slab test (box_entry2) and the shadow bins' pair loop (sphere_pair_bd on GridPair)."""
+    sc = scenes.Scene(scenes.random_spheres_scene(600, 11, 20.0, 4.0, 44.0, "m")[0], scenes.default_scene().planes, scenes.config3_scene().lights, scenes.REF_AMBIENT)
+    w, h = 192, 108
+    cam = scenes.make_camera(width=w, height=h, **scenes.SCALED_CAMERA)
+    a = O.render(sc, cam, w, h, 8, want_hash=True)
+    b = E.render(sc, cam, w, h, 8, tiny=3, debug=False)       # NoDbg: packed bins, early-outs
+    assert np.array_equal(a["pixels"], b["pixels"]), "%d pixels differ" % (a["pixels"] != b["pixels"]).sum()
+    c = E.render(sc, cam, w, h, 8, tiny=3, debug=True)        # FullDbg: scalar bins, packed slab test
+    assert np.array_equal(a["pixels"], c["pixels"]) and np.array_equal(a["hash"], c["hash"])

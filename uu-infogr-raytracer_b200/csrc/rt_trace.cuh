@@ -214,7 +214,7 @@ struct LogDbg {
 // kernel is issue-bound with the FMA pipe ~35 % busy). Operation order per element is exactly :614-621.
 #if defined(RT_HAVE_F32X2)
 template <class PAIR>
-__device__ __forceinline__ void sphere_pair_bd(const PAIR& p, float2 ox, float2 oy, float2 oz, float2 dx, float2 dy, float2 dz,
+RT_D void sphere_pair_bd(const PAIR& p, float2 ox, float2 oy, float2 oz, float2 dx, float2 dy, float2 dz,
                                                float2 na4, float* b_out, float* D_out) {
     const float2 ocx = rt_add2(ox, make_float2(p.ncx[0], p.ncx[1]));                      // :614  o - c
     const float2 ocy = rt_add2(oy, make_float2(p.ncy[0], p.ncy[1]));
@@ -377,7 +377,7 @@ RT_HD float spec_pow(float base, float n) {
 // because ptxas fuses a packed multiply into a following packed add even under -fmad=false. ~130 instead of ~190 instructions
 // per shaded hit with two lights. I0 / I1: the lights' intensities after the shadow test (:581).
 template <class DBG>
-__device__ __forceinline__ void shade_light_pair(const LightPair& lp, const MatRec& m, f3 hit, f3 N, f3 V, float att, float tile,
+RT_D void shade_light_pair(const LightPair& lp, const MatRec& m, f3 hit, f3 N, f3 V, float att, float tile,
                                                  bool is_plane, float I0, float I1, f3* tA, f3* tB, DBG& dbg) {
     float2 Lx = rt_sub2(make_float2(lp.px[0], lp.px[1]), rt_splat2(hit.x));                   // :667  light.position - hit
     float2 Ly = rt_sub2(make_float2(lp.py[0], lp.py[1]), rt_splat2(hit.y));

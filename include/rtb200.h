@@ -207,6 +207,13 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
  * geometry code, same bins; 0.1-0.3 s at 100 k spheres instead of ~2 ms). Takes effect at the next rt_set_scene / rt_update_spheres.
  * Exists for the test that shows both builds agree. */
 #define RT_OPT_HOST_SHADOW_BINS 12
+/* RT_OPT_PRIMARY_BINS: LBVH scenes, single-sample frames — per frame (whenever the camera or the frame size changes) every sphere is
+ * projected to the pixel rectangle outside of which no primary ray can be reported as hitting it (the rectangle of the tiny scenes'
+ * frame gates, csrc/rt_gate.cuh) and entered into the 8 x 8-pixel tiles it touches, on the GPU (three small launches, nothing read
+ * back); a primary ray then runs the reference's sphere test (RayTracer.cs:613-642) over the list of ITS tile and folds as :975-981
+ * does, instead of walking the tree. Tiles with more than 32 spheres (the horizon of the 100 k-sphere scene) keep no list and
+ * traverse as before. Same pixels, hit ids and t bits either way (csrc/rt_primary_bins.cuh). */
+#define RT_OPT_PRIMARY_BINS 13
 /* Options that change WHICH rank writes a pixel (RT_OPT_SHARED_TARGET, RT_OPT_PRIMARY_GATE) must be set identically on every rank
  * of a partition. RT_OPT_COMPACTION may differ: a launch that takes part in a sparse gather always uses the default kernel. */
 int rt_set_option(rt_context* ctx, int option, int value);
@@ -224,6 +231,8 @@ int rt_set_option(rt_context* ctx, int option, int value);
 #define RT_INFO_LAST_TOTAL_NS 8     /* ... from entry to return */
 #define RT_INFO_SHADOW_BINS_NS 11   /* host wall-clock nanoseconds of the last shadow-bin (re)build (rt_set_scene / rt_update_spheres; LBVH scenes) */
 #define RT_INFO_SHADOW_BIN_PAIRS 12 /* sphere pairs stored in the bins of device 0 (32 bytes each) */
+#define RT_INFO_PRIMARY_BIN_BUILDS 13 /* per-frame primary-bin builds so far, all devices (a camera that does not move is cached) */
+#define RT_INFO_PRIMARY_BINS 14     /* 1 if RT_OPT_PRIMARY_BINS is on */
 int rt_get_info(const rt_context* ctx, int what, uint64_t* value);
 
 /* ---- device-pointer / multi-process interface (torchrun: one process per GPU) --------------------------------- */

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <vector>
 #include "../../uu-infogr-raytracer_b200/csrc/rt_scene.cuh"
+#include "../../uu-infogr-raytracer_b200/csrc/rt_primary_bins.cuh"
 #include "../../uu-infogr-raytracer_b200/csrc/rt_gate.cuh"
 #include "../../uu-infogr-raytracer_b200/csrc/rt_tiles.cuh"
 
@@ -65,6 +66,7 @@ static bool g_gate_on = false;
 static FrameGates g_gates;
 template <class SC, class DBG>
 static uint32_t px_of(const SC& sc, const CamRec& cam, int x, int y, int w, int h, int d, int spp, uint32_t seed, HitRec* st, DBG& dbg) {
+    scene_begin_pixel(sc, x, y, spp, 0);          // as render_loop / debug_loop (rtb200.cu)
     if constexpr (!DBG::count_tests) {          // NoDbg (the shipped kernels) and ProdDbg (k_debug_tiny_prod): gated
         if (g_gate_on) {
             // as render_loop (rtb200.cu): gates per span of 4 consecutive pixels (linear index aligned to 4), only inside one row
@@ -84,8 +86,15 @@ static uint32_t px_of(const SC& sc, const CamRec& cam, int x, int y, int w, int 
     return trace_pixel(sc, cam, x, y, w, h, d, spp, seed, st, dbg);
 }
 // use_tiny: 0 global-memory policy, 1 TinyScene<-1> (run-time count), 2 TinyScene<NS> with the exact compile-time count,
-//           3 LBVH policy, 4 shared-memory-staged policy (here: an ordinary host array)
+//           3 LBVH policy, 4 shared-memory-staged policy (here: an ordinary host array), 6 LBVH policy + per-frame primary bins
 static const HostBvh* g_bvh = nullptr;
+static PrimaryBinsHost g_pbh;
+static int g_pb_capacity = -1;                    // emu_set_primary_bins_capacity: < 0 = the device build's rule (16 per sphere ...)
+static int pb_capacity_for(int n, const PbCam& c) {
+    if (g_pb_capacity >= 0) return g_pb_capacity;
+    return pb_list_capacity(n, (long long)c.tiles_x * c.tiles_y);
+}
+extern "C" void emu_set_primary_bins_capacity(int capacity) { g_pb_capacity = capacity; }
 static ShadowGridsHost g_sgh;
 static ShadowGridsView sg_view() {
     ShadowGridsView v; memset(&v, 0, sizeof(v));
@@ -98,6 +107,7 @@ static uint32_t dispatch(int use_tiny, const TinySceneData& t, const GlobalScene
     if (use_tiny == 0) return px_of(GlobalScene(g), cam, x, y, w, h, d, spp, seed, st, dbg);
     if (use_tiny == 3) return px_of(LbvhScene(g, g_bvh->view(), sg_view()), cam, x, y, w, h, d, spp, seed, st, dbg);
     if (use_tiny == 4) return px_of(StagedScene(g, g.sgeom), cam, x, y, w, h, d, spp, seed, st, dbg);
+    if (use_tiny == 6) return px_of(LbvhBinsScene(g, g_bvh->view(), sg_view(), g_pbh.view()), cam, x, y, w, h, d, spp, seed, st, dbg);
     if (use_tiny == 5) {
         // park / resume (the compacting kernel's two passes, sequentially): trace to the second hit, copy the state out the
         // way k_render_tiny_compact parks it, wipe the stack, restore, finish. spp == 1 only.
@@ -155,7 +165,7 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
     g.ns = ns; g.np = np; g.nl = nl; g.amb = mk3(ambient[0], ambient[1], ambient[2]);
     g.sgeom = sg.data(); g.smat = sm.data(); g.planes = pl.data(); g.lights = li.data();
     HostBvh bvh;
-    if (use_tiny == 3) {
+    if (use_tiny == 3 || use_tiny == 6) {
         if (ns < 2) return -2;
         host_build(sg, bvh);
         bvh.nodes_cam = bvh.nodes;
@@ -164,6 +174,7 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         std::vector<f3> lp((size_t)nl);
         for (int i = 0; i < nl; i++) lp[i] = li[i].p;
         shadow_grids_build(sg, lp, &g_sgh);
+        if (use_tiny == 6) { const PbCam pc = make_pb_cam(cam, w, h); primary_bins_build_host(pc, sg.data(), ns, pb_capacity_for(ns, pc), &g_pbh); }
     }
     TinySceneData t; memset(&t, 0, sizeof(t));
     if (use_tiny == 1 || use_tiny == 2 || use_tiny == 5 || use_tiny == 11 || use_tiny == 12) {
@@ -363,6 +374,54 @@ extern "C" int emu_shadow_bins_check(const float* spheres, int ns, const float* 
         }
     }
     out[0] = decided_n; out[1] = bad; out[2] = undecided; out[3] = occ_n; out[4] = tests;
+    return 0;
+}
+
+// Primary bins (rt_primary_bins.cuh), checked directly: for every pixel of the frame the kernel's own primary ray (primary_ray) is
+// tested against ALL spheres with the reference's test (:613-642, :975-981); every sphere that reports a hit must be in the list of
+// the pixel's tile (or in the everywhere list) unless the tile keeps no list — and the fold over the list must select what the
+// brute-force fold selects. out[0] = pixels answered by the bins, out[1] = pixels left to the traversal, out[2] = reported hits
+// missing from a list (must be 0), out[3] = pixels whose fold differs (id or t bits; must be 0), out[4] = sphere tests run by the
+// bins, out[5] = tiles without a list, out[6] = list entries, out[7] = spheres in the everywhere list, out[8] = bins valid (0 / 1).
+extern "C" int emu_primary_bins_check(const float* spheres, int ns, const float* cam15, int w, int h, uint64_t* out) {
+    std::vector<f4> sg((size_t)ns);
+    for (int i = 0; i < ns; i++) { const float* f = spheres + 18 * (size_t)i; sg[i].x = f[0]; sg[i].y = f[1]; sg[i].z = f[2]; sg[i].w = f[17]; }
+    CamRec cam;
+    cam.pos = mk3(cam15[0], cam15[1], cam15[2]); cam.right = mk3(cam15[3], cam15[4], cam15[5]);
+    cam.up = mk3(cam15[6], cam15[7], cam15[8]); cam.fwd = mk3(cam15[9], cam15[10], cam15[11]);
+    cam.view = mk3(cam15[12], cam15[13], cam15[14]);
+    PrimaryBinsHost pbh;
+    const PbCam pc = make_pb_cam(cam, w, h);
+    primary_bins_build_host(pc, sg.data(), ns, pb_capacity_for(ns, pc), &pbh);
+    const PrimaryBinsView v = pbh.view();
+    uint64_t by_bins = 0, by_tree = 0, missing = 0, differ = 0, tests = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : by_bins, by_tree, missing, differ, tests)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            f3 o, dir;
+            primary_ray(cam, (float)x, (float)y, (float)w, (float)h, 0.0f, 0.0f, &o, &dir);
+            const float a = dot3(dir, dir), a2 = 2 * a, a4 = 4 * a;
+            FullDbg dbg;
+            int sel = -1; float t_sel = RT_INF;
+            if (!primary_bins_nearest(v, x, y, o, dir, a2, a4, &sel, &t_sel, dbg)) { by_tree++; continue; }
+            by_bins++; tests += dbg.sphere_tests;
+            const PbTile tl = v.tiles[(size_t)(y >> PB_TILE_SHIFT) * v.tiles_x + (x >> PB_TILE_SHIFT)];
+            int want = -1; float t_want = RT_INF; NoDbg nd;
+            for (int i = 0; i < ns; i++) {
+                float t;
+                if (!(sphere_hit(sub3(o, mk3(sg[i].x, sg[i].y, sg[i].z)), dir, sg[i].w, a2, a4, 0.0f, &t, nd) && t > 0)) continue;
+                if (t < t_want) { t_want = t; want = i; }                     // :977 strict '>' in array order
+                bool listed = false;
+                for (int k = 0; k < tl.n && !listed; k++) listed = v.orig[tl.start + k] == i;
+                for (int k = 0; k < v.hdr->n_everywhere && k < PB_MAX_EVERYWHERE && !listed; k++) listed = v.hdr->ev_orig[k] == i;
+                if (!listed) missing++;
+            }
+            if (want != sel || f2bits(t_want) != f2bits(t_sel)) differ++;
+        }
+    uint64_t no_list = 0, entries = 0;
+    for (size_t t = 0; t < pbh.tiles.size(); t++) { if (pbh.tiles[t].n < 0) no_list++; else entries += (uint64_t)pbh.tiles[t].n; }
+    out[0] = by_bins; out[1] = by_tree; out[2] = missing; out[3] = differ; out[4] = tests; out[5] = no_list; out[6] = entries;
+    out[7] = pbh.valid ? (uint64_t)pbh.hdr.n_everywhere : 0; out[8] = pbh.valid ? 1 : 0;
     return 0;
 }
 

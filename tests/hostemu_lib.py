@@ -39,6 +39,10 @@ def load():
         _lib.emu_shadow_bins_check.restype = C.c_int
         _lib.emu_tile_cover.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
         _lib.emu_tile_cover.restype = C.c_int
+        _lib.emu_primary_bins_check.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        _lib.emu_primary_bins_check.restype = C.c_int
+        _lib.emu_set_primary_bins_capacity.argtypes = [C.c_int]
+        _lib.emu_set_primary_bins_capacity.restype = None
     return _lib
 
 
@@ -47,7 +51,7 @@ def _fp(a):
 
 
 def render(scene, cam, w, h, max_depth=32, spp=1, seed=0, tiny=0, debug=False):
-    """tiny: 0 global-memory policy, 1 TinyScene<-1>, 2 TinyScene<exact NS>, 3 LBVH, 4 staged (see hostemu.cpp)"""
+    """tiny: 0 global-memory policy, 1 TinyScene<-1>, 2 TinyScene<exact NS>, 3 LBVH, 4 staged, 6 LBVH + primary bins (see hostemu.cpp)"""
     lib = load()
     n = w * h
     px = np.zeros(n, np.int32)
@@ -147,6 +151,22 @@ def shadow_bins_check(spheres, lights, points):
     rc = lib.emu_shadow_bins_check(_fp(spheres), len(spheres), _fp(lights), len(lights), _fp(points), len(points), out.ctypes.data_as(C.POINTER(C.c_uint64)))
     assert rc == 0
     return dict(zip(("decided", "mismatches", "undecided", "occluded", "sphere_tests"), (int(v) for v in out)))
+
+
+def primary_bins_check(spheres, cam, w, h, capacity=-1):
+    """Per-frame primary bins (rt_primary_bins.cuh) against the reference's loop over all spheres for every pixel's primary ray.
+    capacity: entries of the list array (-1 = the device build's rule)."""
+    lib = load()
+    spheres = np.ascontiguousarray(spheres, np.float32); cam = np.ascontiguousarray(cam, np.float32)
+    out = np.zeros(9, np.uint64)
+    lib.emu_set_primary_bins_capacity(int(capacity))
+    try:
+        rc = lib.emu_primary_bins_check(_fp(spheres), len(spheres), _fp(cam), w, h, out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    finally:
+        lib.emu_set_primary_bins_capacity(-1)
+    assert rc == 0
+    return dict(zip(("by_bins", "by_tree", "missing", "differ", "sphere_tests", "tiles_without_list", "entries", "everywhere", "valid"),
+                    (int(v) for v in out)))
 
 
 def tile_cover(kind, ppt, w, h, tile_rows):

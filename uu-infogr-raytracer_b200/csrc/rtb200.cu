@@ -36,6 +36,7 @@ extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource*
 #include "rt_scene.cuh"
 #include "rt_lbvh_build.cuh"
 #include "rt_shadow_grid_build.cuh"
+#include "rt_primary_bins_build.cuh"
 #include "rt_gate.cuh"
 #include "rt_gather.cuh"
 #include "rt_tiles.cuh"
@@ -57,6 +58,9 @@ constexpr int PPT_HEAVY = 1;                // staged / global / LBVH paths: a p
 constexpr int STACK_RECS = RT_MAX_DEPTH + 1;
 constexpr int INLINE_CAMS = 16;
 constexpr int N_DEBUG_COUNTERS = 16;
+#ifndef RT_PRIMARY_BINS_DEFAULT
+#define RT_PRIMARY_BINS_DEFAULT 0      // RT_OPT_PRIMARY_BINS of a new context (environment RTB200_PRIMARY_BINS overrides it at rt_create)
+#endif
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 8      // resident CTAs per SM the register allocator must allow (tuned on B200, profiles/)
 #endif
@@ -183,6 +187,7 @@ __device__ __forceinline__ void render_loop(const SC& sc, const FrameParams& fp,
         for (int q = 0; q < PPT; q++) {
             uint32_t c = 0u;
             if (p0 + q < end) {
+                scene_begin_pixel(sc, x, y, fp.spp, 0);        // policies with per-pixel state (LbvhBinsScene); nothing for the others
                 if constexpr (DBG::enabled) {
                     DBG dbg;
                     c = trace_pixel<SPP1, SPP1>(sc, cam, x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg, fp.rcp_w, fp.rcp_h, bits);
@@ -594,6 +599,12 @@ struct LbvhSceneData { GlobalSceneData g; BvhView bv; ShadowGridsView sg; };
 __global__ void __launch_bounds__(BLOCK, RT_LBVH_MIN_BLOCKS) k_render_lbvh(const __grid_constant__ LbvhSceneData scd, const __grid_constant__ FrameParams fp) {
     render_loop<PPT_HEAVY>(LbvhScene(scd.g, scd.bv, scd.sg), fp);
 }
+// The same with the frame's primary bins (rt_primary_bins.cuh; RT_OPT_PRIMARY_BINS): primary rays fold over the sphere list of their
+// 8 x 8-pixel tile — one list per warp of the 2-D pixel blocks — instead of walking the tree.
+struct LbvhBinsSceneData { LbvhSceneData l; PrimaryBinsView pb; };
+__global__ void __launch_bounds__(BLOCK, RT_LBVH_MIN_BLOCKS) k_render_lbvh_bins(const __grid_constant__ LbvhBinsSceneData scd, const __grid_constant__ FrameParams fp) {
+    render_loop<PPT_HEAVY>(LbvhBinsScene(scd.l.g, scd.l.bv, scd.l.sg, scd.pb), fp);
+}
 
 // Instrumented kernel: one thread per pixel, writes hash / AOVs / counters.
 template <class SC>
@@ -605,6 +616,7 @@ __device__ __forceinline__ void debug_loop(const SC& sc, const FrameParams& fp, 
         const int p = (int)pl;
         FullDbg dbg;
         const int y = p / fp.w, x = p - y * fp.w;
+        scene_begin_pixel(sc, x, y, fp.spp, 0);
         uint32_t c = trace_pixel(sc, fp.cam_inline[0], x, y, fp.w, fp.h, fp.cap, fp.spp, fp.seed, stack, dbg);
         fp.out[p] = c;
         if (dout.hash) dout.hash[p] = dbg.hash;
@@ -647,6 +659,9 @@ __global__ void __launch_bounds__(BLOCK) k_debug_staged(const __grid_constant__ 
 }
 __global__ void __launch_bounds__(BLOCK) k_debug_lbvh(const __grid_constant__ LbvhSceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
     debug_loop(LbvhScene(scd.g, scd.bv, scd.sg), fp, dout);
+}
+__global__ void __launch_bounds__(BLOCK) k_debug_lbvh_bins(const __grid_constant__ LbvhBinsSceneData scd, const __grid_constant__ FrameParams fp, DebugOut dout) {
+    debug_loop(LbvhBinsScene(scd.l.g, scd.l.bv, scd.l.sg, scd.pb), fp, dout);
 }
 
 // Sphere-query kernels (LBVH == brute equality harness, rt_query_spheres).
@@ -766,6 +781,8 @@ struct DeviceState {
     // nodes_cam / the refit arrival counters are ONE buffer per device: a refit issued on another stream than the last LBVH launch
     // first waits for that launch (rt_render_device on several user streams, rt_update_spheres while user-stream frames are in flight)
     cudaEvent_t bvh_done = nullptr; cudaStream_t bvh_last_stream = nullptr; bool bvh_done_valid = false;
+    // per-frame primary bins (rt_primary_bins.cuh): one set of buffers per device, ordered like nodes_cam
+    PrimaryBinsDevice pb; CamRec pb_cam; int pb_w = 0, pb_h = 0; bool pb_valid = false, pb_usable = false; cudaStream_t pb_stream = nullptr;
     // framebuffer ring (device 0 of the context only, unless partitioned multi-process)
     uint32_t* fb = nullptr; size_t fb_pixels = 0;
     // band pipelining (render_frames): copy stream on device 0, per-segment "band rendered" events on every device
@@ -895,6 +912,8 @@ struct rt_context {
     bool has_bvh = false;
     bool has_shadow_grids = false;
     bool host_shadow_bins = false;       // RT_OPT_HOST_SHADOW_BINS: build the bins on the host (tests: device build == host build)
+    bool primary_bins = RT_PRIMARY_BINS_DEFAULT != 0;   // RT_OPT_PRIMARY_BINS
+    std::atomic<uint64_t> pb_builds{0};  // primary-bin builds so far (rt_get_info)
     uint64_t sg_build_ns = 0;            // wall time of the last shadow-bin (re)build (rt_get_info)
     std::vector<f4> host_sgeom; std::vector<f3> host_lights;     // kept for rt_update_spheres (shadow bins are rebuilt on the host)
     f3 sg_lo, sg_hi;
@@ -960,6 +979,7 @@ template <class T> struct DevMem {
 void free_scene(DeviceState& d) {
     cudaSetDevice(d.dev);
     d.bvh.release(); d.bvh_cam_valid = false;
+    d.pb.release(); d.pb_valid = false;
     d.sg.release();
     cudaFree(d.sgeom); cudaFree(d.smat); cudaFree(d.planes); cudaFree(d.lights);
     d.sgeom = nullptr; d.smat = nullptr; d.planes = nullptr; d.lights = nullptr;
@@ -1103,6 +1123,46 @@ LbvhSceneData lbvh_data(const rt_context* ctx, const DeviceState& d, bool with_c
     return l;
 }
 
+LbvhBinsSceneData lbvh_bins_data(const rt_context* ctx, const DeviceState& d) {
+    LbvhBinsSceneData b;
+    memset(&b, 0, sizeof(b));
+    b.l = lbvh_data(ctx, d, true);
+    b.pb = d.pb.view();
+    return b;
+}
+// Per-frame state of the LBVH path on device d, (re)built on `stream` when the camera changed: the camera-inflated copy of the node
+// boxes (depends on the camera position) and, with RT_OPT_PRIMARY_BINS on single-sample frames, the primary bins (depend on the whole
+// camera and the frame size). Both are one set of buffers per device: a rebuild on another stream than the last LBVH launch first
+// waits for that launch. *use_bins: the frame's primary rays may use the bins.
+int prepare_lbvh_frame(rt_context* ctx, DeviceState& d, const CamRec& c, int w, int h, int spp, cudaStream_t stream, bool* use_bins) {
+    *use_bins = false;
+    const bool boxes_ok = d.bvh_cam_valid && d.bvh_cam_stream == stream && d.bvh_cam[0] == c.pos.x && d.bvh_cam[1] == c.pos.y && d.bvh_cam[2] == c.pos.z;
+    const bool want_bins = ctx->primary_bins && spp == 1 && d.bvh.n >= 2;
+    const bool bins_ok = want_bins && d.pb_valid && d.pb_stream == stream && d.pb_w == w && d.pb_h == h && memcmp(&d.pb_cam, &c, sizeof(CamRec)) == 0;
+    if ((!boxes_ok || (want_bins && !bins_ok)) && d.bvh_done_valid && d.bvh_last_stream != stream)
+        CU_TRY(ctx, cudaStreamWaitEvent(stream, d.bvh_done, 0));
+    if (!boxes_ok) {
+        cudaError_t e = d.bvh.refit_for_camera(c.pos.x, c.pos.y, c.pos.z, stream);
+        if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh refit: ") + cudaGetErrorString(e));
+        d.bvh_cam[0] = c.pos.x; d.bvh_cam[1] = c.pos.y; d.bvh_cam[2] = c.pos.z; d.bvh_cam_valid = true; d.bvh_cam_stream = stream;
+        ctx->launches++;
+    }
+    if (want_bins && !bins_ok) {
+        const PbCam pc = make_pb_cam(c, w, h);
+        d.pb_usable = pc.eps >= 0;                       // a camera the gate derivation does not cover: this frame traverses
+        if (d.pb_usable) {
+            uint64_t launches = 0;
+            cudaError_t e = d.pb.build(d.sgeom, ctx->gdata_host.ns, pc, stream, &launches);
+            if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("primary bins: ") + cudaGetErrorString(e));
+            ctx->launches += launches;
+            ctx->pb_builds++;
+        }
+        d.pb_cam = c; d.pb_w = w; d.pb_h = h; d.pb_valid = true; d.pb_stream = stream;
+    }
+    *use_bins = want_bins && d.pb_usable;
+    return RT_OK;
+}
+
 // Per-frame gates of a tiny-scene launch (rt_gate.cuh): computed on the host for each distinct camera; a camera that does not move
 // (and batches of equal cameras) reuse the last result. Host time spent here is accumulated in ctx->gate_host_ns (rt_get_info).
 FrameGates gates_for(rt_context* ctx, const CamRec& cam, int w, int h) {
@@ -1191,15 +1251,10 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
     const bool gather_sink = fp.gather.area != nullptr && fp.rank == 0;      // rank 0 of a packed gather runs the expand pass even without own tiles
     if ((fp.tiles_mine <= 0 && !gather_sink) || fp.chunks_per_tile <= 0 || fp.n_frames <= 0) return RT_OK;
     if (fp.n_frames > 65535) return fail(ctx, RT_ERR_UNSUPPORTED, "more than 65535 frames in one launch");
+    bool use_bins = false;
     if (ctx->path == PATH_LBVH) {
-        const CamRec& c = fp.cam_inline[0];
-        if (!(d.bvh_cam_valid && d.bvh_cam_stream == stream && d.bvh_cam[0] == c.pos.x && d.bvh_cam[1] == c.pos.y && d.bvh_cam[2] == c.pos.z)) {
-            if (d.bvh_done_valid && d.bvh_last_stream != stream) CU_TRY(ctx, cudaStreamWaitEvent(stream, d.bvh_done, 0));
-            cudaError_t e = d.bvh.refit_for_camera(c.pos.x, c.pos.y, c.pos.z, stream);
-            if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh refit: ") + cudaGetErrorString(e));
-            d.bvh_cam[0] = c.pos.x; d.bvh_cam[1] = c.pos.y; d.bvh_cam[2] = c.pos.z; d.bvh_cam_valid = true; d.bvh_cam_stream = stream;
-            ctx->launches++;
-        }
+        int rc = prepare_lbvh_frame(ctx, d, fp.cam_inline[0], fp.w, fp.h, fp.spp, stream, &use_bins);
+        if (rc) return rc;
     }
     const size_t smem = ctx->path == PATH_STAGED ? sizeof(f4) * (size_t)ctx->gdata_host.ns : 0;
     const dim3 grid((unsigned)fp.chunks_per_tile, (unsigned)(fp.tiles_mine < 65535 ? fp.tiles_mine : 65535), (unsigned)fp.n_frames);
@@ -1278,7 +1333,10 @@ int launch_render(rt_context* ctx, DeviceState& d, const FrameParams& fp, cudaSt
         }
         case PATH_STAGED: k_render_staged<<<grid, BLOCK, smem, stream>>>(global_data(ctx, d), fp); break;
         case PATH_GLOBAL: k_render_global<<<grid, BLOCK, 0, stream>>>(global_data(ctx, d), fp); break;
-        default: k_render_lbvh<<<grid, BLOCK, 0, stream>>>(lbvh_data(ctx, d, true), fp); break;
+        default:
+            if (use_bins) k_render_lbvh_bins<<<grid, BLOCK, 0, stream>>>(lbvh_bins_data(ctx, d), fp);
+            else k_render_lbvh<<<grid, BLOCK, 0, stream>>>(lbvh_data(ctx, d, true), fp);
+            break;
     }
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
@@ -1314,6 +1372,7 @@ int rt_create(rt_context** out, const int* device_ids, int n_devices) {
     if (e != cudaSuccess || count == 0)
         return fail(nullptr, RT_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (librtb200 has no CPU fallback)");
     rt_context* ctx = new rt_context();
+    if (getenv("RTB200_PRIMARY_BINS")) ctx->primary_bins = atoi(getenv("RTB200_PRIMARY_BINS")) != 0;
     ctx->devs.resize((size_t)n_devices);
     for (int i = 0; i < n_devices; i++) {
         int dev = device_ids ? device_ids[i] : i;
@@ -1501,7 +1560,7 @@ int rt_update_spheres(rt_context* ctx, const float* spheres, int first, int coun
             if (r2max > d.bvh.r2max) d.bvh.r2max = r2max;
             cudaError_t e = d.bvh.refit_geometry(d.sgeom, d.stream);
             if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh refit: ") + cudaGetErrorString(e));
-            d.bvh_cam_valid = false;
+            d.bvh_cam_valid = false; d.pb_valid = false;
             ctx->launches++;
         }
         CU_TRY(ctx, cudaStreamSynchronize(d.stream));     // sg / sm go out of scope; later launches may use another stream
@@ -1524,6 +1583,7 @@ int rt_set_option(rt_context* ctx, int option, int value) {
         case RT_OPT_SINK_TILES: ctx->sink_tiles = value < 0 ? 0 : value; return RT_OK;
         case RT_OPT_PEER_TILES: ctx->peer_tiles = value < 0 ? 0 : value; return RT_OK;
         case RT_OPT_HOST_SHADOW_BINS: ctx->host_shadow_bins = value != 0; return RT_OK;
+        case RT_OPT_PRIMARY_BINS: ctx->primary_bins = value != 0; return RT_OK;
         case RT_OPT_HOST_ZERO_COPY: ctx->zero_copy = value < 0 ? 0 : (value > 2 ? 2 : value); return RT_OK;
         default: return fail(ctx, RT_ERR_INVALID, "unknown option");
     }
@@ -2116,11 +2176,16 @@ int rt_render_debug(rt_context* ctx, const rt_camera* cam, int w, int h, int dep
         case PATH_STAGED: k_debug_staged<<<(unsigned)grid, BLOCK, sizeof(f4) * (size_t)ctx->gdata_host.ns, d.stream>>>(global_data(ctx, d), fp, dout); break;
         case PATH_GLOBAL: k_debug_global<<<(unsigned)grid, BLOCK, 0, d.stream>>>(global_data(ctx, d), fp, dout); break;
         default: {
-            if (d.bvh_done_valid && d.bvh_last_stream != d.stream) CU_TRY(ctx, cudaStreamWaitEvent(d.stream, d.bvh_done, 0));
-            cudaError_t e = d.bvh.refit_for_camera(fp.cam_inline[0].pos.x, fp.cam_inline[0].pos.y, fp.cam_inline[0].pos.z, d.stream);
-            if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("lbvh refit: ") + cudaGetErrorString(e));
-            d.bvh_cam_valid = false;
-            k_debug_lbvh<<<(unsigned)grid, BLOCK, 0, d.stream>>>(lbvh_data(ctx, d, true), fp, dout);
+            // the same per-frame state as the production launch (launch_render), incl. the primary bins when they are switched on: the
+            // chain hashes / counters of this kernel then certify the binned primary fold (node_visits_primary counts what still traverses)
+            bool use_bins = false;
+            int prc = prepare_lbvh_frame(ctx, d, fp.cam_inline[0], w, h, spp, d.stream, &use_bins);
+            if (prc) return prc;
+            if (use_bins) k_debug_lbvh_bins<<<(unsigned)grid, BLOCK, 0, d.stream>>>(lbvh_bins_data(ctx, d), fp, dout);
+            else k_debug_lbvh<<<(unsigned)grid, BLOCK, 0, d.stream>>>(lbvh_data(ctx, d, true), fp, dout);
+            CU_TRY(ctx, cudaGetLastError());
+            CU_TRY(ctx, cudaEventRecord(d.bvh_done, d.stream));
+            d.bvh_done_valid = true; d.bvh_last_stream = d.stream;
             break;
         }
     }
@@ -2392,6 +2457,8 @@ int rt_get_info(const rt_context* ctx, int what, uint64_t* value) {
         case RT_INFO_LAST_ENQUEUE_NS: *value = ctx->last_enqueue_ns; return RT_OK;
         case RT_INFO_LAST_TOTAL_NS: *value = ctx->last_total_ns; return RT_OK;
         case RT_INFO_SHADOW_BINS_NS: *value = ctx->sg_build_ns; return RT_OK;
+        case RT_INFO_PRIMARY_BIN_BUILDS: *value = ctx->pb_builds.load(); return RT_OK;
+        case RT_INFO_PRIMARY_BINS: *value = ctx->primary_bins ? 1u : 0u; return RT_OK;
         case RT_INFO_SHADOW_BIN_PAIRS: *value = (ctx->has_shadow_grids && !ctx->devs.empty()) ? (uint64_t)ctx->devs[0].sg.n_pairs : 0u; return RT_OK;
         default: return RT_ERR_INVALID;
     }

@@ -31,6 +31,8 @@ RT_OPT_HOST_PRECLEARED = 7
 RT_OPT_HOST_ZERO_COPY = 8
 RT_OPT_GATHER_MODE, RT_OPT_SINK_TILES, RT_OPT_PEER_TILES = 9, 10, 11
 RT_OPT_HOST_SHADOW_BINS = 12
+RT_OPT_PRIMARY_BINS = 13
+RT_INFO_PRIMARY_BIN_BUILDS, RT_INFO_PRIMARY_BINS = 13, 14
 RT_INFO_SHADOW_BINS_NS, RT_INFO_SHADOW_BIN_PAIRS = 11, 12
 RT_INFO_GATHER_TIMEOUTS, RT_INFO_GATHER_ACTIVE = 9, 10
 RT_INFO_GATE_HOST_NS, RT_INFO_GATE_COMPUTES, RT_INFO_LAST_D2H_BYTES, RT_INFO_SCENE_PATH = 1, 2, 3, 4

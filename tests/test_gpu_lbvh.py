@@ -233,3 +233,145 @@ def test_update_spheres_rebuilds_the_bins_on_the_gpu(rt):
     assert np.array_equal(got, ref)
     print("rt_update_spheres(100k): %.2f ms total, shadow bins %.2f ms" % (min(ts) * 1e3, bins_ms))
     assert bins_ms < 20.0
+
+
+# ---- per-frame primary bins (csrc/rt_primary_bins.cuh, RT_OPT_PRIMARY_BINS) -------------------------------------------------------
+def _ctx(rt, sc, accel, bins):
+    ctx = rt.Context([0])
+    ctx.set_option(rt.RT_OPT_PRIMARY_BINS, bins)
+    ctx.set_scene(sc, accel)
+    return ctx
+
+
+def _same_debug(a, b):
+    assert np.array_equal(a["pixels"], b["pixels"])
+    assert np.array_equal(a["hash"], b["hash"])
+    assert np.array_equal(a["aov_id"], b["aov_id"]) and np.array_equal(a["aov_t"].view(np.uint32), b["aov_t"].view(np.uint32))
+    for k in ("primary", "shadow", "secondary", "plane_tests", "shade_diffuse", "shade_specular", "shade_mirror", "shaded_hits"):
+        assert a["counters"][k] == b["counters"][k], k
+
+
+def test_primary_bins_config3_4k_same_hits_as_the_tree(rt):
+    """BASELINE configs[2] at full size: with the bins the primary rays take the same hits (chain hash = ids + t bits of every ray,
+    primary AOVs) and the frame is the same, while (almost) no primary ray walks the tree; a pixel subset against the oracle."""
+    sc = scenes.config3_scene()
+    w, h = 3840, 2160
+    cam = scenes.make_camera(width=w, height=h, **scenes.SCALED_CAMERA)
+    res = {}
+    for bins in (0, 1):
+        ctx = _ctx(rt, sc, rt.RT_ACCEL_LBVH, bins)
+        dbg = ctx.render_debug(cam, w, h, 8)
+        px, _ = ctx.render(cam, w, h, 8)
+        assert np.array_equal(px, dbg["pixels"])
+        builds = ctx.get_info(rt.RT_INFO_PRIMARY_BIN_BUILDS)
+        res[bins] = dbg
+        ctx.close()
+    _same_debug(res[0], res[1])
+    assert builds == 1                                       # (the context with bins) debug and render share the frame's bins
+    assert res[0]["lbvh"]["node_visits_primary"] > 4 * w * h
+    assert res[1]["lbvh"]["node_visits_primary"] < 0.05 * res[0]["lbvh"]["node_visits_primary"]
+    assert res[1]["lbvh"]["node_visits_secondary"] == res[0]["lbvh"]["node_visits_secondary"]
+    idx = np.random.default_rng(7).choice(w * h, 4096, replace=False).astype(np.int32)
+    ref = O.render(sc, cam, w, h, 8, subset=idx, want_hash=True)
+    assert np.array_equal(res[1]["pixels"].reshape(-1)[idx], ref["pixels"])
+    assert np.array_equal(res[1]["hash"].reshape(-1)[idx], ref["hash"])
+
+
+def test_primary_bins_config4_100k_same_frame_and_oracle_subset(rt):
+    """BASELINE configs[3]: 100k spheres at 4K. Crowded horizon tiles keep no list and traverse; everything else folds over its list."""
+    sc = scenes.config4_scene()
+    w, h = 3840, 2160
+    cam = scenes.make_camera(width=w, height=h, **scenes.SCALED_CAMERA)
+    res = {}
+    for bins in (0, 1):
+        ctx = _ctx(rt, sc, rt.RT_ACCEL_AUTO, bins)
+        px, _ = ctx.render(cam, w, h, 8)
+        dbg = ctx.render_debug(cam, w, h, 8)
+        assert np.array_equal(px, dbg["pixels"])
+        res[bins] = dbg
+        ctx.close()
+    _same_debug(res[0], res[1])
+    assert res[1]["lbvh"]["node_visits_primary"] < 0.5 * res[0]["lbvh"]["node_visits_primary"]
+    idx = np.random.default_rng(7).choice(w * h, 8192, replace=False).astype(np.int32)
+    ref = O.render(sc, cam, w, h, 8, subset=idx, want_hash=True)
+    assert np.array_equal(res[1]["pixels"].reshape(-1)[idx], ref["pixels"])
+    assert np.array_equal(res[1]["hash"].reshape(-1)[idx], ref["hash"])
+
+
+def test_primary_bins_follow_the_camera_the_frame_size_and_the_scene(rt):
+    """The bins are per (camera, frame size, sphere records): a moving / turning camera, alternating frame sizes, a batch of distinct
+    cameras, rt_update_spheres — each frame equals the frame of a context without bins; a camera that stands still does not rebuild."""
+    sc = scenes.config3_scene()
+    a = _ctx(rt, sc, rt.RT_ACCEL_LBVH, 1)
+    b = _ctx(rt, sc, rt.RT_ACCEL_LBVH, 0)
+    rng = np.random.default_rng(3)
+    frames = [((480, 270), dict(pos=(0.0, 3.0, -6.0), yaw=0.0, pitch=0.25)), ((480, 270), dict(pos=(0.0, 3.0, -6.0), yaw=0.0, pitch=0.25)),
+              ((480, 270), dict(pos=(0.0, 3.0, -6.0), yaw=0.01, pitch=0.25)), ((333, 187), dict(pos=(0.0, 3.0, -6.0), yaw=0.01, pitch=0.25)),
+              ((480, 270), dict(pos=(7.5, 1.25, 9.0), yaw=0.9, pitch=-0.2)), ((640, 360), dict(pos=(-11.0, 6.0, 30.0), yaw=2.8, pitch=0.6)),
+              ((640, 360), dict(pos=(0.3, 0.2, 20.0), yaw=-1.3, pitch=0.05)), ((200, 120), dict(pos=(3.0, 40.0, 25.0), yaw=0.2, pitch=1.45))]
+    builds = []
+    for (w, h), kw in frames:
+        cam = scenes.make_camera(width=w, height=h, **kw)
+        pa, _ = a.render(cam, w, h, 8)
+        pb, _ = b.render(cam, w, h, 8)
+        assert np.array_equal(pa, pb), kw
+        builds.append(a.get_info(rt.RT_INFO_PRIMARY_BIN_BUILDS))
+    # a batch of distinct cameras (one launch per frame on the LBVH path, each with its own bins)
+    w, h = 320, 180
+    cams = np.stack([scenes.make_camera(width=w, height=h, pos=(0.0, 3.0, -6.0 + 0.5 * k), yaw=0.02 * k, pitch=0.25) for k in range(4)])
+    fa, _ = a.render_batch(cams, w, h, 8, headless=False)
+    fb, _ = b.render_batch(cams, w, h, 8, headless=False)
+    assert np.array_equal(fa, fb) and not np.array_equal(fa[0], fa[3])
+    # the scene changes under a standing camera
+    cam = scenes.make_camera(width=w, height=h, **scenes.SCALED_CAMERA)
+    before, _ = a.render(cam, w, h, 8)
+    moved = sc.spheres.copy()
+    moved[100:400, 0:3] += rng.normal(size=(300, 3)).astype(np.float32) * np.float32(1.5)
+    moved[100:400, 3] *= rng.uniform(0.5, 2.0, 300).astype(np.float32); moved[100:400, 17] = moved[100:400, 3] * moved[100:400, 3]
+    for c in (a, b):
+        c.update_spheres(moved[100:400], first=100)
+    pa, _ = a.render(cam, w, h, 8)
+    pb, _ = b.render(cam, w, h, 8)
+    assert np.array_equal(pa, pb) and not np.array_equal(pa, before)
+    assert np.array_equal(pa, O.render(scenes.Scene(moved, sc.planes, sc.lights, sc.ambient), cam, w, h, 8)["pixels"])
+    assert builds == [1, 1, 2, 3, 4, 5, 6, 7] and b.get_info(rt.RT_INFO_PRIMARY_BIN_BUILDS) == 0
+    a.close(); b.close()
+
+
+def test_primary_bins_fallbacks_supersampling_and_partitions(rt):
+    """Frames the bins do not serve are the tree's: a camera outside the gate derivation (basis not orthonormal), the eye inside spheres,
+    non-finite sphere records, supersampled frames; and a row-tile partition renders its tiles from the frame's bins."""
+    rng = np.random.default_rng(12)
+    sph, _ = scenes.random_spheres_scene(600, 5, 12.0, 2.0, 40.0, "pb")
+    sph = sph.copy()
+    sph[0, 0:3] = (0.0, 3.0, -6.0); sph[0, 3] = 2.0; sph[0, 17] = 4.0                 # the eye of SCALED_CAMERA is inside this one
+    sph[7, 0] = np.nan; sph[9, 17] = np.inf; sph[11, 2] = -np.inf
+    d = scenes.config3_scene()
+    sc = scenes.Scene(sph, d.planes, d.lights, d.ambient)
+    w, h = 400, 225
+    cam = scenes.make_camera(width=w, height=h, **scenes.SCALED_CAMERA)
+    skew = cam.copy(); skew[3:6] *= np.float32(1.01)
+    a = _ctx(rt, sc, rt.RT_ACCEL_LBVH, 1)
+    b = _ctx(rt, sc, rt.RT_ACCEL_LBVH, 0)
+    for c_, spp in ((cam, 1), (skew, 1), (cam, 4)):
+        pa, _ = a.render(c_, w, h, 8, spp, 9)
+        pb, _ = b.render(c_, w, h, 8, spp, 9)
+        assert np.array_equal(pa, pb)
+    assert np.array_equal(a.render(cam, w, h, 8)[0], O.render(sc, cam, w, h, 8)["pixels"])
+    _same_debug(a.render_debug(cam, w, h, 8), b.render_debug(cam, w, h, 8))
+    full, _ = b.render(cam, w, h, 8)
+    b.close()
+    # two ranks of a partition on this GPU store their tiles into one poisoned buffer
+    buf = a.dev_alloc(w * h * 4)
+    try:
+        a.dev_memset(buf, 0xAB, w * h * 4)
+        r1 = _ctx(rt, sc, rt.RT_ACCEL_LBVH, 1)
+        a.set_partition(0, 2, 8); r1.set_partition(1, 2, 8)
+        a.render_device(cam[None], w, h, 8, 1, 0, buf); r1.render_device(cam[None], w, h, 8, 1, 0, buf)
+        a.sync(); r1.sync()
+        got = a.dev_to_host(buf, w * h * 4).reshape(h, w)
+        assert np.array_equal(got, full)
+        r1.close()
+    finally:
+        a.dev_free(buf)
+    a.close()

@@ -30,7 +30,10 @@ namespace rtb {
 #define RT_PB_MARGIN_PX 2.0                  // overridable only to demonstrate that the margin is needed (tests/test_primary_bins.py)
 #endif
 constexpr int PB_TILE_SHIFT = 3;            // 8 x 8-pixel tiles: the LBVH kernels' warps are 8 x 4 pixels, so a warp reads one list
-constexpr int PB_CAP = 32;                  // longest list a tile keeps
+#ifndef RT_PB_CAP
+#define RT_PB_CAP 32                         // measured alternatives: profiles/r02/tuning.md
+#endif
+constexpr int PB_CAP = RT_PB_CAP;            // longest list a tile keeps
 constexpr int PB_MAX_EVERYWHERE = 8;        // spheres tested for every pixel (unbounded / huge projections)
 constexpr int PB_MAX_TILES = 4096;          // a sphere touching more tiles than this counts as "everywhere"
 

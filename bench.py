@@ -188,22 +188,26 @@ def per_config_extras(rtb200, local_rank, peaks):
                "frame_equals_instrumented_render": bool(np.array_equal(px, dbg["pixels"])), "scene_upload_s": upload_s,
                "path": ["tiny", "staged", "global", "lbvh"][ctx.get_info(rtb200.RT_INFO_SCENE_PATH)]}
         if rec["path"] == "lbvh":
-            # RT_OPT_PRIMARY_BINS both ways in this context: a camera that stands still (per-frame LBVH state cached) and one that moves
-            # every frame (camera-inflated boxes refit + primary bins rebuilt inside the timed region); frames compared each time
-            cam_b = scenes.make_camera(width=w, height=h, **dict(camkw, yaw=camkw.get("yaw", 0.0) + 1e-3))
+            # RT_OPT_PRIMARY_BINS (on by default) both ways in this context: a camera that stands still (per-frame LBVH state cached) and
+            # one that moves every frame (camera-inflated boxes refit + primary bins rebuilt inside the timed region); frames compared
             default_on = ctx.get_info(rtb200.RT_INFO_PRIMARY_BINS)
             pbs = {"default": bool(default_on)}
-            for setting in (0, 1):
-                ctx.set_option(rtb200.RT_OPT_PRIMARY_BINS, setting)
-                for _ in range(2):
-                    ctx.render(cam, w, h, depth, spp, 0, headless=True)
-                still = [ctx.render(cam, w, h, depth, spp, 0, headless=True)[1].kernel_ms for _ in range(5)]
-                moving = [ctx.render(cam_b if k % 2 == 0 else cam, w, h, depth, spp, 0, headless=True)[1].kernel_ms for k in range(6)]
-                px2, _ = ctx.render(cam, w, h, depth, spp, 0)
-                nv = ctx.render_debug(cam, w, h, depth, spp, 0, arrays=False)["lbvh"]["node_visits_primary"]
-                pbs["on" if setting else "off"] = {"kernel_ms": min(still), "kernel_ms_moving_camera": min(moving), "node_visits_primary": nv,
-                                                   "frame_equals_instrumented_render": bool(np.array_equal(px2, dbg["pixels"]))}
-            ctx.set_option(rtb200.RT_OPT_PRIMARY_BINS, default_on)
+            try:
+                cam_b = scenes.make_camera(width=w, height=h, **dict(camkw, yaw=camkw.get("yaw", 0.0) + 1e-3))
+                for setting in (0, 1):
+                    ctx.set_option(rtb200.RT_OPT_PRIMARY_BINS, setting)
+                    for _ in range(2):
+                        ctx.render(cam, w, h, depth, spp, 0, headless=True)
+                    still = [ctx.render(cam, w, h, depth, spp, 0, headless=True)[1].kernel_ms for _ in range(5)]
+                    moving = [ctx.render(cam_b if k % 2 == 0 else cam, w, h, depth, spp, 0, headless=True)[1].kernel_ms for k in range(6)]
+                    px2, _ = ctx.render(cam, w, h, depth, spp, 0)
+                    nv = ctx.render_debug(cam, w, h, depth, spp, 0, arrays=False)["lbvh"]["node_visits_primary"]
+                    pbs["on" if setting else "off"] = {"kernel_ms": min(still), "kernel_ms_moving_camera": min(moving), "node_visits_primary": nv,
+                                                       "frame_equals_instrumented_render": bool(np.array_equal(px2, dbg["pixels"]))}
+            except Exception as e:                        # an auxiliary A/B: never lose the bench line over it
+                pbs["error"] = repr(e)
+            finally:
+                ctx.set_option(rtb200.RT_OPT_PRIMARY_BINS, default_on)
             rec["primary_bins"] = pbs
             lb = dbg["lbvh"]
             visits = lb["node_visits_primary"] + lb["node_visits_secondary"] + lb["node_visits_shadow"]

@@ -207,7 +207,7 @@ int rt_selftest(rt_context* ctx, int test, uint64_t* n_checked, uint64_t* n_mism
  * geometry code, same bins; 0.1-0.3 s at 100 k spheres instead of ~2 ms). Takes effect at the next rt_set_scene / rt_update_spheres.
  * Exists for the test that shows both builds agree. */
 #define RT_OPT_HOST_SHADOW_BINS 12
-/* RT_OPT_PRIMARY_BINS: LBVH scenes, single-sample frames — per frame (whenever the camera or the frame size changes) every sphere is
+/* RT_OPT_PRIMARY_BINS (default 1; environment RTB200_PRIMARY_BINS overrides the default at rt_create): LBVH scenes, single-sample frames — per frame (whenever the camera or the frame size changes) every sphere is
  * projected to the pixel rectangle outside of which no primary ray can be reported as hitting it (the rectangle of the tiny scenes'
  * frame gates, csrc/rt_gate.cuh) and entered into the 8 x 8-pixel tiles it touches, on the GPU (three small launches, nothing read
  * back); a primary ray then runs the reference's sphere test (RayTracer.cs:613-642) over the list of ITS tile and folds as :975-981

@@ -59,7 +59,7 @@ constexpr int STACK_RECS = RT_MAX_DEPTH + 1;
 constexpr int INLINE_CAMS = 16;
 constexpr int N_DEBUG_COUNTERS = 16;
 #ifndef RT_PRIMARY_BINS_DEFAULT
-#define RT_PRIMARY_BINS_DEFAULT 0      // RT_OPT_PRIMARY_BINS of a new context (environment RTB200_PRIMARY_BINS overrides it at rt_create)
+#define RT_PRIMARY_BINS_DEFAULT 1      // RT_OPT_PRIMARY_BINS of a new context (environment RTB200_PRIMARY_BINS overrides it at rt_create)
 #endif
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 8      // resident CTAs per SM the register allocator must allow (tuned on B200, profiles/)

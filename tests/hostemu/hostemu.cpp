@@ -13,6 +13,7 @@ using namespace rtb;
 
 // Host-side LBVH build with the same pieces the CUDA build kernels use (morton_key, karras_node, sphere_box, box_union).
 #include <algorithm>
+#include <random>
 struct HostBvh {
     std::vector<BvhNode> nodes, nodes_cam; std::vector<f4> sorted; std::vector<int> orig; float r2max = 0; int n = 0;
     BvhView view() const {
@@ -95,6 +96,69 @@ static int pb_capacity_for(int n, const PbCam& c) {
     return pb_list_capacity(n, (long long)c.tiles_x * c.tiles_y);
 }
 extern "C" void emu_set_primary_bins_capacity(int capacity) { g_pb_capacity = capacity; }
+// The DEVICE build's algorithm (rt_primary_bins_build.cuh: k_pb_bin<false>, k_pb_alloc, k_pb_bin<true>) replayed on the host with the
+// freedom its atomics have: spheres are counted and filled in two independent random orders (the order in which warps reach their
+// atomics), "everywhere" slots are handed out in count order, runs of the list array are handed out per group of 32 consecutive tiles
+// (k_pb_alloc's warp: prefix sum inside, one cursor atomic per warp) in a random group order, the rectangle of the count pass is kept for
+// the fill pass, and every sphere walks its rectangle with the kernel's own step -> tile arithmetic (pb_walk_tile).
+static uint64_t g_pb_shuffle = 0;                 // emu_set_primary_bins_shuffle: 0 = primary_bins_build_host, else the seed of the replay
+extern "C" void emu_set_primary_bins_shuffle(uint64_t seed) { g_pb_shuffle = seed; }
+static void primary_bins_build_device_order(const PbCam& c, const f4* sgeom, int n, int capacity, uint64_t seed, PrimaryBinsHost* out) {
+    out->valid = false;
+    memset(&out->hdr, 0, sizeof(out->hdr));
+    if (c.eps < 0 || n <= 0) return;
+    out->tiles_x = c.tiles_x; out->tiles_y = c.tiles_y;
+    const size_t nt = (size_t)c.tiles_x * (size_t)c.tiles_y;
+    std::vector<int> count(nt, 0), fill(nt, 0);
+    out->tiles.assign(nt, PbTile{-1, 0});
+    out->geom.assign((size_t)capacity, f4()); out->orig.assign((size_t)capacity, -1);
+    struct Rect { int x0, y0, x1, y1; };
+    std::vector<Rect> rects((size_t)n, Rect{0, 0, -1, -1});
+    std::mt19937_64 rng(seed);
+    std::vector<int> order((size_t)n);
+    for (int i = 0; i < n; i++) order[(size_t)i] = i;
+    std::shuffle(order.begin(), order.end(), rng);
+    for (int i : order) {                                                    // k_pb_bin<false>
+        int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+        const int kind = pb_sphere_tiles(c, sgeom[i], &x0, &y0, &x1, &y1);
+        if (kind == 2) { const int s = out->hdr.n_everywhere++; if (s < PB_MAX_EVERYWHERE) { out->hdr.ev_geom[s] = sgeom[i]; out->hdr.ev_orig[s] = i; } }
+        if (kind != 1) continue;
+        rects[(size_t)i] = Rect{x0, y0, x1, y1};
+        const int tw = x1 - x0 + 1, cells = tw * (y1 - y0 + 1);
+        for (int k = 0; k < cells; k++) count[(size_t)pb_walk_tile(k, tw, x0, y0, c.tiles_x)]++;
+    }
+    std::vector<size_t> groups((nt + 31) / 32);                              // k_pb_alloc
+    for (size_t g = 0; g < groups.size(); g++) groups[g] = g;
+    std::shuffle(groups.begin(), groups.end(), rng);
+    for (size_t g : groups) {
+        int incl = 0;
+        const int base = out->hdr.cursor;
+        for (size_t t = g * 32; t < g * 32 + 32 && t < nt; t++) {
+            const int cnt = count[t] > PB_CAP ? 0 : count[t];
+            incl += cnt;
+            out->tiles[t] = pb_tile_decide(count[t], base + incl - cnt, capacity);
+        }
+        out->hdr.cursor += incl;
+    }
+    std::shuffle(order.begin(), order.end(), rng);
+    for (int i : order) {                                                    // k_pb_bin<true>
+        const Rect r = rects[(size_t)i];
+        if (r.x1 < r.x0 || r.y1 < r.y0) continue;
+        const int tw = r.x1 - r.x0 + 1, cells = tw * (r.y1 - r.y0 + 1);
+        for (int k = 0; k < cells; k++) {
+            const size_t t = (size_t)pb_walk_tile(k, tw, r.x0, r.y0, c.tiles_x);
+            const PbTile tl = out->tiles[t];
+            if (tl.n < 0) continue;
+            const int s = tl.start + fill[t]++;
+            out->geom[(size_t)s] = sgeom[i]; out->orig[(size_t)s] = i;
+        }
+    }
+    out->valid = true;
+}
+static void build_primary_bins(const PbCam& c, const f4* sgeom, int n, PrimaryBinsHost* out) {
+    if (g_pb_shuffle) primary_bins_build_device_order(c, sgeom, n, pb_capacity_for(n, c), g_pb_shuffle, out);
+    else primary_bins_build_host(c, sgeom, n, pb_capacity_for(n, c), out);
+}
 static ShadowGridsHost g_sgh;
 static ShadowGridsView sg_view() {
     ShadowGridsView v; memset(&v, 0, sizeof(v));
@@ -174,7 +238,7 @@ extern "C" int emu_render(const float* spheres, int ns, const float* planes, int
         std::vector<f3> lp((size_t)nl);
         for (int i = 0; i < nl; i++) lp[i] = li[i].p;
         shadow_grids_build(sg, lp, &g_sgh);
-        if (use_tiny == 6) { const PbCam pc = make_pb_cam(cam, w, h); primary_bins_build_host(pc, sg.data(), ns, pb_capacity_for(ns, pc), &g_pbh); }
+        if (use_tiny == 6) { const PbCam pc = make_pb_cam(cam, w, h); build_primary_bins(pc, sg.data(), ns, &g_pbh); }
     }
     TinySceneData t; memset(&t, 0, sizeof(t));
     if (use_tiny == 1 || use_tiny == 2 || use_tiny == 5 || use_tiny == 11 || use_tiny == 12) {
@@ -392,7 +456,7 @@ extern "C" int emu_primary_bins_check(const float* spheres, int ns, const float*
     cam.view = mk3(cam15[12], cam15[13], cam15[14]);
     PrimaryBinsHost pbh;
     const PbCam pc = make_pb_cam(cam, w, h);
-    primary_bins_build_host(pc, sg.data(), ns, pb_capacity_for(ns, pc), &pbh);
+    build_primary_bins(pc, sg.data(), ns, &pbh);
     const PrimaryBinsView v = pbh.view();
     uint64_t by_bins = 0, by_tree = 0, missing = 0, differ = 0, tests = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : by_bins, by_tree, missing, differ, tests)

@@ -43,6 +43,8 @@ def load():
         _lib.emu_primary_bins_check.restype = C.c_int
         _lib.emu_set_primary_bins_capacity.argtypes = [C.c_int]
         _lib.emu_set_primary_bins_capacity.restype = None
+        _lib.emu_set_primary_bins_shuffle.argtypes = [C.c_uint64]
+        _lib.emu_set_primary_bins_shuffle.restype = None
     return _lib
 
 
@@ -153,17 +155,25 @@ def shadow_bins_check(spheres, lights, points):
     return dict(zip(("decided", "mismatches", "undecided", "occluded", "sphere_tests"), (int(v) for v in out)))
 
 
-def primary_bins_check(spheres, cam, w, h, capacity=-1):
+def set_primary_bins_shuffle(seed):
+    """0: the bins of the emulation are built by primary_bins_build_host; else by the replay of the DEVICE build's algorithm with its
+    atomics resolved in a random order drawn from `seed` (hostemu.cpp: primary_bins_build_device_order)."""
+    load().emu_set_primary_bins_shuffle(int(seed))
+
+
+def primary_bins_check(spheres, cam, w, h, capacity=-1, shuffle=0):
     """Per-frame primary bins (rt_primary_bins.cuh) against the reference's loop over all spheres for every pixel's primary ray.
-    capacity: entries of the list array (-1 = the device build's rule)."""
+    capacity: entries of the list array (-1 = the device build's rule); shuffle: see set_primary_bins_shuffle."""
     lib = load()
     spheres = np.ascontiguousarray(spheres, np.float32); cam = np.ascontiguousarray(cam, np.float32)
     out = np.zeros(9, np.uint64)
     lib.emu_set_primary_bins_capacity(int(capacity))
+    lib.emu_set_primary_bins_shuffle(int(shuffle))
     try:
         rc = lib.emu_primary_bins_check(_fp(spheres), len(spheres), _fp(cam), w, h, out.ctypes.data_as(C.POINTER(C.c_uint64)))
     finally:
         lib.emu_set_primary_bins_capacity(-1)
+        lib.emu_set_primary_bins_shuffle(0)
     assert rc == 0
     return dict(zip(("by_bins", "by_tree", "missing", "differ", "sphere_tests", "tiles_without_list", "entries", "everywhere", "valid"),
                     (int(v) for v in out)))

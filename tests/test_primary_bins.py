@@ -182,3 +182,56 @@ def test_packed_slab_build_of_the_emulation_agrees(built):
     finally:
         E.use_variant("")
     assert np.array_equal(got, ref)
+
+
+# ---- the DEVICE build's algorithm, replayed on the host with its atomics resolved in random orders -----------------------------------
+@pytest.mark.parametrize("seed", [1, 2, 0xC0FFEE])
+def test_device_build_replay_is_order_independent(built, seed):
+    """rt_primary_bins_build.cuh hands out list slots, "everywhere" slots and runs of the list array in whatever order its atomics
+    resolve. Replayed on the host (hostemu.cpp: primary_bins_build_device_order — random sphere orders for the count and the fill pass,
+    random order of k_pb_alloc's 32-tile groups, the kernel's own step -> tile arithmetic): every reported hit is listed, every fold
+    selects the reference's sphere, and the lists hold as many entries in as many tiles as the sequential host build's."""
+    sc = scenes.config3_scene()
+    w, h = 384, 216
+    for ci in (0, 2, 5):
+        cam = scenes.make_camera(width=w, height=h, **CAMERAS[ci])
+        seq = check(sc.spheres, cam, w, h)
+        r = E.primary_bins_check(sc.spheres, cam, w, h, shuffle=seed)
+        assert r["missing"] == 0 and r["differ"] == 0 and r["valid"] == 1, r
+        for k in ("by_bins", "by_tree", "tiles_without_list", "entries", "everywhere", "sphere_tests"):
+            assert r[k] == seq[k], (k, r, seq)
+
+
+def test_device_build_replay_with_a_full_list_array_and_everywhere_spheres(built):
+    """Which tiles lose their list when the array is full, and which slot an "everywhere" sphere takes, depends on the order — the
+    answers must not: crowded tiles, a list array too small for the frame, the eye inside spheres, non-finite records."""
+    rng = np.random.default_rng(9)
+    sph = np.stack([mk((rng.normal() * 0.2, rng.normal() * 0.2, 5 + 0.2 * i), 0.3) for i in range(400)] +
+                   [mk((rng.uniform(-20, 20), rng.uniform(-5, 9), rng.uniform(8, 60)), rng.uniform(0.2, 0.8)) for _ in range(300)] +
+                   [mk((0.0, 0.0, 0.0), 1.5), mk((0.2, 0.1, -0.3), 3.0), mk((0.0, -50.0, 0.0), 49.0)])
+    sph[17, 0] = np.nan; sph[23, 17] = np.inf
+    w, h = 320, 180
+    cam = scenes.make_camera(width=w, height=h, pos=(0.0, 0.0, 0.0), yaw=0.0, pitch=0.0)
+    seq = check(sph, cam, w, h)
+    assert seq["everywhere"] >= 2 and seq["tiles_without_list"] > 0, seq
+    for seed in (3, 4, 5):
+        r = E.primary_bins_check(sph, cam, w, h, shuffle=seed)
+        assert r["missing"] == 0 and r["differ"] == 0, r
+        assert r["entries"] == seq["entries"] and r["everywhere"] == seq["everywhere"]
+        for cap in (0, 1, 37, seq["entries"] // 2, seq["entries"] - 1):
+            r2 = E.primary_bins_check(sph, cam, w, h, capacity=cap, shuffle=seed)
+            assert r2["missing"] == 0 and r2["differ"] == 0 and r2["entries"] <= cap, r2
+
+
+def test_device_build_replay_renders_the_oracles_frame(built):
+    """The whole LbvhBinsScene policy over bins built in device order: pixels and chain hashes equal the oracle's."""
+    sc, (w, h) = scenes.config3_scene(), (320, 180)
+    cam = scenes.make_camera(width=w, height=h, **scenes.SCALED_CAMERA)
+    ref = O.render(sc, cam, w, h, 8, want_hash=True)
+    try:
+        for seed in (7, 8):
+            E.set_primary_bins_shuffle(seed)
+            got = E.render(sc, cam, w, h, 8, tiny=BINS, debug=True)
+            assert np.array_equal(got["pixels"], ref["pixels"]) and np.array_equal(got["hash"], ref["hash"])
+    finally:
+        E.set_primary_bins_shuffle(0)

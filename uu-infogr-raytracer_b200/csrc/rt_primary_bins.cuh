@@ -64,6 +64,13 @@ RT_HD PbTile pb_tile_decide(int count, int start, int capacity) {
     return t;
 }
 
+// Step k of the walk over a sphere's tile rectangle (tw tiles wide, top-left tile (sx0, sy0), row-major inside the rectangle) -> tile
+// index of the frame. The device build's lanes take the steps 32 apart (rt_primary_bins_build.cuh); tests/hostemu replays them.
+RT_HD int pb_walk_tile(int k, int tw, int sx0, int sy0, int tiles_x) {
+    const int ry = k / tw;
+    return (sy0 + ry) * tiles_x + sx0 + (k - ry * tw);
+}
+
 RT_HD PbTile pb_load_tile(const PbTile* p) {
 #if defined(__CUDA_ARCH__)
     const int2 v = __ldg(reinterpret_cast<const int2*>(p));

@@ -11,7 +11,9 @@
 //                     no list (PbTile.n = -1): its pixels traverse the LBVH.
 //   k_pb_bin<true>    same walk; each (tile, sphere) takes a slot of the tile's run and stores the sphere record + original index
 // The order of the spheres inside a list depends on the atomics; the query folds with the lexicographic minimum over (t, original
-// index), which does not. Host twin: primary_bins_build_host (rt_primary_bins.cuh; tests/hostemu), same lists as sets.
+// index), which does not. Host twin: primary_bins_build_host (rt_primary_bins.cuh; tests/hostemu), same lists as sets; the three passes
+// below are also replayed on the host with their atomics resolved in random orders (tests/hostemu/hostemu.cpp:
+// primary_bins_build_device_order, tests/test_primary_bins.py::test_device_build_replay_*).
 #pragma once
 #include "rt_primary_bins.cuh"
 
@@ -67,8 +69,7 @@ __global__ void __launch_bounds__(256) k_pb_bin(const f4* __restrict__ sgeom, in
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int k = k0 + 32 * j;
-                const int ry = k / tw;
-                t[j] = k < cells ? (sy0 + ry) * cam.tiles_x + sx0 + (k - ry * tw) : -1;
+                t[j] = k < cells ? pb_walk_tile(k, tw, sx0, sy0, cam.tiles_x) : -1;
             }
             if (!FILL) {
 #pragma unroll

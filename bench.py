@@ -158,7 +158,8 @@ def time_steps(torch, stream, fn, n):
 def per_config_extras(rtb200, local_rank, peaks):
     """BASELINE.json configs[0], [2], [3], [4] on ONE GPU, after the headline loop, in this process: single-frame launches through
     rt_render (headless), kernel time from CUDA events inside the library (best of 5 after 2 warm-ups), ray / LBVH counters from the
-    instrumented kernel, and the returned frame compared with the instrumented render of the same frame."""
+    instrumented kernel, and the returned frame compared with the instrumented render of the same frame. LBVH configs also carry
+    `primary_bins`: RT_OPT_PRIMARY_BINS off and on in the same context, camera standing still and moving every frame."""
     import zlib
     out = {}
     l2_gbs = None

@@ -59,3 +59,62 @@ def test_b200_arm_line(built):
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "Mrays/s"
+
+
+def test_per_config_extras_against_a_stub_library():
+    """bench.per_config_extras walks every BASELINE.json config through the binding's API; run here against a stub of that API (no GPU)
+    so that a slip in the harness cannot cost the bench line: keys, the primary-bins A/B of the LBVH configs, option restored."""
+    import types
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Stats:
+        kernel_ms = 1.0
+
+    class Ctx:
+        options = []
+
+        def __init__(self, devs):
+            self.bins = 1
+            self.path = 0
+
+        def set_scene(self, sc, accel):
+            self.path = 3 if len(sc.spheres) >= 48 and accel != 1 else (1 if len(sc.spheres) >= 48 else 0)
+
+        def render_debug(self, cam, w, h, depth, spp, seed, arrays=True):
+            cnt = dict(primary=w * h * spp, shadow=w * h, secondary=w * h // 2, sphere_tests=10 * w * h, sphere_disc_pos=w * h, plane_tests=w * h,
+                       shade_diffuse=w * h, shade_specular=w * h // 2, shade_mirror=w * h // 4, shaded_hits=w * h)
+            return dict(pixels=np.zeros((h, w), np.int32), counters=cnt, stats=Stats(),
+                        lbvh=dict(node_visits_primary=w * h * (1 if self.bins else 11), node_visits_secondary=w * h, node_visits_shadow=0, brute_fallbacks=0))
+
+        def render(self, cam, w, h, depth, spp=1, seed=0, headless=False):
+            return (None if headless else np.zeros((h, w), np.int32)), Stats()
+
+        def get_info(self, what):
+            return {stub.RT_INFO_SCENE_PATH: self.path, stub.RT_INFO_PRIMARY_BINS: self.bins}[what]
+
+        def set_option(self, opt, value):
+            assert opt == stub.RT_OPT_PRIMARY_BINS
+            self.bins = int(value); Ctx.options.append(int(value))
+
+        def measure_l2_read(self, nbytes):
+            return 18400.0
+
+        def close(self):
+            pass
+
+    stub = types.SimpleNamespace(Context=Ctx, RT_ACCEL_AUTO=0, RT_ACCEL_BRUTE=1, RT_ACCEL_LBVH=2, RT_INFO_SCENE_PATH=4, RT_INFO_PRIMARY_BINS=14,
+                                 RT_OPT_PRIMARY_BINS=13)
+    out = bench.per_config_extras(stub, 0, dict(hbm_gbs=6548.0, sm_max_mhz=1965.0))
+    assert len(out) == 5
+    n_lbvh = 0
+    for name, rec in out.items():
+        assert rec["frame_equals_instrumented_render"] and rec["kernel_ms"] == 1.0 and "roofline" in rec, name
+        if rec["path"] == "lbvh":
+            n_lbvh += 1
+            pb = rec["primary_bins"]
+            assert "error" not in pb, pb
+            assert pb["default"] is True and pb["off"]["node_visits_primary"] > pb["on"]["node_visits_primary"]
+            assert rec["roofline"]["bound"] == "L2"
+    assert n_lbvh == 2 and Ctx.options == [0, 1, 1, 0, 1, 1]          # off, on, restored — per LBVH config

@@ -235,3 +235,10 @@ def test_device_build_replay_renders_the_oracles_frame(built):
             assert np.array_equal(got["pixels"], ref["pixels"]) and np.array_equal(got["hash"], ref["hash"])
     finally:
         E.set_primary_bins_shuffle(0)
+
+
+def test_fuzz_slice(built):
+    """A short slice of tests/fuzz_primary_bins.py (the campaign itself: 28 000 cases in round 2, none bad)."""
+    import fuzz_primary_bins
+    bad, valid, with_lists = fuzz_primary_bins.run(5, 150, verbose=False)
+    assert bad == 0 and with_lists >= 60
